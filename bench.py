@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s at the 1M-unknown sparse least-squares workload (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--g 1024]
+
+A *step* is one Levenberg-Marquardt loop body (LMSolver.h:110-188): fused assembly of
+rhs / ||rhs||_inf / damping / H, the damped sparse solve, the trial evaluation, acceptance and
+the lambda update.  Workload: config C2, "LF-1M" (sparse analogue of
+benchmark/linear_function: g x g torus, n = g^2 unknowns, m = 2n residuals, 8 nnz/row; g=1024).
+  value : steps/s with the traits evaluated on the device (inputs resident in HBM), K loop
+          bodies of one solve started at x0 (lambda follows the LM rule, stop tests off).
+  e2e   : the same hot path through the C ABI with HOST buffers -- every step uploads the
+          Jacobian values and the residual from pinned host memory, runs assemble + factorize +
+          solve, and downloads the step vector and ||rhs||_inf.
+  roofline : the dominant kernel (the PCG's SpMV) re-timed per launch with CUDA events.
+  cpu_baseline / --impl reference : the CPU oracle (Eigen restatement, 1 thread) on a bounded
+          sample of the same workload.
+N>1: one process per GPU (torchrun), each rank solves its own independent LF problem (different
+seed): the "batches of independent problems split per GPU" sharding -- no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def lf_sizes(g):
+    n = g * g
+    return n, 2 * n, 16 * n
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(args, sample_g=None, steps=None, warmup=None):
+    """The reference's own CPU path (oracle: Eigen restatement, SimplicialLLT with AMD, 1 thread)
+    on a bounded sample of the workload.  Returns (steps_per_s_scaled, info)."""
+    from oracle import sp_oracle as orc
+    g_full = args.g
+    gs = sample_g or min(g_full, 160)
+    steps = steps or 2
+    warmup = 0 if warmup is None else warmup
+    n_s, m_s, _ = lf_sizes(gs)
+    t0 = time.time()
+    r = orc.lm_solve("lf", iparam0=gs, iparam1=2, seed=20211, maxIterations=max(0, warmup + steps - 1), funcTolerance=0.0,
+                     fooTolerance=0.0, verbose=False, solver_kind=0)
+    wall = time.time() - t0
+    bodies = max(1, r.factorizations)
+    per_iter = (r.times["assembly"] + r.times["factor"] + r.times["solve"]) / bodies
+    n_full = g_full * g_full
+    scale = n_s / float(n_full)  # linear extrapolation in the unknown count: optimistic for the CPU
+    info = {"kind": "port", "cores": 1,
+            "sample": "oracle (Eigen restatement: conservative SpGEMM + AMD + scalar up-looking LLT), LF g=%d (n=%d, 1/%.0f of the "
+                      "unknowns), %d loop bodies, assembly+factor+solve %.3f s/iteration, scaled linearly in n to g=%d "
+                      "(factorisation cost grows faster than n, so this over-states the CPU rate)" % (gs, n_s, 1.0 / scale, bodies, per_iter, g_full),
+            "seconds_per_iteration_sample": per_iter, "wall_s": wall,
+            "split_s": {k: v / bodies for k, v in r.times.items()}}
+    return (1.0 / per_iter) * scale, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, info = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    n, m, nnzJ = lf_sizes(args.g)
+    info["value"] = val
+    line = {"impl": "reference", "metric": "LM iterations/s", "value": val, "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "benchmark/linear_function LF-1M (C2): g=%d torus, n=%d, m=%d, nnzJ=%d" % (args.g, n, m, nnzJ)},
+            "cpu_baseline": info,
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import saddlepoint_b200 as spb
+
+    K, W, g = args.steps, max(args.warmup, 3), args.g
+    n, m, nnzJ = lf_sizes(g)
+    stream = torch.cuda.current_stream().cuda_stream
+    h = spb.Handle(local, stream)
+    h.set_solver(spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211 + rank)
+    ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
+    x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident run (value) -------------------------------------------------------
+    lm.solve(False, dedupe_evaluations=True, fixed_iterations=W, x_out=x_dev)  # warm-up (+ one-time analysis)
+    analyze_s = lm.seconds_analyze
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = h.launch_count()
+    ms = timed(lambda: lm.solve(False, dedupe_evaluations=True, fixed_iterations=K, x_out=x_dev))
+    launches = h.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    lin_iters = int(lm.linear_iterations)
+    value = world * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: same K steps, every launch bracketed by CUDA events
+    h.stage_reset(True)
+    lm.solve(False, dedupe_evaluations=True, fixed_iterations=K, x_out=x_dev)
+    stages = h.stage_ms()
+    h.stage_reset(False)
+    nnzH = h.h_nnz()
+    peaks, peak_kind = _peaks()
+    spmv_ms, spmv_launches = stages["spmv"]
+    # B_spmv = 12*nnzH + 4(n+1) + 8n + 8n bytes per product
+    b_spmv = 12 * nnzH + 4 * (n + 1) + 16 * n
+    live_spmv = max(1, lin_iters)  # launches that did work (post-convergence launches exit on the device flag)
+    achieved = b_spmv * live_spmv / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    asm_ms, asm_launches = stages["assembly"]
+    b_asm = 12 * nnzJ + 4 * (m + 1) + 8 * m + 8 * nnzH + 16 * n
+    roof = {"bound": "hbm", "kernel": "spmv_sell_kernel<true> (PCG SpMV + p.q)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+            "bytes_per_launch": b_spmv, "avg_launch_us": 1e3 * spmv_ms / max(1, live_spmv), "launches_timed": int(spmv_launches),
+            "share_of_step": spmv_ms / max(1e-9, sum(v[0] for v in stages.values())),
+            "assembly": {"achieved": b_asm * K / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0, "bytes_per_step": b_asm,
+                         "ms_per_step": asm_ms / K},
+            "stage_ms_per_step": {k: v[0] / K for k, v in stages.items()}}
+    roof["assembly"]["frac"] = roof["assembly"]["achieved"] / peaks["hbm_gbs"]
+
+    # ---- e2e: the C-ABI hot path with HOST buffers (H2D + D2H inside the timed region) -------
+    mrows, ncols, colptr, rowidx = prob.pattern()
+    Jv_host = torch.empty(nnzJ, dtype=torch.float64).pin_memory()
+    E_host = torch.empty(m, dtype=torch.float64).pin_memory()
+    dir_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    # contents: the problem's own J values and residual at x0 (generated on the device, copied out once)
+    Tt = prob.c_traits()
+    xd = torch.ones(n, dtype=torch.float64, device="cuda")
+    Ed = torch.empty(m, dtype=torch.float64, device="cuda")
+    Jd = torch.empty(nnzJ, dtype=torch.float64, device="cuda")
+    Tt.objective_jacobian(Tt.user, xd.data_ptr(), Ed.data_ptr(), Jd.data_ptr(), stream)
+    torch.cuda.synchronize()
+    Jv_host.copy_(Jd)
+    E_host.copy_(Ed)
+    del xd, Ed, Jd
+    Jn, En, dn_ = Jv_host.numpy(), E_host.numpy(), dir_host.numpy()
+
+    def e2e_steps(k):
+        for _ in range(k):
+            h.assemble(Jn, En, 0.01)
+            h.factorize()
+            h.solve(None, out=dn_)
+
+    e2e_steps(min(W, 3))
+    ms_e2e = timed(lambda: e2e_steps(K))
+    e2e_val = world * K / (ms_e2e * 1e-3)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cpu = cpu_reference(args)
+        cpu["value"] = v
+        cpu["unit"] = "iterations/s"
+
+    if rank == 0:
+        line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "benchmark/linear_function LF-1M (C2): g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (g, n, m, nnzJ, nnzH),
+                           "per_gpu": "one independent problem per GPU (seed 20211+rank)", "solver": "pcg_jacobi rtol=%g" % args.pcg_rtol,
+                           "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
+                           "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s},
+                "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--g", type=int, default=1024)
+    ap.add_argument("--pcg-rtol", type=float, default=1e-13)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/* saddlepoint_b200.h -- C ABI of the B200-native Levenberg-Marquardt inner step.
+ *
+ * This is the drop-in boundary underneath SaddlePoint's header-only concept API.  The
+ * reference has no FFI of its own (its plug-in mechanism is C++ template duck typing,
+ * LMSolver.h:22); every entry point below names the reference call site it replaces.  The
+ * concept-conforming C++ classes that sit on top of this ABI are in
+ * include/saddlepoint_b200/ (LMSolver, DiagonalDamping, B200SolverWrapper).
+ *
+ * Conventions: plain pointers and sizes only; `mem` says whether value pointers are host
+ * (SPB_HOST) or device (SPB_DEVICE) memory; pattern arrays are always host memory; indices
+ * are int32 and values FP64 exactly like Eigen::SparseMatrix<double> (column-major CSC,
+ * sorted inner indices, explicit zeros kept).  Every call returns an spb_status; no
+ * exceptions cross the ABI.  One host thread per handle; all device work is ordered on the
+ * handle's stream.  There is no CPU fallback: without a CUDA device spb_create fails.
+ */
+#ifndef SADDLEPOINT_B200_H
+#define SADDLEPOINT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spb_context* spb_handle;
+
+typedef enum {
+  SPB_OK = 0,
+  SPB_NOT_SPD = 1,        /* factorisation met a pivot <= 0  (EigenSolverWrapper.h:59 -> false) */
+  SPB_ERR_ARG = 2,
+  SPB_ERR_CUDA = 3,
+  SPB_ERR_STATE = 4,      /* call order violated (e.g. assemble before analyze)            */
+  SPB_NOT_CONVERGED = 5,  /* PCG hit maxit                                                 */
+  SPB_ERR_NCCL = 6
+} spb_status;
+
+typedef enum { SPB_HOST = 0, SPB_DEVICE = 1 } spb_mem;
+
+typedef enum {
+  SPB_SOLVER_CHOLESKY = 0,   /* supernodal LL^T: the SimplicialLLT replacement            */
+  SPB_SOLVER_PCG_JACOBI = 1, /* Jacobi-preconditioned CG on the same SpMV                 */
+  SPB_SOLVER_PCG_IC0 = 2     /* IC(0)-preconditioned CG                                   */
+} spb_solver;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* stream: a cudaStream_t (or NULL for a library-owned stream). */
+spb_status spb_create(int device, void* stream, spb_handle* out);
+spb_status spb_destroy(spb_handle h);
+const char* spb_last_error(spb_handle h);
+/* version / build info; callable without a GPU */
+const char* spb_version(void);
+
+/* ---- solver selection ------------------------------------------------------------------ */
+spb_status spb_set_solver(spb_handle h, int solver /* spb_solver */, double pcg_rtol, int pcg_maxit);
+
+/* ---- symbolic analysis (one-time per pattern) ------------------------------------------ */
+/* Replaces EigenSolverWrapper::analyze(JPattern) (EigenSolverWrapper.h:30-52; note the
+ * reference never calls it, LMSolver.h:69-73, and re-derives the pattern every iteration
+ * inside the product at LMSolver.h:136).  Input: pattern of the m x n Jacobian in CSC.
+ * Builds: the structural pattern of dampJ^T*dampJ (full symmetric, sorted, full diagonal),
+ * the map from every H nonzero to its contributing J entry pairs in ascending residual-row
+ * order, the SpMV layout, and (lazily, on first Cholesky use) ordering/etree/supernodes. */
+spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx);
+/* Cheap re-validation (the seamless-integration driver grows J between solves):
+ * returns SPB_OK and *same=1 if (m,n,colptr,rowidx) matches the analysed pattern. */
+spb_status spb_pattern_matches(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int* same);
+/* H pattern export (host), for parity tests: colptr[n+1], rowidx[nnz]. */
+spb_status spb_h_nnz(spb_handle h, int64_t* nnz);
+spb_status spb_h_pattern(spb_handle h, int32_t* colptr, int32_t* rowidx);
+/* H values in the CSC order of spb_h_pattern. */
+spb_status spb_h_values(spb_handle h, double* vals, int mem);
+
+/* Host-only views of the symbolic phase (no GPU, no handle): the structural pattern, and a
+ * self-check of the assembly plan (stats[8]: nslots, npairs, nchunks, rec_bits, padded SpMV
+ * entries, nnz(H), ncolchunks, invariant violations).  Used by the CPU test tier. */
+spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* nnz,
+                                  int32_t* h_colptr, int32_t* h_rowidx);
+spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats);
+
+/* ---- numeric assembly ------------------------------------------------------------------- */
+/* One call replaces, for the J / EVec of the last computeJacobian=true evaluation:
+ *   rhs = -(J^T * EVec)                          LMSolver.h:117
+ *   fooOptimality = rhs.lpNorm<Infinity>()       LMSolver.h:119
+ *   dampVector(j) = sum_r (lambda*v)*v, sqrt, augmented rows   DiagonalDamping.h:31-43,73-85
+ *   dampJ^T * dampJ                              LMSolver.h:136
+ * Jvals: nnz(J) values in the CSC order given to spb_analyze; EVec: m values (may be NULL to
+ * skip the gradient); foo: host out (may be NULL).  H and rhs stay on the device. */
+spb_status spb_assemble(spb_handle h, const double* Jvals, const double* EVec, double lambda, int mem, double* foo);
+/* copies of the assembled gradient rhs (n) and the damping vector d (n) */
+spb_status spb_get_rhs(spb_handle h, double* rhs, int mem);
+spb_status spb_get_damping(spb_handle h, double* d, int mem);
+
+/* ---- LinearSolver concept ---------------------------------------------------------------- */
+/* Load an explicit symmetric matrix (both triangles, CSC) instead of assembling it: this is
+ * LinearSolver::factorize(const SparseMatrix<double>) (EigenSolverWrapper.h:54-60) for
+ * callers that keep the reference's LMSolver.h unchanged and pass dampJ^T*dampJ themselves.
+ * The pattern is analysed on first use and whenever it changes. */
+spb_status spb_set_matrix(spb_handle h, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* vals, int mem);
+/* Replaces solver.compute(A) + info()==Success (EigenSolverWrapper.h:58-59): numeric
+ * factorisation of the current H.  SPB_NOT_SPD <=> the reference's `false`. */
+spb_status spb_factorize(spb_handle h);
+/* Replaces x = solver.solve(rhs) (EigenSolverWrapper.h:76; matrix RHS :62-70, nrhs columns,
+ * column-major).  rhs==NULL means "use the assembled gradient". iters: PCG iterations or 0. */
+spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int mem, int* iters);
+
+/* ---- vector reductions used by the LM loop (LMSolver.h:119,146,155,157,175) ------------- */
+spb_status spb_squared_norm(spb_handle h, const double* v, int64_t len, int mem, double* out);
+spb_status spb_inf_norm(spb_handle h, const double* v, int64_t len, int mem, double* out);
+/* y = H * x with the current H (the SpMV the PCG path is built on); exported for tests. */
+spb_status spb_spmv(spb_handle h, const double* x, double* y, int mem);
+
+/* ---- whole LM loop ---------------------------------------------------------------------- */
+/* SolverTraits concept (LMSolver.h:75-80,90,106,111,181) as C callbacks.  With
+ * mem==SPB_DEVICE the x / EVec / Jvals pointers are device pointers and the callback must
+ * enqueue its work on `stream`; with SPB_HOST they are host pointers. */
+typedef struct {
+  int32_t xSize, ESize;
+  const int32_t* colptr; /* CSC pattern of J (host), fixed for the duration of a solve */
+  const int32_t* rowidx;
+  int mem;
+  void* user;
+  void (*initial_solution)(void* user, double* x0_host);
+  /* Jvals==NULL <=> computeJacobian=false */
+  void (*objective_jacobian)(void* user, const double* x, double* EVec, double* Jvals, void* stream);
+  void (*pre_iteration)(void* user, const double* x);  /* may be NULL */
+  int (*post_iteration)(void* user, const double* x);  /* may be NULL; nonzero => stop   */
+} spb_traits;
+
+typedef struct {
+  int32_t maxIterations;   /* LMSolver::init default 100 (LMSolver.h:58)                  */
+  double funcTolerance;    /* default 10e-10 (LMSolver.h:59)                              */
+  double fooTolerance;     /* default 10e-10 (LMSolver.h:60)                              */
+  double lambda0;          /* DiagonalDamping ctor default 0.01 (DiagonalDamping.h:93)    */
+  int32_t verbose;         /* also selects the first-order-optimality break (LMSolver.h:125) */
+  int32_t dedupe_evaluations; /* 0: the reference's exact 5 objective calls per iteration;
+                                 1: reuse the bit-identical residuals (2 calls)           */
+  int32_t fixed_iterations;   /* >0: benchmark mode, run exactly this many loop bodies with
+                                 the stop tests disabled                                   */
+} spb_lm_options;
+
+typedef struct {
+  int32_t ret;             /* the bool LMSolver::solve returns                            */
+  int32_t exit_path;       /* 1 foo 2 factorize failed 3 direction small 4 func-tol 5 traits stop 6 max-iter */
+  int32_t currIter;
+  int32_t factorizations;
+  double energy, fooOptimality, lambda;
+  int64_t linear_iterations; /* total PCG iterations                                      */
+  double seconds_total, seconds_analyze;
+} spb_lm_result;
+
+void spb_lm_default_options(spb_lm_options* o);
+/* x_out: xSize values (host or device per x_mem).  trace (optional, host, 8 doubles per loop
+ * body that reached the solve, at most trace_cap records): prevEnergy2,newEnergy2,lambda,
+ * foo,dirnorm,accepted,lin_iters,reserved. */
+spb_status spb_lm_solve(spb_handle h, const spb_traits* traits, const spb_lm_options* opt, spb_lm_result* res,
+                        double* x_out, int x_mem, double* trace, int32_t trace_cap, int32_t* trace_len);
+
+/* ---- built-in device-resident benchmark traits --------------------------- */
+typedef struct spb_problem* spb_problem_t;
+/* "LF": sparse analogue of benchmark/linear_function: g x g torus, m=rows_mult*n,
+ * 8 nnz/row, counter-based splitmix64 data, f = A x - 1, x0 = 1. */
+spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, spb_problem_t* out);
+/* Extended Rosenbrock of benchmark/rosenbrock/main.cpp:11,47-62 over nblocks blocks;
+ * x0: 2*nblocks host values or NULL for (-100,100) repeated (main.cpp:43). */
+spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out);
+spb_status spb_problem_traits(spb_problem_t p, spb_traits* out);
+spb_status spb_problem_destroy(spb_problem_t p);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t spb_launch_count(spb_handle h);
+/* per-stage device time accumulated since the last reset, milliseconds (CUDA events):
+ * stage 0 assembly, 1 spmv, 2 pcg-vector, 3 factor, 4 trisolve, 5 reductions, 6 traits */
+spb_status spb_stage_ms(spb_handle h, int stage, double* ms, int64_t* launches);
+spb_status spb_stage_reset(spb_handle h, int enable_timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

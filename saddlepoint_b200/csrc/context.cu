@@ -1,0 +1,413 @@
+// context.cu -- handle lifetime, error plumbing, per-stage CUDA-event timing, and the
+// granular C ABI (analyze / assemble / factorize / solve / reductions).
+#include <cstring>
+#include <new>
+
+#include "spb_internal.h"
+
+namespace spb {
+
+static cudaEvent_t get_event(spb_context* h) {
+  if (!h->timing.pool.empty()) {
+    cudaEvent_t e = h->timing.pool.back();
+    h->timing.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  SPB_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+void timing_flush(spb_context* h) {
+  if (h->timing.pending.empty()) return;
+  SPB_CUDA(cudaStreamSynchronize(h->stream));
+  for (auto& p : h->timing.pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) h->timing.ms[p.stage] += ms;
+    h->timing.pool.push_back(p.a);
+    h->timing.pool.push_back(p.b);
+  }
+  h->timing.pending.clear();
+}
+
+void stage_begin(spb_context* h, int stage) {
+  if (!h->timing.enabled) return;
+  if (h->timing.pending.size() >= 2048) timing_flush(h);
+  Timing::Pending p;
+  p.a = get_event(h);
+  p.b = get_event(h);
+  p.stage = stage;
+  SPB_CUDA(cudaEventRecord(p.a, h->stream));
+  h->timing.pending.push_back(p);
+}
+
+void stage_end(spb_context* h, int stage, int nlaunch) {
+  h->launches += nlaunch;
+  h->timing.count[stage] += nlaunch;
+  if (!h->timing.enabled) return;
+  SPB_CUDA(cudaEventRecord(h->timing.pending.back().b, h->stream));
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+// Translates internal failures to status codes; nothing throws across the ABI.
+template <class F>
+static spb_status guarded(spb_handle h, F&& f) {
+  try {
+    return f();
+  } catch (const CudaFail& e) {
+    if (h) h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
+    return SPB_ERR_CUDA;
+  } catch (const ArgFail& e) {
+    if (h) h->err = e.msg;
+    return SPB_ERR_ARG;
+  } catch (const StateFail& e) {
+    if (h) h->err = e.msg;
+    return SPB_ERR_STATE;
+  } catch (const std::bad_alloc&) {
+    if (h) h->err = "host allocation failed";
+    return SPB_ERR_ARG;
+  }
+}
+
+// Stage a host vector into a device buffer (or pass a device pointer through).
+static const double* to_device(spb_handle h, const double* p, size_t len, int mem, DevBuf<double>& stage) {
+  if (!p) return nullptr;
+  if (mem == SPB_DEVICE) return p;
+  SPB_CUDA(stage.alloc(len));
+  SPB_CUDA(cudaMemcpyAsync(stage.p, p, len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return stage.p;
+}
+
+extern "C" {
+
+const char* spb_version(void) { return "saddlepoint_b200 0.1 (sm_100a)"; }
+
+spb_status spb_create(int device, void* stream, spb_handle* out) {
+  if (!out) return SPB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return SPB_ERR_CUDA;  // no CPU fallback: without a GPU there is no handle
+  }
+  spb_context* h = new (std::nothrow) spb_context;
+  if (!h) return SPB_ERR_ARG;
+  spb_status s = guarded(h, [&]() {
+    h->device = device;
+    SPB_CUDA(cudaSetDevice(device));
+    if (stream) {
+      h->stream = (cudaStream_t)stream;
+    } else {
+      SPB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+      h->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    SPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    SPB_CUDA(cudaMallocHost((void**)&h->h_sc, sizeof(PcgScalars)));
+    SPB_CUDA(cudaMallocHost((void**)&h->h_scalar, 8 * sizeof(double)));
+    memset(h->h_sc, 0, sizeof(PcgScalars));
+    return SPB_OK;
+  });
+  if (s != SPB_OK) {
+    delete h;
+    return s;
+  }
+  *out = h;
+  return SPB_OK;
+}
+
+spb_status spb_destroy(spb_handle h) {
+  if (!h) return SPB_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  chol_release(h);
+  for (auto& p : h->timing.pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto e : h->timing.pool) cudaEventDestroy(e);
+  if (h->h_sc) cudaFreeHost(h->h_sc);
+  if (h->h_scalar) cudaFreeHost(h->h_scalar);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SPB_OK;
+}
+
+const char* spb_last_error(spb_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+spb_status spb_set_solver(spb_handle h, int solver, double pcg_rtol, int pcg_maxit) {
+  if (!h || solver < 0 || solver > 2) return SPB_ERR_ARG;
+  h->solver = solver;
+  if (pcg_rtol > 0) h->pcg_rtol = pcg_rtol;
+  if (pcg_maxit > 0) h->pcg_maxit = pcg_maxit;
+  h->factor_valid = false;
+  return SPB_OK;
+}
+
+static void validate_csc(int m, int n, const int32_t* colptr, const int32_t* rowidx) {
+  if (m < 0 || n < 0 || !colptr || (colptr[n] > 0 && !rowidx)) throw ArgFail{"bad pattern arguments"};
+  if (colptr[0] != 0) throw ArgFail{"colptr[0] must be 0"};
+  for (int j = 0; j < n; ++j)
+    if (colptr[j + 1] < colptr[j]) throw ArgFail{"colptr must be non-decreasing"};
+}
+
+spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx) {
+  if (!h) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    validate_csc(m, n, colptr, rowidx);
+    h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+    chol_release(h);
+    h->m = m;
+    h->n = n;
+    h->nnzJ = colptr[n];
+    build_h_pattern(m, n, colptr, rowidx, h->H);
+    build_sell(h->H, h->S);
+    AssemblyPlan P;
+    build_assembly_plan(m, n, colptr, rowidx, h->H, P);
+    upload_h_layout(h);
+    upload_analysis(h, colptr, rowidx, P);
+    h->fingerprint = pattern_fingerprint(m, n, colptr, rowidx);
+    h->h_fingerprint = 0;
+    h->analyzed = true;
+    h->have_h = true;
+    return SPB_OK;
+  });
+}
+
+spb_status spb_pattern_matches(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int* same) {
+  if (!h || !same || !colptr) return SPB_ERR_ARG;
+  *same = (h->analyzed && h->m == m && h->n == n && h->nnzJ == colptr[n] &&
+           h->fingerprint == pattern_fingerprint(m, n, colptr, rowidx))
+              ? 1
+              : 0;
+  return SPB_OK;
+}
+
+spb_status spb_h_nnz(spb_handle h, int64_t* nnz) {
+  if (!h || !nnz) return SPB_ERR_ARG;
+  if (!h->have_h) return SPB_ERR_STATE;
+  *nnz = h->H.nnz();
+  return SPB_OK;
+}
+
+spb_status spb_h_pattern(spb_handle h, int32_t* colptr, int32_t* rowidx) {
+  if (!h) return SPB_ERR_ARG;
+  if (!h->have_h) return SPB_ERR_STATE;
+  if (colptr) memcpy(colptr, h->H.colptr.data(), sizeof(int32_t) * ((size_t)h->n + 1));
+  if (rowidx) memcpy(rowidx, h->H.rowidx.data(), sizeof(int32_t) * (size_t)h->H.nnz());
+  return SPB_OK;
+}
+
+spb_status spb_h_values(spb_handle h, double* vals, int mem) {
+  if (!h || !vals) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->h_valid) throw StateFail{"no numeric H: call spb_assemble or spb_set_matrix first"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    size_t nnz = (size_t)h->H.nnz();
+    if (mem == SPB_DEVICE) {
+      gather_h_values(h, vals);
+    } else {
+      SPB_CUDA(h->d_vec_stage.alloc(nnz));
+      gather_h_values(h, h->d_vec_stage.p);
+      SPB_CUDA(cudaMemcpyAsync(vals, h->d_vec_stage.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+}
+
+spb_status spb_assemble(spb_handle h, const double* Jvals, const double* EVec, double lambda, int mem, double* foo) {
+  if (!h || !Jvals) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->analyzed) throw StateFail{"spb_assemble before spb_analyze"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    const double* dJ = to_device(h, Jvals, (size_t)h->nnzJ, mem, h->d_Jv_stage);
+    const double* dF = to_device(h, EVec, (size_t)h->m, mem, h->d_f_stage);
+    run_assembly(h, dJ, dF, lambda, foo);
+    if (mem == SPB_HOST) SPB_CUDA(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+    return SPB_OK;
+  });
+}
+
+static spb_status copy_out(spb_handle h, const double* d_src, double* dst, size_t len, int mem) {
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    SPB_CUDA(cudaMemcpyAsync(dst, d_src, len * sizeof(double), mem == SPB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             h->stream));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+}
+spb_status spb_get_rhs(spb_handle h, double* rhs, int mem) {
+  if (!h || !rhs) return SPB_ERR_ARG;
+  if (!h->h_valid || !h->analyzed) return SPB_ERR_STATE;
+  return copy_out(h, h->d_rhs.p, rhs, (size_t)h->n, mem);
+}
+spb_status spb_get_damping(spb_handle h, double* d, int mem) {
+  if (!h || !d) return SPB_ERR_ARG;
+  if (!h->h_valid || !h->analyzed) return SPB_ERR_STATE;
+  return copy_out(h, h->d_dvec.p, d, (size_t)h->n, mem);
+}
+
+spb_status spb_set_matrix(spb_handle h, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* vals, int mem) {
+  if (!h || !vals) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    validate_csc(n, n, colptr, rowidx);
+    uint64_t fp = pattern_fingerprint(n, n, colptr, rowidx);
+    if (!(h->have_h && !h->analyzed && h->n == n && h->h_fingerprint == fp)) {
+      // new explicit pattern: must be structurally symmetric with a full diagonal
+      h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+      chol_release(h);
+      h->n = n;
+      h->m = 0;
+      h->nnzJ = 0;
+      HPattern& H = h->H;
+      H.n = n;
+      H.colptr.assign(colptr, colptr + n + 1);
+      H.rowidx.assign(rowidx, rowidx + colptr[n]);
+      H.nup1.assign(n, 0);
+      for (int j = 0; j < n; ++j) {
+        int up = 0, prev = -1;
+        bool diag = false;
+        for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+          int i = rowidx[q];
+          if (i < 0 || i >= n || i <= prev) throw ArgFail{"matrix pattern must have ascending in-range row indices"};
+          prev = i;
+          if (i <= j) ++up;
+          if (i == j) diag = true;
+        }
+        if (!diag) throw ArgFail{"matrix must have a structurally full diagonal"};
+        H.nup1[j] = up;
+      }
+      build_sell(h->H, h->S);
+      upload_h_layout(h);
+      h->h_fingerprint = fp;
+      h->have_h = true;
+    }
+    size_t nnz = (size_t)h->H.nnz();
+    const double* dv = to_device(h, vals, nnz, mem, h->d_vec_stage);
+    scatter_h_values(h, dv);
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+}
+
+spb_status spb_factorize(spb_handle h) {
+  if (!h) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->h_valid) throw StateFail{"spb_factorize without a numeric H"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    spb_status s = SPB_OK;
+    if (h->solver == SPB_SOLVER_CHOLESKY) s = chol_factorize(h);
+    // PCG: the Jacobi diagonal is a by-product of assembly; nothing to factor.
+    if (s == SPB_OK) h->factor_valid = true;
+    return s;
+  });
+}
+
+spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int mem, int* iters) {
+  if (!h || !x || nrhs < 1) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->factor_valid) throw StateFail{"spb_solve before spb_factorize"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n;
+    int total_iters = 0;
+    spb_status worst = SPB_OK;
+    for (int c = 0; c < nrhs; ++c) {
+      const double* db;
+      if (!rhs) {
+        if (!h->analyzed) throw StateFail{"no assembled gradient to solve for"};
+        db = h->d_rhs.p;
+      } else {
+        db = to_device(h, rhs + (size_t)c * n, n, mem, h->d_vec_stage);
+      }
+      double* dx = x + (size_t)c * n;
+      if (mem == SPB_HOST) {
+        SPB_CUDA(h->d_x.alloc(n));
+        dx = h->d_x.p;
+      }
+      int it = 0;
+      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx) : pcg_solve(h, db, dx, &it);
+      total_iters += it;
+      if (s != SPB_OK && worst == SPB_OK) worst = s;
+      if (mem == SPB_HOST) {
+        SPB_CUDA(cudaMemcpyAsync(x + (size_t)c * n, dx, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        SPB_CUDA(cudaStreamSynchronize(h->stream));
+      }
+    }
+    if (iters) *iters = total_iters;
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return worst;
+  });
+}
+
+spb_status spb_squared_norm(spb_handle h, const double* v, int64_t len, int mem, double* out) {
+  if (!h || !out || (len > 0 && !v)) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    const double* dv = to_device(h, v, (size_t)len, mem, h->d_vec_stage);
+    dev_squared_norm(h, dv, len, out);
+    return SPB_OK;
+  });
+}
+spb_status spb_inf_norm(spb_handle h, const double* v, int64_t len, int mem, double* out) {
+  if (!h || !out || (len > 0 && !v)) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    const double* dv = to_device(h, v, (size_t)len, mem, h->d_vec_stage);
+    dev_inf_norm(h, dv, len, out);
+    return SPB_OK;
+  });
+}
+
+spb_status spb_spmv(spb_handle h, const double* x, double* y, int mem) {
+  if (!h || !x || !y) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->h_valid) throw StateFail{"spb_spmv without a numeric H"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n;
+    const double* dx = to_device(h, x, n, mem, h->d_vec_stage);
+    double* dy = y;
+    if (mem == SPB_HOST) {
+      SPB_CUDA(h->d_vec_stage2.alloc(n));
+      dy = h->d_vec_stage2.p;
+    }
+    dev_spmv(h, dx, dy);
+    if (mem == SPB_HOST) SPB_CUDA(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+}
+
+int64_t spb_launch_count(spb_handle h) { return h ? h->launches : 0; }
+
+spb_status spb_stage_ms(spb_handle h, int stage, double* ms, int64_t* launches) {
+  if (!h || stage < 0 || stage >= ST_COUNT) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    timing_flush(h);
+    if (ms) *ms = h->timing.ms[stage];
+    if (launches) *launches = h->timing.count[stage];
+    return SPB_OK;
+  });
+}
+
+spb_status spb_stage_reset(spb_handle h, int enable_timing) {
+  if (!h) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    timing_flush(h);
+    for (int s = 0; s < ST_COUNT; ++s) {
+      h->timing.ms[s] = 0;
+      h->timing.count[s] = 0;
+    }
+    h->timing.enabled = enable_timing != 0;
+    return SPB_OK;
+  });
+}
+
+}  // extern "C"

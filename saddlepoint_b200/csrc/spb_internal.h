@@ -1,0 +1,224 @@
+// spb_internal.h -- shared declarations of the library's translation units (not public).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/saddlepoint_b200.h"
+
+namespace spb {
+
+// ---- device buffer --------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+struct CudaFail {
+  cudaError_t e;
+  const char* where;
+};
+#define SPB_CUDA(expr)                                     \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) throw spb::CudaFail{_e, #expr}; \
+  } while (0)
+
+struct ArgFail {
+  std::string msg;
+};
+struct StateFail {
+  std::string msg;
+};
+
+// ---- host symbolic products ---------------------------------------------------------
+// Full symmetric structural pattern of dampJ^T*dampJ (LMSolver.h:136), CSC == CSR.
+struct HPattern {
+  int n = 0;
+  std::vector<int> colptr, rowidx;
+  std::vector<int> nup1;  // per column: number of entries with row <= column (diag rank + 1)
+  int64_t nnz() const { return colptr.empty() ? 0 : colptr[n]; }
+};
+
+// SpMV storage of H: sliced ELL, slice height 32, column-major inside a slice; row r of the
+// symmetric H is column r of the CSC pattern; entry k of row r sits at
+// slice_off[r>>5] + k*32 + (r&31).  Padding entries have value 0 and are never read
+// (rowlen guards them).
+struct SellLayout {
+  int n = 0, nslices = 0;
+  std::vector<int64_t> slice_off;  // nslices+1, in entries
+  std::vector<int> col;            // padded column indices
+  std::vector<int> rowlen;         // n
+  int64_t padded = 0;
+  int64_t pos(int row, int k) const { return slice_off[row >> 5] + (int64_t)k * 32 + (row & 31); }
+};
+
+// Assembly plan; record formats are documented in assembly.cu.
+struct AssemblyPlan {
+  int m = 0, n = 0;
+  int64_t nnzJ = 0;
+  int rec_bits = 16;  // 16: [first:1][po:7][qo:7] (J columns <= 128 entries); 32: [first:1][po:15][qo:15]
+  std::vector<uint16_t> rec16;  // pair stream: slot-major, ascending residual row, chunks padded to 32
+  std::vector<uint32_t> rec32;
+  std::vector<uint16_t> grp_slot;  // per 32-record group: chunk-local slot of its first record
+  // chunk c covers strictly-lower slots [chunk_slot[c], chunk_slot[c+1]) and padded records
+  // [chunk_rec[c], chunk_rec[c]+chunk_npairs[c])
+  std::vector<int> chunk_slot;
+  std::vector<int64_t> chunk_rec;
+  std::vector<int> chunk_npairs;
+  // per strictly-lower slot, column-major, ascending row inside a column
+  std::vector<int> low_colptr;      // n+1
+  std::vector<int> low_row;         // row index i of the slot
+  std::vector<uint16_t> low_rank;   // rank of column j inside row i of H (position of H(i,j) in row i)
+  int64_t npairs = 0;
+  int nslots = 0;
+  // column kernel chunks: chunk c covers columns [colchunk[c], colchunk[c+1])
+  std::vector<int> colchunk;
+};
+
+// tunables shared by host planning and kernels
+constexpr int kPairTile = 2048;   // products staged per tile
+constexpr int kSlotCap = 1024;    // strictly-lower slots per chunk
+constexpr int kEntTile = 2048;    // J entries staged per tile in the column kernel
+constexpr int kColCap = 512;      // columns per column-kernel chunk
+
+void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H);
+void build_sell(const HPattern& H, SellLayout& S);
+void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P);
+uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx);
+
+}  // namespace spb
+
+// ---- the handle -------------------------------------------------------------------------
+namespace spb {
+
+enum Stage { ST_ASSEMBLY = 0, ST_SPMV = 1, ST_PCGVEC = 2, ST_FACTOR = 3, ST_TRISOLVE = 4, ST_REDUCE = 5, ST_TRAITS = 6, ST_COUNT = 7 };
+
+// Scalars of the PCG recurrences and of the LM reductions; lives in device memory with a
+// pinned host mirror that is refreshed by explicit async copies.
+struct PcgScalars {
+  double rz, pq, rr, bb, alpha, beta, thresh;
+  int iters, done, maxit, breakdown;
+  unsigned int ticket_a, ticket_b;
+  int pad0, pad1;
+};
+
+struct Timing {
+  bool enabled = false;
+  double ms[ST_COUNT] = {0};
+  int64_t count[ST_COUNT] = {0};
+  struct Pending {
+    cudaEvent_t a, b;
+    int stage;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+};
+
+}  // namespace spb
+
+struct spb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int num_sms = 148;
+
+  int solver = SPB_SOLVER_PCG_JACOBI;
+  double pcg_rtol = 1e-13;
+  int pcg_maxit = 10000;
+
+  // pattern state
+  bool analyzed = false;      // J pattern analysed (assembly possible)
+  bool have_h = false;        // H pattern + SpMV layout present (analyze or set_matrix)
+  bool h_valid = false;       // numeric H present
+  bool factor_valid = false;
+  uint64_t fingerprint = 0;   // of the J pattern
+  uint64_t h_fingerprint = 0; // of an explicitly set H pattern
+  int m = 0, n = 0;
+  int64_t nnzJ = 0;
+  spb::HPattern H;            // host copy kept for export and for the Cholesky symbolic phase
+  spb::SellLayout S;          // host: only slice_off/rowlen kept after upload
+  int rec_bits = 16;
+  int nchunks = 0, ncolchunks = 0, nslots = 0;
+  int64_t npairs = 0;
+
+  // device: J pattern + assembly plan
+  spb::DevBuf<int> d_Jcolptr, d_Jrow;
+  spb::DevBuf<uint16_t> d_rec16;
+  spb::DevBuf<uint32_t> d_rec32;
+  spb::DevBuf<uint16_t> d_grp_slot, d_low_rank;
+  spb::DevBuf<int> d_chunk_slot, d_chunk_npairs, d_chunk_col0, d_low_colptr, d_low_row, d_colchunk, d_nup1;
+  spb::DevBuf<int64_t> d_chunk_rec;
+  // device: H in SpMV layout
+  spb::DevBuf<int> d_sell_col, d_rowlen;
+  spb::DevBuf<int64_t> d_slice_off;
+  spb::DevBuf<int64_t> d_pos_of_slot;  // lazily built: CSC slot -> storage position
+  spb::DevBuf<double> d_hval, d_hdiag;
+  // device: vectors
+  spb::DevBuf<double> d_rhs, d_dvec, d_Jv_stage, d_f_stage, d_vec_stage, d_vec_stage2;
+  spb::DevBuf<double> d_r, d_p, d_q, d_x, d_partial;
+  spb::DevBuf<spb::PcgScalars> d_sc;
+  spb::DevBuf<unsigned long long> d_foo_bits;
+  spb::PcgScalars* h_sc = nullptr;      // pinned
+  double* h_scalar = nullptr;           // pinned scratch (8 doubles)
+
+  int64_t launches = 0;
+  spb::Timing timing;
+  void* chol = nullptr;  // spb::CholeskyState*, owned (cholesky.cu)
+};
+
+namespace spb {
+// timing helpers (context.cu)
+void stage_begin(spb_context* h, int stage);
+void stage_end(spb_context* h, int stage, int nlaunch);
+void timing_flush(spb_context* h);
+
+// assembly.cu
+void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, AssemblyPlan& P);
+void upload_h_layout(spb_context* h);
+void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double lambda, double* foo_host);
+void ensure_pos_of_slot(spb_context* h);
+void gather_h_values(spb_context* h, double* d_out);   // CSC order
+void scatter_h_values(spb_context* h, const double* d_in);  // CSC order -> storage (+ hdiag)
+
+// blas1.cu
+void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);
+void dev_inf_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);
+void dev_add(spb_context* h, const double* a, const double* b, double* out, int64_t len);  // out=a+b
+
+// pcg.cu
+void dev_spmv(spb_context* h, const double* d_x, double* d_y);
+spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters);
+
+// cholesky.cu
+spb_status chol_factorize(spb_context* h);
+spb_status chol_solve(spb_context* h, const double* d_b, double* d_x);
+void chol_release(spb_context* h);
+}  // namespace spb

@@ -1,0 +1,255 @@
+// symbolic.cpp -- one-time host symbolic analysis of the Jacobian pattern.
+//
+// The reference re-derives the structure of dampJ^T*dampJ inside Eigen's sparse product on
+// every LM iteration (LMSolver.h:136) and never calls its own analyze
+// (LMSolver.h:69-73, EigenSolverWrapper.h:30-52).  The fixed-pattern idea exists only in
+// the legacy GNSolver (MatrixPattern/S2D, GNSolver.h:44-83): a list of contributing J-entry
+// pairs per normal-matrix entry.  This file builds that map once, in a form the GPU can
+// stream: every strictly-lower entry H(i,j) gets the list of (position in column i,
+// position in column j) pairs of J entries that share a residual row, in ascending row
+// order -- the accumulation order of the reference's product.
+#include <algorithm>
+#include <cstring>
+
+#include "spb_internal.h"
+
+namespace spb {
+
+uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx) {
+  // FNV-1a over sizes, column pointers and row indices (8 bytes at a time where possible)
+  uint64_t h = 1469598103934665603ULL;
+  auto mix = [&h](uint64_t v) {
+    h ^= v;
+    h *= 1099511628211ULL;
+  };
+  mix((uint64_t)m);
+  mix((uint64_t)n);
+  for (int j = 0; j <= n; ++j) mix((uint64_t)(uint32_t)colptr[j]);
+  int64_t nz = colptr[n];
+  for (int64_t q = 0; q < nz; ++q) mix((uint64_t)(uint32_t)rowidx[q] + 0x9E3779B97F4A7C15ULL * (uint64_t)q);
+  return h;
+}
+
+namespace {
+// CSR view of the J pattern with, per entry, its position inside its CSC column.
+struct RowView {
+  std::vector<int64_t> ptr;  // m+1
+  std::vector<int> col;
+  std::vector<int> pos_in_col;
+};
+void build_row_view(int m, int n, const int* colptr, const int* rowidx, RowView& R) {
+  int64_t nz = colptr[n];
+  R.ptr.assign((size_t)m + 1, 0);
+  for (int64_t q = 0; q < nz; ++q) {
+    int r = rowidx[q];
+    if (r < 0 || r >= m) throw ArgFail{"row index out of range in J pattern"};
+    R.ptr[(size_t)r + 1]++;
+  }
+  for (int r = 0; r < m; ++r) R.ptr[(size_t)r + 1] += R.ptr[r];
+  R.col.resize(nz);
+  R.pos_in_col.resize(nz);
+  std::vector<int64_t> cur(R.ptr.begin(), R.ptr.end() - 1);
+  for (int j = 0; j < n; ++j) {
+    int prev = -1;
+    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+      int r = rowidx[q];
+      if (r <= prev) throw ArgFail{"J pattern must have strictly ascending row indices per column"};
+      prev = r;
+      int64_t d = cur[r]++;
+      R.col[d] = j;  // columns visited ascending => ascending inside each row
+      R.pos_in_col[d] = q - colptr[j];
+    }
+  }
+}
+}  // namespace
+
+void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H) {
+  RowView R;
+  build_row_view(m, n, colptr, rowidx, R);
+  H.n = n;
+  H.colptr.assign((size_t)n + 1, 0);
+  H.rowidx.clear();
+  H.rowidx.reserve((size_t)colptr[n] * 2);
+  H.nup1.assign(n, 0);
+  std::vector<int> mark(n, -1), tmp;
+  for (int j = 0; j < n; ++j) {
+    tmp.clear();
+    mark[j] = j;  // the damping row makes the diagonal structural even for empty columns
+    tmp.push_back(j);
+    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+      int r = rowidx[q];
+      for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
+        int i = R.col[t];
+        if (mark[i] != j) {
+          mark[i] = j;
+          tmp.push_back(i);
+        }
+      }
+    }
+    std::sort(tmp.begin(), tmp.end());
+    int up = 0;
+    for (int i : tmp) {
+      if (i <= j) ++up;
+      H.rowidx.push_back(i);
+    }
+    H.nup1[j] = up;
+    if (H.rowidx.size() > (size_t)0x7fffffff) throw ArgFail{"H pattern exceeds int32 indexing"};
+    H.colptr[(size_t)j + 1] = (int)H.rowidx.size();
+  }
+}
+
+void build_sell(const HPattern& H, SellLayout& S) {
+  int n = H.n;
+  S.n = n;
+  S.nslices = (n + 31) / 32;
+  S.slice_off.assign((size_t)S.nslices + 1, 0);
+  S.rowlen.resize(n);
+  for (int r = 0; r < n; ++r) S.rowlen[r] = H.colptr[(size_t)r + 1] - H.colptr[r];
+  for (int s = 0; s < S.nslices; ++s) {
+    int w = 0;
+    for (int r = s * 32; r < std::min(n, s * 32 + 32); ++r) w = std::max(w, S.rowlen[r]);
+    S.slice_off[(size_t)s + 1] = S.slice_off[s] + (int64_t)w * 32;
+  }
+  S.padded = S.slice_off[S.nslices];
+  S.col.assign((size_t)S.padded, 0);
+  for (int r = 0; r < n; ++r) {
+    int64_t base = S.slice_off[r >> 5] + (r & 31);
+    int k = 0;
+    for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) S.col[(size_t)(base + (int64_t)k * 32)] = H.rowidx[q];
+    int w = (int)((S.slice_off[(size_t)(r >> 5) + 1] - S.slice_off[r >> 5]) / 32);
+    for (; k < w; ++k) S.col[(size_t)(base + (int64_t)k * 32)] = r;
+  }
+}
+
+void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P) {
+  RowView R;
+  build_row_view(m, n, colptr, rowidx, R);
+  P.m = m;
+  P.n = n;
+  P.nnzJ = colptr[n];
+  int maxcol = 0;
+  for (int j = 0; j < n; ++j) maxcol = std::max(maxcol, colptr[j + 1] - colptr[j]);
+  if (maxcol > 32768) throw ArgFail{"a Jacobian column with more than 32768 entries is not supported"};
+  P.rec_bits = maxcol <= 128 ? 16 : 32;
+  // strictly-lower slots
+  P.low_colptr.assign((size_t)n + 1, 0);
+  for (int j = 0; j < n; ++j) P.low_colptr[(size_t)j + 1] = P.low_colptr[j] + (H.colptr[(size_t)j + 1] - H.colptr[j] - H.nup1[j]);
+  P.nslots = P.low_colptr[n];
+  P.low_row.resize(P.nslots);
+  P.low_rank.resize(P.nslots);
+  for (int j = 0; j < n; ++j) {
+    int s = P.low_colptr[j];
+    for (int q = H.colptr[j] + H.nup1[j]; q < H.colptr[(size_t)j + 1]; ++q, ++s) P.low_row[s] = H.rowidx[q];
+  }
+  // rank of column j inside row i (== column i of the symmetric pattern), for i > j: count as we sweep j
+  {
+    std::vector<int> seen(n, 0);  // entries of row i with column < current j already emitted
+    for (int j = 0; j < n; ++j) {
+      for (int s = P.low_colptr[j]; s < P.low_colptr[(size_t)j + 1]; ++s) {
+        int i = P.low_row[s];
+        int rk = seen[i]++;
+        if (rk > 65535) throw ArgFail{"H row longer than 65535 entries is not supported"};
+        P.low_rank[s] = (uint16_t)rk;
+      }
+    }
+  }
+  // pair stream
+  std::vector<int> where(n, -1);
+  struct Tmp {
+    int slot, po, qo;
+  };
+  std::vector<Tmp> tmp;
+  std::vector<int> cnt, start;
+  std::vector<uint32_t> colrecs;     // records of the current column, slot-major
+  std::vector<int> slot_npairs(P.nslots, 0);
+  // First pass materialises records per column into one big stream (slot-major); chunking
+  // and 32-padding are applied in a second pass over slots.
+  std::vector<uint32_t> stream;
+  stream.reserve((size_t)P.nnzJ * 4);
+  const int pobits = P.rec_bits == 16 ? 7 : 15;
+  for (int j = 0; j < n; ++j) {
+    int s0 = P.low_colptr[j], s1 = P.low_colptr[(size_t)j + 1];
+    int ns = s1 - s0;
+    if (ns == 0) continue;
+    for (int s = s0; s < s1; ++s) where[P.low_row[s]] = s - s0;
+    tmp.clear();
+    cnt.assign(ns, 0);
+    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+      int r = rowidx[q];
+      int qo = q - colptr[j];
+      for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
+        int i = R.col[t];
+        if (i <= j) continue;
+        int sl = where[i];
+        tmp.push_back({sl, R.pos_in_col[t], qo});
+        cnt[sl]++;
+      }
+    }
+    start.assign((size_t)ns + 1, 0);
+    for (int k = 0; k < ns; ++k) start[(size_t)k + 1] = start[k] + cnt[k];
+    colrecs.resize(tmp.size());
+    std::vector<int>& cur = cnt;  // reuse as cursor
+    for (int k = 0; k < ns; ++k) cur[k] = start[k];
+    for (const Tmp& e : tmp) {
+      int d = cur[e.slot]++;
+      uint32_t first = (d == start[e.slot]) ? 1u : 0u;
+      colrecs[d] = (first << (2 * pobits)) | ((uint32_t)e.po << pobits) | (uint32_t)e.qo;
+    }
+    for (int k = 0; k < ns; ++k) slot_npairs[s0 + k] = start[(size_t)k + 1] - start[k];
+    stream.insert(stream.end(), colrecs.begin(), colrecs.end());
+    for (int s = s0; s < s1; ++s) where[P.low_row[s]] = -1;
+  }
+  P.npairs = (int64_t)stream.size();
+  // chunking
+  P.chunk_slot.clear();
+  P.chunk_rec.clear();
+  P.chunk_npairs.clear();
+  P.grp_slot.clear();
+  P.rec16.clear();
+  P.rec32.clear();
+  if (P.rec_bits == 16) P.rec16.reserve(stream.size() + stream.size() / 16);
+  else P.rec32.reserve(stream.size() + stream.size() / 16);
+  int64_t src = 0;
+  int s = 0;
+  while (s < P.nslots) {
+    int cs = s;
+    int np = 0;
+    while (s < P.nslots && (s - cs) < kSlotCap && (np == 0 || np + slot_npairs[s] <= kPairTile)) {
+      np += slot_npairs[s];
+      ++s;
+    }
+    int64_t rec0 = P.rec_bits == 16 ? (int64_t)P.rec16.size() : (int64_t)P.rec32.size();
+    P.chunk_slot.push_back(cs);
+    P.chunk_rec.push_back(rec0);
+    P.chunk_npairs.push_back(np);
+    // copy records + per-group first slot
+    int sl = -1;  // chunk-local slot of the record being copied
+    for (int t = 0; t < np; ++t) {
+      uint32_t rec = stream[(size_t)(src + t)];
+      if (rec >> (2 * pobits)) ++sl;
+      if ((t & 31) == 0) P.grp_slot.push_back((uint16_t)sl);
+      if (P.rec_bits == 16) P.rec16.push_back((uint16_t)rec); else P.rec32.push_back(rec);
+    }
+    int pad = (32 - (np & 31)) & 31;
+    for (int t = 0; t < pad; ++t) {
+      if (P.rec_bits == 16) P.rec16.push_back(0); else P.rec32.push_back(0);
+    }
+    src += np;
+  }
+  P.chunk_slot.push_back(P.nslots);
+  // column kernel chunks: by entry count and column count
+  P.colchunk.clear();
+  int j = 0;
+  while (j < n) {
+    P.colchunk.push_back(j);
+    int cj = j;
+    int64_t ne = 0;
+    while (j < n && (j - cj) < kColCap && (ne == 0 || ne + (colptr[j + 1] - colptr[j]) <= kEntTile)) {
+      ne += colptr[j + 1] - colptr[j];
+      ++j;
+    }
+  }
+  P.colchunk.push_back(n);
+}
+
+}  // namespace spb

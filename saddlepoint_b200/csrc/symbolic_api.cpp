@@ -1,0 +1,88 @@
+// symbolic_api.cpp -- host-only entry points of the symbolic phase (no GPU needed): used by
+// the CPU test tier to check the pattern and the assembly plan's invariants.
+#include <algorithm>
+#include <cstring>
+
+#include "spb_internal.h"
+
+using namespace spb;
+
+extern "C" {
+
+spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* nnz,
+                                  int32_t* h_colptr, int32_t* h_rowidx) {
+  if (!colptr || !nnz || m < 0 || n < 0) return SPB_ERR_ARG;
+  try {
+    HPattern H;
+    build_h_pattern(m, n, colptr, rowidx, H);
+    *nnz = H.nnz();
+    if (h_colptr) memcpy(h_colptr, H.colptr.data(), sizeof(int32_t) * ((size_t)n + 1));
+    if (h_rowidx) memcpy(h_rowidx, H.rowidx.data(), sizeof(int32_t) * (size_t)H.nnz());
+    return SPB_OK;
+  } catch (const ArgFail&) {
+    return SPB_ERR_ARG;
+  }
+}
+
+// stats: 0 nslots, 1 npairs, 2 nchunks, 3 rec_bits, 4 padded SELL entries, 5 nnz(H),
+//        6 ncolchunks, 7 number of invariant violations (must be 0)
+spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats) {
+  if (!colptr || !stats || m < 0 || n < 0) return SPB_ERR_ARG;
+  try {
+    HPattern H;
+    build_h_pattern(m, n, colptr, rowidx, H);
+    SellLayout S;
+    build_sell(H, S);
+    AssemblyPlan P;
+    build_assembly_plan(m, n, colptr, rowidx, H, P);
+    int64_t bad = 0;
+    const int pobits = P.rec_bits == 16 ? 7 : 15;
+    const uint32_t mask = (1u << pobits) - 1u;
+    int nch = (int)P.chunk_npairs.size();
+    int64_t pairs_seen = 0;
+    for (int c = 0; c < nch; ++c) {
+      int s0 = P.chunk_slot[c], s1 = P.chunk_slot[c + 1];
+      int64_t r0 = P.chunk_rec[c];
+      if (r0 % 32) ++bad;
+      int sl = -1, prev_row = -1;
+      for (int t = 0; t < P.chunk_npairs[c]; ++t) {
+        uint32_t rec = P.rec_bits == 16 ? (uint32_t)P.rec16[(size_t)(r0 + t)] : P.rec32[(size_t)(r0 + t)];
+        if (rec >> (2 * pobits)) { ++sl; prev_row = -1; }
+        if ((t & 31) == 0 && P.grp_slot[(size_t)(r0 / 32 + t / 32)] != (uint16_t)sl) ++bad;
+        if (sl < 0 || s0 + sl >= s1) { ++bad; continue; }
+        int s = s0 + sl;
+        int i = P.low_row[s];
+        // column of the slot
+        int j = (int)(std::upper_bound(P.low_colptr.begin(), P.low_colptr.end(), s) - P.low_colptr.begin()) - 1;
+        int po = (int)((rec >> pobits) & mask), qo = (int)(rec & mask);
+        if (colptr[i] + po >= colptr[i + 1] || colptr[j] + qo >= colptr[j + 1]) { ++bad; continue; }
+        int rp = rowidx[colptr[i] + po], rq = rowidx[colptr[j] + qo];
+        if (rp != rq) ++bad;            // both J entries must share the residual row
+        if (rp <= prev_row) ++bad;      // ascending residual row inside a slot
+        prev_row = rp;
+        if (!(i > j)) ++bad;
+        ++pairs_seen;
+      }
+      if (sl + 1 != s1 - s0) ++bad;
+    }
+    if (pairs_seen != P.npairs) ++bad;
+    // rank check: H(i,j) must sit at rank low_rank in row i of the symmetric pattern
+    for (int j = 0; j < n; ++j)
+      for (int s = P.low_colptr[j]; s < P.low_colptr[j + 1]; ++s) {
+        int i = P.low_row[s];
+        if (H.rowidx[(size_t)H.colptr[i] + P.low_rank[s]] != j) ++bad;
+      }
+    stats[0] = P.nslots;
+    stats[1] = P.npairs;
+    stats[2] = nch;
+    stats[3] = P.rec_bits;
+    stats[4] = S.padded;
+    stats[5] = H.nnz();
+    stats[6] = (int64_t)P.colchunk.size() - 1;
+    stats[7] = bad;
+    return SPB_OK;
+  } catch (const ArgFail&) {
+    return SPB_ERR_ARG;
+  }
+}
+}

@@ -1,0 +1,111 @@
+"""CPU tier: the C-ABI library loads, exports every symbol the header declares, refuses to run
+without a GPU (no CPU fallback), and its host-only symbolic phase matches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import random_jacobian
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(spb):
+    L = spb.capi.load()
+    header = open(os.path.join(ROOT, "include", "saddlepoint_b200.h")).read()
+    declared = set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"spb_handle"}
+    bound = {name for name, _, _ in spb.capi.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.spb_version()
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu(spb):
+    L = spb.capi.load()
+    h = C.c_void_p()
+    assert L.spb_create(0, None, C.byref(h)) == spb.capi.SPB_ERR_CUDA and not h.value
+    with pytest.raises(spb.SpbError):
+        spb.Handle(0)
+
+
+def test_product_does_not_reference_oracle():
+    # the product tree must not import/link anything under oracle/
+    for base, _, files in os.walk(os.path.join(ROOT, "saddlepoint_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(base, f)).read()
+                assert "sp_oracle" not in src and "oracle/" not in src, os.path.join(base, f)
+
+
+def _h_pattern(L, m, n, colptr, rowidx):
+    nnz = C.c_int64(0)
+    assert L.spb_symbolic_h_pattern(m, n, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), None, None) == 0
+    hp = np.empty(n + 1, np.int32)
+    hi = np.empty(nnz.value, np.int32)
+    assert L.spb_symbolic_h_pattern(m, n, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), hp.ctypes.data, hi.ctypes.data) == 0
+    return hp, hi
+
+
+@pytest.mark.parametrize("case", ["random", "empty_cols_rows", "rosenbrock", "lf", "dense_cols"])
+def test_symbolic_pattern_bit_exact_vs_oracle(spb, orc, case):
+    L = spb.capi.load()
+    rng = np.random.default_rng(5)
+    if case == "random":
+        m, n = 500, 200
+        colptr, rowidx, vals = random_jacobian(rng, m, n, 4, explicit_zero_frac=0.2)
+    elif case == "empty_cols_rows":
+        m, n = 200, 90
+        colptr, rowidx, vals = random_jacobian(rng, m, n, 3, empty_cols=[0, 17, 89], empty_rows=[0, 5, 199])
+    elif case == "rosenbrock":
+        nb = 50
+        m = n = 2 * nb
+        colptr = (2 * np.arange(n + 1)).astype(np.int32)
+        rowidx = np.repeat(2 * np.arange(nb), 4).astype(np.int32) + np.tile([0, 1, 0, 1], nb).astype(np.int32)
+        vals = rng.standard_normal(4 * nb)
+        vals[3::4] = 0.0  # the reference's explicit structural zero
+    elif case == "lf":
+        J = orc.lf_matrix(20, 2, 20211)
+        colptr, rowidx, vals = J.csc()
+        m, n = J.shape
+    else:  # columns longer than 128 entries => 32-bit pair records
+        m, n = 400, 6
+        A = (rng.random((m, n)) < 0.7) * rng.standard_normal((m, n))
+        import scipy.sparse as sp
+        S = sp.csc_matrix(A)
+        S.sort_indices()
+        colptr, rowidx, vals = S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data
+    J = orc.from_csc(m, n, colptr, rowidx, vals)
+    D, _ = orc.damp_build(J, 0.01)
+    hp_ref, hi_ref, _ = orc.ata(D).csc()
+    hp, hi = _h_pattern(L, m, n, colptr, rowidx)
+    assert (hp == hp_ref).all() and (hi == hi_ref).all()
+    stats = np.zeros(8, np.int64)
+    assert L.spb_symbolic_plan_check(m, n, colptr.ctypes.data, rowidx.ctypes.data, stats.ctypes.data) == 0
+    assert stats[7] == 0, "assembly plan invariants violated"
+    assert stats[5] == len(hi_ref)
+    assert stats[3] == (32 if case == "dense_cols" else 16)
+    # every strictly-lower slot has at least one contributing pair
+    assert stats[1] >= stats[0]
+
+
+def test_symbolic_rejects_bad_patterns(spb):
+    L = spb.capi.load()
+    nnz = C.c_int64(0)
+    colptr = np.array([0, 2], np.int32)
+    rowidx = np.array([1, 0], np.int32)  # not ascending
+    assert L.spb_symbolic_h_pattern(2, 1, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), None, None) == spb.capi.SPB_ERR_ARG
+    rowidx = np.array([0, 5], np.int32)  # out of range
+    assert L.spb_symbolic_h_pattern(2, 1, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), None, None) == spb.capi.SPB_ERR_ARG

@@ -1,0 +1,159 @@
+"""GPU tier: fused assembly (H, rhs, damping, ||rhs||_inf) through the C ABI vs the oracle.
+Bar: pattern bit-exact; values bit-exact (the kernels reproduce the reference's summation
+order with separate multiply/add), including explicit zeros, empty columns/rows and inf/NaN."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import random_jacobian
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference(orc, m, n, colptr, rowidx, vals, E, lam):
+    J = orc.from_csc(m, n, colptr, rowidx, vals)
+    D, d = orc.damp_build(J, lam)
+    hp, hi, hx = orc.ata(D).csc()
+    g = orc.jt_vec_neg(J, E)
+    return hp, hi, hx, g, d
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _check(handle, orc, m, n, colptr, rowidx, vals, E, lam):
+    handle.analyze(m, n, colptr, rowidx)
+    foo = handle.assemble(vals, E, lam)
+    hp, hi, hx, g, d = _reference(orc, m, n, colptr, rowidx, vals, E, lam)
+    cp, ri = handle.h_pattern()
+    assert (cp == hp).all() and (ri == hi).all(), "H pattern differs"
+    hv = handle.h_values()
+    assert (_bits(hv) == _bits(hx)).all(), "H values not bit-exact: max rel %g" % np.nanmax(np.abs(hv - hx) / (np.abs(hx) + 1e-300))
+    assert (_bits(handle.rhs()) == _bits(g)).all(), "rhs not bit-exact"
+    assert (_bits(handle.damping()) == _bits(d)).all(), "damping vector not bit-exact"
+    finite = np.abs(g[~np.isnan(g)])
+    assert foo == (finite.max() if len(finite) else 0.0)
+
+
+@pytest.mark.parametrize("seed,m,n,k", [(0, 64, 20, 3), (1, 1000, 400, 4), (2, 5000, 5000, 6), (3, 300, 900, 2)])
+def test_random_patterns(handle, orc, seed, m, n, k):
+    rng = np.random.default_rng(seed)
+    colptr, rowidx, vals = random_jacobian(rng, m, n, k, explicit_zero_frac=0.05)
+    _check(handle, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), 0.01)
+
+
+def test_empty_columns_and_rows(handle, orc):
+    rng = np.random.default_rng(7)
+    m, n = 400, 150
+    colptr, rowidx, vals = random_jacobian(rng, m, n, 3, empty_cols=[0, 31, 32, 149], empty_rows=[0, 1, 399])
+    _check(handle, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), 0.5)
+
+
+def test_rosenbrock_c1_with_explicit_zero(handle, orc):
+    # config C1: 500 blocks, J triplets incl. the structural zero (benchmark/rosenbrock/main.cpp:57-60)
+    nb = 500
+    n = m = 2 * nb
+    x = np.tile([-100.0, 100.0], nb)
+    colptr = (2 * np.arange(n + 1)).astype(np.int32)
+    rowidx = (np.repeat(2 * np.arange(nb), 4) + np.tile([0, 1, 0, 1], nb)).astype(np.int32)
+    vals = np.empty(4 * nb)
+    vals[0::4] = -50.0 * x[0::2]
+    vals[1::4] = -1.0
+    vals[2::4] = 25.0
+    vals[3::4] = 0.0
+    E = np.empty(m)
+    E[0::2] = 25.0 * (x[1::2] - x[0::2] ** 2)
+    E[1::2] = 1.0 - x[0::2]
+    _check(handle, orc, m, n, colptr, rowidx, vals, E, 0.01)
+    assert handle.h_nnz() == 2000
+
+
+@pytest.mark.parametrize("g", [8, 33, 100])
+def test_lf_workload(handle, orc, g):
+    J = orc.lf_matrix(g, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    E = J.scipy() @ np.ones(n) - 1.0
+    _check(handle, orc, m, n, colptr, rowidx, vals, E, 0.01)
+
+
+def test_dense_columns_use_wide_records_and_multi_tile_slots(handle, orc):
+    # columns with >128 entries (32-bit records) and slots with >2048 pairs (multi-tile path);
+    # this is the shape of the reference's dense linear_function Jacobian (m=1000, n=250 there)
+    rng = np.random.default_rng(11)
+    m, n = 3000, 5
+    A = rng.standard_normal((m, n))
+    A[rng.random((m, n)) < 0.1] = 0.0
+    S = sp.csc_matrix(A)
+    S.sort_indices()
+    _check(handle, orc, m, n, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data, rng.standard_normal(m), 0.01)
+
+
+def test_reference_linear_function_jacobian(handle, orc):
+    m, n = 1000, 250
+    A = np.vstack([np.eye(n) - 2.0 / m, -2.0 / m * np.ones((m - n, n))])
+    colptr = (m * np.arange(n + 1)).astype(np.int32)
+    rowidx = np.tile(np.arange(m), n).astype(np.int32)
+    vals = np.ascontiguousarray(A.T).ravel()
+    _check(handle, orc, m, n, colptr, rowidx, vals, A @ np.ones(n) - 1.0, 0.01)
+
+
+def test_inf_and_nan_entries_propagate_like_the_reference(handle, orc):
+    # the seamless barrier injects inf into J on purpose (SIInitialSolutionTraits.h:163,227-228)
+    rng = np.random.default_rng(13)
+    m, n = 200, 60
+    colptr, rowidx, vals = random_jacobian(rng, m, n, 3)
+    vals[5] = np.inf
+    vals[17] = -np.inf
+    vals[40] = np.nan
+    handle.analyze(m, n, colptr, rowidx)
+    E = rng.standard_normal(m)
+    handle.assemble(vals, E, 0.01)
+    hp, hi, hx, g, d = _reference(orc, m, n, colptr, rowidx, vals, E, 0.01)
+    hv = handle.h_values()
+    assert (np.isnan(hv) == np.isnan(hx)).all()
+    ok = ~np.isnan(hx)
+    assert (hv[ok] == hx[ok]).all()
+    gg = handle.rhs()
+    assert (np.isnan(gg) == np.isnan(g)).all() and (gg[~np.isnan(g)] == g[~np.isnan(g)]).all()
+
+
+def test_lambda_changes_only_the_diagonal(handle, orc):
+    rng = np.random.default_rng(17)
+    m, n = 500, 200
+    colptr, rowidx, vals = random_jacobian(rng, m, n, 4)
+    E = rng.standard_normal(m)
+    handle.analyze(m, n, colptr, rowidx)
+    handle.assemble(vals, E, 0.01)
+    H1 = handle.h_scipy()
+    handle.assemble(vals, E, 10.0)
+    H2 = handle.h_scipy()
+    Dm = (H2 - H1).tocsc()
+    Dm.eliminate_zeros()
+    assert (Dm - sp.diags(Dm.diagonal())).nnz == 0
+    _check(handle, orc, m, n, colptr, rowidx, vals, E, 10.0)
+
+
+def test_device_pointers_and_reanalysis(handle, orc):
+    import torch
+    rng = np.random.default_rng(19)
+    m, n = 800, 300
+    colptr, rowidx, vals = random_jacobian(rng, m, n, 4)
+    E = rng.standard_normal(m)
+    handle.analyze(m, n, colptr, rowidx)
+    assert handle.pattern_matches(m, n, colptr, rowidx)
+    foo = handle.assemble(torch.tensor(vals, device="cuda"), torch.tensor(E, device="cuda"), 0.01)
+    hp, hi, hx, g, d = _reference(orc, m, n, colptr, rowidx, vals, E, 0.01)
+    assert (handle.h_values() == hx).all() and foo == np.abs(g).max()
+    # a grown pattern (one more residual row) is detected and re-analysed
+    colptr2, rowidx2, vals2 = random_jacobian(rng, m + 1, n, 4)
+    assert not handle.pattern_matches(m + 1, n, colptr2, rowidx2)
+    _check(handle, orc, m + 1, n, colptr2, rowidx2, vals2, rng.standard_normal(m + 1), 0.01)
+
+
+def test_call_order_errors(spb):
+    h = spb.Handle(0)
+    with pytest.raises(spb.SpbError):
+        h.assemble(np.zeros(3), np.zeros(3), 0.01)
+    h.close()

@@ -1,0 +1,126 @@
+"""GPU tier: the whole LM loop (LMSolver::solve) vs the oracle.
+Bar (north_star): iteration count bit-exact; final x / energy within 1e-10 relative (energies
+that are pure rounding noise, e.g. Rosenbrock's ~1e-23, are compared through x and against
+max(E_final, 1e-16*E_initial); SURVEY 7 'hard parts')."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _energy_close(a, b, e0):
+    return abs(a - b) <= 1e-10 * max(abs(b), 1e-16 * e0, 1e-300)
+
+
+def _run_builtin(spb, handle, kind, verbose=True, maxit=1000, dedupe=False, **kw):
+    prob = spb.BuiltinProblem(handle, kind, **kw)
+    ls = spb.B200SolverWrapper(handle)
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), maxit)
+    ret = lm.solve(verbose, dedupe_evaluations=dedupe)
+    return ret, lm
+
+
+@pytest.mark.parametrize("nblocks", [1, 500])
+@pytest.mark.parametrize("dedupe", [False, True])
+def test_rosenbrock_iteration_parity(spb, handle, orc, nblocks, dedupe):
+    ret, lm = _run_builtin(spb, handle, "rosenbrock", nblocks=nblocks, dedupe=dedupe)
+    ref = orc.lm_solve("rosenbrock", iparam0=nblocks, maxIterations=1000)
+    assert ret == ref.ret and lm.exit_path == ref.exit_path
+    assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
+    assert (lm.trace["accepted"] == ref.trace["accepted"]).all()
+    np.testing.assert_allclose(lm.trace["lambda"], ref.trace["lambda"], rtol=0, atol=0)
+    np.testing.assert_allclose(lm.x, ref.x, rtol=1e-10, atol=1e-12)
+    assert _energy_close(lm.energy, ref.energy, ref.trace["prevEnergy2"][0])
+    np.testing.assert_allclose(lm.trace["newEnergy2"][:50], ref.trace["newEnergy2"][:50], rtol=1e-9)
+
+
+def test_rosenbrock_mgh_start(spb, handle, orc):
+    x0 = np.tile([-1.2, 1.0], 500)
+    ret, lm = _run_builtin(spb, handle, "rosenbrock", nblocks=500, x0=x0)
+    ref = orc.lm_solve("rosenbrock", iparam0=500, x0=x0, maxIterations=1000)
+    assert lm.currIter == ref.currIter == 98 and lm.exit_path == ref.exit_path
+    np.testing.assert_allclose(lm.x, ref.x, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("g", [16, 48])
+def test_lf_iteration_parity_and_step(spb, handle, orc, g):
+    ret, lm = _run_builtin(spb, handle, "lf", g=g, rows_mult=2, seed=20211, maxit=100)
+    ref = orc.lm_solve("lf", iparam0=g, iparam1=2, seed=20211, maxIterations=100, keep_first=True)
+    assert ret == ref.ret and lm.exit_path == ref.exit_path
+    assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
+    np.testing.assert_allclose(lm.trace["lambda"], ref.trace["lambda"], rtol=0, atol=0)
+    assert np.linalg.norm(lm.x - ref.x) <= 1e-10 * np.linalg.norm(ref.x)
+    assert _energy_close(lm.energy, ref.energy, ref.trace["prevEnergy2"][0])
+    # first-iteration quantities: foo bit-exact, step norm within tolerance
+    assert lm.trace["foo"][0] == ref.trace["foo"][0]
+    assert abs(lm.trace["dirnorm"][0] - ref.trace["dirnorm"][0]) <= 1e-10 * ref.trace["dirnorm"][0]
+
+
+class PyRosenbrock:
+    """Host traits in the style of benchmark/rosenbrock/main.cpp (gen-3 objective_jacobian form)."""
+
+    def __init__(self, nb):
+        self.nb = nb
+        self.xSize = self.ESize = 2 * nb
+        self.calls = 0
+        n = 2 * nb
+        self.colptr = (2 * np.arange(n + 1)).astype(np.int32)
+        self.rowidx = (np.repeat(2 * np.arange(nb), 4) + np.tile([0, 1, 0, 1], nb)).astype(np.int32)
+
+    def initial_solution(self):
+        return np.tile([-100.0, 100.0], self.nb)
+
+    def objective_jacobian(self, x, cj):
+        self.calls += 1
+        E = np.empty(2 * self.nb)
+        E[0::2] = 25.0 * (x[1::2] - x[0::2] * x[0::2])
+        E[1::2] = 1.0 - x[0::2]
+        if not cj:
+            return E, None
+        v = np.empty(4 * self.nb)
+        v[0::4] = -2.0 * 25.0 * x[0::2]
+        v[1::4] = -1.0
+        v[2::4] = 25.0
+        v[3::4] = 0.0
+        return E, sp.csc_matrix((v, self.rowidx, self.colptr), shape=(2 * self.nb, 2 * self.nb))
+
+
+def test_host_traits_drop_in_path_and_call_counts(spb, handle, orc):
+    # host SolverTraits (user code on the CPU), GPU everything else: the e2e drop-in path
+    st = PyRosenbrock(4)
+    ls = spb.B200SolverWrapper(handle)
+    lm = spb.LMSolver()
+    lm.init(ls, st, spb.DiagonalDamping(0.01), 1000)
+    ret = lm.solve(True)
+    ref = orc.lm_solve("rosenbrock", iparam0=4, maxIterations=1000)
+    assert ret == ref.ret and lm.currIter == ref.currIter and lm.exit_path == ref.exit_path
+    np.testing.assert_allclose(lm.x, ref.x, rtol=1e-10, atol=1e-12)
+    # reference call sequence: 1 + 5 per completed loop body + 2 in the breaking one
+    # (+1 pattern-discovery call made by the Python binding)
+    assert st.calls == 1 + 1 + 5 * lm.currIter + 2
+    st2 = PyRosenbrock(4)
+    lm.init(ls, st2, spb.DiagonalDamping(0.01), 1000)
+    lm.solve(True, dedupe_evaluations=True)
+    assert lm.currIter == ref.currIter and st2.calls < st.calls / 2
+
+
+def test_quirks_max_iter_and_foo(spb, handle, orc):
+    ret, lm = _run_builtin(spb, handle, "rosenbrock", nblocks=3, maxit=5)
+    assert lm.exit_path == "max_iter" and lm.currIter == 6 and lm.factorizations == 6 and ret is False
+    x0 = np.tile([1.0, 1.0], 3)
+    ret, lm = _run_builtin(spb, handle, "rosenbrock", nblocks=3, x0=x0, verbose=True)
+    assert lm.exit_path == "foo" and lm.factorizations == 0
+    ret, lm = _run_builtin(spb, handle, "rosenbrock", nblocks=3, x0=x0, verbose=False)
+    ref = orc.lm_solve("rosenbrock", iparam0=3, x0=x0, verbose=False)
+    assert lm.exit_path == ref.exit_path and lm.currIter == ref.currIter
+
+
+def test_fixed_iterations_benchmark_mode(spb, handle):
+    prob = spb.BuiltinProblem(handle, "lf", g=32, rows_mult=2, seed=20211)
+    ls = spb.B200SolverWrapper(handle)
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0)
+    lm.solve(False, dedupe_evaluations=True, fixed_iterations=7)
+    assert lm.factorizations == 7 and len(lm.trace["lambda"]) == 7

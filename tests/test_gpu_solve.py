@@ -1,0 +1,116 @@
+"""GPU tier: SpMV, reductions and the LinearSolver concept (factorize/solve) vs the oracle's
+SimplicialLLT restatement.  Bar (north_star): step vectors within 1e-10 relative in FP64."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import random_jacobian
+
+pytestmark = pytest.mark.gpu
+
+STEP_RTOL = 1e-10  # north_star: "step vectors ... within 1e-10 relative in FP64"
+
+
+def _assembled(handle, orc, rng, m, n, k, lam=0.01):
+    colptr, rowidx, vals = random_jacobian(rng, m, n, k)
+    E = rng.standard_normal(m)
+    handle.analyze(m, n, colptr, rowidx)
+    handle.assemble(vals, E, lam)
+    J = orc.from_csc(m, n, colptr, rowidx, vals)
+    D, _ = orc.damp_build(J, lam)
+    return orc.ata(D), orc.jt_vec_neg(J, E)
+
+
+def test_spmv_matches_scipy(handle, orc):
+    rng = np.random.default_rng(0)
+    H, g = _assembled(handle, orc, rng, 3000, 1000, 5)
+    x = rng.standard_normal(1000)
+    y = handle.spmv(x)
+    yref = H.scipy().tocsr() @ x
+    np.testing.assert_allclose(y, yref, rtol=1e-13, atol=1e-12)
+
+
+def test_reductions(handle):
+    rng = np.random.default_rng(1)
+    for n in (1, 31, 257, 100003):
+        v = rng.standard_normal(n)
+        assert abs(handle.squared_norm(v) - float(v @ v)) <= 1e-13 * float(v @ v)
+        assert handle.inf_norm(v) == np.abs(v).max()
+    # deterministic: same bits on repeated calls
+    v = rng.standard_normal(777777)
+    assert handle.squared_norm(v) == handle.squared_norm(v)
+
+
+@pytest.mark.parametrize("seed,m,n,k", [(0, 900, 300, 3), (1, 6000, 2500, 5)])
+def test_pcg_step_matches_llt(handle, spb, orc, seed, m, n, k):
+    rng = np.random.default_rng(seed)
+    H, g = _assembled(handle, orc, rng, m, n, k)
+    handle.set_solver(spb.SOLVER_PCG_JACOBI, 1e-13, 10000)
+    assert handle.factorize()
+    x, iters, st = handle.solve()  # solves for the assembled gradient
+    assert st == 0 and iters > 0
+    F = orc.LLT(H, 1)
+    assert F.ok
+    xref = F.solve(g)
+    assert np.linalg.norm(x - xref) <= STEP_RTOL * np.linalg.norm(xref)
+    # explicit rhs path, host and device
+    b = rng.standard_normal(n)
+    x2, _, _ = handle.solve(b)
+    assert np.linalg.norm(x2 - F.solve(b)) <= STEP_RTOL * np.linalg.norm(F.solve(b))
+    import torch
+    x3, _, _ = handle.solve(torch.tensor(b, device="cuda"))
+    assert (x3.cpu().numpy() == x2).all()  # deterministic and pointer-kind independent
+
+
+def test_pcg_iteration_count_close_to_cpu_twin(handle, spb, orc):
+    J = orc.lf_matrix(40, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    E = J.scipy() @ np.ones(n) - 1.0
+    handle.analyze(m, n, colptr, rowidx)
+    handle.assemble(vals, E, 0.01)
+    handle.set_solver(spb.SOLVER_PCG_JACOBI, 1e-13, 10000)
+    handle.factorize()
+    x, iters, st = handle.solve()
+    D, _ = orc.damp_build(J, 0.01)
+    H = orc.ata(D)
+    xr, itr, rr = orc.pcg_jacobi(H, orc.jt_vec_neg(J, E), 1e-13, 10000)
+    assert abs(iters - itr) <= 2
+    assert np.linalg.norm(x - xr) <= 1e-11 * np.linalg.norm(xr)
+
+
+def test_linear_solver_concept_with_explicit_matrix(spb, orc):
+    # LinearSolver::factorize(SparseMatrix) / solve(rhs, x): the pure drop-in path used when the
+    # reference's own LMSolver.h passes dampJ^T*dampJ (LMSolver.h:136,143)
+    rng = np.random.default_rng(3)
+    m, n = 1200, 500
+    colptr, rowidx, vals = random_jacobian(rng, m, n, 4)
+    J = orc.from_csc(m, n, colptr, rowidx, vals)
+    D, _ = orc.damp_build(J, 0.01)
+    H = orc.ata(D)
+    ls = spb.B200SolverWrapper()
+    assert ls.factorize(H.scipy()) is True
+    b = rng.standard_normal(n)
+    x = ls.solve(b)
+    xref = orc.LLT(H, 1).solve(b)
+    assert np.linalg.norm(x - xref) <= STEP_RTOL * np.linalg.norm(xref)
+    # matrix right-hand side (EigenSolverWrapper.h:62-70)
+    B = rng.standard_normal((n, 3))
+    X = ls.solve(B)
+    for c in range(3):
+        xr = orc.LLT(H, 1).solve(B[:, c])
+        assert np.linalg.norm(X[:, c] - xr) <= STEP_RTOL * np.linalg.norm(xr)
+    # same pattern, new values: no re-analysis needed, results follow the values
+    assert ls.factorize(2.0 * H.scipy()) is True
+    np.testing.assert_allclose(ls.solve(b), 0.5 * x, rtol=1e-9)
+    ls.handle.close()
+
+
+def test_not_spd_is_reported(spb):
+    # indefinite matrix: the reference's factorize returns false (EigenSolverWrapper.h:59)
+    A = sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [2.0, 1.0, 0.0], [0.0, 0.0, 1.0]]))
+    ls = spb.B200SolverWrapper()
+    ok = ls.factorize(A)
+    x, it, st = ls.handle.solve(np.array([1.0, -1.0, 0.5])) if ok else (None, 0, spb.capi.SPB_NOT_SPD)
+    assert (not ok) or st == spb.capi.SPB_NOT_SPD
+    ls.handle.close()

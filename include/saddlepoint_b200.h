@@ -116,6 +116,9 @@ typedef struct {
   int32_t xSize, ESize;
   const int32_t* colptr; /* CSC pattern of J (host), fixed for the duration of a solve */
   const int32_t* rowidx;
+  uint64_t pattern_version; /* 0: unknown (the library fingerprints the arrays on every solve);
+                               nonzero: caller's promise that the pattern is unchanged while this
+                               value and the colptr pointer are unchanged                         */
   int mem;
   void* user;
   void (*initial_solution)(void* user, double* x0_host);
@@ -169,7 +172,8 @@ spb_status spb_problem_destroy(spb_problem_t p);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t spb_launch_count(spb_handle h);
 /* per-stage device time accumulated since the last reset, milliseconds (CUDA events):
- * stage 0 assembly, 1 spmv, 2 pcg-vector, 3 factor, 4 trisolve, 5 reductions, 6 traits */
+ * stage 0 assembly, 1 spmv, 2 pcg-vector, 3 factor, 4 trisolve, 5 reductions, 6 traits,
+ * 7 fused persistent PCG solve */
 spb_status spb_stage_ms(spb_handle h, int stage, double* ms, int64_t* launches);
 spb_status spb_stage_reset(spb_handle h, int enable_timing);
 

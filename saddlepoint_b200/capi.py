@@ -22,7 +22,7 @@ POST_CB = C.CFUNCTYPE(C.c_int, vp, vp)
 
 
 class Traits(C.Structure):
-    _fields_ = [("xSize", C.c_int32), ("ESize", C.c_int32), ("colptr", vp), ("rowidx", vp), ("mem", C.c_int),
+    _fields_ = [("xSize", C.c_int32), ("ESize", C.c_int32), ("colptr", vp), ("rowidx", vp), ("pattern_version", C.c_uint64), ("mem", C.c_int),
                 ("user", vp), ("initial_solution", INIT_CB), ("objective_jacobian", OBJJAC_CB),
                 ("pre_iteration", PRE_CB), ("post_iteration", POST_CB)]
 

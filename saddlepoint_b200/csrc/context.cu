@@ -107,6 +107,9 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     cudaDeviceProp prop;
     SPB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SPB_PCG_MULTI")) h->pcg_persistent = !(e[0] == '1');
+    if (!prop.cooperativeLaunch) h->pcg_persistent = false;
+    if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
     SPB_CUDA(cudaMallocHost((void**)&h->h_sc, sizeof(PcgScalars)));
     SPB_CUDA(cudaMallocHost((void**)&h->h_scalar, 8 * sizeof(double)));
     memset(h->h_sc, 0, sizeof(PcgScalars));
@@ -125,6 +128,7 @@ spb_status spb_destroy(spb_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   chol_release(h);
+  lm_release(h);
   for (auto& p : h->timing.pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
@@ -161,6 +165,7 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
     SPB_CUDA(cudaSetDevice(h->device));
     validate_csc(m, n, colptr, rowidx);
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+    h->pcg_last_iters = 0;
     chol_release(h);
     h->m = m;
     h->n = n;
@@ -305,7 +310,8 @@ spb_status spb_factorize(spb_handle h) {
     SPB_CUDA(cudaSetDevice(h->device));
     spb_status s = SPB_OK;
     if (h->solver == SPB_SOLVER_CHOLESKY) s = chol_factorize(h);
-    // PCG: the Jacobi diagonal is a by-product of assembly; nothing to factor.
+    // PCG: the Jacobi diagonal is a by-product of assembly; "factorisation" is its inverse.
+    else dev_invert_diag(h);
     if (s == SPB_OK) h->factor_valid = true;
     return s;
   });

@@ -20,7 +20,11 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cooperative_groups.h>
+
 #include "spb_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace spb {
 
@@ -103,17 +107,21 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ 
 }
 
 __global__ void add_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t len) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < len) out[i] = a[i] + b[i];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+__global__ void invert_kernel(const double* __restrict__ a, double* __restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = 1.0 / a[i];
 }
 
-static int reduce_grid(int64_t len) {
-  int64_t g = (len + 256 * 8 - 1) / (256 * 8);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(g, 1184));  // 8 x 148 SMs
+// Grids are sized from the SM count, not the problem: a fixed number of fat blocks keeps the
+// work per SM balanced (no partial last wave), keeps the number of same-address ticket
+// atomics small, and makes the reduction order a function of (len, grid) only.
+static int vec_grid(const spb_context* h, int64_t len) {
+  int64_t want = (len + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->num_sms * 8));
 }
-
 static void ensure_pcg_buffers(spb_context* h) {
-  size_t need = std::max<size_t>(1184 * 2, (size_t)((h->n + 255) / 256) * 2 + 16);
+  size_t need = (size_t)h->num_sms * 8 * 3 + 64;
   SPB_CUDA(h->d_partial.alloc(need + 8));
   if (!h->d_sc.p) {
     SPB_CUDA(h->d_sc.alloc(1));
@@ -125,13 +133,12 @@ static void dev_reduce(spb_context* h, int op, const double* d_v, int64_t len, d
   ensure_pcg_buffers(h);
   cudaStream_t st = h->stream;
   double* result = h->d_partial.p + (h->d_partial.n - 1);
-  stage_begin(h, ST_REDUCE);
   if (len <= 0) {
     *host_out = 0.0;
-    stage_end(h, ST_REDUCE, 0);
     return;
   }
-  int g = reduce_grid(len);
+  stage_begin(h, ST_REDUCE);
+  int g = vec_grid(h, len);
   unsigned int* ticket = &h->d_sc.p->ticket_a;
   if (op == 0) reduce_kernel<0><<<g, 256, 0, st>>>(d_v, len, h->d_partial.p, result, ticket);
   else reduce_kernel<1><<<g, 256, 0, st>>>(d_v, len, h->d_partial.p, result, ticket);
@@ -145,38 +152,41 @@ void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* ho
 void dev_inf_norm(spb_context* h, const double* d_v, int64_t len, double* host_out) { dev_reduce(h, 1, d_v, len, host_out); }
 void dev_add(spb_context* h, const double* a, const double* b, double* out, int64_t len) {
   if (len <= 0) return;
-  add_kernel<<<(unsigned)((len + 255) / 256), 256, 0, h->stream>>>(a, b, out, len);
+  add_kernel<<<vec_grid(h, len), 256, 0, h->stream>>>(a, b, out, len);
+  h->launches++;
+  SPB_CUDA(cudaGetLastError());
+}
+void dev_invert_diag(spb_context* h) {
+  if (h->n == 0) return;
+  SPB_CUDA(h->d_dinv.alloc(h->n));
+  invert_kernel<<<vec_grid(h, h->n), 256, 0, h->stream>>>(h->d_hdiag.p, h->d_dinv.p, h->n);
   h->launches++;
   SPB_CUDA(cudaGetLastError());
 }
 
 // ---- SpMV ----------------------------------------------------------------------------
-// y = H x; lane == row inside a 32-row slice.  WITH_DOT additionally produces the PCG's
-// p.q partials and, in the last block, alpha = rz / pq.
-template <bool WITH_DOT>
-__global__ void __launch_bounds__(256) spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
-                                                        const int* __restrict__ rowlen, const double* __restrict__ hval,
-                                                        const double* __restrict__ x, double* __restrict__ y, int n,
-                                                        double* __restrict__ partial, PcgScalars* sc) {
-  __shared__ double sm[8];
-  if (WITH_DOT) {
-    if (sc->done) return;
-  }
-  const int row = blockIdx.x * 256 + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int slice = row >> 5;
-  double acc = 0.0;
-  if (slice * 32 < n) {
+// y = H x over the slice range [s_begin, s_end); lane == row inside a 32-row slice; the 8
+// warps of a block stride over the range.  Returns this thread's share of x.y.
+// NC=true: x is immutable for the kernel's lifetime, gathers may use the non-coherent path.
+template <bool NC>
+__device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
+                                             const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
+                                             double* y, int n, int s_begin, int s_end) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double loc = 0.0;
+  for (int slice = s_begin + warp; slice < s_end; slice += 8) {
+    const int row = slice * 32 + lane;
     const int64_t off = slice_off[slice];
     const int width = (int)((slice_off[slice + 1] - off) >> 5);
     const int len = row < n ? rowlen[row] : 0;
     const int* cp = col + off + lane;
     const double* vp = hval + off + lane;
+    double acc = 0.0;
     int k = 0;
     for (; k + 4 <= width; k += 4) {
       const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32), c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
       const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32), v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
-      const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      const double x0 = NC ? __ldg(x + c0) : x[c0], x1 = NC ? __ldg(x + c1) : x[c1], x2 = NC ? __ldg(x + c2) : x[c2], x3 = NC ? __ldg(x + c3) : x[c3];
       if (k + 0 < len) acc = fma(v0, x0, acc);
       if (k + 1 < len) acc = fma(v1, x1, acc);
       if (k + 2 < len) acc = fma(v2, x2, acc);
@@ -185,13 +195,31 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(const int64_t* __restric
     for (; k < width; ++k) {
       const int c0 = __ldcs(cp + k * 32);
       const double v0 = __ldcs(vp + k * 32);
-      const double x0 = __ldg(x + c0);
+      const double x0 = NC ? __ldg(x + c0) : x[c0];
       if (k < len) acc = fma(v0, x0, acc);
     }
-    if (row < n) y[row] = acc;
+    if (row < n) {
+      y[row] = acc;
+      loc = fma(NC ? __ldg(x + row) : x[row], acc, loc);
+    }
   }
+  return loc;
+}
+
+// Stand-alone SpMV (+ optional PCG dot): block b owns slices [nslices*b/G, nslices*(b+1)/G).
+template <bool WITH_DOT>
+__global__ void __launch_bounds__(256) spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
+                                                        const int* __restrict__ rowlen, const double* __restrict__ hval,
+                                                        const double* __restrict__ x, double* __restrict__ y, int n, int nslices,
+                                                        double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
   if (WITH_DOT) {
-    double loc = row < n ? x[row] * acc : 0.0;
+    if (sc->done) return;
+  }
+  const int s_begin = (int)(((int64_t)nslices * blockIdx.x) / gridDim.x);
+  const int s_end = (int)(((int64_t)nslices * (blockIdx.x + 1)) / gridDim.x);
+  double loc = spmv_range<true>(slice_off, col, rowlen, hval, x, y, n, s_begin, s_end);
+  if (WITH_DOT) {
     double b = block_sum_256(loc, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = b;
     if (take_ticket(&sc->ticket_a, gridDim.x) && threadIdx.x < 32) {
@@ -210,21 +238,159 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(const int64_t* __restric
   }
 }
 
+// ---- the whole PCG solve as ONE persistent cooperative kernel ---------------------------
+// All blocks are co-resident (grid = SMs x occupancy); phases are separated by grid-wide
+// barriers instead of kernel boundaries, so an iteration costs three barriers (~2 us each)
+// rather than three launches plus their drain/fill tails, no launch is wasted after
+// convergence, and the host is not involved until the solve is over.  Reductions are
+// finalised redundantly by every block from the per-block partials in one fixed order:
+// every block computes bit-identical alpha/beta/stop decisions, so no broadcast, atomics or
+// fences are needed and the result is deterministic.
+__device__ __forceinline__ double block_total(const double* part, int count, double* sm, double* bc) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) s += __ldcg(part + i);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = sm[0];
+    for (int w = 1; w < 8; ++w) r += sm[w];
+    *bc = r;
+  }
+  __syncthreads();
+  const double r = *bc;
+  __syncthreads();
+  return r;
+}
+
+struct PcgParams {
+  const int64_t* slice_off;
+  const int* col;
+  const int* rowlen;
+  const double* hval;
+  const double* b;
+  const double* dinv;
+  double* x;
+  double* r;
+  double* p;
+  double* q;
+  double* partial;  // 3 * gridDim.x
+  PcgScalars* sc;
+  int n, nslices, maxit;
+  double rtol;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[8];
+  __shared__ double bc;
+  const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
+  const int n = P.n;
+  const int stride = G * 256;
+  double* partA = P.partial;
+  double* partB = P.partial + G;
+  double* partC = P.partial + 2 * G;
+  const int s_begin = (int)(((int64_t)P.nslices * blk) / G);
+  const int s_end = (int)(((int64_t)P.nslices * (blk + 1)) / G);
+  // init: r = b, p = z = dinv*r, x = 0
+  {
+    double rz = 0.0, bb = 0.0;
+    for (int i = blk * 256 + tid; i < n; i += stride) {
+      const double bi = P.b[i];
+      const double z = bi * P.dinv[i];
+      P.x[i] = 0.0;
+      P.r[i] = bi;
+      P.p[i] = z;
+      rz = fma(bi, z, rz);
+      bb = fma(bi, bi, bb);
+    }
+    const double s1 = block_sum_256(rz, sm);
+    const double s2 = block_sum_256(bb, sm);
+    if (tid == 0) {
+      partB[blk] = s1;
+      partC[blk] = s2;
+    }
+  }
+  grid.sync();
+  double rz = block_total(partB, G, sm, &bc);
+  const double bb = block_total(partC, G, sm, &bc);
+  const double thresh = P.rtol * P.rtol * bb;
+  double rr = bb, pq = 0.0;
+  int iters = 0, breakdown = 0;
+  bool run = (bb > thresh) && P.maxit > 0;
+  grid.sync();  // partB/partC are about to be reused
+  while (run) {
+    // phase 1: q = H p, partial p.q
+    {
+      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end);
+      const double bs = block_sum_256(loc, sm);
+      if (tid == 0) partA[blk] = bs;
+    }
+    grid.sync();
+    pq = block_total(partA, G, sm, &bc);
+    if (!(pq > 0.0)) {  // not SPD (or NaN)
+      breakdown = 1;
+      break;
+    }
+    const double alpha = rz / pq;
+    // phase 2: x += alpha p, r -= alpha q, partial r.z and r.r
+    {
+      double a1 = 0.0, a2 = 0.0;
+      for (int i = blk * 256 + tid; i < n; i += stride) {
+        P.x[i] = fma(alpha, P.p[i], P.x[i]);
+        const double ri = fma(-alpha, P.q[i], P.r[i]);
+        P.r[i] = ri;
+        const double z = ri * P.dinv[i];
+        a1 = fma(ri, z, a1);
+        a2 = fma(ri, ri, a2);
+      }
+      const double s1 = block_sum_256(a1, sm);
+      const double s2 = block_sum_256(a2, sm);
+      if (tid == 0) {
+        partB[blk] = s1;
+        partC[blk] = s2;
+      }
+    }
+    grid.sync();
+    const double rz_new = block_total(partB, G, sm, &bc);
+    rr = block_total(partC, G, sm, &bc);
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    ++iters;
+    if (!(rr > thresh) || iters >= P.maxit) break;
+    // phase 3: p = dinv*r + beta p
+    for (int i = blk * 256 + tid; i < n; i += stride) P.p[i] = fma(beta, P.p[i], P.r[i] * P.dinv[i]);
+    grid.sync();
+  }
+  if (blk == 0 && tid == 0) {
+    PcgScalars* sc = P.sc;
+    sc->rz = rz;
+    sc->pq = pq;
+    sc->rr = rr;
+    sc->bb = bb;
+    sc->thresh = thresh;
+    sc->iters = iters;
+    sc->breakdown = breakdown;
+    sc->maxit = P.maxit;
+    sc->done = 1;
+  }
+}
+
 // r = b, z = dinv*r, p = z, x = 0; rz = r.z, bb = b.b
-__global__ void __launch_bounds__(256) pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ hdiag,
+__global__ void __launch_bounds__(256) pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv,
                                                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
                                                        int n, double* __restrict__ partial, PcgScalars* sc, double rtol, int maxit) {
   __shared__ double sm[8];
-  const int i = blockIdx.x * 256 + threadIdx.x;
   double rz = 0.0, bb = 0.0;
-  if (i < n) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const double bi = b[i];
-    const double z = bi * (1.0 / hdiag[i]);
+    const double z = bi * dinv[i];
     x[i] = 0.0;
     r[i] = bi;
     p[i] = z;
-    rz = bi * z;
-    bb = bi * bi;
+    rz = fma(bi, z, rz);
+    bb = fma(bi, bi, bb);
   }
   double s1 = block_sum_256(rz, sm);
   double s2 = block_sum_256(bb, sm);
@@ -251,21 +417,20 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(const double* __restrict_
 }
 
 // x += alpha p; r -= alpha q; partial rz' = sum r*(dinv*r), rr = sum r*r; last block: beta, stop test
-__global__ void __launch_bounds__(256) pcg_update_kernel(const double* __restrict__ hdiag, const double* __restrict__ p,
+__global__ void __launch_bounds__(256) pcg_update_kernel(const double* __restrict__ dinv, const double* __restrict__ p,
                                                          const double* __restrict__ q, double* __restrict__ x,
                                                          double* __restrict__ r, int n, double* __restrict__ partial, PcgScalars* sc) {
   __shared__ double sm[8];
   if (sc->done) return;
   const double alpha = sc->alpha;
-  const int i = blockIdx.x * 256 + threadIdx.x;
   double rz = 0.0, rr = 0.0;
-  if (i < n) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     x[i] = fma(alpha, p[i], x[i]);
     const double ri = fma(-alpha, q[i], r[i]);
     r[i] = ri;
-    const double z = ri * (1.0 / hdiag[i]);
-    rz = ri * z;
-    rr = ri * ri;
+    const double z = ri * dinv[i];
+    rz = fma(ri, z, rz);
+    rr = fma(ri, ri, rr);
   }
   double s1 = block_sum_256(rz, sm);
   double s2 = block_sum_256(rr, sm);
@@ -288,19 +453,31 @@ __global__ void __launch_bounds__(256) pcg_update_kernel(const double* __restric
 }
 
 // p = dinv*r + beta p
-__global__ void __launch_bounds__(256) pcg_direction_kernel(const double* __restrict__ hdiag, const double* __restrict__ r,
+__global__ void __launch_bounds__(256) pcg_direction_kernel(const double* __restrict__ dinv, const double* __restrict__ r,
                                                             double* __restrict__ p, int n, const PcgScalars* sc) {
   if (sc->done) return;
   const double beta = sc->beta;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) p[i] = fma(beta, p[i], r[i] * (1.0 / hdiag[i]));
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) p[i] = fma(beta, p[i], r[i] * dinv[i]);
+}
+
+// blocks per SM the kernel can keep resident (queried once): a persistent grid must not
+// spill into a second, half-empty wave
+static int spmv_grid(spb_context* h) {
+  if (h->occ_spmv == 0) {
+    int occ = 0;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_sell_kernel<true>, 256, 0));
+    h->occ_spmv = std::max(1, occ);
+  }
+  int nslices = (h->n + 31) / 32;
+  int64_t want = (nslices + 7) / 8;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)h->num_sms * h->occ_spmv));
 }
 
 void dev_spmv(spb_context* h, const double* d_x, double* d_y) {
   if (h->n == 0) return;
   stage_begin(h, ST_SPMV);
-  spmv_sell_kernel<false><<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p,
-                                                                      h->d_hval.p, d_x, d_y, h->n, nullptr, nullptr);
+  spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, h->stream>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, d_x,
+                                                              d_y, h->n, (h->n + 31) / 32, nullptr, nullptr);
   SPB_CUDA(cudaGetLastError());
   stage_end(h, ST_SPMV, 1);
 }
@@ -314,22 +491,62 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
   SPB_CUDA(h->d_r.alloc(n));
   SPB_CUDA(h->d_p.alloc(n));
   SPB_CUDA(h->d_q.alloc(n));
-  const int grid = (n + 255) / 256;
+  const int gv = vec_grid(h, n), gs = spmv_grid(h), nslices = (n + 31) / 32;
   PcgScalars* sc = h->d_sc.p;
+  if (h->pcg_persistent) {
+    void* kern = h->pcg_minb >= 5 ? (void*)pcg_persistent_kernel<5> : (void*)pcg_persistent_kernel<4>;
+    if (h->occ_pcg == 0) {
+      int occ = 0;
+      if (h->pcg_minb >= 5) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_persistent_kernel<5>, 256, 0));
+      else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_persistent_kernel<4>, 256, 0));
+      h->occ_pcg = std::max(1, occ);
+    }
+    const int G = std::max(1, std::min((nslices + 7) / 8, h->num_sms * h->occ_pcg));
+    PcgParams P;
+    P.slice_off = h->d_slice_off.p;
+    P.col = h->d_sell_col.p;
+    P.rowlen = h->d_rowlen.p;
+    P.hval = h->d_hval.p;
+    P.b = d_b;
+    P.dinv = h->d_dinv.p;
+    P.x = d_x;
+    P.r = h->d_r.p;
+    P.p = h->d_p.p;
+    P.q = h->d_q.p;
+    P.partial = h->d_partial.p;
+    P.sc = sc;
+    P.n = n;
+    P.nslices = nslices;
+    P.maxit = h->pcg_maxit;
+    P.rtol = h->pcg_rtol;
+    void* args[] = {&P};
+    stage_begin(h, ST_PCG);
+    SPB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(256), args, 0, st));
+    stage_end(h, ST_PCG, 1);
+    SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    h->pcg_last_iters = h->h_sc->iters;
+    if (iters) *iters = h->h_sc->iters;
+    if (h->h_sc->breakdown) return SPB_NOT_SPD;
+    if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
+    return SPB_OK;
+  }
   stage_begin(h, ST_PCGVEC);
-  pcg_init_kernel<<<grid, 256, 0, st>>>(d_b, h->d_hdiag.p, d_x, h->d_r.p, h->d_p.p, n, h->d_partial.p, sc, h->pcg_rtol, h->pcg_maxit);
+  pcg_init_kernel<<<gv, 256, 0, st>>>(d_b, h->d_dinv.p, d_x, h->d_r.p, h->d_p.p, n, h->d_partial.p, sc, h->pcg_rtol, h->pcg_maxit);
   stage_end(h, ST_PCGVEC, 1);
+  // The host only looks at the device's convergence flag between batches; the first batch is
+  // sized from the previous solve on this handle (LM systems change slowly between iterations).
   int launched = 0;
-  int batch = 16;
+  int batch = h->pcg_last_iters > 0 ? std::min(h->pcg_last_iters + 2, h->pcg_maxit) : 16;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       stage_begin(h, ST_SPMV);
-      spmv_sell_kernel<true><<<grid, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, h->d_p.p,
-                                                   h->d_q.p, n, h->d_partial.p, sc);
+      spmv_sell_kernel<true><<<gs, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, h->d_p.p, h->d_q.p,
+                                                 n, nslices, h->d_partial.p, sc);
       stage_end(h, ST_SPMV, 1);
       stage_begin(h, ST_PCGVEC);
-      pcg_update_kernel<<<grid, 256, 0, st>>>(h->d_hdiag.p, h->d_p.p, h->d_q.p, d_x, h->d_r.p, n, h->d_partial.p, sc);
-      pcg_direction_kernel<<<grid, 256, 0, st>>>(h->d_hdiag.p, h->d_r.p, h->d_p.p, n, sc);
+      pcg_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_p.p, h->d_q.p, d_x, h->d_r.p, n, h->d_partial.p, sc);
+      pcg_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, h->d_p.p, n, sc);
       stage_end(h, ST_PCGVEC, 2);
     }
     launched += batch;
@@ -337,8 +554,10 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     SPB_CUDA(cudaStreamSynchronize(st));
     if (h->h_sc->done) break;
-    if (launched >= h->pcg_maxit + batch) break;  // cannot happen: done is set at maxit
+    batch = 8;
+    if (launched >= h->pcg_maxit + 64) break;  // cannot happen: done is set at maxit
   }
+  h->pcg_last_iters = h->h_sc->iters;
   if (iters) *iters = h->h_sc->iters;
   if (h->h_sc->breakdown) return SPB_NOT_SPD;
   if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;

@@ -210,6 +210,7 @@ spb_status spb_problem_traits(spb_problem_t P, spb_traits* T) {
   T->ESize = P->m;
   T->colptr = P->colptr.data();
   T->rowidx = P->rowidx.data();
+  T->pattern_version = (uint64_t)(uintptr_t)P | 1u;  // pattern is immutable for the problem's lifetime
   T->mem = SPB_DEVICE;
   T->user = P;
   T->initial_solution = any_x0;

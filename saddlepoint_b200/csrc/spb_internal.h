@@ -118,7 +118,7 @@ uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx)
 // ---- the handle -------------------------------------------------------------------------
 namespace spb {
 
-enum Stage { ST_ASSEMBLY = 0, ST_SPMV = 1, ST_PCGVEC = 2, ST_FACTOR = 3, ST_TRISOLVE = 4, ST_REDUCE = 5, ST_TRAITS = 6, ST_COUNT = 7 };
+enum Stage { ST_ASSEMBLY = 0, ST_SPMV = 1, ST_PCGVEC = 2, ST_FACTOR = 3, ST_TRISOLVE = 4, ST_REDUCE = 5, ST_TRAITS = 6, ST_PCG = 7, ST_COUNT = 8 };
 
 // Scalars of the PCG recurrences and of the LM reductions; lives in device memory with a
 // pinned host mirror that is refreshed by explicit async copies.
@@ -180,7 +180,7 @@ struct spb_context {
   spb::DevBuf<int> d_sell_col, d_rowlen;
   spb::DevBuf<int64_t> d_slice_off;
   spb::DevBuf<int64_t> d_pos_of_slot;  // lazily built: CSC slot -> storage position
-  spb::DevBuf<double> d_hval, d_hdiag;
+  spb::DevBuf<double> d_hval, d_hdiag, d_dinv;
   // device: vectors
   spb::DevBuf<double> d_rhs, d_dvec, d_Jv_stage, d_f_stage, d_vec_stage, d_vec_stage2;
   spb::DevBuf<double> d_r, d_p, d_q, d_x, d_partial;
@@ -189,7 +189,12 @@ struct spb_context {
   spb::PcgScalars* h_sc = nullptr;      // pinned
   double* h_scalar = nullptr;           // pinned scratch (8 doubles)
 
+  int pcg_last_iters = 0;
+  bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
+  int occ_spmv = 0, occ_pcg = 0;
+  int pcg_minb = 5;            // __launch_bounds__ min blocks/SM variant of the persistent kernel
   int64_t launches = 0;
+  void* lm_ws = nullptr;  // spb::LmWorkspace*, owned (lm.cu)
   spb::Timing timing;
   void* chol = nullptr;  // spb::CholeskyState*, owned (cholesky.cu)
 };
@@ -212,6 +217,8 @@ void scatter_h_values(spb_context* h, const double* d_in);  // CSC order -> stor
 void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);
 void dev_inf_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);
 void dev_add(spb_context* h, const double* a, const double* b, double* out, int64_t len);  // out=a+b
+void dev_invert_diag(spb_context* h);  // d_dinv = 1/d_hdiag
+void lm_release(spb_context* h);
 
 // pcg.cu
 void dev_spmv(spb_context* h, const double* d_x, double* d_y);

@@ -191,7 +191,7 @@ class Handle:
         self._check(self.L.spb_stage_reset(self.h, int(enable_timing)))
 
     def stage_ms(self):
-        names = ["assembly", "spmv", "pcg_vector", "factor", "trisolve", "reductions", "traits"]
+        names = ["assembly", "spmv", "pcg_vector", "factor", "trisolve", "reductions", "traits", "pcg_fused"]
         out = {}
         for k, nm in enumerate(names):
             ms = C.c_double(0)
@@ -319,6 +319,7 @@ class LMSolver:
 
             T.xSize, T.ESize = n, m
             T.colptr, T.rowidx = pc, pr
+            T.pattern_version = 0
             T.mem = SPB_HOST
             T.initial_solution = capi.INIT_CB(_init)
             T.objective_jacobian = capi.OBJJAC_CB(_objjac)

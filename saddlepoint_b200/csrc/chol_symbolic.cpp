@@ -1,0 +1,352 @@
+// chol_symbolic.cpp -- host symbolic phase of the supernodal (multifrontal) Cholesky.
+//
+// The reference calls Eigen::SimplicialLLT::compute on every LM iteration
+// (EigenSolverWrapper.h:58): AMD ordering + elimination tree + scalar up-looking numeric
+// factorisation, all redone each time [Eigen-upstream].  Here ordering, tree, supernodes,
+// row structures and every scatter/extend-add map are computed ONCE per pattern; the numeric
+// phase (cholesky.cu) only streams values through them.
+//
+// Ordering: nested dissection by breadth-first level structures (George), because the GPU
+// wants a shallow, balanced assembly tree whose nodes are big dense blocks:
+//   * a connected region is split by the median level of a BFS from a pseudo-peripheral
+//     vertex; the level is a vertex separator by construction;
+//   * a disconnected region is split into two balanced groups of components (no separator);
+//   * regions of <= kLeaf vertices, or whose level structure is too shallow to cut (dense
+//     graphs), become leaves.
+// Every leaf and every separator is ONE supernode whose pivot block is treated as dense
+// (a little explicit fill for much more regular tensor-core work).  Row structures follow
+// from the usual supernodal recurrence struct(s) = adj(cols(s)) U struct(children) above the
+// pivot block; the assembly-tree parent is the supernode owning min(struct(s)).
+#include <algorithm>
+#include <numeric>
+
+#include "chol_internal.h"
+
+namespace spb {
+
+namespace {
+
+constexpr int kLeaf = 48;
+
+struct NdBuilder {
+  int n;
+  const std::vector<int>& Ap;
+  const std::vector<int>& Ai;
+  std::vector<int> region;   // region id per vertex (current recursion owner)
+  std::vector<int> dist;     // BFS scratch
+  std::vector<int> perm;     // output order (perm[new] = old)
+  std::vector<int> sn_col0;  // supernode boundaries in the new order
+  int next_region = 1;
+
+  NdBuilder(int n_, const std::vector<int>& p, const std::vector<int>& i) : n(n_), Ap(p), Ai(i), region(n_, 0), dist(n_, -1) {
+    perm.reserve(n);
+    sn_col0.push_back(0);
+  }
+
+  void emit(const std::vector<int>& verts) {
+    if (verts.empty()) return;
+    for (int v : verts) perm.push_back(v);
+    sn_col0.push_back((int)perm.size());
+  }
+
+  // BFS inside region `rid` from `src`; fills order (visit order) and dist; returns depth
+  int bfs(int src, int rid, std::vector<int>& order) {
+    order.clear();
+    order.push_back(src);
+    dist[src] = 0;
+    int depth = 0;
+    for (size_t h = 0; h < order.size(); ++h) {
+      int v = order[h];
+      depth = dist[v];
+      for (int q = Ap[v]; q < Ap[v + 1]; ++q) {
+        int w = Ai[q];
+        if (region[w] == rid && dist[w] < 0) {
+          dist[w] = dist[v] + 1;
+          order.push_back(w);
+        }
+      }
+    }
+    return depth;
+  }
+  void clear_dist(const std::vector<int>& order) {
+    for (int v : order) dist[v] = -1;
+  }
+
+  void dissect(std::vector<int>& verts) {
+    // explicit stack to avoid deep recursion; each frame owns its vertex list
+    struct Frame {
+      std::vector<int> verts;
+      std::vector<int> sep;  // emitted after the children
+      int stage;
+    };
+    std::vector<Frame> stack;
+    stack.push_back({std::move(verts), {}, 0});
+    std::vector<int> order, order2;
+    while (!stack.empty()) {
+      Frame& F = stack.back();
+      if (F.stage == 1) {  // children done: emit separator
+        emit(F.sep);
+        stack.pop_back();
+        continue;
+      }
+      F.stage = 1;
+      const int sz = (int)F.verts.size();
+      if (sz <= kLeaf) {
+        emit(F.verts);
+        stack.pop_back();
+        continue;
+      }
+      const int rid = next_region++;
+      for (int v : F.verts) region[v] = rid;
+      // connected components
+      std::vector<std::vector<int>> comps;
+      for (int v : F.verts) {
+        if (dist[v] >= 0) continue;
+        bfs(v, rid, order);
+        comps.push_back(order);
+      }
+      for (int v : F.verts) dist[v] = -1;
+      if (comps.size() > 1) {
+        std::sort(comps.begin(), comps.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+        std::vector<int> A, B;
+        for (auto& c : comps) {
+          std::vector<int>& dst = A.size() <= B.size() ? A : B;
+          dst.insert(dst.end(), c.begin(), c.end());
+        }
+        std::vector<int>().swap(F.verts);
+        // no separator; children become independent subtrees
+        stack.push_back({std::move(B), {}, 0});
+        stack.push_back({std::move(A), {}, 0});
+        continue;
+      }
+      // single component: pseudo-peripheral start (two sweeps), then median level cut
+      bfs(F.verts[0], rid, order);
+      int far = order.back();
+      clear_dist(order);
+      int depth = bfs(far, rid, order2);
+      if (depth < 2) {  // too shallow to cut: dense-ish block
+        clear_dist(order2);
+        emit(F.verts);
+        stack.pop_back();
+        continue;
+      }
+      std::vector<int> cnt(depth + 1, 0);
+      for (int v : order2) cnt[dist[v]]++;
+      // choose the level in the middle third (by cumulative size) with the fewest vertices
+      int best = -1;
+      {
+        int cum = 0;
+        for (int l = 0; l <= depth; ++l) {
+          int before = cum;
+          cum += cnt[l];
+          if (l == 0 || l == depth) continue;
+          int after = sz - cum;
+          if (before < sz / 4 || after < sz / 4) continue;
+          if (best < 0 || cnt[l] < cnt[best]) best = l;
+        }
+        if (best < 0) {  // fall back to the median level
+          cum = 0;
+          for (int l = 0; l <= depth; ++l) {
+            cum += cnt[l];
+            if (cum * 2 >= sz) {
+              best = std::min(std::max(l, 1), depth - 1);
+              break;
+            }
+          }
+        }
+      }
+      if (cnt[best] * 2 > sz) {  // separator would swallow the region
+        clear_dist(order2);
+        emit(F.verts);
+        stack.pop_back();
+        continue;
+      }
+      std::vector<int> A, B, S;
+      for (int v : order2) {
+        int d = dist[v];
+        (d < best ? A : d > best ? B : S).push_back(v);
+      }
+      clear_dist(order2);
+      std::vector<int>().swap(F.verts);
+      F.sep = std::move(S);
+      stack.push_back({std::move(B), {}, 0});
+      stack.push_back({std::move(A), {}, 0});
+    }
+  }
+};
+
+}  // namespace
+
+void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
+  const int n = H.n;
+  C.n = n;
+  // ---- ordering + supernode partition
+  {
+    NdBuilder nd(n, H.colptr, H.rowidx);
+    std::vector<int> all(n);
+    std::iota(all.begin(), all.end(), 0);
+    nd.dissect(all);
+    C.perm = std::move(nd.perm);
+    C.sn_col0 = std::move(nd.sn_col0);
+  }
+  if ((int)C.perm.size() != n) throw ArgFail{"internal: nested dissection lost vertices"};
+  C.pinv.assign(n, 0);
+  for (int k = 0; k < n; ++k) C.pinv[C.perm[k]] = k;
+  const int ns = (int)C.sn_col0.size() - 1;
+  C.nsuper = ns;
+  std::vector<int> sn_of_col(n);
+  for (int s = 0; s < ns; ++s)
+    for (int c = C.sn_col0[s]; c < C.sn_col0[s + 1]; ++c) sn_of_col[c] = s;
+  // ---- row structures, parents
+  C.sn_parent.assign(ns, -1);
+  C.struct_ptr.assign((size_t)ns + 1, 0);
+  C.struct_idx.clear();
+  std::vector<std::vector<int>> children(ns);
+  std::vector<int> mark(n, -1), tmp;
+  for (int s = 0; s < ns; ++s) {
+    const int c0 = C.sn_col0[s], c1 = C.sn_col0[s + 1];
+    tmp.clear();
+    for (int c = c0; c < c1; ++c) {
+      const int jo = C.perm[c];
+      for (int q = H.colptr[jo]; q < H.colptr[(size_t)jo + 1]; ++q) {
+        const int a = C.pinv[H.rowidx[q]];
+        if (a >= c1 && mark[a] != s) {
+          mark[a] = s;
+          tmp.push_back(a);
+        }
+      }
+    }
+    for (int ch : children[s])
+      for (int64_t t = C.struct_ptr[ch]; t < C.struct_ptr[(size_t)ch + 1]; ++t) {
+        const int a = C.struct_idx[(size_t)t];
+        if (a >= c1 && mark[a] != s) {
+          mark[a] = s;
+          tmp.push_back(a);
+        }
+      }
+    std::sort(tmp.begin(), tmp.end());
+    C.struct_idx.insert(C.struct_idx.end(), tmp.begin(), tmp.end());
+    C.struct_ptr[(size_t)s + 1] = (int64_t)C.struct_idx.size();
+    if (!tmp.empty()) {
+      const int p = sn_of_col[tmp[0]];
+      C.sn_parent[s] = p;
+      children[p].push_back(s);
+    }
+  }
+  // ---- levels (leaves = 0)
+  C.sn_level.assign(ns, 0);
+  int nlevels = 0;
+  for (int s = 0; s < ns; ++s) {
+    int lv = 0;
+    for (int ch : children[s]) lv = std::max(lv, C.sn_level[ch] + 1);
+    C.sn_level[s] = lv;
+    nlevels = std::max(nlevels, lv + 1);
+  }
+  C.nlevels = nlevels;
+  C.level_ptr.assign((size_t)nlevels + 1, 0);
+  for (int s = 0; s < ns; ++s) C.level_ptr[(size_t)C.sn_level[s] + 1]++;
+  for (int l = 0; l < nlevels; ++l) C.level_ptr[(size_t)l + 1] += C.level_ptr[l];
+  C.level_sn.resize(ns);
+  {
+    std::vector<int> cur(C.level_ptr.begin(), C.level_ptr.end() - 1);
+    for (int s = 0; s < ns; ++s) C.level_sn[cur[C.sn_level[s]]++] = s;
+  }
+  // ---- storage offsets: L panel r x k (ld = r), update matrix u x u (ld = u)
+  C.L_off.assign((size_t)ns + 1, 0);
+  C.U_off.assign((size_t)ns + 1, 0);
+  C.W_off.assign((size_t)ns + 1, 0);
+  C.max_k = C.max_r = 0;
+  C.flops = 0.0;
+  for (int s = 0; s < ns; ++s) {
+    const int64_t k = C.sn_col0[s + 1] - C.sn_col0[s];
+    const int64_t u = C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s];
+    const int64_t r = k + u;
+    C.L_off[(size_t)s + 1] = C.L_off[s] + r * k;
+    C.U_off[(size_t)s + 1] = C.U_off[s] + u * u;
+    C.W_off[(size_t)s + 1] = C.W_off[s] + r;
+    C.max_k = std::max<int>(C.max_k, (int)k);
+    C.max_r = std::max<int>(C.max_r, (int)r);
+    C.flops += (double)k * k * k / 3.0 + (double)u * k * k + (double)u * u * k;
+  }
+  C.nnzL = 0;
+  for (int s = 0; s < ns; ++s) {
+    const int64_t k = C.sn_col0[s + 1] - C.sn_col0[s];
+    const int64_t u = C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s];
+    C.nnzL += k * (k + 1) / 2 + u * k;
+  }
+  // ---- A scatter map: every lower entry (in the permuted order) of H -> position in its panel
+  {
+    const int64_t nlow = (H.nnz() + n) / 2;
+    C.a_src.clear();
+    C.a_dst.clear();
+    C.a_src.reserve((size_t)nlow);
+    C.a_dst.reserve((size_t)nlow);
+    for (int jo = 0; jo < n; ++jo) {
+      const int b = C.pinv[jo];
+      const int s = sn_of_col[b];
+      const int c0 = C.sn_col0[s], c1 = C.sn_col0[s + 1];
+      const int64_t k = c1 - c0;
+      const int64_t r = k + (C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s]);
+      const int* sb = C.struct_idx.data() + C.struct_ptr[s];
+      const int* se = C.struct_idx.data() + C.struct_ptr[(size_t)s + 1];
+      int kk = 0;
+      for (int q = H.colptr[jo]; q < H.colptr[(size_t)jo + 1]; ++q, ++kk) {
+        const int a = C.pinv[H.rowidx[q]];
+        if (a < b) continue;  // the symmetric partner covers it
+        int64_t lrow;
+        if (a < c1) {
+          lrow = a - c0;
+        } else {
+          const int* it = std::lower_bound(sb, se, a);
+          if (it == se || *it != a) throw ArgFail{"internal: H entry outside the symbolic structure"};
+          lrow = k + (it - sb);
+        }
+        C.a_src.push_back(S.pos(jo, kk));  // row jo of the symmetric storage, entry kk == H(rowidx[q], jo)
+        C.a_dst.push_back(C.L_off[s] + (int64_t)(b - c0) * r + lrow);
+      }
+    }
+  }
+  // ---- extend-add maps: child struct -> parent front local indices
+  C.rel_ptr.assign((size_t)ns + 1, 0);
+  C.rel_idx.clear();
+  C.rel_idx.reserve(C.struct_idx.size());
+  for (int s = 0; s < ns; ++s) {
+    const int p = C.sn_parent[s];
+    if (p >= 0) {
+      const int pc0 = C.sn_col0[p], pc1 = C.sn_col0[p + 1];
+      const int pk = pc1 - pc0;
+      const int* pb = C.struct_idx.data() + C.struct_ptr[p];
+      const int* pe = C.struct_idx.data() + C.struct_ptr[(size_t)p + 1];
+      for (int64_t t = C.struct_ptr[s]; t < C.struct_ptr[(size_t)s + 1]; ++t) {
+        const int a = C.struct_idx[(size_t)t];
+        if (a < pc1) {
+          C.rel_idx.push_back(a - pc0);
+        } else {
+          const int* it = std::lower_bound(pb, pe, a);
+          if (it == pe || *it != a) throw ArgFail{"internal: child structure not contained in parent front"};
+          C.rel_idx.push_back(pk + (int)(it - pb));
+        }
+      }
+    }
+    C.rel_ptr[(size_t)s + 1] = (int64_t)C.rel_idx.size();
+  }
+  // ---- child-rank lists per level: rank_list[l][r] = r-th children of the level's parents
+  C.rank_ptr.clear();
+  C.rank_children.clear();
+  C.level_rank_ptr.assign((size_t)nlevels + 1, 0);
+  for (int l = 0; l < nlevels; ++l) {
+    int maxch = 0;
+    for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) maxch = std::max<int>(maxch, (int)children[C.level_sn[t]].size());
+    for (int rk = 0; rk < maxch; ++rk) {
+      C.rank_ptr.push_back((int)C.rank_children.size());
+      for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) {
+        const auto& ch = children[C.level_sn[t]];
+        if ((int)ch.size() > rk) C.rank_children.push_back(ch[rk]);
+      }
+    }
+    C.level_rank_ptr[(size_t)l + 1] = (int)C.rank_ptr.size();
+  }
+  C.rank_ptr.push_back((int)C.rank_children.size());
+}
+
+}  // namespace spb

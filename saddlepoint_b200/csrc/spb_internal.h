@@ -192,7 +192,7 @@ struct spb_context {
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
   int occ_spmv = 0, occ_pcg = 0;
-  int pcg_minb = 5;            // __launch_bounds__ min blocks/SM variant of the persistent kernel
+  int pcg_minb = 4;            // __launch_bounds__ min blocks/SM variant of the persistent kernel
   int64_t launches = 0;
   void* lm_ws = nullptr;  // spb::LmWorkspace*, owned (lm.cu)
   spb::Timing timing;

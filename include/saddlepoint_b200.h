@@ -75,6 +75,10 @@ spb_status spb_h_values(spb_handle h, double* vals, int mem);
 spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* nnz,
                                   int32_t* h_colptr, int32_t* h_rowidx);
 spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats);
+/* Host-only view of the Cholesky symbolic phase (nested-dissection order, supernodes, fronts):
+ * stats[8] = nsuper, nlevels, nnz(L), max pivot block, max front, flops, update-matrix entries,
+ * structural violations; perm (optional, n) receives the fill-reducing order. */
+spb_status spb_symbolic_chol_stats(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats, int32_t* perm);
 
 /* ---- numeric assembly ------------------------------------------------------------------- */
 /* One call replaces, for the J / EVec of the last computeJacobian=true evaluation:
@@ -101,6 +105,10 @@ spb_status spb_factorize(spb_handle h);
 /* Replaces x = solver.solve(rhs) (EigenSolverWrapper.h:76; matrix RHS :62-70, nrhs columns,
  * column-major).  rhs==NULL means "use the assembled gradient". iters: PCG iterations or 0. */
 spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int mem, int* iters);
+
+/* Size of the current Cholesky factor (after the first spb_factorize with SPB_SOLVER_CHOLESKY):
+ * nnz(L) incl. supernodal fill, factorisation flops, supernode and tree-level counts. */
+spb_status spb_factor_info(spb_handle h, int64_t* nnzL, double* flops, int32_t* nsuper, int32_t* nlevels);
 
 /* ---- vector reductions used by the LM loop (LMSolver.h:119,146,155,157,175) ------------- */
 spb_status spb_squared_norm(spb_handle h, const double* v, int64_t len, int mem, double* out);

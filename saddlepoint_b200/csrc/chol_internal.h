@@ -1,0 +1,32 @@
+// chol_internal.h -- data shared by the symbolic (host) and numeric (device) phases of the
+// supernodal Cholesky.
+#pragma once
+#include "spb_internal.h"
+
+namespace spb {
+
+struct CholSymbolic {
+  int n = 0, nsuper = 0, nlevels = 0;
+  std::vector<int> perm, pinv;         // perm[new] = old ; pinv[old] = new
+  std::vector<int> sn_col0;            // nsuper+1: pivot column ranges (new numbering)
+  std::vector<int64_t> struct_ptr;     // nsuper+1
+  std::vector<int> struct_idx;         // rows below the pivot block (new numbering, ascending)
+  std::vector<int> sn_parent, sn_level;
+  std::vector<int> level_ptr, level_sn;  // supernodes grouped by level, leaves first
+  std::vector<int64_t> L_off, U_off, W_off;  // panel (r x k), update matrix (u x u), rhs work (r)
+  std::vector<int64_t> a_src, a_dst;   // H storage position -> panel position (lower entries)
+  std::vector<int64_t> rel_ptr;        // nsuper+1
+  std::vector<int> rel_idx;            // child struct -> parent front local index
+  std::vector<int> child_ptr, child_idx; // children of every supernode (ascending)
+  std::vector<int64_t> dinv_off;         // nsuper+1: inverted 32x32 diagonal blocks (1024 doubles each)
+  std::vector<int> level_rank_ptr;     // nlevels+1 into rank_ptr
+  std::vector<int> rank_ptr;           // per (level, child rank): range in rank_children
+  std::vector<int> rank_children;
+  int max_k = 0, max_r = 0;
+  int64_t nnzL = 0;
+  double flops = 0.0;
+};
+
+void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C);
+
+}  // namespace spb

@@ -330,6 +330,17 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
     }
     C.rel_ptr[(size_t)s + 1] = (int64_t)C.rel_idx.size();
   }
+  C.child_ptr.assign((size_t)ns + 1, 0);
+  C.child_idx.clear();
+  for (int s = 0; s < ns; ++s) {
+    for (int ch : children[s]) C.child_idx.push_back(ch);
+    C.child_ptr[(size_t)s + 1] = (int)C.child_idx.size();
+  }
+  C.dinv_off.assign((size_t)ns + 1, 0);
+  for (int s = 0; s < ns; ++s) {
+    const int64_t k = C.sn_col0[s + 1] - C.sn_col0[s];
+    C.dinv_off[(size_t)s + 1] = C.dinv_off[s] + ((k + 31) / 32) * 1024;
+  }
   // ---- child-rank lists per level: rank_list[l][r] = r-th children of the level's parents
   C.rank_ptr.clear();
   C.rank_children.clear();

@@ -1,7 +1,527 @@
-// cholesky.cu -- supernodal LL^T (placeholder until the numeric phase lands).
-#include "spb_internal.h"
+// cholesky.cu -- numeric phase of the supernodal (multifrontal) LL^T and its triangular
+// solves, sm_100a.  Replaces Eigen::SimplicialLLT::compute / solve behind
+// EigenSolverWrapper::factorize / solve (EigenSolverWrapper.h:54-78):
+//   factorize  -> SPB_NOT_SPD iff some pivot d <= 0 (a NaN pivot passes)
+//   solve      -> x = P^T L^-T L^-1 P b
+//
+// Structure (symbolic phase in chol_symbolic.cpp): every supernode s owns a dense panel
+// P_s (r x k column-major: k pivot columns, r = k + |struct(s)| rows) that becomes the
+// factor, and a temporary update matrix U_s (u x u, u = r - k).  The assembly tree is
+// processed level by level (leaves first), all fronts of a level in the same launches:
+//   1. scatter the H values into the panels (one launch for the whole matrix);
+//   2. extend-add the children's update matrices into the level's fronts, one launch per
+//      child rank so the summation order is fixed (deterministic) and conflict-free;
+//   3. blocked right-looking factorisation of the pivot columns, block size 32:
+//        potrf32 (one CTA per front; also inverts the 32x32 block for the solves)
+//        trsm    (one thread per row below the block)
+//        syrk    (trailing pivot columns; FP64 tensor cores, mma.sync m8n8k4 DMMA)
+//   4. U_s -= L21 L21^T in one K=k SYRK (DMMA), the bulk of the flops.
+// Only steps 3-syrk and 4 are tensor-core work; scatter/extend-add/solves are bandwidth or
+// latency kernels (north_star item 3).  tcgen05 has no FP64 path, so DMMA is the FP64
+// tensor instruction on sm_100a.
+// Solves: level-ordered; forward gathers children's tails in a fixed order inside the
+// parent's CTA, diagonal blocks are applied through their precomputed inverses so a front
+// needs k/32 sequential steps, not k.
+#include <algorithm>
+#include <cmath>
+
+#include "chol_internal.h"
+
 namespace spb {
-spb_status chol_factorize(spb_context* h) { throw StateFail{"Cholesky solver not available yet in this build"}; }
-spb_status chol_solve(spb_context* h, const double*, double*) { throw StateFail{"Cholesky solver not available yet in this build"}; }
-void chol_release(spb_context* h) { h->chol = nullptr; }
+
+struct CholDevice {
+  CholSymbolic sym;
+  DevBuf<int> sn_k, sn_r, col0, struct_idx, rel_idx, parent, child_ptr, child_idx, level_sn, rank_children, perm;
+  DevBuf<int64_t> L_off, U_off, W_off, struct_ptr, rel_ptr, dinv_off, a_src, a_dst;
+  DevBuf<double> Lbuf, Ubuf, Wbuf, Dinv, ywork;
+  DevBuf<int> fail;
+  // per level: groups of fronts of similar size -> ranges in level_sn (fronts sorted by r inside a level)
+  struct Group {
+    int begin, count, max_k, max_r;
+  };
+  std::vector<std::vector<Group>> groups;
+  bool factored = false;
+  int* h_fail = nullptr;
+};
+
+// ---- small device helpers --------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void chol_scatter_a_kernel(const double* __restrict__ hval, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                      int64_t count, double* __restrict__ Lbuf) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) Lbuf[dst[t]] = hval[src[t]];
+}
+
+// children[blockIdx.y]: add its update matrix into the parent's panel / update matrix
+__global__ void __launch_bounds__(256) chol_extend_add_kernel(const int* __restrict__ children, const int* __restrict__ parent,
+                                                              const int* __restrict__ sn_k, const int* __restrict__ sn_r,
+                                                              const int64_t* __restrict__ L_off, const int64_t* __restrict__ U_off,
+                                                              const int64_t* __restrict__ rel_ptr, const int* __restrict__ rel_idx,
+                                                              double* __restrict__ Lbuf, double* __restrict__ Ubuf) {
+  const int c = children[blockIdx.y];
+  const int p = parent[c];
+  const int u = sn_r[c] - sn_k[c];
+  const int pk = sn_k[p], pr = sn_r[p], pu = pr - pk;
+  const double* Uc = Ubuf + U_off[c];
+  double* Pp = Lbuf + L_off[p];
+  double* Up = Ubuf + U_off[p];
+  const int* rel = rel_idx + rel_ptr[c];
+  for (int b = blockIdx.x; b < u; b += gridDim.x) {
+    const int lb = rel[b];
+    for (int a = b + threadIdx.x; a < u; a += 256) {
+      const int la = rel[a];
+      const double v = Uc[(int64_t)b * u + a];
+      if (lb < pk) Pp[(int64_t)lb * pr + la] += v;
+      else Up[(int64_t)(lb - pk) * pu + (la - pk)] += v;
+    }
+  }
+}
+
+// Cholesky of the 32x32 diagonal block at pivot offset kb of every front in the list, plus its
+// inverse (for the triangular solves).  1024 threads = one per block entry.
+__global__ void __launch_bounds__(1024) chol_potrf32_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
+                                                            const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                            const int64_t* __restrict__ dinv_off, double* __restrict__ Lbuf,
+                                                            double* __restrict__ Dinv, int* __restrict__ fail) {
+  __shared__ double S[32][33];
+  const int f = fronts[blockIdx.x];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  const int i = threadIdx.x & 31, c = threadIdx.x >> 5;  // row, column
+  double* D = Lbuf + L_off[f] + (int64_t)kb * r + kb;
+  S[i][c] = (i < nb && c < nb && i >= c) ? D[(int64_t)c * r + i] : (i == c ? 1.0 : 0.0);
+  for (int j = 0; j < nb; ++j) {
+    __syncthreads();
+    if (i == j && c == j) {
+      const double d = S[j][j];
+      if (d <= 0.0) *fail = 1;  // NaN passes, like the reference's `if (d <= 0)`
+      S[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    if (c == j && i > j) S[i][j] = S[i][j] / S[j][j];
+    __syncthreads();
+    if (c > j && i >= c) S[i][c] -= S[i][j] * S[c][j];
+  }
+  __syncthreads();
+  if (i < nb && c < nb && i >= c) D[(int64_t)c * r + i] = S[i][c];
+  // inverse: warp c computes column c of S^-1 by forward substitution, lane t holds x_t
+  double x = 0.0;
+  for (int row = c; row < 32; ++row) {
+    double part = (i >= c && i < row) ? S[row][i] * x : 0.0;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (i == row) x = ((row == c ? 1.0 : 0.0) - part) / S[row][row];
+  }
+  Dinv[dinv_off[f] + (int64_t)(kb >> 5) * 1024 + c * 32 + i] = (i >= c) ? x : 0.0;
+}
+
+// rows below the diagonal block: X = B * D^-T, one thread per row
+__global__ void __launch_bounds__(128) chol_trsm_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
+                                                        const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                        double* __restrict__ Lbuf) {
+  __shared__ double Dm[32][33];
+  const int f = fronts[blockIdx.y];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  const int rb = kb + nb;
+  if ((int64_t)blockIdx.x * 128 >= r - rb) return;
+  double* P = Lbuf + L_off[f];
+  for (int e = threadIdx.x; e < 1024; e += 128) {
+    const int i = e & 31, c = e >> 5;
+    Dm[i][c] = (i < nb && c < nb && i >= c) ? P[(int64_t)(kb + c) * r + kb + i] : (i == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int row = rb + blockIdx.x * 128 + threadIdx.x;
+  if (row >= r) return;
+  double v[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) v[t] = t < nb ? P[(int64_t)(kb + t) * r + row] : 0.0;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    double s = v[t];
+#pragma unroll
+    for (int q = 0; q < t; ++q) s -= v[q] * Dm[t][q];
+    v[t] = s / Dm[t][t];
+  }
+#pragma unroll
+  for (int t = 0; t < 32; ++t)
+    if (t < nb) P[(int64_t)(kb + t) * r + row] = v[t];
+}
+
+// C -= A_i * A_j^T on 64x64 tiles of the lower triangle, FP64 tensor cores (DMMA m8n8k4).
+// mode 0: trailing pivot columns after block kb;  mode 1: the update matrix U (K = k).
+constexpr int kSyrkLd = 68;  // 64 + 4: conflict-free fragment loads
+__global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ fronts, int mode, int kb, const int* __restrict__ sn_k,
+                                                        const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                        const int64_t* __restrict__ U_off, double* __restrict__ Lbuf,
+                                                        double* __restrict__ Ubuf) {
+  __shared__ double As[16 * kSyrkLd], Bs[16 * kSyrkLd];
+  const int f = fronts[blockIdx.z];
+  const int k = sn_k[f], r = sn_r[f];
+  double* P = Lbuf + L_off[f];
+  const double* A;
+  double* C;
+  int64_t ldc;
+  int nrows, ncols, K;
+  if (mode == 0) {
+    if (k <= kb + 32) return;
+    const int rb = kb + 32;
+    A = P + (int64_t)kb * r + rb;
+    C = P + (int64_t)rb * r + rb;
+    ldc = r;
+    nrows = r - rb;
+    ncols = k - rb;
+    K = 32;
+  } else {
+    const int u = r - k;
+    if (u == 0) return;
+    A = P + k;
+    C = Ubuf + U_off[f];
+    ldc = u;
+    nrows = ncols = u;
+    K = k;
+  }
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (ti < tj || ti * 64 >= nrows || tj * 64 >= ncols) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wy = warp >> 1, wx = warp & 1;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int lr = lane >> 2, lk = lane & 3;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // stage 16 columns of the two row blocks (coalesced along rows)
+    for (int e = tid; e < 16 * 64; e += 128) {
+      const int t = e >> 6, i = e & 63;
+      const int gi = ti * 64 + i, gj = tj * 64 + i;
+      const bool kin = (k0 + t) < K;
+      As[t * kSyrkLd + i] = (kin && gi < nrows) ? A[(int64_t)(k0 + t) * r + gi] : 0.0;
+      Bs[t * kSyrkLd + i] = (kin && gj < nrows) ? A[(int64_t)(k0 + t) * r + gj] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = As[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
+        b[q] = Bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma_m8n8k4(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = ti * 64 + wy * 32 + p * 8 + lr;
+        const int j = tj * 64 + wx * 32 + q * 8 + 2 * lk + e;
+        if (i < nrows && j < ncols && i >= j) C[(int64_t)j * ldc + i] -= acc[p][q][e];
+      }
+}
+
+// ---- solves --------------------------------------------------------------------------------
+// forward: one CTA per front.  w = [y_pivots ; 0] + sum of the children's tails (fixed order),
+// pivots solved block by block through the inverted diagonal blocks, tail -= L21 * y_pivots.
+__global__ void __launch_bounds__(256) chol_forward_kernel(const int* __restrict__ fronts, const int* __restrict__ sn_k,
+                                                           const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                           const int64_t* __restrict__ L_off, const int64_t* __restrict__ W_off,
+                                                           const int64_t* __restrict__ dinv_off, const int* __restrict__ child_ptr,
+                                                           const int* __restrict__ child_idx, const int64_t* __restrict__ rel_ptr,
+                                                           const int* __restrict__ rel_idx, const double* __restrict__ Lbuf,
+                                                           const double* __restrict__ Dinv, double* __restrict__ Wbuf, double* __restrict__ y) {
+  extern __shared__ double w[];  // r + 32
+  const int f = fronts[blockIdx.x];
+  const int k = sn_k[f], r = sn_r[f], c0 = col0[f];
+  const int tid = threadIdx.x;
+  double* tmp = w + r;
+  for (int i = tid; i < r; i += 256) w[i] = i < k ? y[c0 + i] : 0.0;
+  __syncthreads();
+  for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {
+    const int c = child_idx[ci];
+    const int ck = sn_k[c], cu = sn_r[c] - ck;
+    const double* tail = Wbuf + W_off[c] + ck;
+    const int* rel = rel_idx + rel_ptr[c];
+    for (int t = tid; t < cu; t += 256) w[rel[t]] += tail[t];
+    __syncthreads();
+  }
+  const double* P = Lbuf + L_off[f];
+  const double* Di = Dinv + dinv_off[f];
+  for (int kb = 0; kb < k; kb += 32) {
+    const int nb = min(32, k - kb);
+    // y_blk = Dinv * w_blk  (lower-triangular 32x32, column-major)
+    if (tid < 32) {
+      double s = 0.0;
+      for (int t = 0; t < nb; ++t) s += Di[(int64_t)(kb >> 5) * 1024 + t * 32 + tid] * w[kb + t];
+      tmp[tid] = s;
+    }
+    __syncthreads();
+    if (tid < nb) w[kb + tid] = tmp[tid];
+    // rows below the block (remaining pivots and the tail): w_i -= sum_t L[i, kb+t] * y_t
+    for (int i = kb + nb + tid; i < r; i += 256) {
+      double s = w[i];
+      for (int t = 0; t < nb; ++t) s -= P[(int64_t)(kb + t) * r + i] * tmp[t];
+      w[i] = s;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < k; i += 256) y[c0 + i] = w[i];
+  double* Wf = Wbuf + W_off[f];
+  for (int i = k + tid; i < r; i += 256) Wf[i] = w[i];
+}
+
+// backward: x_piv = L11^-T (y_piv - L21^T x_struct); ancestors are already final
+__global__ void __launch_bounds__(256) chol_backward_kernel(const int* __restrict__ fronts, const int* __restrict__ sn_k,
+                                                            const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                            const int64_t* __restrict__ L_off, const int64_t* __restrict__ dinv_off,
+                                                            const int64_t* __restrict__ struct_ptr, const int* __restrict__ struct_idx,
+                                                            const double* __restrict__ Lbuf, const double* __restrict__ Dinv,
+                                                            double* __restrict__ y) {
+  extern __shared__ double w[];  // r + 32
+  const int f = fronts[blockIdx.x];
+  const int k = sn_k[f], r = sn_r[f], c0 = col0[f];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* tmp = w + r;
+  const int* st = struct_idx + struct_ptr[f];
+  for (int i = tid; i < r; i += 256) w[i] = i < k ? y[c0 + i] : y[st[i - k]];
+  __syncthreads();
+  const double* P = Lbuf + L_off[f];
+  const double* Di = Dinv + dinv_off[f];
+  const int nblk = (k + 31) / 32;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int kb = bi * 32;
+    const int nb = min(32, k - kb);
+    // z_t = w[kb+t] - sum_{i >= kb+nb} L[i, kb+t] * w[i] : one warp per column, strided
+    for (int t = warp; t < nb; t += 8) {
+      double s = 0.0;
+      const double* col = P + (int64_t)(kb + t) * r;
+      for (int i = kb + nb + lane; i < r; i += 32) s += col[i] * w[i];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) tmp[t] = w[kb + t] - s;
+    }
+    __syncthreads();
+    // x_blk = Dinv^T * z_blk
+    if (tid < nb) {
+      double s = 0.0;
+      for (int t = tid; t < nb; ++t) s += Di[(int64_t)bi * 1024 + tid * 32 + t] * tmp[t];
+      w[kb + tid] = s;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < k; i += 256) y[c0 + i] = w[i];
+}
+
+__global__ void chol_permute_kernel(const double* __restrict__ in, const int* __restrict__ perm, double* __restrict__ out, int n, int dir) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dir == 0) out[i] = in[perm[i]];  // y = P b
+  else out[perm[i]] = in[i];           // x = P^T y
+}
+
+// ---- host orchestration ---------------------------------------------------------------------
+static CholDevice* ensure_symbolic(spb_context* h) {
+  if (h->chol) return (CholDevice*)h->chol;
+  CholDevice* D = new CholDevice;
+  h->chol = D;
+  cudaStream_t st = h->stream;
+  chol_symbolic(h->H, h->S, D->sym);
+  CholSymbolic& C = D->sym;
+  const int ns = C.nsuper;
+  std::vector<int> k(ns), r(ns), col0(ns);
+  for (int s = 0; s < ns; ++s) {
+    k[s] = C.sn_col0[s + 1] - C.sn_col0[s];
+    r[s] = k[s] + (int)(C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s]);
+    col0[s] = C.sn_col0[s];
+  }
+  // sort fronts inside each level by front size and cut groups of similar size
+  D->groups.assign(C.nlevels, {});
+  for (int l = 0; l < C.nlevels; ++l) {
+    int b = C.level_ptr[l], e = C.level_ptr[(size_t)l + 1];
+    std::sort(C.level_sn.begin() + b, C.level_sn.begin() + e, [&](int a, int c) { return r[a] != r[c] ? r[a] < r[c] : a < c; });
+    int g0 = b;
+    while (g0 < e) {
+      int g1 = g0;
+      int lim = std::max(64, 2 * r[C.level_sn[g0]]);
+      int mk = 0, mr = 0;
+      while (g1 < e && r[C.level_sn[g1]] <= lim && g1 - g0 < 32768) {
+        mk = std::max(mk, k[C.level_sn[g1]]);
+        mr = std::max(mr, r[C.level_sn[g1]]);
+        ++g1;
+      }
+      D->groups[l].push_back({g0, g1 - g0, mk, mr});
+      g0 = g1;
+    }
+  }
+  SPB_CUDA(D->sn_k.upload(k, st));
+  SPB_CUDA(D->sn_r.upload(r, st));
+  SPB_CUDA(D->col0.upload(col0, st));
+  SPB_CUDA(D->struct_idx.upload(C.struct_idx, st));
+  SPB_CUDA(D->struct_ptr.upload(C.struct_ptr, st));
+  SPB_CUDA(D->rel_idx.upload(C.rel_idx, st));
+  SPB_CUDA(D->rel_ptr.upload(C.rel_ptr, st));
+  SPB_CUDA(D->parent.upload(C.sn_parent, st));
+  SPB_CUDA(D->child_ptr.upload(C.child_ptr, st));
+  SPB_CUDA(D->child_idx.upload(C.child_idx, st));
+  SPB_CUDA(D->level_sn.upload(C.level_sn, st));
+  SPB_CUDA(D->rank_children.upload(C.rank_children, st));
+  SPB_CUDA(D->perm.upload(C.perm, st));
+  SPB_CUDA(D->L_off.upload(C.L_off, st));
+  SPB_CUDA(D->U_off.upload(C.U_off, st));
+  SPB_CUDA(D->W_off.upload(C.W_off, st));
+  SPB_CUDA(D->dinv_off.upload(C.dinv_off, st));
+  SPB_CUDA(D->a_src.upload(C.a_src, st));
+  SPB_CUDA(D->a_dst.upload(C.a_dst, st));
+  SPB_CUDA(D->Lbuf.alloc((size_t)C.L_off[ns]));
+  SPB_CUDA(D->Ubuf.alloc((size_t)std::max<int64_t>(1, C.U_off[ns])));
+  SPB_CUDA(D->Wbuf.alloc((size_t)C.W_off[ns]));
+  SPB_CUDA(D->Dinv.alloc((size_t)C.dinv_off[ns]));
+  SPB_CUDA(D->ywork.alloc((size_t)h->n));
+  SPB_CUDA(D->fail.alloc(1));
+  SPB_CUDA(cudaMallocHost((void**)&D->h_fail, sizeof(int)));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  // the big host maps are on the device now
+  std::vector<int64_t>().swap(C.a_src);
+  std::vector<int64_t>().swap(C.a_dst);
+  return D;
+}
+
+spb_status chol_factorize(spb_context* h) {
+  if (h->n == 0) return SPB_OK;
+  CholDevice* D = ensure_symbolic(h);
+  CholSymbolic& C = D->sym;
+  cudaStream_t st = h->stream;
+  const int ns = C.nsuper;
+  if ((size_t)(C.max_r + 32) * sizeof(double) > 200 * 1024) throw ArgFail{"front too large for the triangular-solve kernels"};
+  stage_begin(h, ST_FACTOR);
+  int nl = 0;
+  SPB_CUDA(cudaMemsetAsync(D->Lbuf.p, 0, (size_t)C.L_off[ns] * sizeof(double), st));
+  if (C.U_off[ns] > 0) SPB_CUDA(cudaMemsetAsync(D->Ubuf.p, 0, (size_t)C.U_off[ns] * sizeof(double), st));
+  SPB_CUDA(cudaMemsetAsync(D->fail.p, 0, sizeof(int), st));
+  {
+    const int64_t cnt = (int64_t)D->a_src.n;
+    chol_scatter_a_kernel<<<h->num_sms * 8, 256, 0, st>>>(h->d_hval.p, D->a_src.p, D->a_dst.p, cnt, D->Lbuf.p);
+    ++nl;
+  }
+  for (int l = 0; l < C.nlevels; ++l) {
+    // extend-add, one launch per child rank
+    for (int rk = C.level_rank_ptr[l]; rk < C.level_rank_ptr[(size_t)l + 1]; ++rk) {
+      const int b = C.rank_ptr[rk], cnt = C.rank_ptr[(size_t)rk + 1] - b;
+      for (int off = 0; off < cnt; off += 32768) {
+        const int c = std::min(32768, cnt - off);
+        chol_extend_add_kernel<<<dim3(64, c), 256, 0, st>>>(D->rank_children.p + b + off, D->parent.p, D->sn_k.p, D->sn_r.p, D->L_off.p,
+                                                            D->U_off.p, D->rel_ptr.p, D->rel_idx.p, D->Lbuf.p, D->Ubuf.p);
+        ++nl;
+      }
+    }
+    for (const CholDevice::Group& G : D->groups[l]) {
+      const int* list = D->level_sn.p + G.begin;
+      for (int kb = 0; kb < G.max_k; kb += 32) {
+        chol_potrf32_kernel<<<G.count, 1024, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p,
+                                                      D->fail.p);
+        ++nl;
+        const int rows = G.max_r - kb - 1;
+        if (rows > 0) {
+          chol_trsm_kernel<<<dim3((rows + 127) / 128, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->Lbuf.p);
+          ++nl;
+        }
+        if (kb + 32 < G.max_k) {
+          const int nti = (G.max_r - kb - 32 + 63) / 64, ntj = (G.max_k - kb - 32 + 63) / 64;
+          chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
+                                                                  D->Lbuf.p, D->Ubuf.p);
+          ++nl;
+        }
+      }
+      const int umax = G.max_r;  // upper bound on u inside the group
+      const int nt = (umax + 63) / 64;
+      chol_syrk_kernel<<<dim3(nt, nt, G.count), 128, 0, st>>>(list, 1, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
+                                                             D->Ubuf.p);
+      ++nl;
+    }
+  }
+  SPB_CUDA(cudaGetLastError());
+  stage_end(h, ST_FACTOR, nl);
+  SPB_CUDA(cudaMemcpyAsync(D->h_fail, D->fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  D->factored = (*D->h_fail == 0);
+  return D->factored ? SPB_OK : SPB_NOT_SPD;
+}
+
+spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
+  if (h->n == 0) return SPB_OK;
+  CholDevice* D = (CholDevice*)h->chol;
+  if (!D || !D->factored) throw StateFail{"Cholesky solve without a successful factorisation"};
+  CholSymbolic& C = D->sym;
+  cudaStream_t st = h->stream;
+  const int n = h->n;
+  stage_begin(h, ST_TRISOLVE);
+  int nl = 0;
+  chol_permute_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_b, D->perm.p, D->ywork.p, n, 0);
+  ++nl;
+  const size_t smem = (size_t)(C.max_r + 32) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPB_CUDA(cudaFuncSetAttribute(chol_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SPB_CUDA(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  for (int l = 0; l < C.nlevels; ++l) {
+    for (const CholDevice::Group& G : D->groups[l]) {
+      const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);
+      chol_forward_kernel<<<G.count, 256, sm, st>>>(D->level_sn.p + G.begin, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
+                                                    D->dinv_off.p, D->child_ptr.p, D->child_idx.p, D->rel_ptr.p, D->rel_idx.p, D->Lbuf.p,
+                                                    D->Dinv.p, D->Wbuf.p, D->ywork.p);
+      ++nl;
+    }
+  }
+  for (int l = C.nlevels - 1; l >= 0; --l) {
+    for (const CholDevice::Group& G : D->groups[l]) {
+      const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);
+      chol_backward_kernel<<<G.count, 256, sm, st>>>(D->level_sn.p + G.begin, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->dinv_off.p,
+                                                     D->struct_ptr.p, D->struct_idx.p, D->Lbuf.p, D->Dinv.p, D->ywork.p);
+      ++nl;
+    }
+  }
+  (void)smem;
+  chol_permute_kernel<<<(n + 255) / 256, 256, 0, st>>>(D->ywork.p, D->perm.p, d_x, n, 1);
+  ++nl;
+  SPB_CUDA(cudaGetLastError());
+  stage_end(h, ST_TRISOLVE, nl);
+  return SPB_OK;
+}
+
+void chol_release(spb_context* h) {
+  CholDevice* D = (CholDevice*)h->chol;
+  if (D) {
+    if (D->h_fail) cudaFreeHost(D->h_fail);
+    delete D;
+  }
+  h->chol = nullptr;
+}
+
+// exported for tests / bench: nnz(L), flops, supernodes, levels of the current symbolic phase
+bool chol_info(spb_context* h, int64_t* nnzL, double* flops, int* nsuper, int* nlevels) {
+  CholDevice* D = (CholDevice*)h->chol;
+  if (!D) return false;
+  if (nnzL) *nnzL = D->sym.nnzL;
+  if (flops) *flops = D->sym.flops;
+  if (nsuper) *nsuper = D->sym.nsuper;
+  if (nlevels) *nlevels = D->sym.nlevels;
+  return true;
+}
+
 }  // namespace spb

@@ -56,6 +56,7 @@ using namespace spb;
 template <class F>
 static spb_status guarded(spb_handle h, F&& f) {
   try {
+    cudaGetLastError();  // drop a stale (non-sticky) error left by an unrelated earlier call
     return f();
   } catch (const CudaFail& e) {
     if (h) h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
@@ -145,6 +146,10 @@ const char* spb_last_error(spb_handle h) { return h ? h->err.c_str() : "null han
 
 spb_status spb_set_solver(spb_handle h, int solver, double pcg_rtol, int pcg_maxit) {
   if (!h || solver < 0 || solver > 2) return SPB_ERR_ARG;
+  if (solver == SPB_SOLVER_PCG_IC0) {  // fail loudly rather than silently running Jacobi
+    h->err = "SPB_SOLVER_PCG_IC0 is not implemented in this build (use PCG_JACOBI or CHOLESKY)";
+    return SPB_ERR_ARG;
+  }
   h->solver = solver;
   if (pcg_rtol > 0) h->pcg_rtol = pcg_rtol;
   if (pcg_maxit > 0) h->pcg_maxit = pcg_maxit;
@@ -389,6 +394,15 @@ spb_status spb_spmv(spb_handle h, const double* x, double* y, int mem) {
     SPB_CUDA(cudaStreamSynchronize(h->stream));
     return SPB_OK;
   });
+}
+
+spb_status spb_factor_info(spb_handle h, int64_t* nnzL, double* flops, int32_t* nsuper, int32_t* nlevels) {
+  if (!h) return SPB_ERR_ARG;
+  int a = 0, b = 0;
+  if (!chol_info(h, nnzL, flops, &a, &b)) return SPB_ERR_STATE;
+  if (nsuper) *nsuper = a;
+  if (nlevels) *nlevels = b;
+  return SPB_OK;
 }
 
 int64_t spb_launch_count(spb_handle h) { return h ? h->launches : 0; }

@@ -115,6 +115,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
   memset(R, 0, sizeof(*R));
   if (trace_len) *trace_len = 0;
   try {
+    cudaGetLastError();
     SPB_CUDA(cudaSetDevice(h->device));
     auto t_start = std::chrono::steady_clock::now();
     const int n = T->xSize, m = T->ESize;

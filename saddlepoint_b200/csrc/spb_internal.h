@@ -228,4 +228,5 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
 spb_status chol_factorize(spb_context* h);
 spb_status chol_solve(spb_context* h, const double* d_b, double* d_x);
 void chol_release(spb_context* h);
+bool chol_info(spb_context* h, int64_t* nnzL, double* flops, int* nsuper, int* nlevels);
 }  // namespace spb

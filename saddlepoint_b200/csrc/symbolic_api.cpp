@@ -3,7 +3,7 @@
 #include <algorithm>
 #include <cstring>
 
-#include "spb_internal.h"
+#include "chol_internal.h"
 
 using namespace spb;
 
@@ -18,6 +18,48 @@ spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, c
     *nnz = H.nnz();
     if (h_colptr) memcpy(h_colptr, H.colptr.data(), sizeof(int32_t) * ((size_t)n + 1));
     if (h_rowidx) memcpy(h_rowidx, H.rowidx.data(), sizeof(int32_t) * (size_t)H.nnz());
+    return SPB_OK;
+  } catch (const ArgFail&) {
+    return SPB_ERR_ARG;
+  }
+}
+
+// Cholesky symbolic phase on the host: stats[0..7] = nsuper, nlevels, nnz(L), max pivot block,
+// max front, flops (rounded), sum of update-matrix entries, structural violations (must be 0).
+// perm (optional, n ints) receives the fill-reducing order.
+spb_status spb_symbolic_chol_stats(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats, int32_t* perm) {
+  if (!colptr || !stats || m < 0 || n < 0) return SPB_ERR_ARG;
+  try {
+    HPattern H;
+    build_h_pattern(m, n, colptr, rowidx, H);
+    SellLayout S;
+    build_sell(H, S);
+    CholSymbolic C;
+    chol_symbolic(H, S, C);
+    int64_t bad = 0;
+    std::vector<char> seen(n, 0);
+    for (int v : C.perm) {
+      if (v < 0 || v >= n || seen[v]) ++bad; else seen[v] = 1;
+    }
+    for (int s = 0; s < C.nsuper; ++s) {
+      int p = C.sn_parent[s];
+      if (p >= 0 && (p <= s || C.sn_level[p] <= C.sn_level[s])) ++bad;
+      int prev = C.sn_col0[s + 1] - 1;
+      for (int64_t t = C.struct_ptr[s]; t < C.struct_ptr[(size_t)s + 1]; ++t) {
+        if (C.struct_idx[(size_t)t] <= prev) ++bad;
+        prev = C.struct_idx[(size_t)t];
+      }
+    }
+    if ((int64_t)C.a_src.size() != (H.nnz() + n) / 2) ++bad;
+    stats[0] = C.nsuper;
+    stats[1] = C.nlevels;
+    stats[2] = C.nnzL;
+    stats[3] = C.max_k;
+    stats[4] = C.max_r;
+    stats[5] = (int64_t)C.flops;
+    stats[6] = C.U_off[C.nsuper];
+    stats[7] = bad;
+    if (perm) memcpy(perm, C.perm.data(), sizeof(int32_t) * (size_t)n);
     return SPB_OK;
   } catch (const ArgFail&) {
     return SPB_ERR_ARG;

@@ -159,6 +159,11 @@ class Handle:
         st = self._check(self.L.spb_solve(self.h, pr, po, nrhs, mo, C.byref(it)), allow=(SPB_NOT_SPD, SPB_NOT_CONVERGED))
         return out, it.value, st
 
+    def factor_info(self):
+        nnzL, flops, ns, nl = C.c_int64(0), C.c_double(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.L.spb_factor_info(self.h, C.byref(nnzL), C.byref(flops), C.byref(ns), C.byref(nl)))
+        return {"nnzL": nnzL.value, "flops": flops.value, "nsuper": ns.value, "nlevels": nl.value}
+
     def squared_norm(self, v):
         p, m, k = _ptr(v)
         out = C.c_double(0)

@@ -3,10 +3,12 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def random_jacobian(rng, m, n, nnz_per_row, explicit_zero_frac=0.0, empty_cols=(), empty_rows=()):
-    """Random sparse m x n CSC pattern+values with optional explicit zeros / empty rows / columns."""
+def random_jacobian(rng, m, n, nnz_per_row, explicit_zero_frac=0.0, empty_cols=(), empty_rows=(), cover_cols=False):
+    """Random sparse m x n CSC pattern+values with optional explicit zeros / empty rows / columns.
+    cover_cols: give every allowed column at least one entry (so J^T J + D is positive definite)."""
     rows, cols = [], []
     allowed = np.setdiff1d(np.arange(n), np.asarray(empty_cols, int))
+    seen = np.zeros(n, bool)
     for r in range(m):
         if r in empty_rows:
             continue
@@ -14,6 +16,14 @@ def random_jacobian(rng, m, n, nnz_per_row, explicit_zero_frac=0.0, empty_cols=(
         c = rng.choice(allowed, size=k, replace=False)
         rows += [r] * k
         cols += list(c)
+        seen[c] = True
+    if cover_cols:
+        for c in allowed[~seen[allowed]]:
+            r = int(rng.integers(0, m))
+            while r in empty_rows:
+                r = int(rng.integers(0, m))
+            rows.append(r)
+            cols.append(int(c))
     rows = np.array(rows, np.int32)
     cols = np.array(cols, np.int32)
     vals = rng.standard_normal(len(rows))

@@ -1,0 +1,72 @@
+// B200SolverWrapper.hpp -- the GPU LinearSolver concept class.
+//
+// Drop-in for SaddlePoint::EigenSolverWrapper<Eigen::SimplicialLLT<...>>
+// (reference include/SaddlePoint/EigenSolverWrapper.h:23-79): same member functions, same
+// bool results (factorize() == false  <=>  the matrix is not positive definite).
+//   analyze(JPattern)    EigenSolverWrapper.h:30   (takes J's pattern; also analyze_pattern)
+//   factorize(A)         EigenSolverWrapper.h:54   (explicit symmetric matrix, both triangles)
+//   solve(rhs, x)        EigenSolverWrapper.h:72   (vector) / :62 (columns of a matrix)
+// A caller that keeps the reference's own LMSolver.h can plug this class in unchanged: the
+// product dampJ^T*dampJ it passes to factorize() is uploaded and factorised on the GPU.
+// SaddlePoint::LMSolver in this directory goes further and never forms that product on the
+// host (fused GPU assembly), using handle() directly.
+#ifndef SADDLEPOINT_B200_SOLVER_WRAPPER_HPP
+#define SADDLEPOINT_B200_SOLVER_WRAPPER_HPP
+#include <stdexcept>
+#include <string>
+
+#include "../saddlepoint_b200.h"
+
+namespace SaddlePoint {
+
+class B200SolverWrapper {
+ public:
+  explicit B200SolverWrapper(int solver = SPB_SOLVER_CHOLESKY, int device = 0, double pcg_rtol = 1e-13, int pcg_maxit = 10000) {
+    if (spb_create(device, nullptr, &h_) != SPB_OK)
+      throw std::runtime_error("saddlepoint_b200: no CUDA device (there is no CPU fallback)");
+    spb_set_solver(h_, solver, pcg_rtol, pcg_maxit);
+  }
+  ~B200SolverWrapper() { spb_destroy(h_); }
+  B200SolverWrapper(const B200SolverWrapper&) = delete;
+  B200SolverWrapper& operator=(const B200SolverWrapper&) = delete;
+
+  spb_handle handle() const { return h_; }
+  int last_iterations() const { return last_iters_; }
+
+  template <class SparsePattern>
+  bool analyze(const SparsePattern& JPattern) {
+    return spb_analyze(h_, (int32_t)JPattern.rows(), (int32_t)JPattern.cols(), JPattern.outerIndexPtr(), JPattern.innerIndexPtr()) == SPB_OK;
+  }
+  template <class SparsePattern>
+  bool analyze_pattern(const SparsePattern& JPattern) {
+    return analyze(JPattern);
+  }
+
+  template <class SparseMat>
+  bool factorize(const SparseMat& A) {
+    spb_status s = spb_set_matrix(h_, (int32_t)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), SPB_HOST);
+    if (s != SPB_OK) return false;
+    return spb_factorize(h_) == SPB_OK;
+  }
+
+  template <class Vec>
+  bool solve(const Vec& rhs, Vec& x) {
+    x.resize(rhs.size());
+    spb_status s = spb_solve(h_, rhs.data(), x.data(), 1, SPB_HOST, &last_iters_);
+    (void)s;
+    return true;  // the reference's solve always returns true (EigenSolverWrapper.h:69,77)
+  }
+  // matrix right-hand side: nrhs columns, column-major, like the MatrixXd overload
+  bool solve_columns(const double* rhs, int nrhs, double* x) {
+    spb_solve(h_, rhs, x, nrhs, SPB_HOST, &last_iters_);
+    return true;
+  }
+  std::string last_error() const { return spb_last_error(h_); }
+
+ private:
+  spb_handle h_ = nullptr;
+  int last_iters_ = 0;
+};
+
+}  // namespace SaddlePoint
+#endif

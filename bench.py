@@ -183,13 +183,17 @@ def run_ours(args):
         return ms
 
     # ---- device-resident run (value) -------------------------------------------------------
-    lm.solve(False, dedupe_evaluations=True, fixed_iterations=W, x_out=x_dev)  # warm-up (+ one-time analysis)
+    def run_steps(k):
+        lm.DT.currLambda = 0.01  # every solve starts at the reference's lambda0 (the solve writes the final lambda back)
+        return lm.solve(False, dedupe_evaluations=True, fixed_iterations=k, x_out=x_dev)
+
+    run_steps(W)  # warm-up (+ one-time analysis)
     analyze_s = lm.seconds_analyze
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = h.launch_count()
-    ms = timed(lambda: lm.solve(False, dedupe_evaluations=True, fixed_iterations=K, x_out=x_dev))
+    ms = timed(lambda: run_steps(K))
     launches = h.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     lin_iters = int(lm.linear_iterations)
@@ -197,7 +201,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: same K steps, every launch bracketed by CUDA events
     h.stage_reset(True)
-    lm.solve(False, dedupe_evaluations=True, fixed_iterations=K, x_out=x_dev)
+    run_steps(K)
     stages = h.stage_ms()
     h.stage_reset(False)
     nnzH = h.h_nnz()

@@ -127,6 +127,11 @@ typedef struct {
   uint64_t pattern_version; /* 0: unknown (the library fingerprints the arrays on every solve);
                                nonzero: caller's promise that the pattern is unchanged while this
                                value and the colptr pointer are unchanged                         */
+  int32_t row_begin, row_end; /* multi-GPU, one big problem: row_end>row_begin means this rank owns
+                                 residual rows [row_begin,row_end) of the GLOBAL Jacobian described by
+                                 ESize/colptr/rowidx; objective_jacobian then fills only the owned slice
+                                 of EVec and the owned entries of Jvals (global CSC order restricted to
+                                 the owned rows).  0,0: the whole problem (single GPU).            */
   int mem;
   void* user;
   void (*initial_solution)(void* user, double* x0_host);
@@ -175,6 +180,27 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
 spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out);
 spb_status spb_problem_traits(spb_problem_t p, spb_traits* out);
 spb_status spb_problem_destroy(spb_problem_t p);
+
+/* ---- multi-GPU: one large problem, residual rows partitioned across ranks (config C5) ------ */
+/* One process per GPU.  The reference is single-process; this is where the path shards
+ * naturally: J^T J = sum_g J_g^T J_g, J^T f = sum_g J_g^T f_g.  spb_comm_unique_id is called on
+ * one rank and the 128 bytes are distributed by the caller (e.g. torch.distributed broadcast). */
+spb_status spb_comm_unique_id(void* id128);
+spb_status spb_comm_init(spb_handle h, const void* id128, int rank, int nranks);
+spb_status spb_comm_destroy(spb_handle h);
+/* Same GLOBAL Jacobian pattern on every rank; this rank owns residual rows [row_begin,row_end).
+ * Afterwards spb_assemble takes the owned values only (global CSC order restricted to the owned
+ * rows; see spb_local_pattern) and the owned slice of EVec; the partial H / rhs / d of all ranks
+ * are combined with one grouped ncclAllReduce, and spb_solve (PCG) runs the distributed
+ * conjugate gradient (NCCL allreduce of the dot products, allgather of the search direction). */
+spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx,
+                                   int32_t row_begin, int32_t row_end);
+spb_status spb_local_nnz(spb_handle h, int64_t* nnz);
+spb_status spb_local_pattern(spb_handle h, int32_t* colptr, int32_t* rowidx); /* rows renumbered from 0 */
+int64_t spb_collective_count(spb_handle h);
+/* LF benchmark traits restricted to residual rows [row_begin,row_end) (global pattern, local values) */
+spb_status spb_problem_lf_rows(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t row_begin, int32_t row_end,
+                               spb_problem_t* out);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

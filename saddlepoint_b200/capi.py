@@ -22,7 +22,7 @@ POST_CB = C.CFUNCTYPE(C.c_int, vp, vp)
 
 
 class Traits(C.Structure):
-    _fields_ = [("xSize", C.c_int32), ("ESize", C.c_int32), ("colptr", vp), ("rowidx", vp), ("pattern_version", C.c_uint64), ("mem", C.c_int),
+    _fields_ = [("xSize", C.c_int32), ("ESize", C.c_int32), ("colptr", vp), ("rowidx", vp), ("pattern_version", C.c_uint64), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("mem", C.c_int),
                 ("user", vp), ("initial_solution", INIT_CB), ("objective_jacobian", OBJJAC_CB),
                 ("pre_iteration", PRE_CB), ("post_iteration", POST_CB)]
 
@@ -71,6 +71,14 @@ SYMBOLS = [
     ("spb_problem_rosenbrock", C.c_int, [vp, C.c_int32, vp, C.POINTER(vp)]),
     ("spb_problem_traits", C.c_int, [vp, C.POINTER(Traits)]),
     ("spb_problem_destroy", C.c_int, [vp]),
+    ("spb_comm_unique_id", C.c_int, [vp]),
+    ("spb_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
+    ("spb_comm_destroy", C.c_int, [vp]),
+    ("spb_analyze_partitioned", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32]),
+    ("spb_local_nnz", C.c_int, [vp, C.POINTER(C.c_int64)]),
+    ("spb_local_pattern", C.c_int, [vp, vp, vp]),
+    ("spb_collective_count", C.c_int64, [vp]),
+    ("spb_problem_lf_rows", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     ("spb_launch_count", C.c_int64, [vp]),
     ("spb_stage_ms", C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     ("spb_stage_reset", C.c_int, [vp, C.c_int]),

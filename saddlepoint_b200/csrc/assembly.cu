@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(
     const RecT* __restrict__ recs, const uint16_t* __restrict__ grp_slot, const int* __restrict__ chunk_slot,
     const int64_t* __restrict__ chunk_rec, const int* __restrict__ chunk_npairs, const int* __restrict__ chunk_col0,
     const int* __restrict__ low_colptr, const int* __restrict__ low_row, const uint16_t* __restrict__ low_rank,
-    const int* __restrict__ Jcolptr, const int* __restrict__ nup1, const int64_t* __restrict__ slice_off,
+    const uint16_t* __restrict__ low_rank_up, const int* __restrict__ Jcolptr, const int64_t* __restrict__ slice_off,
     const double* __restrict__ Jv, double* __restrict__ hval) {
   __shared__ double prod[kPairTile];
   __shared__ int s_pbase[kSlotCap], s_qbase[kSlotCap], s_col[kSlotCap], s_start[kSlotCap + 1];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(
         const int s = s0 + t;
         const int i = low_row[s], j = s_col[t];
         const int64_t plo = slice_off[i >> 5] + (int64_t)low_rank[s] * 32 + (i & 31);
-        const int64_t pup = slice_off[j >> 5] + (int64_t)(nup1[j] + (s - low_colptr[j])) * 32 + (j & 31);
+        const int64_t pup = slice_off[j >> 5] + (int64_t)low_rank_up[s] * 32 + (j & 31);
         hval[plo] = acc;
         hval[pup] = acc;
       }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(
     const int s = s0;
     const int i = low_row[s], j = s_col[0];
     const int64_t plo = slice_off[i >> 5] + (int64_t)low_rank[s] * 32 + (i & 31);
-    const int64_t pup = slice_off[j >> 5] + (int64_t)(nup1[j] + (s - low_colptr[j])) * 32 + (j & 31);
+    const int64_t pup = slice_off[j >> 5] + (int64_t)low_rank_up[s] * 32 + (j & 31);
     hval[plo] = carry;
     hval[pup] = carry;
   }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
     const int* __restrict__ colchunk, const int* __restrict__ Jcolptr, const int* __restrict__ Jrow,
     const double* __restrict__ Jv, const double* __restrict__ f, double lambda, const int* __restrict__ nup1,
     const int64_t* __restrict__ slice_off, double* __restrict__ hval, double* __restrict__ hdiag,
-    double* __restrict__ rhs, double* __restrict__ dvec, unsigned long long* __restrict__ foo_bits) {
+    double* __restrict__ rhs, double* __restrict__ dvec, unsigned long long* __restrict__ foo_bits, int defer_damping) {
   __shared__ double sv[kEntTile + kEntTile / 16 + 1], sf[kEntTile + kEntTile / 16 + 1];
   __shared__ double s_max[8];
   const int c = blockIdx.x, tid = threadIdx.x;
@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
     if (j < j1) {
       const double sd = sqrt(a_d[k]);                    // sqrt(dampVector(i))  (DiagonalDamping.h:40)
       const double dd = __dmul_rn(sd, sd);               // enters H last, through the augmented row
-      const double hjj = started[k] ? __dadd_rn(a_vv[k], dd) : dd;
+      // defer_damping (row-partitioned mode): this rank only has a partial d; the damping term
+      // is added after the partial sums have been combined (apply_damping_kernel)
+      const double hjj = defer_damping ? (started[k] ? a_vv[k] : 0.0) : (started[k] ? __dadd_rn(a_vv[k], dd) : dd);
       const int64_t pd = slice_off[j >> 5] + (int64_t)(nup1[j] - 1) * 32 + (j & 31);
       hval[pd] = hjj;
       hdiag[j] = hjj;
@@ -195,11 +197,43 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
       }
     }
   }
-  if (f) {
+  if (f && !defer_damping) {
     for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
     if ((tid & 31) == 0) s_max[tid >> 5] = mymax;
     __syncthreads();
     if (tid == 0) {
+      double mx = s_max[0];
+      for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
+      atomicMax(foo_bits, (unsigned long long)__double_as_longlong(mx));
+    }
+  }
+}
+
+// row-partitioned mode, after the allreduce: H_jj += fl(sqrt(d_j))^2 (damping last), Jacobi
+// diagonal, ||rhs||_inf
+__global__ void __launch_bounds__(256) apply_damping_kernel(const double* __restrict__ dvec, const double* __restrict__ rhs,
+                                                            const int* __restrict__ nup1, const int64_t* __restrict__ slice_off, int n,
+                                                            double* __restrict__ hval, double* __restrict__ hdiag,
+                                                            unsigned long long* __restrict__ foo_bits) {
+  __shared__ double s_max[8];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  double mymax = 0.0;
+  if (j < n) {
+    const double sd = sqrt(dvec[j]);
+    const int64_t pd = slice_off[j >> 5] + (int64_t)(nup1[j] - 1) * 32 + (j & 31);
+    const double hjj = __dadd_rn(hval[pd], __dmul_rn(sd, sd));
+    hval[pd] = hjj;
+    hdiag[j] = hjj;
+    if (rhs) {
+      const double ag = fabs(rhs[j]);
+      if (ag > mymax) mymax = ag;
+    }
+  }
+  if (rhs) {
+    for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mymax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
       double mx = s_max[0];
       for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
       atomicMax(foo_bits, (unsigned long long)__double_as_longlong(mx));
@@ -249,6 +283,7 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   if (P.rec_bits == 16) SPB_CUDA(h->d_rec16.upload(P.rec16, st)); else SPB_CUDA(h->d_rec32.upload(P.rec32, st));
   SPB_CUDA(h->d_grp_slot.upload(P.grp_slot, st));
   SPB_CUDA(h->d_low_rank.upload(P.low_rank, st));
+  SPB_CUDA(h->d_low_rank_up.upload(P.low_rank_up, st));
   SPB_CUDA(h->d_chunk_slot.upload(P.chunk_slot, st));
   SPB_CUDA(h->d_chunk_npairs.upload(P.chunk_npairs, st));
   SPB_CUDA(h->d_chunk_rec.upload(P.chunk_rec, st));
@@ -279,23 +314,37 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   stage_begin(h, ST_ASSEMBLY);
   int nl = 0;
   if (d_f) SPB_CUDA(cudaMemsetAsync(h->d_foo_bits.p, 0, sizeof(unsigned long long), st));
+  const bool part = h->partitioned;
+  double* hv = part ? h->d_hval_part.p : h->d_hval.p;
   if (h->ncolchunks > 0) {
     assemble_cols_kernel<<<h->ncolchunks, 256, 0, st>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda,
-                                                        h->d_nup1.p, h->d_slice_off.p, h->d_hval.p, h->d_hdiag.p,
-                                                        h->d_rhs.p, h->d_dvec.p, h->d_foo_bits.p);
+                                                        h->d_nup1.p, h->d_slice_off.p, hv, h->d_hdiag.p,
+                                                        part ? h->d_rhs_part.p : h->d_rhs.p, part ? h->d_dvec_part.p : h->d_dvec.p,
+                                                        h->d_foo_bits.p, part ? 1 : 0);
     ++nl;
   }
   if (h->nchunks > 0) {
     if (h->rec_bits == 16)
       assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(
           h->d_rec16.p, h->d_grp_slot.p, h->d_chunk_slot.p, h->d_chunk_rec.p, h->d_chunk_npairs.p, h->d_chunk_col0.p,
-          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_Jcolptr.p, h->d_nup1.p, h->d_slice_off.p, d_Jv,
-          h->d_hval.p);
+          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_low_rank_up.p, h->d_Jcolptr.p, h->d_slice_off.p, d_Jv,
+          hv);
     else
       assemble_pairs_kernel<uint32_t, 15><<<h->nchunks, 256, 0, st>>>(
           h->d_rec32.p, h->d_grp_slot.p, h->d_chunk_slot.p, h->d_chunk_rec.p, h->d_chunk_npairs.p, h->d_chunk_col0.p,
-          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_Jcolptr.p, h->d_nup1.p, h->d_slice_off.p, d_Jv,
-          h->d_hval.p);
+          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_low_rank_up.p, h->d_Jcolptr.p, h->d_slice_off.p, d_Jv,
+          hv);
+    ++nl;
+  }
+  if (part) {
+    // combine the ranks' partial normal equations: one grouped allreduce over NVLink
+    dist_group_begin(h);
+    dist_allreduce_sum(h, h->d_hval_part.p, h->d_hval.p, (size_t)h->S.padded);
+    dist_allreduce_sum(h, h->d_dvec_part.p, h->d_dvec.p, (size_t)h->n);
+    if (d_f) dist_allreduce_sum(h, h->d_rhs_part.p, h->d_rhs.p, (size_t)h->n);
+    dist_group_end(h);
+    apply_damping_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->d_dvec.p, d_f ? h->d_rhs.p : nullptr, h->d_nup1.p, h->d_slice_off.p, h->n,
+                                                             h->d_hval.p, h->d_hdiag.p, h->d_foo_bits.p);
     ++nl;
   }
   SPB_CUDA(cudaGetLastError());

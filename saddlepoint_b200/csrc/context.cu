@@ -61,6 +61,9 @@ static spb_status guarded(spb_handle h, F&& f) {
   } catch (const CudaFail& e) {
     if (h) h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
     return SPB_ERR_CUDA;
+  } catch (const NcclFail& e) {
+    if (h) h->err = std::string("NCCL error ") + std::to_string(e.code) + " at " + e.where;
+    return SPB_ERR_NCCL;
   } catch (const ArgFail& e) {
     if (h) h->err = e.msg;
     return SPB_ERR_ARG;
@@ -130,6 +133,7 @@ spb_status spb_destroy(spb_handle h) {
   cudaStreamSynchronize(h->stream);
   chol_release(h);
   lm_release(h);
+  dist_release(h);
   for (auto& p : h->timing.pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
@@ -175,6 +179,8 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
     h->m = m;
     h->n = n;
     h->nnzJ = colptr[n];
+    h->partitioned = false;
+    h->m_global = m;
     build_h_pattern(m, n, colptr, rowidx, h->H);
     build_sell(h->H, h->S);
     AssemblyPlan P;
@@ -344,7 +350,7 @@ spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int m
         dx = h->d_x.p;
       }
       int it = 0;
-      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx) : pcg_solve(h, db, dx, &it);
+      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx) : (h->nranks > 1 ? pcg_solve_dist(h, db, dx, &it) : pcg_solve(h, db, dx, &it));
       total_iters += it;
       if (s != SPB_OK && worst == SPB_OK) worst = s;
       if (mem == SPB_HOST) {

@@ -1,0 +1,235 @@
+// dist.cu -- multi-GPU plumbing for ONE large problem (config C5): NCCL communicator owned by
+// the handle, row-partitioned symbolic analysis, and the in-stream collectives used by the
+// assembly (sum of partial H / rhs / d) and by the distributed PCG (dot products, search
+// direction).  One process per GPU; NCCL over NVLink 5 / NVSwitch.
+//
+// Why it shards: residual rows are independent, J^T J = sum_g J_g^T J_g and
+// J^T f = sum_g J_g^T f_g, so every rank assembles the partial normal equations of its row
+// block with the unchanged single-GPU kernels and one grouped ncclAllReduce combines them.
+// The reference has no distributed path (single process, single thread).
+//
+// NCCL is bound at run time (dlopen) so that the library loads on machines without it and
+// shares the copy PyTorch has already loaded when used from bench.py.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "spb_internal.h"
+
+namespace spb {
+
+struct Id128 {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char bytes[128];
+};
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDataType_t::ncclDouble
+constexpr int kNcclSum = 0;      // ncclRedOp_t::ncclSum
+
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // reuse the copy already in the process (PyTorch's)
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+  if (!lib) {
+    err = std::string("cannot load libnccl: ") + dlerror();
+    return false;
+  }
+  auto sym = [&](const char* name) { return dlsym(lib, name); };
+  g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+  g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.GroupStart ||
+      !g_nccl.GroupEnd) {
+    err = "libnccl is missing required symbols";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+
+#define SPB_NCCL(expr)                                 \
+  do {                                                 \
+    int _r = (expr);                                   \
+    if (_r != 0) throw NcclFail{_r, #expr};            \
+  } while (0)
+}  // namespace
+
+// ---- in-stream collectives used by assembly.cu / pcg.cu / lm.cu ---------------------------
+void dist_group_begin(spb_context* h) {
+  if (h->nranks > 1) SPB_NCCL(g_nccl.GroupStart());
+}
+void dist_group_end(spb_context* h) {
+  if (h->nranks > 1) SPB_NCCL(g_nccl.GroupEnd());
+}
+void dist_allreduce_sum(spb_context* h, const double* send, double* recv, size_t count) {
+  if (h->nranks <= 1) {
+    if (send != recv) SPB_CUDA(cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
+  SPB_NCCL(g_nccl.AllReduce(send, recv, count, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  h->collectives++;
+}
+void dist_allgather(spb_context* h, const double* send, double* recv, size_t count_per_rank) {
+  if (h->nranks <= 1) {
+    if (send != recv) SPB_CUDA(cudaMemcpyAsync(recv, send, count_per_rank * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
+  SPB_NCCL(g_nccl.AllGather(send, recv, count_per_rank, kNcclFloat64, h->comm, h->stream));
+  h->collectives++;
+}
+
+void dist_release(spb_context* h) {
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->nranks = 1;
+  h->rank = 0;
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+template <class F>
+static spb_status guarded_dist(spb_handle h, F&& f) {
+  try {
+    cudaGetLastError();
+    return f();
+  } catch (const CudaFail& e) {
+    if (h) h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
+    return SPB_ERR_CUDA;
+  } catch (const NcclFail& e) {
+    if (h) h->err = std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e.code) : "?") + " at " + e.where;
+    return SPB_ERR_NCCL;
+  } catch (const ArgFail& e) {
+    if (h) h->err = e.msg;
+    return SPB_ERR_ARG;
+  } catch (const StateFail& e) {
+    if (h) h->err = e.msg;
+    return SPB_ERR_STATE;
+  }
+}
+
+extern "C" {
+
+spb_status spb_comm_unique_id(void* id128) {
+  if (!id128) return SPB_ERR_ARG;
+  std::string err;
+  if (!load_nccl(err)) return SPB_ERR_NCCL;
+  return g_nccl.GetUniqueId(id128) == 0 ? SPB_OK : SPB_ERR_NCCL;
+}
+
+spb_status spb_comm_init(spb_handle h, const void* id128, int rank, int nranks) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SPB_ERR_ARG;
+  return guarded_dist(h, [&]() {
+    std::string err;
+    if (!load_nccl(err)) {
+      h->err = err;
+      return SPB_ERR_NCCL;
+    }
+    SPB_CUDA(cudaSetDevice(h->device));
+    dist_release(h);
+    Id128 id;
+    memcpy(id.bytes, id128, 128);
+    void* comm = nullptr;
+    SPB_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    h->comm = comm;
+    h->rank = rank;
+    h->nranks = nranks;
+    return SPB_OK;
+  });
+}
+
+spb_status spb_comm_destroy(spb_handle h) {
+  if (!h) return SPB_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  dist_release(h);
+  return SPB_OK;
+}
+
+// Same global Jacobian pattern on every rank; this rank owns residual rows [row_begin,row_end).
+spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int32_t row_begin,
+                                   int32_t row_end) {
+  if (!h || !colptr || row_begin < 0 || row_end < row_begin || row_end > m) return SPB_ERR_ARG;
+  return guarded_dist(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+    h->pcg_last_iters = 0;
+    chol_release(h);
+    // H pattern from the GLOBAL Jacobian (identical on every rank, so the partial H arrays align)
+    build_h_pattern(m, n, colptr, rowidx, h->H);
+    build_sell(h->H, h->S);
+    // local pattern: owned rows, renumbered from 0, CSC order preserved
+    std::vector<int>& lp = h->local_colptr;
+    std::vector<int>& li = h->local_rowidx;
+    lp.assign((size_t)n + 1, 0);
+    li.clear();
+    for (int j = 0; j < n; ++j) {
+      for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+        int r = rowidx[q];
+        if (r >= row_begin && r < row_end) li.push_back(r - row_begin);
+      }
+      lp[(size_t)j + 1] = (int)li.size();
+    }
+    const int ml = row_end - row_begin;
+    h->m = ml;
+    h->n = n;
+    h->nnzJ = (int64_t)li.size();
+    h->m_global = m;
+    h->row_begin = row_begin;
+    h->row_end = row_end;
+    AssemblyPlan P;
+    build_assembly_plan(ml, n, lp.data(), li.data(), h->H, P);
+    upload_h_layout(h);
+    upload_analysis(h, lp.data(), li.data(), P);
+    // partial buffers (inactive slots stay zero forever: they are never written)
+    SPB_CUDA(h->d_hval_part.alloc((size_t)h->S.padded));
+    SPB_CUDA(cudaMemsetAsync(h->d_hval_part.p, 0, (size_t)h->S.padded * sizeof(double), h->stream));
+    SPB_CUDA(h->d_rhs_part.alloc(n));
+    SPB_CUDA(h->d_dvec_part.alloc(n));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    h->fingerprint = pattern_fingerprint(m, n, colptr, rowidx) ^ ((uint64_t)row_begin << 32) ^ (uint64_t)row_end;
+    h->h_fingerprint = 0;
+    h->partitioned = true;
+    h->analyzed = true;
+    h->have_h = true;
+    return SPB_OK;
+  });
+}
+
+spb_status spb_local_nnz(spb_handle h, int64_t* nnz) {
+  if (!h || !nnz) return SPB_ERR_ARG;
+  if (!h->analyzed) return SPB_ERR_STATE;
+  *nnz = h->nnzJ;
+  return SPB_OK;
+}
+
+spb_status spb_local_pattern(spb_handle h, int32_t* colptr, int32_t* rowidx) {
+  if (!h) return SPB_ERR_ARG;
+  if (!h->analyzed || !h->partitioned) return SPB_ERR_STATE;
+  if (colptr) memcpy(colptr, h->local_colptr.data(), sizeof(int32_t) * h->local_colptr.size());
+  if (rowidx) memcpy(rowidx, h->local_rowidx.data(), sizeof(int32_t) * h->local_rowidx.size());
+  return SPB_OK;
+}
+
+int64_t spb_collective_count(spb_handle h) { return h ? h->collectives : 0; }
+
+}  // extern "C"

@@ -118,7 +118,10 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
     cudaGetLastError();
     SPB_CUDA(cudaSetDevice(h->device));
     auto t_start = std::chrono::steady_clock::now();
-    const int n = T->xSize, m = T->ESize;
+    // Row-partitioned traits (multi-GPU, one big problem): ESize/colptr/rowidx describe the GLOBAL
+    // Jacobian, this rank evaluates and owns residual rows [row_begin,row_end) only.
+    const bool part = T->row_end > T->row_begin;
+    const int n = T->xSize, m = part ? (T->row_end - T->row_begin) : T->ESize;
     // pattern: analyse once, re-analyse only when the fingerprint changes
     if (!h->lm_ws) h->lm_ws = new LmWorkspace;
     LmWorkspace& W = *(LmWorkspace*)h->lm_ws;
@@ -126,16 +129,18 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       // a caller-provided pattern_version lets repeated solves skip re-hashing the arrays
       int same = 0;
       if (T->pattern_version != 0 && h->analyzed && W.pattern_version == T->pattern_version && W.pattern_ptr == (const void*)T->colptr &&
-          h->m == m && h->n == n) {
+          h->m == m && h->n == n && h->partitioned == part && (!part || (h->row_begin == T->row_begin && h->row_end == T->row_end))) {
         same = 1;
-      } else {
+      } else if (!part) {
         spb_pattern_matches(h, m, n, T->colptr, T->rowidx, &same);
+        if (h->partitioned) same = 0;
       }
       W.pattern_version = T->pattern_version;
       W.pattern_ptr = (const void*)T->colptr;
       if (!same) {
         auto ta = std::chrono::steady_clock::now();
-        spb_status s = spb_analyze(h, m, n, T->colptr, T->rowidx);
+        spb_status s = part ? spb_analyze_partitioned(h, T->ESize, n, T->colptr, T->rowidx, T->row_begin, T->row_end)
+                            : spb_analyze(h, m, n, T->colptr, T->rowidx);
         if (s != SPB_OK) return s;
         R->seconds_analyze = std::chrono::duration<double>(std::chrono::steady_clock::now() - ta).count();
       }
@@ -218,11 +223,11 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
         prevEnergy2 = cachedPrevEnergy;
       } else {
         if (!dedupe) ev.eval(d_prevx.p, d_E.p, nullptr);  // LMSolver.h:154 (same values as already held)
-        dev_squared_norm(h, d_E.p, m, &prevEnergy2);
+        dev_squared_norm_global(h, d_E.p, m, &prevEnergy2);
       }
       dev_add(h, d_prevx.p, d_dir.p, d_trial.p, n);
       ev.eval(d_trial.p, d_Etrial.p, nullptr);  // LMSolver.h:156
-      dev_squared_norm(h, d_Etrial.p, m, &newEnergy2);
+      dev_squared_norm_global(h, d_Etrial.p, m, &newEnergy2);
       energy = newEnergy2;
       const bool accepted = prevEnergy2 > newEnergy2;
       if (trace && ntrace < trace_cap) {
@@ -243,7 +248,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       // LMSolver.h:174-175: re-linearise at x
       if (!dedupe) {
         ev.eval(d_x.p, d_E.p, d_Jv.p);
-        dev_squared_norm(h, d_E.p, m, &energy);
+        dev_squared_norm_global(h, d_E.p, m, &energy);
       } else if (accepted) {
         ev.eval(d_x.p, d_E.p, d_Jv.p);  // same residual as the trial evaluation, plus the new Jacobian
         energy = newEnergy2;
@@ -257,10 +262,10 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
         double pe = prevEnergy2, ne = newEnergy2;
         if (!dedupe) {
           ev.eval(d_prevx.p, d_Etrial.p, nullptr);
-          dev_squared_norm(h, d_Etrial.p, m, &pe);
+          dev_squared_norm_global(h, d_Etrial.p, m, &pe);
           dev_add(h, d_prevx.p, d_dir.p, d_trial.p, n);
           ev.eval(d_trial.p, d_Etrial.p, nullptr);
-          dev_squared_norm(h, d_Etrial.p, m, &ne);
+          dev_squared_norm_global(h, d_Etrial.p, m, &ne);
         }
         if ((pe > ne) && (ne != std::numeric_limits<double>::infinity())) lambda /= 10.0; else lambda *= 10.0;
       }
@@ -292,6 +297,9 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
   } catch (const CudaFail& e) {
     h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
     return SPB_ERR_CUDA;
+  } catch (const NcclFail& e) {
+    h->err = std::string("NCCL error ") + std::to_string(e.code) + " at " + e.where;
+    return SPB_ERR_NCCL;
   } catch (const ArgFail& e) {
     h->err = e.msg;
     return SPB_ERR_ARG;

@@ -564,4 +564,222 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
   return SPB_OK;
 }
 
+// ---- distributed Jacobi-PCG (config C5) ------------------------------------------------------
+// H is replicated (it is the allreduced sum of the ranks' partial normal equations); the rows of
+// the system -- and with them x, r, q and the owned segment of p -- are split in equal
+// slice-aligned segments.  Per iteration: local SpMV on the owned slices, ONE ncclAllReduce of
+// p.q, local updates, ONE ncclAllReduce of (r.z, r.r), local direction update, ncclAllGather of
+// p.  All scalars stay on the device; tiny single-thread kernels turn the reduced sums into
+// alpha / beta / the stop flag, identically on every rank, so all ranks enqueue the same
+// collectives.
+__global__ void __launch_bounds__(256) dist_spmv_kernel(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
+                                                        const int* __restrict__ rowlen, const double* __restrict__ hval, const double* p,
+                                                        double* __restrict__ q, int n, int s_lo, int s_hi, double* __restrict__ partial,
+                                                        PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  const int ns = s_hi - s_lo;
+  const int s_begin = s_lo + (int)(((int64_t)ns * blockIdx.x) / gridDim.x);
+  const int s_end = s_lo + (int)(((int64_t)ns * (blockIdx.x + 1)) / gridDim.x);
+  const double loc = spmv_range<false>(slice_off, col, rowlen, hval, p, q, n, s_begin, s_end);
+  const double b = block_sum_256(loc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = b;
+  if (take_ticket(&sc->ticket_a, gridDim.x) && threadIdx.x < 32) {
+    const double s = ordered_sum(partial, gridDim.x);
+    if (threadIdx.x == 0) sc->red[0] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) dist_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ p, int row_lo, int row_hi,
+                                                        double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  double rz = 0.0, bb = 0.0;
+  for (int i = row_lo + blockIdx.x * 256 + threadIdx.x; i < row_hi; i += gridDim.x * 256) {
+    const double bi = b[i];
+    const double z = bi * dinv[i];
+    x[i] = 0.0;
+    r[i] = bi;
+    p[i] = z;
+    rz = fma(bi, z, rz);
+    bb = fma(bi, bi, bb);
+  }
+  const double s1 = block_sum_256(rz, sm);
+  const double s2 = block_sum_256(bb, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s1;
+    partial[gridDim.x + blockIdx.x] = s2;
+  }
+  if (take_ticket(&sc->ticket_b, gridDim.x) && threadIdx.x < 32) {
+    const double a = ordered_sum(partial, gridDim.x);
+    const double c = ordered_sum(partial + gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) {
+      sc->red[0] = a;
+      sc->red[1] = c;
+      sc->done = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dist_update_kernel(const double* __restrict__ dinv, const double* p, const double* __restrict__ q,
+                                                          double* __restrict__ x, double* __restrict__ r, int row_lo, int row_hi,
+                                                          double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = row_lo + blockIdx.x * 256 + threadIdx.x; i < row_hi; i += gridDim.x * 256) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    const double z = ri * dinv[i];
+    a1 = fma(ri, z, a1);
+    a2 = fma(ri, ri, a2);
+  }
+  const double s1 = block_sum_256(a1, sm);
+  const double s2 = block_sum_256(a2, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s1;
+    partial[gridDim.x + blockIdx.x] = s2;
+  }
+  if (take_ticket(&sc->ticket_b, gridDim.x) && threadIdx.x < 32) {
+    const double a = ordered_sum(partial, gridDim.x);
+    const double c = ordered_sum(partial + gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) {
+      sc->red[0] = a;
+      sc->red[1] = c;
+    }
+  }
+}
+
+__global__ void dist_direction_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* p, int row_lo, int row_hi,
+                                      const PcgScalars* sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  for (int i = row_lo + blockIdx.x * blockDim.x + threadIdx.x; i < row_hi; i += gridDim.x * blockDim.x) p[i] = fma(beta, p[i], r[i] * dinv[i]);
+}
+
+// phase 0: after the init allreduce; 1: after the p.q allreduce; 2: after the (r.z, r.r) allreduce
+__global__ void dist_scalar_kernel(PcgScalars* sc, int phase, double rtol, int maxit) {
+  if (phase == 0) {
+    sc->rz = sc->red[0];
+    sc->bb = sc->red[1];
+    sc->rr = sc->red[1];
+    sc->thresh = rtol * rtol * sc->red[1];
+    sc->iters = 0;
+    sc->maxit = maxit;
+    sc->breakdown = 0;
+    sc->alpha = sc->beta = 0.0;
+    sc->done = (sc->red[1] > sc->thresh && maxit > 0) ? 0 : 1;
+  } else if (sc->done) {
+    return;
+  } else if (phase == 1) {
+    const double pq = sc->red[0];
+    sc->pq = pq;
+    if (!(pq > 0.0)) {
+      sc->breakdown = 1;
+      sc->done = 1;
+      sc->alpha = 0.0;
+    } else {
+      sc->alpha = sc->rz / pq;
+    }
+  } else {
+    sc->beta = sc->red[0] / sc->rz;
+    sc->rz = sc->red[0];
+    sc->rr = sc->red[1];
+    const int it = sc->iters + 1;
+    sc->iters = it;
+    if (!(sc->rr > sc->thresh) || it >= sc->maxit) sc->done = 1;
+  }
+}
+
+spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* iters) {
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  if (iters) *iters = 0;
+  if (n == 0) return SPB_OK;
+  ensure_pcg_buffers(h);
+  const int R = h->nranks;
+  const int nslices = (n + 31) / 32;
+  const int seg_slices = (nslices + R - 1) / R;
+  const int seg_rows = seg_slices * 32;
+  const int s_lo = std::min(nslices, h->rank * seg_slices), s_hi = std::min(nslices, s_lo + seg_slices);
+  const int row_lo = std::min(n, h->rank * seg_rows), row_hi = std::min(n, row_lo + seg_rows);
+  const size_t full = (size_t)seg_rows * R;
+  SPB_CUDA(h->d_r.alloc(n));
+  SPB_CUDA(h->d_q.alloc(n));
+  if (h->d_pfull.n < full) {
+    SPB_CUDA(h->d_pfull.alloc(full));
+    SPB_CUDA(h->d_xfull.alloc(full));
+    SPB_CUDA(cudaMemsetAsync(h->d_pfull.p, 0, full * sizeof(double), st));
+    SPB_CUDA(cudaMemsetAsync(h->d_xfull.p, 0, full * sizeof(double), st));
+  }
+  double* p = h->d_pfull.p;
+  double* x = h->d_xfull.p;
+  PcgScalars* sc = h->d_sc.p;
+  const int rows = row_hi - row_lo;
+  const int gv = std::max(1, std::min((rows + 255) / 256, h->num_sms * 8));
+  const int gs = std::max(1, std::min((s_hi - s_lo + 7) / 8, h->num_sms * std::max(1, h->occ_spmv ? h->occ_spmv : 6)));
+  stage_begin(h, ST_PCG);
+  int nl = 0;
+  dist_init_kernel<<<gv, 256, 0, st>>>(d_b, h->d_dinv.p, x, h->d_r.p, p, row_lo, row_hi, h->d_partial.p, sc);
+  dist_allreduce_sum(h, sc->red, sc->red, 2);
+  dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 0, h->pcg_rtol, h->pcg_maxit);
+  dist_allgather(h, p + (size_t)h->rank * seg_rows, p, (size_t)seg_rows);
+  nl += 2;
+  int launched = 0;
+  int batch = h->pcg_last_iters > 0 ? std::min(h->pcg_last_iters + 2, h->pcg_maxit) : 16;
+  for (;;) {
+    for (int k = 0; k < batch; ++k) {
+      dist_spmv_kernel<<<gs, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n, s_lo, s_hi,
+                                           h->d_partial.p, sc);
+      dist_allreduce_sum(h, sc->red, sc->red, 1);
+      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);
+      dist_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, x, h->d_r.p, row_lo, row_hi, h->d_partial.p, sc);
+      dist_allreduce_sum(h, sc->red, sc->red, 2);
+      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 2, 0.0, 0);
+      dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, row_lo, row_hi, sc);
+      dist_allgather(h, p + (size_t)h->rank * seg_rows, p, (size_t)seg_rows);
+      nl += 5;
+    }
+    launched += batch;
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    if (h->h_sc->done) break;  // identical on every rank: the scalars come out of the same allreduce
+    batch = 4;
+    if (launched >= h->pcg_maxit + 64) break;
+  }
+  dist_allgather(h, x + (size_t)h->rank * seg_rows, x, (size_t)seg_rows);
+  SPB_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  stage_end(h, ST_PCG, nl);
+  h->pcg_last_iters = h->h_sc->iters;
+  if (iters) *iters = h->h_sc->iters;
+  if (h->h_sc->breakdown) return SPB_NOT_SPD;
+  if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
+  return SPB_OK;
+}
+
+void dev_squared_norm_global(spb_context* h, const double* d_v, int64_t len, double* host_out) {
+  if (h->nranks <= 1) {
+    dev_squared_norm(h, d_v, len, host_out);
+    return;
+  }
+  ensure_pcg_buffers(h);
+  cudaStream_t st = h->stream;
+  double* result = h->d_partial.p + (h->d_partial.n - 1);
+  if (len > 0) {
+    stage_begin(h, ST_REDUCE);
+    reduce_kernel<0><<<vec_grid(h, len), 256, 0, st>>>(d_v, len, h->d_partial.p, result, &h->d_sc.p->ticket_a);
+    SPB_CUDA(cudaGetLastError());
+    stage_end(h, ST_REDUCE, 1);
+  } else {
+    SPB_CUDA(cudaMemsetAsync(result, 0, sizeof(double), st));
+  }
+  dist_allreduce_sum(h, result, result, 1);
+  SPB_CUDA(cudaMemcpyAsync(h->h_scalar, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  *host_out = h->h_scalar[0];
+}
+
 }  // namespace spb

@@ -18,7 +18,8 @@ using namespace spb;
 struct spb_problem {
   spb_context* h = nullptr;
   int kind = 0;  // 0 LF, 1 Rosenbrock
-  int n = 0, m = 0;
+  int n = 0, m = 0;           // m: residual rows evaluated by this object (the owned rows when partitioned)
+  int m_global = 0, row_begin = 0, row_end = 0;
   int64_t nnzJ = 0;
   std::vector<int> colptr, rowidx;  // CSC pattern of J (host)
   std::vector<double> x0;
@@ -94,7 +95,7 @@ void any_x0(void* user, double* x0) {
 
 extern "C" {
 
-spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, spb_problem_t* out) {
+static spb_status build_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t rb, int32_t re, bool part, spb_problem_t* out) {
   if (!h || !out || g < 3 || rows_mult < 1) return SPB_ERR_ARG;
   if ((int64_t)g * g * rows_mult * 8 > 0x7fffffffLL) return SPB_ERR_ARG;
   *out = nullptr;
@@ -103,28 +104,42 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
     SPB_CUDA(cudaSetDevice(h->device));
     P->h = h;
     P->kind = 0;
-    const int n = g * g, m = rows_mult * n;
+    const int n = g * g, mg = rows_mult * n;
+    if (!part) {
+      rb = 0;
+      re = mg;
+    }
+    if (rb < 0 || re > mg || re < rb) {
+      delete P;
+      return SPB_ERR_ARG;
+    }
+    const int ml = re - rb;
     P->n = n;
-    P->m = m;
-    P->nnzJ = (int64_t)m * 8;
+    P->m = ml;
+    P->m_global = mg;
+    P->row_begin = part ? rb : 0;
+    P->row_end = part ? re : 0;
     P->x0.assign(n, 1.0);
-    std::vector<int> rc((size_t)m * 8);
-    std::vector<double> rv((size_t)m * 8);
+    // column indices of every row (the global pattern is needed on every rank); values of owned rows
+    std::vector<int> rc((size_t)mg * 8);
+    std::vector<double> rv((size_t)ml * 8);
     static const int dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
     static const int dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-    for (int r = 0; r < m; ++r) {
+    for (int r = 0; r < mg; ++r) {
       const int c0 = r % n, y0 = c0 / g, x0 = c0 % g;
       const uint64_t h0 = splitmix64_at(seed, (uint64_t)r * 8);
       const int drop = (int)(h0 & 7);
+      const bool own = r >= rb && r < re;
       int* c = &rc[(size_t)r * 8];
-      double* v = &rv[(size_t)r * 8];
+      double vbuf[8];
+      double* v = own ? &rv[(size_t)(r - rb) * 8] : vbuf;
       c[0] = c0;
-      v[0] = 2.0 + unit_pm1(h0);
+      v[0] = own ? 2.0 + unit_pm1(h0) : 0.0;
       int s = 1;
       for (int k = 0; k < 8; ++k) {
         if (k == drop) continue;
         c[s] = ((y0 + dy[k] + g) % g) * g + (x0 + dx[k] + g) % g;
-        v[s] = unit_pm1(splitmix64_at(seed, (uint64_t)r * 8 + s));
+        v[s] = own ? unit_pm1(splitmix64_at(seed, (uint64_t)r * 8 + s)) : 0.0;
         ++s;
       }
       // ascending column inside the row (insertion sort of 8)
@@ -141,28 +156,35 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
         v[b + 1] = vv;
       }
     }
-    // CSC by counting sort over columns (rows visited ascending => sorted columns)
+    // global CSC pattern by counting sort over columns (rows visited ascending => sorted columns);
+    // owned values in the same order restricted to the owned rows
     P->colptr.assign((size_t)n + 1, 0);
     for (size_t e = 0; e < rc.size(); ++e) P->colptr[(size_t)rc[e] + 1]++;
     for (int j = 0; j < n; ++j) P->colptr[(size_t)j + 1] += P->colptr[j];
     P->rowidx.resize(rc.size());
-    std::vector<double> cv(rc.size());
     {
       std::vector<int> cur(P->colptr.begin(), P->colptr.end() - 1);
-      for (int r = 0; r < m; ++r)
-        for (int k = 0; k < 8; ++k) {
-          int d = cur[rc[(size_t)r * 8 + k]]++;
-          P->rowidx[d] = r;
-          cv[d] = rv[(size_t)r * 8 + k];
-        }
+      for (int r = 0; r < mg; ++r)
+        for (int k = 0; k < 8; ++k) P->rowidx[cur[rc[(size_t)r * 8 + k]]++] = r;
     }
-    // ELL (k-major) copies for the residual kernel
-    std::vector<int> ec((size_t)m * 8);
-    std::vector<double> evv((size_t)m * 8);
-    for (int r = 0; r < m; ++r)
+    std::vector<int> lptr((size_t)n + 1, 0);
+    for (int r = rb; r < re; ++r)
+      for (int k = 0; k < 8; ++k) lptr[(size_t)rc[(size_t)r * 8 + k] + 1]++;
+    for (int j = 0; j < n; ++j) lptr[(size_t)j + 1] += lptr[j];
+    std::vector<double> cv((size_t)ml * 8);
+    {
+      std::vector<int> cur(lptr.begin(), lptr.end() - 1);
+      for (int r = rb; r < re; ++r)
+        for (int k = 0; k < 8; ++k) cv[cur[rc[(size_t)r * 8 + k]]++] = rv[(size_t)(r - rb) * 8 + k];
+    }
+    P->nnzJ = (int64_t)ml * 8;
+    // ELL (k-major) copies of the owned rows for the residual kernel
+    std::vector<int> ec((size_t)ml * 8);
+    std::vector<double> evv((size_t)ml * 8);
+    for (int r = 0; r < ml; ++r)
       for (int k = 0; k < 8; ++k) {
-        ec[(size_t)k * m + r] = rc[(size_t)r * 8 + k];
-        evv[(size_t)k * m + r] = rv[(size_t)r * 8 + k];
+        ec[(size_t)k * ml + r] = rc[(size_t)(r + rb) * 8 + k];
+        evv[(size_t)k * ml + r] = rv[(size_t)r * 8 + k];
       }
     SPB_CUDA(P->d_ell_col.upload(ec, h->stream));
     SPB_CUDA(P->d_ell_val.upload(evv, h->stream));
@@ -175,6 +197,15 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
   }
   *out = P;
   return SPB_OK;
+}
+
+spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, spb_problem_t* out) {
+  return build_lf(h, g, rows_mult, seed, 0, 0, false, out);
+}
+
+spb_status spb_problem_lf_rows(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t row_begin, int32_t row_end,
+                               spb_problem_t* out) {
+  return build_lf(h, g, rows_mult, seed, row_begin, row_end, true, out);
 }
 
 spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out) {
@@ -207,7 +238,9 @@ spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x
 spb_status spb_problem_traits(spb_problem_t P, spb_traits* T) {
   if (!P || !T) return SPB_ERR_ARG;
   T->xSize = P->n;
-  T->ESize = P->m;
+  T->ESize = P->row_end > P->row_begin ? P->m_global : P->m;
+  T->row_begin = P->row_begin;
+  T->row_end = P->row_end;
   T->colptr = P->colptr.data();
   T->rowidx = P->rowidx.data();
   T->pattern_version = (uint64_t)(uintptr_t)P | 1u;  // pattern is immutable for the problem's lifetime

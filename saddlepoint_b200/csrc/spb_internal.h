@@ -53,6 +53,10 @@ struct CudaFail {
 struct ArgFail {
   std::string msg;
 };
+struct NcclFail {
+  int code;
+  const char* where;
+};
 struct StateFail {
   std::string msg;
 };
@@ -96,6 +100,7 @@ struct AssemblyPlan {
   std::vector<int> low_colptr;      // n+1
   std::vector<int> low_row;         // row index i of the slot
   std::vector<uint16_t> low_rank;   // rank of column j inside row i of H (position of H(i,j) in row i)
+  std::vector<uint16_t> low_rank_up;  // rank of row i inside row j of H (position of the mirror H(j,i))
   int64_t npairs = 0;
   int nslots = 0;
   // column kernel chunks: chunk c covers columns [colchunk[c], colchunk[c+1])
@@ -127,6 +132,7 @@ struct PcgScalars {
   int iters, done, maxit, breakdown;
   unsigned int ticket_a, ticket_b;
   int pad0, pad1;
+  double red[4];  // local partial sums handed to ncclAllReduce by the distributed PCG
 };
 
 struct Timing {
@@ -173,7 +179,7 @@ struct spb_context {
   spb::DevBuf<int> d_Jcolptr, d_Jrow;
   spb::DevBuf<uint16_t> d_rec16;
   spb::DevBuf<uint32_t> d_rec32;
-  spb::DevBuf<uint16_t> d_grp_slot, d_low_rank;
+  spb::DevBuf<uint16_t> d_grp_slot, d_low_rank, d_low_rank_up;
   spb::DevBuf<int> d_chunk_slot, d_chunk_npairs, d_chunk_col0, d_low_colptr, d_low_row, d_colchunk, d_nup1;
   spb::DevBuf<int64_t> d_chunk_rec;
   // device: H in SpMV layout
@@ -188,6 +194,15 @@ struct spb_context {
   spb::DevBuf<unsigned long long> d_foo_bits;
   spb::PcgScalars* h_sc = nullptr;      // pinned
   double* h_scalar = nullptr;           // pinned scratch (8 doubles)
+
+  // multi-GPU (dist.cu): NCCL communicator, row partition of the residuals
+  void* comm = nullptr;        // ncclComm_t
+  int rank = 0, nranks = 1;
+  bool partitioned = false;    // spb_analyze_partitioned: this rank owns residual rows [row_begin,row_end)
+  int m_global = 0, row_begin = 0, row_end = 0;
+  std::vector<int> local_colptr, local_rowidx;
+  spb::DevBuf<double> d_hval_part, d_rhs_part, d_dvec_part, d_pfull, d_xfull;
+  int64_t collectives = 0;
 
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
@@ -223,6 +238,17 @@ void lm_release(spb_context* h);
 // pcg.cu
 void dev_spmv(spb_context* h, const double* d_x, double* d_y);
 spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters);
+
+// dist.cu: in-stream collectives (no-ops / local copies when nranks == 1)
+void dist_group_begin(spb_context* h);
+void dist_group_end(spb_context* h);
+void dist_allreduce_sum(spb_context* h, const double* send, double* recv, size_t count);
+void dist_allgather(spb_context* h, const double* send, double* recv, size_t count_per_rank);
+void dist_release(spb_context* h);
+// pcg.cu: distributed Jacobi-PCG over a row partition of H (replicated H, partitioned vectors)
+spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* iters);
+// sum of squares of a vector whose entries are split across ranks (allreduce of the local sums)
+void dev_squared_norm_global(spb_context* h, const double* d_v, int64_t len, double* host_out);
 
 // cholesky.cu
 spb_status chol_factorize(spb_context* h);

@@ -200,6 +200,34 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
     for (int s = s0; s < s1; ++s) where[P.low_row[s]] = -1;
   }
   P.npairs = (int64_t)stream.size();
+  // Position of the mirror entry H(j,i) in row j, and compaction to the slots that actually
+  // receive products.  With a full Jacobian every structural slot is active; under row
+  // partitioning (dist.cu) a rank only owns the pairs of its residual rows and the other slots
+  // stay zero in its partial H.
+  {
+    P.low_rank_up.resize(P.nslots);
+    int w = 0;
+    std::vector<int> new_colptr((size_t)n + 1, 0);
+    for (int j = 0; j < n; ++j) {
+      for (int s = P.low_colptr[j]; s < P.low_colptr[(size_t)j + 1]; ++s) {
+        if (slot_npairs[s] == 0) continue;
+        int up = H.nup1[j] + (s - P.low_colptr[j]);
+        if (up > 65535) throw ArgFail{"H row longer than 65535 entries is not supported"};
+        P.low_row[w] = P.low_row[s];
+        P.low_rank[w] = P.low_rank[s];
+        P.low_rank_up[w] = (uint16_t)up;
+        slot_npairs[w] = slot_npairs[s];
+        ++w;
+      }
+      new_colptr[(size_t)j + 1] = w;
+    }
+    P.low_colptr.swap(new_colptr);
+    P.nslots = w;
+    P.low_row.resize(w);
+    P.low_rank.resize(w);
+    P.low_rank_up.resize(w);
+    slot_npairs.resize(w);
+  }
   // chunking
   P.chunk_slot.clear();
   P.chunk_rec.clear();

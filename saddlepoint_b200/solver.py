@@ -79,6 +79,40 @@ class Handle:
         self._check(self.L.spb_analyze(self.h, m, n, pc, pr))
         self.m, self.n, self.nnzJ = m, n, int(colptr[-1])
 
+    # ---- multi-GPU (one big problem, rows partitioned across ranks)
+    def comm_init(self, unique_id, rank, nranks):
+        """Attach an NCCL communicator (unique_id: 128 bytes from comm_unique_id() on one rank)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.L.spb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def comm_unique_id():
+        L = capi.load()
+        buf = (C.c_char * 128)()
+        st = L.spb_comm_unique_id(C.cast(buf, C.c_void_p))
+        if st != SPB_OK:
+            raise SpbError(st, "ncclGetUniqueId failed (is libnccl available?)")
+        return bytes(buf)
+
+    def analyze_partitioned(self, m, n, colptr, rowidx, row_begin, row_end):
+        colptr, pc = _i32(colptr)
+        rowidx, pr = _i32(rowidx)
+        self._check(self.L.spb_analyze_partitioned(self.h, m, n, pc, pr, row_begin, row_end))
+        self.m, self.n = row_end - row_begin, n
+        nnz = C.c_int64(0)
+        self._check(self.L.spb_local_nnz(self.h, C.byref(nnz)))
+        self.nnzJ = nnz.value
+
+    def local_pattern(self):
+        colptr = np.empty(self.n + 1, np.int32)
+        rowidx = np.empty(self.nnzJ, np.int32)
+        self._check(self.L.spb_local_pattern(self.h, C.c_void_p(colptr.ctypes.data), C.c_void_p(rowidx.ctypes.data)))
+        return colptr, rowidx
+
+    def collective_count(self):
+        return int(self.L.spb_collective_count(self.h))
+
     def pattern_matches(self, m, n, colptr, rowidx):
         colptr, pc = _i32(colptr)
         rowidx, pr = _i32(rowidx)
@@ -374,6 +408,9 @@ class BuiltinProblem:
         p = C.c_void_p()
         if kind == "lf":
             st = L.spb_problem_lf(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), C.byref(p))
+        elif kind == "lf_rows":  # row-partitioned LF: this rank owns residual rows [row_begin,row_end)
+            st = L.spb_problem_lf_rows(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), kw["row_begin"], kw["row_end"],
+                                       C.byref(p))
         elif kind == "rosenbrock":
             x0 = kw.get("x0")
             if x0 is not None:

@@ -329,8 +329,11 @@ class LMSolver:
             ST = self.ST
             x0 = np.ascontiguousarray(ST.initial_solution(), np.float64)
             n, m = int(ST.xSize), int(ST.ESize)
-            E0, J0 = ST.objective_jacobian(x0.copy(), True)
-            rows, cols, colptr, rowidx, _ = _as_csc(J0)
+            if hasattr(ST, "colptr") and hasattr(ST, "rowidx"):  # traits that publish their fixed CSC pattern
+                colptr, rowidx = ST.colptr, ST.rowidx
+            else:
+                E0, J0 = ST.objective_jacobian(x0.copy(), True)
+                rows, cols, colptr, rowidx, _ = _as_csc(J0)
             colptr, pc = _i32(colptr)
             rowidx, pr = _i32(rowidx)
             nnz = int(colptr[-1])

@@ -1,0 +1,64 @@
+"""GPU tier: config C3 stand-in (seamless-integration Jacobian structure: four stacked blocks with
+weights 1e4 / 1 / 1e4 / 1e-4 and a barrier that yields 0, finite or inf entries) through the host
+traits drop-in path, direct solver, against the oracle driven by the same traits."""
+import numpy as np
+import pytest
+
+from c3_problem import SeamlessLikeTraits
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(orc, st, maxit):
+    return orc.lm_solve("callback", x0=st.initial_solution(), pattern=(st.ESize, st.xSize, st.colptr, st.rowidx),
+                        callback=lambda x, cj: st.objective_jacobian(x, cj), maxIterations=maxit, keep_first=True)
+
+
+def test_c3_structure_assembly_bit_exact(spb, orc):
+    st = SeamlessLikeTraits(7, 6)
+    x0 = st.initial_solution()
+    E, Jv = st.objective_jacobian(x0, True)
+    h = spb.Handle(0)
+    h.analyze(st.ESize, st.xSize, st.colptr, st.rowidx)
+    foo = h.assemble(Jv, E, 0.01)
+    J = orc.from_csc(st.ESize, st.xSize, st.colptr, st.rowidx, Jv)
+    D, d = orc.damp_build(J, 0.01)
+    hp, hi, hx = orc.ata(D).csc()
+    cp, ri = h.h_pattern()
+    assert (cp == hp).all() and (ri == hi).all()
+    assert (h.h_values() == hx).all() and (h.rhs() == orc.jt_vec_neg(J, E)).all()
+    h.close()
+
+
+def test_c3_lm_parity_direct_solver(spb, orc):
+    st_gpu, st_ref = SeamlessLikeTraits(7, 6), SeamlessLikeTraits(7, 6)
+    ls = spb.B200SolverWrapper(solver=spb.SOLVER_CHOLESKY)
+    lm = spb.LMSolver()
+    lm.init(ls, st_gpu, spb.DiagonalDamping(0.01), 30)
+    ret = lm.solve(True)
+    ref = _oracle(orc, st_ref, 30)
+    assert ret == ref.ret and lm.exit_path == ref.exit_path
+    assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
+    assert (lm.trace["accepted"] == ref.trace["accepted"]).all()
+    np.testing.assert_allclose(lm.trace["lambda"], ref.trace["lambda"], rtol=0)
+    assert np.linalg.norm(lm.x - ref.x) <= 1e-9 * np.linalg.norm(ref.x)   # kappa ~ (1e4/1e-4)^2: tolerance scaled accordingly
+    assert abs(lm.energy - ref.energy) <= 1e-9 * max(abs(ref.energy), 1e-16 * ref.trace["prevEnergy2"][0])
+    assert st_gpu.calls == st_ref.calls  # same objective call sequence as the reference loop
+    ls.handle.close()
+
+
+def test_c3_infinite_barrier_follows_reference_nan_semantics(spb, orc):
+    # an infeasible start puts inf into EVec and J (SIInitialSolutionTraits.h:163,227-228): NaN
+    # pivots do not fail the factorisation, the step is NaN, the trial is rejected, lambda grows
+    st_gpu, st_ref = SeamlessLikeTraits(5, 5, flip_face=3), SeamlessLikeTraits(5, 5, flip_face=3)
+    ls = spb.B200SolverWrapper(solver=spb.SOLVER_CHOLESKY)
+    lm = spb.LMSolver()
+    lm.init(ls, st_gpu, spb.DiagonalDamping(0.01), 6)
+    ret = lm.solve(True)
+    ref = _oracle(orc, st_ref, 6)
+    assert ret == ref.ret and lm.exit_path == ref.exit_path == "max_iter"
+    assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
+    assert (lm.trace["accepted"] == 0).all() and (ref.trace["accepted"] == 0).all()
+    np.testing.assert_allclose(lm.trace["lambda"], ref.trace["lambda"], rtol=0)
+    assert np.array_equal(lm.x, st_gpu.initial_solution())
+    ls.handle.close()

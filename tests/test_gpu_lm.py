@@ -98,8 +98,8 @@ def test_host_traits_drop_in_path_and_call_counts(spb, handle, orc):
     assert ret == ref.ret and lm.currIter == ref.currIter and lm.exit_path == ref.exit_path
     np.testing.assert_allclose(lm.x, ref.x, rtol=1e-10, atol=1e-12)
     # reference call sequence: 1 + 5 per completed loop body + 2 in the breaking one
-    # (+1 pattern-discovery call made by the Python binding)
-    assert st.calls == 1 + 1 + 5 * lm.currIter + 2
+    # (the traits publish colptr/rowidx, so the binding makes no pattern-discovery call)
+    assert st.calls == 1 + 5 * lm.currIter + 2
     st2 = PyRosenbrock(4)
     lm.init(ls, st2, spb.DiagonalDamping(0.01), 1000)
     lm.solve(True, dedupe_evaluations=True)

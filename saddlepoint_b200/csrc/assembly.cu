@@ -12,15 +12,19 @@
 // with separate IEEE multiply and add (__dmul_rn/__dadd_rn: no FMA contraction, matching the
 // reference's x86-64 -O3 build), so the results are bit-identical to the CPU path.
 //
-// Two kernels, both "coalesced stage -> sequential segment sum":
-//  * assemble_pairs: one CTA per chunk of strictly-lower H slots.  The chunk's pair records
-//    ([first:1][po][qo], 2 bytes for J columns <=128 entries) are streamed coalesced; each
-//    lane gathers its two J values (read-only path, L1/L2 resident: a slot's partners sit
-//    in one or two 128-byte lines), multiplies, and parks the product in shared memory.
-//    The slot of a record is recovered without per-record indices from a warp ballot of
-//    the `first` flags plus one uint16 per 32 records.  Then one thread per slot adds its
-//    products in order and writes H(i,j) and its mirror H(j,i) straight into the SpMV
-//    storage (sliced ELL), so no second pass over H is needed.
+// Two kernels, both "coalesced stage -> ordered segment sum":
+//  * assemble_pairs: one CTA per chunk of strictly-lower H slots (whole H columns).  The chunk's
+//    stage list -- the J columns its pairs touch: its own columns j and the row-columns i of
+//    its slots -- is copied into shared memory once (one warp per column, coalesced), as are
+//    the chunk's pair records ([first:1][po][qo], 2 bytes for J columns <=128 entries).  One
+//    thread per slot then walks its records in order, multiplies the two staged J values and
+//    adds the products left to right (first product assigned), and writes H(i,j) and its mirror
+//    H(j,i) straight into the SpMV storage (sliced ELL), so no second pass over H is needed.
+//    All loads that do not depend on another load (slot metadata, records, stage entries) are
+//    issued before the first barrier; the only dependent chain is stage entry -> J values.
+//    Chunks whose stage list does not fit in shared memory (very long J columns) gather from
+//    global memory instead; a single slot with more pairs than a tile (dense column pairs) is
+//    walked by one thread from global memory.
 //  * assemble_cols: one CTA per chunk of J columns.  Values, row indices and the gathered
 //    residuals are staged coalesced in (bank-skewed) shared memory, then one thread per
 //    column walks its column in order producing sum v*f, sum (lambda*v)*v and sum v*v, and
@@ -32,97 +36,130 @@
 
 namespace spb {
 
-template <typename RecT, int POBITS>
-__global__ void __launch_bounds__(256) assemble_pairs_kernel(
-    const RecT* __restrict__ recs, const uint16_t* __restrict__ grp_slot, const int* __restrict__ chunk_slot,
-    const int64_t* __restrict__ chunk_rec, const int* __restrict__ chunk_npairs, const int* __restrict__ chunk_col0,
-    const int* __restrict__ low_colptr, const int* __restrict__ low_row, const uint16_t* __restrict__ low_rank,
-    const uint16_t* __restrict__ low_rank_up, const int* __restrict__ Jcolptr, const int64_t* __restrict__ slice_off,
-    const double* __restrict__ Jv, double* __restrict__ hval) {
-  __shared__ double prod[kPairTile];
-  __shared__ int s_pbase[kSlotCap], s_qbase[kSlotCap], s_col[kSlotCap], s_start[kSlotCap + 1];
-  const int c = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int s0 = chunk_slot[c], ns = chunk_slot[c + 1] - s0;
-  const int64_t rec0 = chunk_rec[c];
-  const int np = chunk_npairs[c];
+// ordered sum of one slot's products: first product assigned, the rest added left to right
+template <typename RecT, int POBITS, bool SMEM>
+__device__ __forceinline__ double slot_sum(const RecT* rec, const double* vi, const double* vj, int beg, int end) {
   constexpr uint32_t MASK = (1u << POBITS) - 1u;
+  uint32_t r = (uint32_t)rec[beg];
+  double a = SMEM ? vi[(r >> POBITS) & MASK] : __ldg(vi + ((r >> POBITS) & MASK));
+  double b = SMEM ? vj[r & MASK] : __ldg(vj + (r & MASK));
+  double acc = __dmul_rn(a, b);
+  for (int q = beg + 1; q < end; ++q) {
+    r = (uint32_t)rec[q];
+    a = SMEM ? vi[(r >> POBITS) & MASK] : __ldg(vi + ((r >> POBITS) & MASK));
+    b = SMEM ? vj[r & MASK] : __ldg(vj + (r & MASK));
+    acc = __dadd_rn(acc, __dmul_rn(a, b));
+  }
+  return acc;
+}
 
-  // phase 0: per-slot bases.  The column of a slot is found by bisection over the chunk's
-  // column range (columns without strictly-lower entries make the range loose, not wrong).
-  {
-    const int jlo = chunk_col0[c], jhi = chunk_col0[c + 1];
-    for (int t = tid; t < ns; t += 256) {
-      const int s = s0 + t;
-      int lo = jlo, hi = jhi;  // find j with low_colptr[j] <= s < low_colptr[j+1]
-      while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (low_colptr[mid] <= s) lo = mid; else hi = mid - 1;
-      }
-      s_col[t] = lo;
-      s_qbase[t] = Jcolptr[lo];
-      s_pbase[t] = Jcolptr[low_row[s]];
+template <typename RecT, int POBITS>
+__global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restrict__ recs, const ChunkDesc* __restrict__ chunks,
+                                                             const StageEntry* __restrict__ stage, const SlotMeta* __restrict__ slots,
+                                                             const uint16_t* __restrict__ slot_start, const double* __restrict__ Jv,
+                                                             double* __restrict__ hval) {
+  __shared__ double sval[kStageVals];
+  __shared__ RecT srec[kPairTile];
+  __shared__ int s_src[kStageCols];
+  __shared__ unsigned s_offlen[kStageCols];
+  __shared__ int64_t s_sbase[kStageCols];
+  const int tid = threadIdx.x;
+  const ChunkDesc cd = chunks[blockIdx.x];
+  const int s0 = cd.slot0, ns = cd.nslots, np = cd.npairs, st0 = cd.stage0, nst = cd.nstage;
+  const int64_t rec0 = cd.rec0;
+  const bool staged = cd.staged != 0;
+  const bool small_list = nst <= kStageCols;
+  const bool one_tile = np <= kPairTile;
+  constexpr uint32_t MASK = (1u << POBITS) - 1u;
+  constexpr int SPT = kSlotCap / 256;  // slots per thread
+
+  // Independent loads first: per-slot metadata, the chunk's pair records (coalesced, into shared
+  // memory) and the stage list.  The only dependent chain left is stage entry -> J values.
+  SlotMeta mreg[SPT];
+  int beg[SPT], end[SPT];
+#pragma unroll
+  for (int k = 0; k < SPT; ++k) {
+    const int t = tid + k * 256;
+    beg[k] = end[k] = 0;
+    if (t < ns) {
+      mreg[k] = slots[s0 + t];
+      beg[k] = slot_start[s0 + t];
+      end[k] = t + 1 < ns ? (int)slot_start[s0 + t + 1] : np;
+    }
+  }
+  if (one_tile)
+    for (int t = tid; t < np; t += 256) srec[t] = recs[rec0 + t];
+  if (small_list) {
+    for (int t = tid; t < nst; t += 256) {
+      const StageEntry e = stage[st0 + t];
+      s_src[t] = e.src;
+      s_offlen[t] = ((unsigned)e.off << 16) | e.len;
+      s_sbase[t] = e.slice_base;
     }
   }
   __syncthreads();
-
-  const bool multi = np > kPairTile;  // only possible for a single-slot chunk
-  double carry = 0.0;
-  bool have = false;
-  for (int a = 0; a < np; a += kPairTile) {
-    const int b = min(np, a + kPairTile);
-    const int bround = (b + 31) & ~31;
-    // phase A: products
-    for (int t = a + tid; t < bround; t += 256) {
-      const uint32_t rec = (uint32_t)recs[rec0 + t];  // chunks are padded to 32 records with zeros
-      const uint32_t first = rec >> (2 * POBITS);
-      const unsigned ballot = __ballot_sync(0xffffffffu, first != 0);
-      const int g = (int)((rec0 + (t - lane)) >> 5);
-      const int sl = (int)grp_slot[g] + __popc(ballot & ((2u << lane) - 1u) & ~1u);
-      if (t < b) {
-        const int po = (int)((rec >> POBITS) & MASK), qo = (int)(rec & MASK);
-        const double vp = __ldg(Jv + s_pbase[sl] + po);
-        const double vq = __ldg(Jv + s_qbase[sl] + qo);
-        prod[t - a] = __dmul_rn(vp, vq);
-        if (first) s_start[sl] = t - a;
+  if (staged) {
+    // Copy the listed J columns into shared memory: one warp per column and pass (columns of up
+    // to 32 entries in one go), four columns in flight per thread before the first store.
+    const int sub = tid & 31, cg = tid >> 5;
+    for (int t0 = 0; t0 < nst; t0 += 32) {
+      double v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * 8 + cg;
+        dst[u] = -1;
+        if (t < nst) {
+          const unsigned ol = s_offlen[t];
+          if (sub < (int)(ol & 0xffffu)) {
+            dst[u] = (int)(ol >> 16) + sub;
+            v[u] = Jv[s_src[t] + sub];
+          }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0) sval[dst[u]] = v[u];
     }
-    if (tid == 0) {
-      s_start[ns] = b - a;
-      if (a > 0) s_start[0] = 0;  // continuing slot of a multi-tile chunk
-    }
-    __syncthreads();
-    // phase B: ordered sums
-    if (!multi) {
-      for (int t = tid; t < ns; t += 256) {
-        const int beg = s_start[t], end = s_start[t + 1];
-        double acc = prod[beg];
-        for (int k = beg + 1; k < end; ++k) acc = __dadd_rn(acc, prod[k]);
-        const int s = s0 + t;
-        const int i = low_row[s], j = s_col[t];
-        const int64_t plo = slice_off[i >> 5] + (int64_t)low_rank[s] * 32 + (i & 31);
-        const int64_t pup = slice_off[j >> 5] + (int64_t)low_rank_up[s] * 32 + (j & 31);
-        hval[plo] = acc;
-        hval[pup] = acc;
+    if (cd.staged & 2) {  // columns longer than 32 entries: the rest of each column
+      for (int t = cg; t < nst; t += 8) {
+        const unsigned ol = s_offlen[t];
+        const int off = (int)(ol >> 16), len = (int)(ol & 0xffffu), src = s_src[t];
+        for (int e = 32 + sub; e < len; e += 32) sval[off + e] = Jv[src + e];
       }
-    } else if (tid == 0) {
-      int k = 0;
-      if (!have) {
-        carry = prod[0];
-        have = true;
-        k = 1;
-      }
-      for (; k < b - a; ++k) carry = __dadd_rn(carry, prod[k]);
     }
     __syncthreads();
   }
-  if (multi && tid == 0) {
-    const int s = s0;
-    const int i = low_row[s], j = s_col[0];
-    const int64_t plo = slice_off[i >> 5] + (int64_t)low_rank[s] * 32 + (i & 31);
-    const int64_t pup = slice_off[j >> 5] + (int64_t)low_rank_up[s] * 32 + (j & 31);
-    hval[plo] = carry;
-    hval[pup] = carry;
+
+  // One thread per slot: products added in ascending residual row, first product assigned
+  // (exactly the accumulation order of the reference's sparse product).
+#pragma unroll
+  for (int k = 0; k < SPT; ++k) {
+    const int t = tid + k * 256;
+    if (t < ns) {
+      const SlotMeta mt = mreg[k];
+      int bx, by;
+      int64_t bi, bj;
+      if (small_list) {
+        bx = staged ? (int)(s_offlen[mt.il] >> 16) : s_src[mt.il];
+        by = staged ? (int)(s_offlen[mt.jl] >> 16) : s_src[mt.jl];
+        bi = s_sbase[mt.il];
+        bj = s_sbase[mt.jl];
+      } else {
+        const StageEntry ei = stage[st0 + mt.il], ej = stage[st0 + mt.jl];
+        bx = ei.src;
+        by = ej.src;
+        bi = ei.slice_base;
+        bj = ej.slice_base;
+      }
+      double acc;
+      if (staged && one_tile) acc = slot_sum<RecT, POBITS, true>(srec, sval + bx, sval + by, beg[k], end[k]);
+      else if (one_tile) acc = slot_sum<RecT, POBITS, false>(srec, Jv + bx, Jv + by, beg[k], end[k]);
+      else if (staged) acc = slot_sum<RecT, POBITS, true>(recs + rec0, sval + bx, sval + by, beg[k], end[k]);
+      else acc = slot_sum<RecT, POBITS, false>(recs + rec0, Jv + bx, Jv + by, beg[k], end[k]);
+      hval[bi + (int64_t)mt.rank * 32] = acc;
+      hval[bj + (int64_t)mt.rank_up * 32] = acc;
+    }
   }
 }
 
@@ -281,27 +318,40 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   SPB_CUDA(h->d_Jrow.upload(ri, st));
   h->rec_bits = P.rec_bits;
   if (P.rec_bits == 16) SPB_CUDA(h->d_rec16.upload(P.rec16, st)); else SPB_CUDA(h->d_rec32.upload(P.rec32, st));
-  SPB_CUDA(h->d_grp_slot.upload(P.grp_slot, st));
-  SPB_CUDA(h->d_low_rank.upload(P.low_rank, st));
-  SPB_CUDA(h->d_low_rank_up.upload(P.low_rank_up, st));
-  SPB_CUDA(h->d_chunk_slot.upload(P.chunk_slot, st));
-  SPB_CUDA(h->d_chunk_npairs.upload(P.chunk_npairs, st));
-  SPB_CUDA(h->d_chunk_rec.upload(P.chunk_rec, st));
-  SPB_CUDA(h->d_low_colptr.upload(P.low_colptr, st));
-  SPB_CUDA(h->d_low_row.upload(P.low_row, st));
-  SPB_CUDA(h->d_colchunk.upload(P.colchunk, st));
-  // first column of every chunk (+ sentinel): bisection bounds for the slot->column search
-  h->nchunks = (int)P.chunk_npairs.size();
-  std::vector<int> col0((size_t)h->nchunks + 1, h->n > 0 ? h->n - 1 : 0);
   {
-    int j = 0;
-    for (int c = 0; c < h->nchunks; ++c) {
-      int s = P.chunk_slot[c];
-      while (P.low_colptr[(size_t)j + 1] <= s) ++j;
-      col0[c] = j;
+    // packed device forms: one descriptor per chunk, one entry per staged column, one record per slot
+    const int nch = (int)P.chunk_npairs.size();
+    std::vector<ChunkDesc> cd((size_t)nch);
+    for (int c = 0; c < nch; ++c) {
+      cd[c].slot0 = P.chunk_slot[c];
+      cd[c].nslots = P.chunk_slot[(size_t)c + 1] - P.chunk_slot[c];
+      cd[c].npairs = P.chunk_npairs[c];
+      cd[c].stage0 = P.chunk_stage_ptr[c];
+      cd[c].nstage = P.chunk_stage_ptr[(size_t)c + 1] - P.chunk_stage_ptr[c];
+      cd[c].staged = P.chunk_staged[c];
+      if (cd[c].staged)
+        for (int t = P.chunk_stage_ptr[c]; t < P.chunk_stage_ptr[(size_t)c + 1]; ++t)
+          if (colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]] > 32) cd[c].staged |= 2;
+      cd[c].rec0 = P.chunk_rec[c];
     }
+    std::vector<StageEntry> se(P.stage_cols.size());
+    for (size_t t = 0; t < se.size(); ++t) {
+      const int col = P.stage_cols[t];
+      se[t].src = colptr[col];
+      se[t].off = (uint16_t)std::min(P.stage_off[t], 65535);
+      se[t].len = (uint16_t)std::min(colptr[col + 1] - colptr[col], 65535);
+      se[t].slice_base = h->S.slice_off[col >> 5] + (col & 31);
+    }
+    std::vector<SlotMeta> sm((size_t)P.nslots);
+    for (int s = 0; s < P.nslots; ++s) sm[s] = SlotMeta{P.slot_il[s], P.slot_jl[s], P.low_rank[s], P.low_rank_up[s]};
+    SPB_CUDA(h->d_chunk_desc.upload(cd, st));
+    SPB_CUDA(h->d_stage_ent.upload(se, st));
+    SPB_CUDA(h->d_slot_meta.upload(sm, st));
+    SPB_CUDA(h->d_slot_start.upload(P.slot_start, st));
+    SPB_CUDA(h->d_colchunk.upload(P.colchunk, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
   }
-  SPB_CUDA(h->d_chunk_col0.upload(col0, st));
+  h->nchunks = (int)P.chunk_npairs.size();
   h->ncolchunks = (int)P.colchunk.size() - 1;
   h->nslots = P.nslots;
   h->npairs = P.npairs;
@@ -325,15 +375,11 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   }
   if (h->nchunks > 0) {
     if (h->rec_bits == 16)
-      assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(
-          h->d_rec16.p, h->d_grp_slot.p, h->d_chunk_slot.p, h->d_chunk_rec.p, h->d_chunk_npairs.p, h->d_chunk_col0.p,
-          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_low_rank_up.p, h->d_Jcolptr.p, h->d_slice_off.p, d_Jv,
-          hv);
+      assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
+                                                                     h->d_slot_start.p, d_Jv, hv);
     else
-      assemble_pairs_kernel<uint32_t, 15><<<h->nchunks, 256, 0, st>>>(
-          h->d_rec32.p, h->d_grp_slot.p, h->d_chunk_slot.p, h->d_chunk_rec.p, h->d_chunk_npairs.p, h->d_chunk_col0.p,
-          h->d_low_colptr.p, h->d_low_row.p, h->d_low_rank.p, h->d_low_rank_up.p, h->d_Jcolptr.p, h->d_slice_off.p, d_Jv,
-          hv);
+      assemble_pairs_kernel<uint32_t, 15><<<h->nchunks, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
+                                                                      h->d_slot_start.p, d_Jv, hv);
     ++nl;
   }
   if (part) {

@@ -114,6 +114,7 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     if (const char* e = getenv("SPB_PCG_MULTI")) h->pcg_persistent = !(e[0] == '1');
     if (!prop.cooperativeLaunch) h->pcg_persistent = false;
     if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
+    if (const char* e = getenv("SPB_PCG_PIN_MB")) h->pcg_pin_mb = atof(e);
     SPB_CUDA(cudaMallocHost((void**)&h->h_sc, sizeof(PcgScalars)));
     SPB_CUDA(cudaMallocHost((void**)&h->h_scalar, 8 * sizeof(double)));
     memset(h->h_sc, 0, sizeof(PcgScalars));

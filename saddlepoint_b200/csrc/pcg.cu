@@ -168,40 +168,81 @@ void dev_invert_diag(spb_context* h) {
 // y = H x over the slice range [s_begin, s_end); lane == row inside a 32-row slice; the 8
 // warps of a block stride over the range.  Returns this thread's share of x.y.
 // NC=true: x is immutable for the kernel's lifetime, gathers may use the non-coherent path.
+// Loads of the H stream.  PIN=false: evict-first streaming loads (ld.global.cs), so the stream
+// never displaces the PCG vectors from L2.  PIN=true: L2 evict_last policy -- the persistent PCG
+// kernel re-reads the same H every iteration, so a fixed leading part of every block's slice
+// range is kept resident in the 126 MB L2 across iterations and only the rest comes from HBM.
+template <bool PIN>
+__device__ __forceinline__ int ld_h_i32(const int* p, uint64_t pol) {
+  if (!PIN) return __ldcs(p);
+  int v;
+  asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <bool PIN>
+__device__ __forceinline__ double ld_h_f64(const double* p, uint64_t pol) {
+  if (!PIN) return __ldcs(p);
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+template <bool NC, bool PIN>
+__device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
+                                             const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
+                                             double* y, int n, int slice, int lane, uint64_t pol) {
+  const int row = slice * 32 + lane;
+  const int64_t off = slice_off[slice];
+  const int width = (int)((slice_off[slice + 1] - off) >> 5);
+  const int len = row < n ? rowlen[row] : 0;
+  const int* cp = col + off + lane;
+  const double* vp = hval + off + lane;
+  double acc = 0.0;
+  int k = 0;
+  for (; k + 4 <= width; k += 4) {
+    const int c0 = ld_h_i32<PIN>(cp + (k + 0) * 32, pol), c1 = ld_h_i32<PIN>(cp + (k + 1) * 32, pol), c2 = ld_h_i32<PIN>(cp + (k + 2) * 32, pol),
+              c3 = ld_h_i32<PIN>(cp + (k + 3) * 32, pol);
+    const double v0 = ld_h_f64<PIN>(vp + (k + 0) * 32, pol), v1 = ld_h_f64<PIN>(vp + (k + 1) * 32, pol),
+                 v2 = ld_h_f64<PIN>(vp + (k + 2) * 32, pol), v3 = ld_h_f64<PIN>(vp + (k + 3) * 32, pol);
+    const double x0 = NC ? __ldg(x + c0) : x[c0], x1 = NC ? __ldg(x + c1) : x[c1], x2 = NC ? __ldg(x + c2) : x[c2], x3 = NC ? __ldg(x + c3) : x[c3];
+    if (k + 0 < len) acc = fma(v0, x0, acc);
+    if (k + 1 < len) acc = fma(v1, x1, acc);
+    if (k + 2 < len) acc = fma(v2, x2, acc);
+    if (k + 3 < len) acc = fma(v3, x3, acc);
+  }
+  for (; k < width; ++k) {
+    const int c0 = ld_h_i32<PIN>(cp + k * 32, pol);
+    const double v0 = ld_h_f64<PIN>(vp + k * 32, pol);
+    const double x0 = NC ? __ldg(x + c0) : x[c0];
+    if (k < len) acc = fma(v0, x0, acc);
+  }
+  if (row < n) {
+    y[row] = acc;
+    return (NC ? __ldg(x + row) : x[row]) * acc;
+  }
+  return 0.0;
+}
+
+// y = H x over the slice range [s_begin, s_end); lane == row inside a 32-row slice; the 8
+// warps of a block stride over the range.  Returns this thread's share of x.y.
+// NC=true: x is immutable for the kernel's lifetime, gathers may use the non-coherent path.
+// Slices below s_pin_end are loaded with the L2 evict_last policy (see ld_h_*).
 template <bool NC>
 __device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
                                              const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
-                                             double* y, int n, int s_begin, int s_end) {
+                                             double* y, int n, int s_begin, int s_end, int s_pin_end = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double loc = 0.0;
+  uint64_t pol = 0;
+  if (s_pin_end > s_begin) pol = l2_evict_last_policy();
   for (int slice = s_begin + warp; slice < s_end; slice += 8) {
-    const int row = slice * 32 + lane;
-    const int64_t off = slice_off[slice];
-    const int width = (int)((slice_off[slice + 1] - off) >> 5);
-    const int len = row < n ? rowlen[row] : 0;
-    const int* cp = col + off + lane;
-    const double* vp = hval + off + lane;
-    double acc = 0.0;
-    int k = 0;
-    for (; k + 4 <= width; k += 4) {
-      const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32), c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
-      const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32), v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
-      const double x0 = NC ? __ldg(x + c0) : x[c0], x1 = NC ? __ldg(x + c1) : x[c1], x2 = NC ? __ldg(x + c2) : x[c2], x3 = NC ? __ldg(x + c3) : x[c3];
-      if (k + 0 < len) acc = fma(v0, x0, acc);
-      if (k + 1 < len) acc = fma(v1, x1, acc);
-      if (k + 2 < len) acc = fma(v2, x2, acc);
-      if (k + 3 < len) acc = fma(v3, x3, acc);
-    }
-    for (; k < width; ++k) {
-      const int c0 = __ldcs(cp + k * 32);
-      const double v0 = __ldcs(vp + k * 32);
-      const double x0 = NC ? __ldg(x + c0) : x[c0];
-      if (k < len) acc = fma(v0, x0, acc);
-    }
-    if (row < n) {
-      y[row] = acc;
-      loc = fma(NC ? __ldg(x + row) : x[row], acc, loc);
-    }
+    if (slice < s_pin_end) loc += spmv_slice<NC, true>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol);
+    else loc += spmv_slice<NC, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol);
   }
   return loc;
 }
@@ -278,6 +319,7 @@ struct PcgParams {
   PcgScalars* sc;
   int n, nslices, maxit;
   double rtol;
+  double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
 };
 
 template <int MINB>
@@ -293,6 +335,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
   double* partC = P.partial + 2 * G;
   const int s_begin = (int)(((int64_t)P.nslices * blk) / G);
   const int s_end = (int)(((int64_t)P.nslices * (blk + 1)) / G);
+  const int s_pin_end = s_begin + (int)((s_end - s_begin) * P.pin_fraction);
   // init: r = b, p = z = dinv*r, x = 0
   {
     double rz = 0.0, bb = 0.0;
@@ -323,7 +366,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
   while (run) {
     // phase 1: q = H p, partial p.q
     {
-      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end);
+      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, s_pin_end);
       const double bs = block_sum_256(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
@@ -519,6 +562,11 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     P.nslices = nslices;
     P.maxit = h->pcg_maxit;
     P.rtol = h->pcg_rtol;
+    {
+      // keep up to pcg_pin_mb of the H stream (12 B per padded entry) resident in L2 across iterations
+      const double h_bytes = 12.0 * (double)h->S.padded;
+      P.pin_fraction = h_bytes > 0 ? std::min(1.0, std::max(0.0, h->pcg_pin_mb * 1048576.0 / h_bytes)) : 0.0;
+    }
     void* args[] = {&P};
     stage_begin(h, ST_PCG);
     SPB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(256), args, 0, st));

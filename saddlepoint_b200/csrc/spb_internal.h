@@ -96,6 +96,12 @@ struct AssemblyPlan {
   std::vector<int> chunk_slot;
   std::vector<int64_t> chunk_rec;
   std::vector<int> chunk_npairs;
+  // stage list of chunk c: J columns [chunk_stage_ptr[c], chunk_stage_ptr[c+1]) of stage_cols, with their
+  // offsets in the shared-memory value buffer; chunk_staged[c]==0: list too big, gather from global
+  std::vector<int> chunk_stage_ptr, stage_cols, stage_off;
+  std::vector<uint8_t> chunk_staged;
+  std::vector<uint16_t> slot_start;        // per slot: first record of the slot, relative to its chunk
+  std::vector<uint16_t> slot_il, slot_jl;  // per slot: stage-list index of its row column i / its column j
   // per strictly-lower slot, column-major, ascending row inside a column
   std::vector<int> low_colptr;      // n+1
   std::vector<int> low_row;         // row index i of the slot
@@ -108,10 +114,26 @@ struct AssemblyPlan {
 };
 
 // tunables shared by host planning and kernels
-constexpr int kPairTile = 2048;   // products staged per tile
-constexpr int kSlotCap = 1024;    // strictly-lower slots per chunk
+constexpr int kPairTile = 1024;   // products staged per tile
+constexpr int kSlotCap = 512;     // strictly-lower slots per chunk
+constexpr int kStageVals = 2048;  // J values staged in shared memory per chunk
+constexpr int kStageCols = 192;   // J columns in a chunk's stage list
 constexpr int kEntTile = 2048;    // J entries staged per tile in the column kernel
 constexpr int kColCap = 512;      // columns per column-kernel chunk
+
+// device-side packed forms of the plan (built by upload_analysis)
+struct ChunkDesc {   // 32 bytes
+  int slot0, nslots, npairs, stage0, nstage, staged;
+  int64_t rec0;
+};
+struct StageEntry {  // 16 bytes: one J column of a chunk's stage list
+  int src;             // Jcolptr[col]
+  uint16_t off, len;   // offset in the shared value buffer, column length
+  int64_t slice_base;  // slice_off[col>>5] + (col&31): storage position of H row `col`, entry 0
+};
+struct SlotMeta {    // 8 bytes
+  uint16_t il, jl, rank, rank_up;
+};
 
 void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H);
 void build_sell(const HPattern& H, SellLayout& S);
@@ -180,7 +202,12 @@ struct spb_context {
   spb::DevBuf<uint16_t> d_rec16;
   spb::DevBuf<uint32_t> d_rec32;
   spb::DevBuf<uint16_t> d_grp_slot, d_low_rank, d_low_rank_up;
-  spb::DevBuf<int> d_chunk_slot, d_chunk_npairs, d_chunk_col0, d_low_colptr, d_low_row, d_colchunk, d_nup1;
+  spb::DevBuf<int> d_chunk_slot, d_chunk_npairs, d_chunk_stage_ptr, d_stage_cols, d_stage_off, d_colchunk, d_nup1;
+  spb::DevBuf<uint8_t> d_chunk_staged;
+  spb::DevBuf<spb::ChunkDesc> d_chunk_desc;
+  spb::DevBuf<spb::StageEntry> d_stage_ent;
+  spb::DevBuf<spb::SlotMeta> d_slot_meta;
+  spb::DevBuf<uint16_t> d_slot_il, d_slot_jl, d_slot_start;
   spb::DevBuf<int64_t> d_chunk_rec;
   // device: H in SpMV layout
   spb::DevBuf<int> d_sell_col, d_rowlen;
@@ -207,6 +234,7 @@ struct spb_context {
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
   int occ_spmv = 0, occ_pcg = 0;
+  double pcg_pin_mb = 0.0;     // MB of H the persistent PCG keeps in L2 (evict_last) across iterations
   int pcg_minb = 4;            // __launch_bounds__ min blocks/SM variant of the persistent kernel
   int64_t launches = 0;
   void* lm_ws = nullptr;  // spb::LmWorkspace*, owned (lm.cu)

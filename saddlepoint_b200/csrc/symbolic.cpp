@@ -228,43 +228,119 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
     P.low_rank_up.resize(w);
     slot_npairs.resize(w);
   }
-  // chunking
+  // Chunking.  A chunk is a run of whole H columns (split inside a column only when one column
+  // alone exceeds the caps) together with its *stage list*: the J columns whose values its pairs
+  // touch (the chunk's own columns j and the row-columns i of its slots).  The kernel copies
+  // those columns into shared memory once (coalesced) and the per-pair gathers become shared
+  // memory reads; a chunk whose stage list does not fit (very long J columns) is flagged
+  // unstaged and gathers from global memory instead.
   P.chunk_slot.clear();
   P.chunk_rec.clear();
   P.chunk_npairs.clear();
+  P.chunk_stage_ptr.clear();
+  P.chunk_staged.clear();
+  P.stage_cols.clear();
+  P.stage_off.clear();
+  P.slot_il.assign(P.nslots, 0);
+  P.slot_jl.assign(P.nslots, 0);
+  P.slot_start.assign(P.nslots, 0);
   P.grp_slot.clear();
   P.rec16.clear();
   P.rec32.clear();
   if (P.rec_bits == 16) P.rec16.reserve(stream.size() + stream.size() / 16);
   else P.rec32.reserve(stream.size() + stream.size() / 16);
-  int64_t src = 0;
-  int s = 0;
-  while (s < P.nslots) {
-    int cs = s;
-    int np = 0;
-    while (s < P.nslots && (s - cs) < kSlotCap && (np == 0 || np + slot_npairs[s] <= kPairTile)) {
-      np += slot_npairs[s];
-      ++s;
+  {
+    std::vector<int> local_of(n, -1);   // column -> index in the current chunk's stage list
+    std::vector<int> cur_list;          // stage list being built
+    int64_t src = 0;                    // cursor in `stream`
+    int cs = 0;                         // first slot of the open chunk
+    int c_np = 0, c_ns = 0, c_vals = 0;
+    auto add_col = [&](int col) {
+      if (local_of[col] < 0) {
+        local_of[col] = (int)cur_list.size();
+        cur_list.push_back(col);
+        c_vals += colptr[col + 1] - colptr[col];
+      }
+      return local_of[col];
+    };
+    auto close_chunk = [&](int s_end) {
+      if (s_end == cs) return;
+      const int np = c_np;
+      int64_t rec0 = P.rec_bits == 16 ? (int64_t)P.rec16.size() : (int64_t)P.rec32.size();
+      P.chunk_slot.push_back(cs);
+      P.chunk_rec.push_back(rec0);
+      P.chunk_npairs.push_back(np);
+      P.chunk_stage_ptr.push_back((int)P.stage_cols.size());
+      const bool staged = c_vals <= kStageVals && (int)cur_list.size() <= kStageCols;
+      P.chunk_staged.push_back(staged ? 1 : 0);
+      int off = 0;
+      for (int col : cur_list) {
+        P.stage_cols.push_back(col);
+        P.stage_off.push_back(off);
+        off += colptr[col + 1] - colptr[col];
+        local_of[col] = -1;
+      }
+      int sl = -1;  // chunk-local slot of the record being copied
+      for (int t = 0; t < np; ++t) {
+        uint32_t rec = stream[(size_t)(src + t)];
+        if (rec >> (2 * pobits)) {
+          ++sl;
+          P.slot_start[(size_t)cs + sl] = (uint16_t)std::min(t, 65535);
+        }
+        if ((t & 31) == 0) P.grp_slot.push_back((uint16_t)sl);
+        if (P.rec_bits == 16) P.rec16.push_back((uint16_t)rec); else P.rec32.push_back(rec);
+      }
+      int pad = (32 - (np & 31)) & 31;
+      for (int t = 0; t < pad; ++t) {
+        if (P.rec_bits == 16) P.rec16.push_back(0); else P.rec32.push_back(0);
+      }
+      src += np;
+      cur_list.clear();
+      cs = s_end;
+      c_np = c_ns = c_vals = 0;
+    };
+    for (int j = 0; j < n; ++j) {
+      const int s0 = P.low_colptr[j], s1 = P.low_colptr[(size_t)j + 1];
+      if (s1 == s0) continue;
+      int pj = 0;
+      for (int s = s0; s < s1; ++s) pj += slot_npairs[s];
+      // would this whole column fit into the open chunk?
+      int new_cols = 0, new_vals = 0;
+      if (local_of[j] < 0) { ++new_cols; new_vals += colptr[j + 1] - colptr[j]; }
+      for (int s = s0; s < s1; ++s) {
+        int i = P.low_row[s];
+        if (local_of[i] < 0) { ++new_cols; new_vals += colptr[i + 1] - colptr[i]; }
+      }
+      const bool fits = c_np + pj <= kPairTile && c_ns + (s1 - s0) <= kSlotCap && (int)cur_list.size() + new_cols <= kStageCols &&
+                        c_vals + new_vals <= kStageVals;
+      if (!fits && c_ns > 0) close_chunk(s0);
+      const bool alone_ok = pj <= kPairTile && (s1 - s0) <= kSlotCap;
+      if (alone_ok) {
+        const int jl = add_col(j);
+        for (int s = s0; s < s1; ++s) {
+          P.slot_il[s] = (uint16_t)add_col(P.low_row[s]);
+          P.slot_jl[s] = (uint16_t)jl;
+        }
+        c_np += pj;
+        c_ns += s1 - s0;
+      } else {
+        // a column too big for one chunk: split by slots (a single slot may exceed the pair tile:
+        // the kernel's multi-tile path handles a one-slot chunk of any length)
+        for (int s = s0; s < s1; ++s) {
+          if (c_ns > 0 && (c_np + slot_npairs[s] > kPairTile || c_ns + 1 > kSlotCap || (int)cur_list.size() + 2 > kStageCols)) close_chunk(s);
+          const int jl = add_col(j);
+          P.slot_il[s] = (uint16_t)add_col(P.low_row[s]);
+          P.slot_jl[s] = (uint16_t)jl;
+          c_np += slot_npairs[s];
+          c_ns += 1;
+        }
+        close_chunk(s1);
+      }
     }
-    int64_t rec0 = P.rec_bits == 16 ? (int64_t)P.rec16.size() : (int64_t)P.rec32.size();
-    P.chunk_slot.push_back(cs);
-    P.chunk_rec.push_back(rec0);
-    P.chunk_npairs.push_back(np);
-    // copy records + per-group first slot
-    int sl = -1;  // chunk-local slot of the record being copied
-    for (int t = 0; t < np; ++t) {
-      uint32_t rec = stream[(size_t)(src + t)];
-      if (rec >> (2 * pobits)) ++sl;
-      if ((t & 31) == 0) P.grp_slot.push_back((uint16_t)sl);
-      if (P.rec_bits == 16) P.rec16.push_back((uint16_t)rec); else P.rec32.push_back(rec);
-    }
-    int pad = (32 - (np & 31)) & 31;
-    for (int t = 0; t < pad; ++t) {
-      if (P.rec_bits == 16) P.rec16.push_back(0); else P.rec32.push_back(0);
-    }
-    src += np;
+    close_chunk(P.nslots);
   }
   P.chunk_slot.push_back(P.nslots);
+  P.chunk_stage_ptr.push_back((int)P.stage_cols.size());
   // column kernel chunks: by entry count and column count
   P.colchunk.clear();
   int j = 0;

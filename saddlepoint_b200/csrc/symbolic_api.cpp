@@ -106,6 +106,21 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
         ++pairs_seen;
       }
       if (sl + 1 != s1 - s0) ++bad;
+      // stage list: every slot's (i, j) columns are in the chunk's list at the recorded local index,
+      // offsets are the running sum of the listed columns' lengths, and the staged flag respects the caps
+      const int st0 = P.chunk_stage_ptr[c], st1 = P.chunk_stage_ptr[c + 1];
+      int off = 0;
+      for (int t = st0; t < st1; ++t) {
+        if (P.stage_off[t] != off) ++bad;
+        off += colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]];
+      }
+      if (P.chunk_staged[c] && (off > kStageVals || st1 - st0 > kStageCols)) ++bad;
+      for (int s = s0; s < s1; ++s) {
+        int j = (int)(std::upper_bound(P.low_colptr.begin(), P.low_colptr.end(), s) - P.low_colptr.begin()) - 1;
+        if (st0 + P.slot_il[s] >= st1 || P.stage_cols[st0 + P.slot_il[s]] != P.low_row[s]) ++bad;
+        if (st0 + P.slot_jl[s] >= st1 || P.stage_cols[st0 + P.slot_jl[s]] != j) ++bad;
+      }
+      if (s1 - s0 > kSlotCap || (P.chunk_npairs[c] > kPairTile && s1 - s0 != 1)) ++bad;
     }
     if (pairs_seen != P.npairs) ++bad;
     // rank check: H(i,j) must sit at rank low_rank in row i of the symmetric pattern

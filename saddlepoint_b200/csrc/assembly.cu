@@ -36,6 +36,34 @@
 
 namespace spb {
 
+// ---- TMA (bulk async copy) helpers: global -> shared with mbarrier completion ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ordered sum of one slot's products: first product assigned, the rest added left to right
 template <typename RecT, int POBITS, bool SMEM>
 __device__ __forceinline__ double slot_sum(const RecT* rec, const double* vi, const double* vj, int beg, int end) {
@@ -54,11 +82,12 @@ __device__ __forceinline__ double slot_sum(const RecT* rec, const double* vi, co
 }
 
 template <typename RecT, int POBITS>
-__global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restrict__ recs, const ChunkDesc* __restrict__ chunks,
+__global__ void __launch_bounds__(256, 8) assemble_pairs_kernel(const RecT* __restrict__ recs, const ChunkDesc* __restrict__ chunks,
                                                              const StageEntry* __restrict__ stage, const SlotMeta* __restrict__ slots,
-                                                             const uint16_t* __restrict__ slot_start, const double* __restrict__ Jv,
-                                                             double* __restrict__ hval) {
-  __shared__ double sval[kStageVals];
+                                                             const uint32_t* __restrict__ slot_start, const double* __restrict__ Jv,
+                                                             double* __restrict__ hval, int bulk_ok) {
+  __shared__ __align__(16) double sval[kStageVals];
+  __shared__ uint64_t bar;
   __shared__ RecT srec[kPairTile];
   __shared__ int s_src[kStageCols];
   __shared__ unsigned s_offlen[kStageCols];
@@ -67,11 +96,16 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restr
   const ChunkDesc cd = chunks[blockIdx.x];
   const int s0 = cd.slot0, ns = cd.nslots, np = cd.npairs, st0 = cd.stage0, nst = cd.nstage;
   const int64_t rec0 = cd.rec0;
-  const bool staged = cd.staged != 0;
+  const bool staged = (cd.flags & 1) != 0;
+  const bool bulk = bulk_ok && (cd.flags & 4);  // every column's 16-byte-aligned window is inside the J value array
   const bool small_list = nst <= kStageCols;
   const bool one_tile = np <= kPairTile;
-  constexpr uint32_t MASK = (1u << POBITS) - 1u;
   constexpr int SPT = kSlotCap / 256;  // slots per thread
+  if (bulk) {
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();  // the barrier object must be initialised before any copy can signal it
+    if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cd.stage_bytes);
+  }
 
   // Independent loads first: per-slot metadata, the chunk's pair records (coalesced, into shared
   // memory) and the stage list.  The only dependent chain left is stage entry -> J values.
@@ -83,8 +117,9 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restr
     beg[k] = end[k] = 0;
     if (t < ns) {
       mreg[k] = slots[s0 + t];
-      beg[k] = slot_start[s0 + t];
-      end[k] = t + 1 < ns ? (int)slot_start[s0 + t + 1] : np;
+      const uint32_t sc = slot_start[s0 + t];  // (start << 16) | count; a multi-tile slot is alone in its chunk
+      beg[k] = (int)(sc >> 16);
+      end[k] = ns == 1 ? np : beg[k] + (int)(sc & 0xffffu);
     }
   }
   if (one_tile)
@@ -95,10 +130,20 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restr
       s_src[t] = e.src;
       s_offlen[t] = ((unsigned)e.off << 16) | e.len;
       s_sbase[t] = e.slice_base;
+      if (staged && bulk) {
+        // TMA: one bulk async copy per listed J column (its 16-byte-aligned window), issued by
+        // the thread that just read the entry, all completing on one mbarrier -- no per-element
+        // instructions, and the copy is in flight while the other loads of this phase land.
+        const int a = e.src & 1;
+        const int nal = ((int)e.len + a + 1) & ~1;
+        if (nal > 0) tma_bulk_g2s(sval + ((int)e.off - a), Jv + (e.src - a), (uint32_t)nal * 8u, &bar);
+      }
     }
   }
   __syncthreads();
-  if (staged) {
+  if (staged && bulk) {
+    mbar_wait(&bar, 0);
+  } else if (staged) {
     // Copy the listed J columns into shared memory: one warp per column and pass (columns of up
     // to 32 entries in one go), four columns in flight per thread before the first store.
     const int sub = tid & 31, cg = tid >> 5;
@@ -121,7 +166,7 @@ __global__ void __launch_bounds__(256) assemble_pairs_kernel(const RecT* __restr
       for (int u = 0; u < 4; ++u)
         if (dst[u] >= 0) sval[dst[u]] = v[u];
     }
-    if (cd.staged & 2) {  // columns longer than 32 entries: the rest of each column
+    if (cd.flags & 2) {  // columns longer than 32 entries: the rest of each column
       for (int t = cg; t < nst; t += 8) {
         const unsigned ol = s_offlen[t];
         const int off = (int)(ol >> 16), len = (int)(ol & 0xffffu), src = s_src[t];
@@ -298,6 +343,8 @@ __global__ void extract_diag_kernel(const double* __restrict__ hval, const int* 
 void upload_h_layout(spb_context* h) {
   cudaStream_t st = h->stream;
   SPB_CUDA(h->d_sell_col.upload(h->S.col, st));
+  SPB_CUDA(h->d_sell_col16.upload(h->S.col16, st));
+  SPB_CUDA(h->d_slice16.upload(h->S.slice16, st));
   SPB_CUDA(h->d_rowlen.upload(h->S.rowlen, st));
   SPB_CUDA(h->d_slice_off.upload(h->S.slice_off, st));
   SPB_CUDA(h->d_nup1.upload(h->H.nup1, st));
@@ -307,7 +354,8 @@ void upload_h_layout(spb_context* h) {
   SPB_CUDA(h->d_rhs.alloc(h->n));
   SPB_CUDA(h->d_dvec.alloc(h->n));
   SPB_CUDA(cudaStreamSynchronize(st));
-  std::vector<int>().swap(h->S.col);  // the big host copy is no longer needed
+  std::vector<int>().swap(h->S.col);  // the big host copies are no longer needed
+  std::vector<uint16_t>().swap(h->S.col16);
   h->d_pos_of_slot.release();
 }
 
@@ -327,11 +375,23 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
       cd[c].nslots = P.chunk_slot[(size_t)c + 1] - P.chunk_slot[c];
       cd[c].npairs = P.chunk_npairs[c];
       cd[c].stage0 = P.chunk_stage_ptr[c];
-      cd[c].nstage = P.chunk_stage_ptr[(size_t)c + 1] - P.chunk_stage_ptr[c];
-      cd[c].staged = P.chunk_staged[c];
-      if (cd[c].staged)
-        for (int t = P.chunk_stage_ptr[c]; t < P.chunk_stage_ptr[(size_t)c + 1]; ++t)
-          if (colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]] > 32) cd[c].staged |= 2;
+      cd[c].nstage = (uint16_t)std::min(P.chunk_stage_ptr[(size_t)c + 1] - P.chunk_stage_ptr[c], 65535);
+      cd[c].flags = P.chunk_staged[c];
+      cd[c].stage_bytes = 0;
+      if (cd[c].flags) {
+        bool inside = true;
+        int bytes = 0;
+        for (int t = P.chunk_stage_ptr[c]; t < P.chunk_stage_ptr[(size_t)c + 1]; ++t) {
+          const int col = P.stage_cols[t];
+          const int start = colptr[col], len = colptr[col + 1] - start, a = start & 1;
+          const int nal = (len + a + 1) & ~1;
+          if (len > 32) cd[c].flags |= 2;
+          if ((int64_t)start - a + nal > (int64_t)colptr[h->n]) inside = false;  // window would run past the value array
+          bytes += nal * 8;
+        }
+        if (inside) cd[c].flags |= 4;
+        cd[c].stage_bytes = bytes;
+      }
       cd[c].rec0 = P.chunk_rec[c];
     }
     std::vector<StageEntry> se(P.stage_cols.size());
@@ -343,11 +403,16 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
       se[t].slice_base = h->S.slice_off[col >> 5] + (col & 31);
     }
     std::vector<SlotMeta> sm((size_t)P.nslots);
-    for (int s = 0; s < P.nslots; ++s) sm[s] = SlotMeta{P.slot_il[s], P.slot_jl[s], P.low_rank[s], P.low_rank_up[s]};
+    std::vector<uint32_t> sc((size_t)P.nslots);
+    for (int pos = 0; pos < P.nslots; ++pos) {  // processing order (see symbolic.cpp)
+      const int s = P.proc_perm[pos];
+      sm[pos] = SlotMeta{P.slot_il[s], P.slot_jl[s], P.low_rank[s], P.low_rank_up[s]};
+      sc[pos] = ((uint32_t)P.slot_start[s] << 16) | P.slot_cnt[s];
+    }
     SPB_CUDA(h->d_chunk_desc.upload(cd, st));
     SPB_CUDA(h->d_stage_ent.upload(se, st));
     SPB_CUDA(h->d_slot_meta.upload(sm, st));
-    SPB_CUDA(h->d_slot_start.upload(P.slot_start, st));
+    SPB_CUDA(h->d_slot_start.upload(sc, st));
     SPB_CUDA(h->d_colchunk.upload(P.colchunk, st));
     SPB_CUDA(cudaStreamSynchronize(st));
   }
@@ -374,12 +439,13 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     ++nl;
   }
   if (h->nchunks > 0) {
+    const int bulk_ok = (((uintptr_t)d_Jv) & 15) == 0 ? 1 : 0;  // TMA bulk copies need a 16-byte aligned source
     if (h->rec_bits == 16)
       assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
-                                                                     h->d_slot_start.p, d_Jv, hv);
+                                                                     h->d_slot_start.p, d_Jv, hv, bulk_ok);
     else
       assemble_pairs_kernel<uint32_t, 15><<<h->nchunks, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
-                                                                      h->d_slot_start.p, d_Jv, hv);
+                                                                      h->d_slot_start.p, d_Jv, hv, bulk_ok);
     ++nl;
   }
   if (part) {

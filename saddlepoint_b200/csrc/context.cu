@@ -115,6 +115,7 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     if (!prop.cooperativeLaunch) h->pcg_persistent = false;
     if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
     if (const char* e = getenv("SPB_PCG_PIN_MB")) h->pcg_pin_mb = atof(e);
+    if (const char* e = getenv("SPB_PCG_COL16")) h->pcg_col16 = e[0] != '0';
     SPB_CUDA(cudaMallocHost((void**)&h->h_sc, sizeof(PcgScalars)));
     SPB_CUDA(cudaMallocHost((void**)&h->h_scalar, 8 * sizeof(double)));
     memset(h->h_sc, 0, sizeof(PcgScalars));

@@ -192,21 +192,35 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
   return pol;
 }
 
-template <bool NC, bool PIN>
+// C16: the slice's column indices are read from the 16-bit stream (column = row + delta - 32768),
+// 10 instead of 12 bytes per entry; slices with a delta that does not fit keep the 32-bit stream.
+template <bool NC, bool PIN, bool C16>
 __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
                                              const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
-                                             double* y, int n, int slice, int lane, uint64_t pol) {
+                                             double* y, int n, int slice, int lane, uint64_t pol, const uint16_t* __restrict__ col16) {
   const int row = slice * 32 + lane;
   const int64_t off = slice_off[slice];
   const int width = (int)((slice_off[slice + 1] - off) >> 5);
   const int len = row < n ? rowlen[row] : 0;
   const int* cp = col + off + lane;
+  const uint16_t* cp16 = col16 + off + lane;
   const double* vp = hval + off + lane;
+  const int rbase = row - 32768;
   double acc = 0.0;
   int k = 0;
   for (; k + 4 <= width; k += 4) {
-    const int c0 = ld_h_i32<PIN>(cp + (k + 0) * 32, pol), c1 = ld_h_i32<PIN>(cp + (k + 1) * 32, pol), c2 = ld_h_i32<PIN>(cp + (k + 2) * 32, pol),
-              c3 = ld_h_i32<PIN>(cp + (k + 3) * 32, pol);
+    int c0, c1, c2, c3;
+    if (C16) {
+      c0 = rbase + (int)__ldcs(cp16 + (k + 0) * 32);
+      c1 = rbase + (int)__ldcs(cp16 + (k + 1) * 32);
+      c2 = rbase + (int)__ldcs(cp16 + (k + 2) * 32);
+      c3 = rbase + (int)__ldcs(cp16 + (k + 3) * 32);
+    } else {
+      c0 = ld_h_i32<PIN>(cp + (k + 0) * 32, pol);
+      c1 = ld_h_i32<PIN>(cp + (k + 1) * 32, pol);
+      c2 = ld_h_i32<PIN>(cp + (k + 2) * 32, pol);
+      c3 = ld_h_i32<PIN>(cp + (k + 3) * 32, pol);
+    }
     const double v0 = ld_h_f64<PIN>(vp + (k + 0) * 32, pol), v1 = ld_h_f64<PIN>(vp + (k + 1) * 32, pol),
                  v2 = ld_h_f64<PIN>(vp + (k + 2) * 32, pol), v3 = ld_h_f64<PIN>(vp + (k + 3) * 32, pol);
     const double x0 = NC ? __ldg(x + c0) : x[c0], x1 = NC ? __ldg(x + c1) : x[c1], x2 = NC ? __ldg(x + c2) : x[c2], x3 = NC ? __ldg(x + c3) : x[c3];
@@ -216,7 +230,7 @@ __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_o
     if (k + 3 < len) acc = fma(v3, x3, acc);
   }
   for (; k < width; ++k) {
-    const int c0 = ld_h_i32<PIN>(cp + k * 32, pol);
+    const int c0 = C16 ? rbase + (int)__ldcs(cp16 + k * 32) : ld_h_i32<PIN>(cp + k * 32, pol);
     const double v0 = ld_h_f64<PIN>(vp + k * 32, pol);
     const double x0 = NC ? __ldg(x + c0) : x[c0];
     if (k < len) acc = fma(v0, x0, acc);
@@ -235,14 +249,16 @@ __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_o
 template <bool NC>
 __device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
                                              const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
-                                             double* y, int n, int s_begin, int s_end, int s_pin_end = 0) {
+                                             double* y, int n, int s_begin, int s_end, int s_pin_end = 0,
+                                             const uint16_t* __restrict__ col16 = nullptr, const uint8_t* __restrict__ s16 = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double loc = 0.0;
   uint64_t pol = 0;
   if (s_pin_end > s_begin) pol = l2_evict_last_policy();
   for (int slice = s_begin + warp; slice < s_end; slice += 8) {
-    if (slice < s_pin_end) loc += spmv_slice<NC, true>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol);
-    else loc += spmv_slice<NC, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol);
+    if (col16 && s16[slice]) loc += spmv_slice<NC, false, true>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
+    else if (slice < s_pin_end) loc += spmv_slice<NC, true, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
+    else loc += spmv_slice<NC, false, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
   }
   return loc;
 }
@@ -307,6 +323,8 @@ __device__ __forceinline__ double block_total(const double* part, int count, dou
 struct PcgParams {
   const int64_t* slice_off;
   const int* col;
+  const uint16_t* col16;  // 16-bit column deltas (may be null)
+  const uint8_t* s16;     // per slice: 1 = use col16
   const int* rowlen;
   const double* hval;
   const double* b;
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
   while (run) {
     // phase 1: q = H p, partial p.q
     {
-      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, s_pin_end);
+      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, s_pin_end, P.col16, P.s16);
       const double bs = block_sum_256(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
@@ -548,6 +566,8 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     PcgParams P;
     P.slice_off = h->d_slice_off.p;
     P.col = h->d_sell_col.p;
+    P.col16 = h->pcg_col16 ? h->d_sell_col16.p : nullptr;
+    P.s16 = h->d_slice16.p;
     P.rowlen = h->d_rowlen.p;
     P.hval = h->d_hval.p;
     P.b = d_b;

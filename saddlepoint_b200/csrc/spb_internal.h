@@ -78,6 +78,8 @@ struct SellLayout {
   int n = 0, nslices = 0;
   std::vector<int64_t> slice_off;  // nslices+1, in entries
   std::vector<int> col;            // padded column indices
+  std::vector<uint16_t> col16;     // column - row + 32768 where it fits (compressed index stream)
+  std::vector<uint8_t> slice16;    // per slice: every delta of the slice fits 16 bits
   std::vector<int> rowlen;         // n
   int64_t padded = 0;
   int64_t pos(int row, int k) const { return slice_off[row >> 5] + (int64_t)k * 32 + (row & 31); }
@@ -101,6 +103,8 @@ struct AssemblyPlan {
   std::vector<int> chunk_stage_ptr, stage_cols, stage_off;
   std::vector<uint8_t> chunk_staged;
   std::vector<uint16_t> slot_start;        // per slot: first record of the slot, relative to its chunk
+  std::vector<uint16_t> slot_cnt;          // per slot: number of records (saturated; multi-tile slots are alone in their chunk)
+  std::vector<int> proc_perm;              // processing order: position -> slot, sorted by descending count inside a chunk
   std::vector<uint16_t> slot_il, slot_jl;  // per slot: stage-list index of its row column i / its column j
   // per strictly-lower slot, column-major, ascending row inside a column
   std::vector<int> low_colptr;      // n+1
@@ -123,7 +127,9 @@ constexpr int kColCap = 512;      // columns per column-kernel chunk
 
 // device-side packed forms of the plan (built by upload_analysis)
 struct ChunkDesc {   // 32 bytes
-  int slot0, nslots, npairs, stage0, nstage, staged;
+  int slot0, nslots, npairs, stage0;
+  uint16_t nstage, flags;  // flags: 1 staged in shared memory, 2 has columns > 32 entries, 4 TMA-safe windows
+  int stage_bytes;         // sum of the 16-byte-aligned column windows (mbarrier expect_tx)
   int64_t rec0;
 };
 struct StageEntry {  // 16 bytes: one J column of a chunk's stage list
@@ -207,10 +213,13 @@ struct spb_context {
   spb::DevBuf<spb::ChunkDesc> d_chunk_desc;
   spb::DevBuf<spb::StageEntry> d_stage_ent;
   spb::DevBuf<spb::SlotMeta> d_slot_meta;
-  spb::DevBuf<uint16_t> d_slot_il, d_slot_jl, d_slot_start;
+  spb::DevBuf<uint16_t> d_slot_il, d_slot_jl;
+  spb::DevBuf<uint32_t> d_slot_start;  // (start << 16) | count, in processing order
   spb::DevBuf<int64_t> d_chunk_rec;
   // device: H in SpMV layout
   spb::DevBuf<int> d_sell_col, d_rowlen;
+  spb::DevBuf<uint16_t> d_sell_col16;
+  spb::DevBuf<uint8_t> d_slice16;
   spb::DevBuf<int64_t> d_slice_off;
   spb::DevBuf<int64_t> d_pos_of_slot;  // lazily built: CSC slot -> storage position
   spb::DevBuf<double> d_hval, d_hdiag, d_dinv;
@@ -234,6 +243,7 @@ struct spb_context {
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
   int occ_spmv = 0, occ_pcg = 0;
+  bool pcg_col16 = true;       // persistent PCG reads 16-bit column deltas where a slice allows it
   double pcg_pin_mb = 0.0;     // MB of H the persistent PCG keeps in L2 (evict_last) across iterations
   int pcg_minb = 4;            // __launch_bounds__ min blocks/SM variant of the persistent kernel
   int64_t launches = 0;

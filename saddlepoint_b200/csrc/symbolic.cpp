@@ -112,13 +112,22 @@ void build_sell(const HPattern& H, SellLayout& S) {
   }
   S.padded = S.slice_off[S.nslices];
   S.col.assign((size_t)S.padded, 0);
+  S.col16.assign((size_t)S.padded, 32768);
+  S.slice16.assign((size_t)S.nslices, 1);
   for (int r = 0; r < n; ++r) {
     int64_t base = S.slice_off[r >> 5] + (r & 31);
     int k = 0;
-    for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) S.col[(size_t)(base + (int64_t)k * 32)] = H.rowidx[q];
+    for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) {
+      const int c = H.rowidx[q];
+      S.col[(size_t)(base + (int64_t)k * 32)] = c;
+      const int d = c - r + 32768;
+      if (d < 0 || d > 65535) S.slice16[(size_t)(r >> 5)] = 0;
+      else S.col16[(size_t)(base + (int64_t)k * 32)] = (uint16_t)d;
+    }
     int w = (int)((S.slice_off[(size_t)(r >> 5) + 1] - S.slice_off[r >> 5]) / 32);
-    for (; k < w; ++k) S.col[(size_t)(base + (int64_t)k * 32)] = r;
+    for (; k < w; ++k) S.col[(size_t)(base + (int64_t)k * 32)] = r;  // padding: own row, delta 0
   }
+  // rows past n in the last slice never load; their col16 entries stay at delta 0
 }
 
 void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P) {
@@ -244,6 +253,8 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
   P.slot_il.assign(P.nslots, 0);
   P.slot_jl.assign(P.nslots, 0);
   P.slot_start.assign(P.nslots, 0);
+  P.slot_cnt.assign(P.nslots, 0);
+  P.proc_perm.resize(P.nslots);
   P.grp_slot.clear();
   P.rec16.clear();
   P.rec32.clear();
@@ -259,7 +270,7 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       if (local_of[col] < 0) {
         local_of[col] = (int)cur_list.size();
         cur_list.push_back(col);
-        c_vals += colptr[col + 1] - colptr[col];
+        c_vals += (colptr[col + 1] - colptr[col] + (colptr[col] & 1) + 1) & ~1;  // 16-byte aligned window
       }
       return local_of[col];
     };
@@ -275,9 +286,10 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       P.chunk_staged.push_back(staged ? 1 : 0);
       int off = 0;
       for (int col : cur_list) {
+        const int a = colptr[col] & 1;  // the column's window starts one element early when it is odd-aligned
         P.stage_cols.push_back(col);
-        P.stage_off.push_back(off);
-        off += colptr[col + 1] - colptr[col];
+        P.stage_off.push_back(off + a);
+        off += (colptr[col + 1] - colptr[col] + a + 1) & ~1;
         local_of[col] = -1;
       }
       int sl = -1;  // chunk-local slot of the record being copied
@@ -294,6 +306,15 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       for (int t = 0; t < pad; ++t) {
         if (P.rec_bits == 16) P.rec16.push_back(0); else P.rec32.push_back(0);
       }
+      // processing order inside the chunk: slots sorted by descending pair count, so the 32
+      // slots a warp walks in lock step have (nearly) equal trip counts -- no divergence waste.
+      // Records stay slot-major; every slot carries its own (start, count).
+      for (int s = cs; s < s_end; ++s) {
+        P.slot_cnt[s] = (uint16_t)std::min(slot_npairs[s], 65535);
+        P.proc_perm[s] = s;
+      }
+      std::stable_sort(P.proc_perm.begin() + cs, P.proc_perm.begin() + s_end,
+                       [&](int a, int b) { return slot_npairs[a] > slot_npairs[b]; });
       src += np;
       cur_list.clear();
       cs = s_end;
@@ -306,10 +327,10 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       for (int s = s0; s < s1; ++s) pj += slot_npairs[s];
       // would this whole column fit into the open chunk?
       int new_cols = 0, new_vals = 0;
-      if (local_of[j] < 0) { ++new_cols; new_vals += colptr[j + 1] - colptr[j]; }
+      if (local_of[j] < 0) { ++new_cols; new_vals += colptr[j + 1] - colptr[j] + 2; }
       for (int s = s0; s < s1; ++s) {
         int i = P.low_row[s];
-        if (local_of[i] < 0) { ++new_cols; new_vals += colptr[i + 1] - colptr[i]; }
+        if (local_of[i] < 0) { ++new_cols; new_vals += colptr[i + 1] - colptr[i] + 2; }
       }
       const bool fits = c_np + pj <= kPairTile && c_ns + (s1 - s0) <= kSlotCap && (int)cur_list.size() + new_cols <= kStageCols &&
                         c_vals + new_vals <= kStageVals;

@@ -111,8 +111,9 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
       const int st0 = P.chunk_stage_ptr[c], st1 = P.chunk_stage_ptr[c + 1];
       int off = 0;
       for (int t = st0; t < st1; ++t) {
-        if (P.stage_off[t] != off) ++bad;
-        off += colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]];
+        const int a = colptr[P.stage_cols[t]] & 1;  // 16-byte aligned windows (TMA bulk copies)
+        if (P.stage_off[t] != off + a) ++bad;
+        off += (colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]] + a + 1) & ~1;
       }
       if (P.chunk_staged[c] && (off > kStageVals || st1 - st0 > kStageCols)) ++bad;
       for (int s = s0; s < s1; ++s) {
@@ -121,6 +122,17 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
         if (st0 + P.slot_jl[s] >= st1 || P.stage_cols[st0 + P.slot_jl[s]] != j) ++bad;
       }
       if (s1 - s0 > kSlotCap || (P.chunk_npairs[c] > kPairTile && s1 - s0 != 1)) ++bad;
+      // processing order: a permutation of the chunk's slots with non-increasing pair counts
+      {
+        std::vector<int> seen(s1 - s0, 0);
+        int prevc = 1 << 30;
+        for (int pos = s0; pos < s1; ++pos) {
+          int sidx = P.proc_perm[pos];
+          if (sidx < s0 || sidx >= s1 || seen[sidx - s0]++) { ++bad; continue; }
+          if (P.slot_cnt[sidx] > prevc) ++bad;
+          prevc = P.slot_cnt[sidx];
+        }
+      }
     }
     if (pairs_seen != P.npairs) ++bad;
     // rank check: H(i,j) must sit at rank low_rank in row i of the symmetric pattern

@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) chol_extend_add_kernel(const int* __restr
 }
 
 // Cholesky of the 32x32 diagonal block at pivot offset kb of every front in the list, plus its
-// inverse (for the triangular solves).  1024 threads = one per block entry.
+// inverse (for the triangular solves).  1024 threads = one per block entry.  (A single-warp
+// register/shuffle variant was measured slower: the leaf levels run tens of thousands of these
+// blocks at once and want all 1024 threads per block.)
 __global__ void __launch_bounds__(1024) chol_potrf32_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
                                                             const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
                                                             const int64_t* __restrict__ dinv_off, double* __restrict__ Lbuf,
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(1024) chol_potrf32_kernel(const int* __restric
   Dinv[dinv_off[f] + (int64_t)(kb >> 5) * 1024 + c * 32 + i] = (i >= c) ? x : 0.0;
 }
 
-// rows below the diagonal block: X = B * D^-T, one thread per row
+// rows below the diagonal block: X = B * D^-T, one thread per row, column-oriented substitution
+// (after x_q is final every later entry takes its update independently: ILP instead of one
+// 496-long dependent chain; the accumulation order per entry is unchanged)
 __global__ void __launch_bounds__(128) chol_trsm_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
                                                         const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
                                                         double* __restrict__ Lbuf) {
@@ -144,11 +148,11 @@ __global__ void __launch_bounds__(128) chol_trsm_kernel(const int* __restrict__ 
 #pragma unroll
   for (int t = 0; t < 32; ++t) v[t] = t < nb ? P[(int64_t)(kb + t) * r + row] : 0.0;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    double s = v[t];
+  for (int q = 0; q < 32; ++q) {
+    const double xq = v[q] / Dm[q][q];
+    v[q] = xq;
 #pragma unroll
-    for (int q = 0; q < t; ++q) s -= v[q] * Dm[t][q];
-    v[t] = s / Dm[t][t];
+    for (int t = q + 1; t < 32; ++t) v[t] -= xq * Dm[t][q];
   }
 #pragma unroll
   for (int t = 0; t < 32; ++t)
@@ -156,13 +160,20 @@ __global__ void __launch_bounds__(128) chol_trsm_kernel(const int* __restrict__ 
 }
 
 // C -= A_i * A_j^T on 64x64 tiles of the lower triangle, FP64 tensor cores (DMMA m8n8k4).
-// mode 0: trailing pivot columns after block kb;  mode 1: the update matrix U (K = k).
+// mode 0: pivot columns [ke, min(cend, k)) are updated with the factor columns [ka, ke) -- used
+//         twice: inside a 256-column panel (ka = kb, ke = kb+32, cend = panel end; K = 32) and once
+//         per panel for everything right of it (ka = panel start, ke = panel end, cend = inf; K = 256).
+//         Two-level blocking keeps the narrow K=32 updates inside the panel, so the bulk of the
+//         trailing matrix is read and written once per 256 columns, not once per 32.
+// mode 1: the update matrix U (K = k).
 constexpr int kSyrkLd = 68;  // 64 + 4: conflict-free fragment loads
-__global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ fronts, int mode, int kb, const int* __restrict__ sn_k,
+constexpr int kSyrkKC = 16;  // K columns staged per pipeline stage
+__global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ fronts, int mode, int ka, int ke, int cend,
+                                                        const int* __restrict__ sn_k,
                                                         const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
                                                         const int64_t* __restrict__ U_off, double* __restrict__ Lbuf,
                                                         double* __restrict__ Ubuf) {
-  __shared__ double As[16 * kSyrkLd], Bs[16 * kSyrkLd];
+  __shared__ double As[2 * kSyrkKC * kSyrkLd], Bs[2 * kSyrkKC * kSyrkLd];
   const int f = fronts[blockIdx.z];
   const int k = sn_k[f], r = sn_r[f];
   double* P = Lbuf + L_off[f];
@@ -171,14 +182,13 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
   int64_t ldc;
   int nrows, ncols, K;
   if (mode == 0) {
-    if (k <= kb + 32) return;
-    const int rb = kb + 32;
-    A = P + (int64_t)kb * r + rb;
-    C = P + (int64_t)rb * r + rb;
+    if (k <= ke) return;  // no pivot column right of the block
+    A = P + (int64_t)ka * r + ke;
+    C = P + (int64_t)ke * r + ke;
     ldc = r;
-    nrows = r - rb;
-    ncols = k - rb;
-    K = 32;
+    nrows = r - ke;
+    ncols = min(cend, k) - ke;
+    K = ke - ka;
   } else {
     const int u = r - k;
     if (u == 0) return;
@@ -198,23 +208,46 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int lr = lane >> 2, lk = lane & 3;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // stage 16 columns of the two row blocks (coalesced along rows)
-    for (int e = tid; e < 16 * 64; e += 128) {
+  // Two-stage software pipeline: the next K-chunk of both row blocks is copied global -> shared
+  // asynchronously (cp.async, zero-filled outside the matrix) while the tensor cores work on
+  // the current one.
+  auto stage_load = [&](int st, int k0) {
+    double* as = As + st * (kSyrkKC * kSyrkLd);
+    double* bs = Bs + st * (kSyrkKC * kSyrkLd);
+    for (int e = tid; e < kSyrkKC * 64; e += 128) {
       const int t = e >> 6, i = e & 63;
       const int gi = ti * 64 + i, gj = tj * 64 + i;
       const bool kin = (k0 + t) < K;
-      As[t * kSyrkLd + i] = (kin && gi < nrows) ? A[(int64_t)(k0 + t) * r + gi] : 0.0;
-      Bs[t * kSyrkLd + i] = (kin && gj < nrows) ? A[(int64_t)(k0 + t) * r + gj] : 0.0;
+      const bool ia = kin && gi < nrows, ib = kin && gj < nrows;
+      const double* sa = ia ? A + (int64_t)(k0 + t) * r + gi : A;
+      const double* sb = ib ? A + (int64_t)(k0 + t) * r + gj : A;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(as + t * kSyrkLd + i)), "l"(sa),
+                   "r"(ia ? 8 : 0));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(bs + t * kSyrkLd + i)), "l"(sb),
+                   "r"(ib ? 8 : 0));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nchunks = (K + kSyrkKC - 1) / kSyrkKC;
+  stage_load(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c + 1 < nchunks) {
+      stage_load(st ^ 1, (c + 1) * kSyrkKC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const double* as = As + st * (kSyrkKC * kSyrkLd);
+    const double* bs = Bs + st * (kSyrkKC * kSyrkLd);
 #pragma unroll
-    for (int kk = 0; kk < 16; kk += 4) {
+    for (int kk = 0; kk < kSyrkKC; kk += 4) {
       double a[4], b[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        a[q] = As[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
-        b[q] = Bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
+        a[q] = as[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
+        b[q] = bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p)
@@ -326,6 +359,115 @@ __global__ void __launch_bounds__(256) chol_backward_kernel(const int* __restric
   for (int i = tid; i < k; i += 256) y[c0 + i] = w[i];
 }
 
+// ---- big fronts: one launch per 32-column block step, many CTAs per front -------------------
+// A front with thousands of rows cannot be swept by one CTA at memory speed; for those the work
+// vector lives in global memory (Wbuf) and every block step is a grid-wide launch: all CTAs
+// recompute the 32-entry block solution through the inverted diagonal block, each updates its own
+// 256 rows (forward) or 256 earlier pivots (backward).
+constexpr int kBigFront = 1536;
+
+__global__ void __launch_bounds__(256) chol_fwd_gather_kernel(const int* __restrict__ fronts, const int* __restrict__ sn_k,
+                                                              const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                              const int64_t* __restrict__ W_off, const int* __restrict__ child_ptr,
+                                                              const int* __restrict__ child_idx, const int64_t* __restrict__ rel_ptr,
+                                                              const int* __restrict__ rel_idx, double* __restrict__ Wbuf,
+                                                              const double* __restrict__ y) {
+  const int f = fronts[blockIdx.x];
+  const int k = sn_k[f], r = sn_r[f], c0 = col0[f];
+  double* w = Wbuf + W_off[f];
+  for (int i = threadIdx.x; i < r; i += 256) w[i] = i < k ? y[c0 + i] : 0.0;
+  __syncthreads();
+  for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {  // fixed child order: deterministic
+    const int c = child_idx[ci];
+    const int ck = sn_k[c], cu = sn_r[c] - ck;
+    const double* tail = Wbuf + W_off[c] + ck;
+    const int* rel = rel_idx + rel_ptr[c];
+    for (int t = threadIdx.x; t < cu; t += 256) w[rel[t]] += tail[t];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) chol_fwd_step_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
+                                                            const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                            const int64_t* __restrict__ L_off, const int64_t* __restrict__ W_off,
+                                                            const int64_t* __restrict__ dinv_off, const double* __restrict__ Lbuf,
+                                                            const double* __restrict__ Dinv, double* __restrict__ Wbuf, double* __restrict__ y) {
+  __shared__ double yb[32];
+  const int f = fronts[blockIdx.y];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  const int row0 = kb + nb + blockIdx.x * 256;
+  if (row0 >= r && blockIdx.x > 0) return;
+  double* w = Wbuf + W_off[f];
+  const double* Di = Dinv + dinv_off[f] + (int64_t)(kb >> 5) * 1024;
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int t = 0; t < nb; ++t) s += Di[t * 32 + threadIdx.x] * w[kb + t];
+    yb[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < nb) y[col0[f] + kb + threadIdx.x] = yb[threadIdx.x];
+  const int i = row0 + threadIdx.x;
+  if (i < r) {
+    const double* P = Lbuf + L_off[f];
+    double s = w[i];
+    for (int t = 0; t < nb; ++t) s -= P[(int64_t)(kb + t) * r + i] * yb[t];
+    w[i] = s;
+  }
+}
+
+// w_piv = y_piv - L21^T x_struct : one warp per pivot column
+__global__ void __launch_bounds__(256) chol_bwd_tail_kernel(const int* __restrict__ fronts, const int* __restrict__ sn_k,
+                                                            const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                            const int64_t* __restrict__ L_off, const int64_t* __restrict__ W_off,
+                                                            const int64_t* __restrict__ struct_ptr, const int* __restrict__ struct_idx,
+                                                            const double* __restrict__ Lbuf, double* __restrict__ Wbuf,
+                                                            const double* __restrict__ y) {
+  const int f = fronts[blockIdx.y];
+  const int k = sn_k[f], r = sn_r[f];
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= k) return;
+  const int* st = struct_idx + struct_ptr[f];
+  const double* col = Lbuf + L_off[f] + (int64_t)j * r;
+  double s = 0.0;
+  for (int i = k + lane; i < r; i += 32) s += col[i] * y[st[i - k]];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) Wbuf[W_off[f] + j] = y[col0[f] + j] - s;
+}
+
+__global__ void __launch_bounds__(256) chol_bwd_step_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
+                                                            const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                            const int64_t* __restrict__ L_off, const int64_t* __restrict__ W_off,
+                                                            const int64_t* __restrict__ dinv_off, const double* __restrict__ Lbuf,
+                                                            const double* __restrict__ Dinv, double* __restrict__ Wbuf, double* __restrict__ y) {
+  __shared__ double xb[32];
+  const int f = fronts[blockIdx.y];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= kb && blockIdx.x > 0) return;
+  double* w = Wbuf + W_off[f];
+  const double* Di = Dinv + dinv_off[f] + (int64_t)(kb >> 5) * 1024;
+  if (threadIdx.x < 32) {  // x_blk = Dinv^T * w_blk
+    double s = 0.0;
+    for (int t = threadIdx.x; t < nb; ++t) s += Di[threadIdx.x * 32 + t] * w[kb + t];
+    xb[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < nb) y[col0[f] + kb + threadIdx.x] = xb[threadIdx.x];
+  if (j < kb) {  // earlier pivots: w_j -= sum_t L[kb+t, j] * x_t  (32 consecutive doubles of column j)
+    const double* col = Lbuf + L_off[f] + (int64_t)j * r + kb;
+    double s = w[j];
+    for (int t = 0; t < nb; ++t) s -= col[t] * xb[t];
+    w[j] = s;
+  }
+}
+
 __global__ void chol_permute_kernel(const double* __restrict__ in, const int* __restrict__ perm, double* __restrict__ out, int n, int dir) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -430,25 +572,35 @@ spb_status chol_factorize(spb_context* h) {
     }
     for (const CholDevice::Group& G : D->groups[l]) {
       const int* list = D->level_sn.p + G.begin;
-      for (int kb = 0; kb < G.max_k; kb += 32) {
-        chol_potrf32_kernel<<<G.count, 1024, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p,
-                                                      D->fail.p);
-        ++nl;
-        const int rows = G.max_r - kb - 1;
-        if (rows > 0) {
-          chol_trsm_kernel<<<dim3((rows + 127) / 128, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->Lbuf.p);
+      constexpr int kPanel = 256;
+      for (int ob = 0; ob < G.max_k; ob += kPanel) {
+        const int oe = ob + kPanel;
+        for (int kb = ob; kb < std::min(oe, G.max_k); kb += 32) {
+          chol_potrf32_kernel<<<G.count, 1024, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p,
+                                                        D->fail.p);
           ++nl;
+          const int rows = G.max_r - kb - 1;
+          if (rows > 0) {
+            chol_trsm_kernel<<<dim3((rows + 127) / 128, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->Lbuf.p);
+            ++nl;
+          }
+          if (kb + 32 < std::min(oe, G.max_k)) {  // narrow update, confined to the panel's columns
+            const int nti = (G.max_r - kb - 32 + 63) / 64, ntj = (std::min(oe, G.max_k) - kb - 32 + 63) / 64;
+            chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, kb, kb + 32, oe, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
+                                                                    D->Lbuf.p, D->Ubuf.p);
+            ++nl;
+          }
         }
-        if (kb + 32 < G.max_k) {
-          const int nti = (G.max_r - kb - 32 + 63) / 64, ntj = (G.max_k - kb - 32 + 63) / 64;
-          chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
-                                                                  D->Lbuf.p, D->Ubuf.p);
+        if (oe < G.max_k) {  // everything right of the panel, once, with K = 256
+          const int nti = (G.max_r - oe + 63) / 64, ntj = (G.max_k - oe + 63) / 64;
+          chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, ob, oe, 0x7fffffff, D->sn_k.p, D->sn_r.p, D->L_off.p,
+                                                                  D->U_off.p, D->Lbuf.p, D->Ubuf.p);
           ++nl;
         }
       }
       const int umax = G.max_r;  // upper bound on u inside the group
       const int nt = (umax + 63) / 64;
-      chol_syrk_kernel<<<dim3(nt, nt, G.count), 128, 0, st>>>(list, 1, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
+      chol_syrk_kernel<<<dim3(nt, nt, G.count), 128, 0, st>>>(list, 1, 0, 0, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
                                                              D->Ubuf.p);
       ++nl;
     }
@@ -481,6 +633,20 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
   }
   for (int l = 0; l < C.nlevels; ++l) {
     for (const CholDevice::Group& G : D->groups[l]) {
+      const int* list = D->level_sn.p + G.begin;
+      if (G.max_r > kBigFront) {
+        chol_fwd_gather_kernel<<<G.count, 256, 0, st>>>(list, D->sn_k.p, D->sn_r.p, D->col0.p, D->W_off.p, D->child_ptr.p, D->child_idx.p,
+                                                        D->rel_ptr.p, D->rel_idx.p, D->Wbuf.p, D->ywork.p);
+        ++nl;
+        for (int kb = 0; kb < G.max_k; kb += 32) {
+          const int rows = std::max(1, G.max_r - kb - 1);
+          chol_fwd_step_kernel<<<dim3((rows + 255) / 256, G.count), 256, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p,
+                                                                                D->W_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p, D->Wbuf.p,
+                                                                                D->ywork.p);
+          ++nl;
+        }
+        continue;
+      }
       const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);
       chol_forward_kernel<<<G.count, 256, sm, st>>>(D->level_sn.p + G.begin, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
                                                     D->dinv_off.p, D->child_ptr.p, D->child_idx.p, D->rel_ptr.p, D->rel_idx.p, D->Lbuf.p,
@@ -490,6 +656,20 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
   }
   for (int l = C.nlevels - 1; l >= 0; --l) {
     for (const CholDevice::Group& G : D->groups[l]) {
+      const int* list = D->level_sn.p + G.begin;
+      if (G.max_r > kBigFront) {
+        chol_bwd_tail_kernel<<<dim3((G.max_k + 7) / 8, G.count), 256, 0, st>>>(list, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
+                                                                              D->struct_ptr.p, D->struct_idx.p, D->Lbuf.p, D->Wbuf.p,
+                                                                              D->ywork.p);
+        ++nl;
+        for (int kb = ((G.max_k - 1) / 32) * 32; kb >= 0; kb -= 32) {
+          chol_bwd_step_kernel<<<dim3(std::max(1, (kb + 255) / 256), G.count), 256, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->col0.p,
+                                                                                           D->L_off.p, D->W_off.p, D->dinv_off.p, D->Lbuf.p,
+                                                                                           D->Dinv.p, D->Wbuf.p, D->ywork.p);
+          ++nl;
+        }
+        continue;
+      }
       const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);
       chol_backward_kernel<<<G.count, 256, sm, st>>>(D->level_sn.p + G.begin, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->dinv_off.p,
                                                      D->struct_ptr.p, D->struct_idx.p, D->Lbuf.p, D->Dinv.p, D->ywork.p);

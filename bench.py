@@ -88,6 +88,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ncu --set full capture of pcg_persistent_kernel on LF-1M (profiles/r1b_ncu_raw_metrics.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum = 25.06 GB + 0.34 GB for the 96-iteration solve of the
+# third LM iteration (6.458 ms) = 264.6 MB per PCG iteration: the 10-byte/entry H stream (FP64 value +
+# 16-bit column delta, 26.2 M padded entries); the PCG vectors never leave the 126 MB L2.
+NCU_DRAM_BYTES_PER_PCG_ITERATION = 25.394e9 / 96.0
+
+
 def lf_sizes(g):
     n = g * g
     return n, 2 * n, 16 * n
@@ -221,8 +228,11 @@ def run_ours(args):
     achieved = k_bytes_total / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     asm_ms, asm_launches = stages["assembly"]
     b_asm = 12 * nnzJ + 4 * (m + 1) + 8 * m + 8 * nnzH + 16 * n
+    # DRAM bytes per launch from the committed ncu --set full capture (profiles/): per PCG iteration
+    # dram__bytes_read+write, scaled by this launch's iteration count; only valid for the g=1024 workload
+    traffic = NCU_DRAM_BYTES_PER_PCG_ITERATION * max(1, lin_iters) / max(1, k_launches) if (fused_ms > 0 and g == 1024) else None
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
             "bytes_per_launch": k_bytes_total / max(1, k_launches), "avg_launch_us": 1e3 * k_ms / max(1, k_launches),
             "launches_timed": int(k_launches), "pcg_iterations_timed": lin_iters, "us_per_pcg_iteration": 1e3 * k_ms / max(1, lin_iters),
             "share_of_step": k_ms / total_ms,
@@ -258,6 +268,29 @@ def run_ours(args):
     ms_e2e = timed(lambda: e2e_steps(K))
     e2e_val = world * K / (ms_e2e * 1e-3)
 
+    # ---- the direct path (supernodal Cholesky) on the same system, for the record (N=1 only) --
+    direct = None
+    if rank == 0 and world == 1 and not args.no_direct:
+        h.set_solver(spb.SOLVER_CHOLESKY)
+        h.assemble(Jn, En, 0.01)
+        h.factorize()  # includes the one-time symbolic phase (ordering, supernodes, maps)
+        h.solve(None, out=dn_)
+        h.stage_reset(True)
+        reps = 3
+        for _ in range(reps):
+            h.assemble(Jn, En, 0.01)
+            h.factorize()
+            h.solve(None, out=dn_)
+        st2 = h.stage_ms()
+        h.stage_reset(False)
+        info = h.factor_info()
+        direct = {"factor_ms": st2["factor"][0] / reps, "solve_ms": st2["trisolve"][0] / reps, "nnzL": info["nnzL"], "flops": info["flops"],
+                  "factor_tflops_fp64": info["flops"] / (st2["factor"][0] / reps * 1e-3) / 1e12, "supernodes": info["nsuper"],
+                  "tree_levels": info["nlevels"],
+                  "note": "multifrontal LL^T, nested-dissection order; SYRK/GEMM on FP64 tensor cores (DMMA); LM steps/s with this "
+                          "solver = 1000/(assembly+factor+solve ms)"}
+        h.set_solver(spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -275,7 +308,7 @@ def run_ours(args):
                            "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s},
                 "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "direct_solver": direct}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -290,6 +323,7 @@ def main():
     ap.add_argument("--g", type=int, default=1024)
     ap.add_argument("--pcg-rtol", type=float, default=1e-13)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-direct", action="store_true", help="skip the supernodal-Cholesky timing block")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -157,3 +157,36 @@ def test_call_order_errors(spb):
     with pytest.raises(spb.SpbError):
         h.assemble(np.zeros(3), np.zeros(3), 0.01)
     h.close()
+
+
+def test_degenerate_shapes(spb, orc):
+    # structurally empty Jacobian: H is the (zero) structural diagonal, the gradient is zero, and the
+    # factorisation reports failure like the reference's LLT on a singular matrix (quirk F)
+    for m, n in [(5, 3), (0, 4), (1, 1)]:
+        h = spb.Handle(0)
+        colptr = np.zeros(n + 1, np.int32)
+        rowidx = np.zeros(0, np.int32)
+        h.analyze(m, n, colptr, rowidx)
+        foo = h.assemble(np.zeros(0), np.zeros(m), 0.01)
+        assert foo == 0.0
+        cp, ri = h.h_pattern()
+        assert (cp == np.arange(n + 1)).all() and (ri == np.arange(n)).all()
+        assert (h.h_values() == 0).all() and (h.rhs() == 0).all()
+        for solver in (spb.SOLVER_CHOLESKY, spb.SOLVER_PCG_JACOBI):
+            h.set_solver(solver)
+            ok = h.factorize()
+            st = spb.capi.SPB_NOT_SPD if not ok else h.solve()[2]
+            assert st == spb.capi.SPB_NOT_SPD or (solver == spb.SOLVER_PCG_JACOBI and st == 0)  # PCG with rhs == 0 has nothing to iterate
+        h.close()
+
+
+def test_single_dense_row_and_single_column(handle, orc):
+    rng = np.random.default_rng(23)
+    # one residual row touching every unknown: H is dense rank-1 + damping
+    n = 40
+    colptr = np.arange(n + 1, dtype=np.int32)
+    rowidx = np.zeros(n, np.int32)
+    _check(handle, orc, 1, n, colptr, rowidx, rng.standard_normal(n), rng.standard_normal(1), 0.3)
+    # one unknown, many residuals: H is 1 x 1
+    m = 500
+    _check(handle, orc, m, 1, np.array([0, m], np.int32), np.arange(m, dtype=np.int32), rng.standard_normal(m), rng.standard_normal(m), 0.01)

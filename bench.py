@@ -163,9 +163,10 @@ def run_ours(args):
     n, m, nnzJ = lf_sizes(g)
     stream = torch.cuda.current_stream().cuda_stream
     h = spb.Handle(local, stream)
-    h.set_solver(spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+    solver_id = spb.SOLVER_PCG_IC0 if args.solver == "pcg_ic0" else spb.SOLVER_PCG_JACOBI
+    h.set_solver(solver_id, args.pcg_rtol, 10000)
     prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211 + rank)
-    ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+    ls = spb.B200SolverWrapper(h, solver_id, args.pcg_rtol, 10000)
     lm = spb.LMSolver()
     lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
     x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -289,7 +290,7 @@ def run_ours(args):
                   "tree_levels": info["nlevels"],
                   "note": "multifrontal LL^T, nested-dissection order; SYRK/GEMM on FP64 tensor cores (DMMA); LM steps/s with this "
                           "solver = 1000/(assembly+factor+solve ms)"}
-        h.set_solver(spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+        h.set_solver(solver_id, args.pcg_rtol, 10000)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------
     cpu = None
@@ -303,7 +304,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "benchmark/linear_function LF-1M (C2): g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (g, n, m, nnzJ, nnzH),
-                           "per_gpu": "one independent problem per GPU (seed 20211+rank)", "solver": "pcg_jacobi rtol=%g" % args.pcg_rtol,
+                           "per_gpu": "one independent problem per GPU (seed 20211+rank)", "solver": "%s rtol=%g" % (args.solver, args.pcg_rtol),
                            "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
                            "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s},
                 "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--g", type=int, default=1024)
     ap.add_argument("--pcg-rtol", type=float, default=1e-13)
+    ap.add_argument("--solver", default="pcg_jacobi", choices=["pcg_jacobi", "pcg_ic0"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the supernodal-Cholesky timing block")
     args = ap.parse_args()

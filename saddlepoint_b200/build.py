@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsaddlepoint_b200.so")
-SOURCES = ["context.cu", "assembly.cu", "pcg.cu", "lm.cu", "problems.cu", "cholesky.cu", "dist.cu", "symbolic.cpp", "symbolic_api.cpp", "chol_symbolic.cpp"]
+SOURCES = ["context.cu", "assembly.cu", "pcg.cu", "lm.cu", "problems.cu", "cholesky.cu", "dist.cu", "symbolic.cpp", "symbolic_api.cpp", "chol_symbolic.cpp", "ic0_symbolic.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 

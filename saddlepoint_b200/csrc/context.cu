@@ -134,6 +134,7 @@ spb_status spb_destroy(spb_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   chol_release(h);
+  ic0_release(h);
   lm_release(h);
   dist_release(h);
   for (auto& p : h->timing.pending) {
@@ -152,10 +153,6 @@ const char* spb_last_error(spb_handle h) { return h ? h->err.c_str() : "null han
 
 spb_status spb_set_solver(spb_handle h, int solver, double pcg_rtol, int pcg_maxit) {
   if (!h || solver < 0 || solver > 2) return SPB_ERR_ARG;
-  if (solver == SPB_SOLVER_PCG_IC0) {  // fail loudly rather than silently running Jacobi
-    h->err = "SPB_SOLVER_PCG_IC0 is not implemented in this build (use PCG_JACOBI or CHOLESKY)";
-    return SPB_ERR_ARG;
-  }
   h->solver = solver;
   if (pcg_rtol > 0) h->pcg_rtol = pcg_rtol;
   if (pcg_maxit > 0) h->pcg_maxit = pcg_maxit;
@@ -178,6 +175,7 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
     h->pcg_last_iters = 0;
     chol_release(h);
+    ic0_release(h);
     h->m = m;
     h->n = n;
     h->nnzJ = colptr[n];
@@ -282,6 +280,7 @@ spb_status spb_set_matrix(spb_handle h, int32_t n, const int32_t* colptr, const 
       // new explicit pattern: must be structurally symmetric with a full diagonal
       h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
       chol_release(h);
+      ic0_release(h);
       h->n = n;
       h->m = 0;
       h->nnzJ = 0;
@@ -323,6 +322,7 @@ spb_status spb_factorize(spb_handle h) {
     SPB_CUDA(cudaSetDevice(h->device));
     spb_status s = SPB_OK;
     if (h->solver == SPB_SOLVER_CHOLESKY) s = chol_factorize(h);
+    else if (h->solver == SPB_SOLVER_PCG_IC0) s = ic0_factorize(h);
     // PCG: the Jacobi diagonal is a by-product of assembly; "factorisation" is its inverse.
     else dev_invert_diag(h);
     if (s == SPB_OK) h->factor_valid = true;
@@ -352,7 +352,9 @@ spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int m
         dx = h->d_x.p;
       }
       int it = 0;
-      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx) : (h->nranks > 1 ? pcg_solve_dist(h, db, dx, &it) : pcg_solve(h, db, dx, &it));
+      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx)
+                     : h->solver == SPB_SOLVER_PCG_IC0 ? pcg_ic0_solve(h, db, dx, &it)
+                     : (h->nranks > 1 ? pcg_solve_dist(h, db, dx, &it) : pcg_solve(h, db, dx, &it));
       total_iters += it;
       if (s != SPB_OK && worst == SPB_OK) worst = s;
       if (mem == SPB_HOST) {

@@ -174,6 +174,7 @@ spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
     h->pcg_last_iters = 0;
     chol_release(h);
+    ic0_release(h);
     // H pattern from the GLOBAL Jacobian (identical on every rank, so the partial H arrays align)
     build_h_pattern(m, n, colptr, rowidx, h->H);
     build_sell(h->H, h->S);

@@ -1,0 +1,30 @@
+// ic0.h -- multicolour IC(0) preconditioner: host symbolic data and the device state.
+#pragma once
+#include "spb_internal.h"
+
+namespace spb {
+
+struct Ic0Symbolic {
+  int n = 0, ncolors = 0;
+  std::vector<int> perm;        // perm[new] = old, rows grouped by colour
+  std::vector<int> color_ptr;   // ncolors+1: row ranges (new numbering) of every colour
+  std::vector<int> Lptr, Lcol;  // strict lower triangle of the permuted H, CSR, ascending columns
+  std::vector<int64_t> a_pos;   // H storage position of every strict-lower entry
+  std::vector<int64_t> a_diag;  // H storage position of every diagonal entry
+  std::vector<int> Uptr, Ucol;  // U = L^T (strict), CSR
+  std::vector<int> u_from;      // U slot -> L slot
+};
+
+void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I);
+
+struct Ic0Device {
+  int n = 0, ncolors = 0;
+  int64_t nz = 0;
+  DevBuf<int> perm, color_ptr, Lptr, Lcol, Uptr, Ucol, u_from;
+  DevBuf<int64_t> a_pos, a_diag;
+  DevBuf<double> Lval, Uval, invd, y, zc, z;
+  DevBuf<int> flags;  // [0]: number of pivots that had to fall back to the unmodified diagonal
+  int breakdowns = 0;
+};
+
+}  // namespace spb

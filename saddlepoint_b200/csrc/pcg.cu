@@ -22,6 +22,7 @@
 
 #include <cooperative_groups.h>
 
+#include "ic0.h"
 #include "spb_internal.h"
 
 namespace cg = cooperative_groups;
@@ -625,6 +626,331 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     batch = 8;
     if (launched >= h->pcg_maxit + 64) break;  // cannot happen: done is set at maxit
   }
+  h->pcg_last_iters = h->h_sc->iters;
+  if (iters) *iters = h->h_sc->iters;
+  if (h->h_sc->breakdown) return SPB_NOT_SPD;
+  if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
+  return SPB_OK;
+}
+
+// ---- multicolour IC(0)-preconditioned CG ------------------------------------------------------
+// M = L L^T with L the incomplete Cholesky factor (pattern of tril(H)) in a multicolour ordering
+// (ic0_symbolic.cpp): the numeric factorisation and both triangular solves are `ncolors`
+// parallel phases separated by grid-wide barriers, all inside cooperative kernels.  The whole
+// PCG solve is again one persistent launch.
+struct IcView {
+  const int* perm;
+  const int* color_ptr;
+  const int* Lptr;
+  const int* Lcol;
+  const int* Uptr;
+  const int* Ucol;
+  const int* u_from;
+  const int64_t* a_pos;
+  const int64_t* a_diag;
+  double* Lval;
+  double* Uval;
+  double* invd;
+  double* y;
+  double* zc;
+  int n, ncolors;
+  int64_t nz;
+};
+
+__global__ void __launch_bounds__(256) ic0_factor_kernel(IcView V, const double* __restrict__ hval, int* __restrict__ flags) {
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
+  for (int c = 0; c < V.ncolors; ++c) {
+    const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
+    for (int i = r0 + gtid; i < r1; i += gstride) {
+      const int s = V.Lptr[i], e = V.Lptr[i + 1];
+      for (int p = s; p < e; ++p) {
+        const int j = V.Lcol[p];
+        double acc = hval[V.a_pos[p]];
+        int a = s, b = V.Lptr[j];
+        const int eb = V.Lptr[j + 1];
+        while (a < p && b < eb) {  // sparse dot of the finished parts of rows i and j
+          const int ca = V.Lcol[a], cb = V.Lcol[b];
+          if (ca == cb) {
+            acc -= V.Lval[a] * V.Lval[b];
+            ++a;
+            ++b;
+          } else if (ca < cb) {
+            ++a;
+          } else {
+            ++b;
+          }
+        }
+        V.Lval[p] = acc * V.invd[j];
+      }
+      const double d = hval[V.a_diag[i]];
+      double ds = d;
+      for (int p = s; p < e; ++p) ds -= V.Lval[p] * V.Lval[p];
+      if (!(ds > 0.0)) {  // IC(0) breakdown on a non-M-matrix: keep the unmodified diagonal for this row
+        ds = d;
+        atomicAdd(flags, 1);
+      }
+      V.invd[i] = 1.0 / sqrt(ds);
+    }
+    grid.sync();
+  }
+  for (int64_t t = gtid; t < V.nz; t += gstride) V.Uval[t] = V.Lval[V.u_from[t]];
+}
+
+// z = P^T (L L^T)^-1 P r ; every phase ends with a grid barrier
+__device__ __forceinline__ void ic0_apply(cg::grid_group& grid, const IcView& V, const double* r, double* z) {
+  const int gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
+  for (int c = 0; c < V.ncolors; ++c) {
+    const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
+    for (int i = r0 + gtid; i < r1; i += gstride) {
+      double s = r[V.perm[i]];
+      for (int p = V.Lptr[i]; p < V.Lptr[i + 1]; ++p) s -= __ldcs(V.Lval + p) * V.y[__ldcs(V.Lcol + p)];
+      V.y[i] = s * V.invd[i];
+    }
+    grid.sync();
+  }
+  for (int c = V.ncolors - 1; c >= 0; --c) {
+    const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
+    for (int i = r0 + gtid; i < r1; i += gstride) {
+      double s = V.y[i];
+      for (int p = V.Uptr[i]; p < V.Uptr[i + 1]; ++p) s -= __ldcs(V.Uval + p) * V.zc[__ldcs(V.Ucol + p)];
+      const double v = s * V.invd[i];
+      V.zc[i] = v;
+      z[V.perm[i]] = v;
+    }
+    grid.sync();
+  }
+}
+
+struct IcPcgParams {
+  PcgParams pc;
+  IcView ic;
+  double* z;
+};
+
+__global__ void __launch_bounds__(256, 4) pcg_ic0_persistent_kernel(IcPcgParams Q) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[8];
+  __shared__ double bc;
+  const PcgParams& P = Q.pc;
+  const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
+  const int n = P.n;
+  const int stride = G * 256;
+  double* partA = P.partial;
+  double* partB = P.partial + G;
+  double* partC = P.partial + 2 * G;
+  const int s_begin = (int)(((int64_t)P.nslices * blk) / G);
+  const int s_end = (int)(((int64_t)P.nslices * (blk + 1)) / G);
+  {  // r = b, x = 0, bb
+    double bb = 0.0;
+    for (int i = blk * 256 + tid; i < n; i += stride) {
+      const double bi = P.b[i];
+      P.x[i] = 0.0;
+      P.r[i] = bi;
+      bb = fma(bi, bi, bb);
+    }
+    const double s2 = block_sum_256(bb, sm);
+    if (tid == 0) partC[blk] = s2;
+  }
+  grid.sync();
+  const double bb = block_total(partC, G, sm, &bc);
+  const double thresh = P.rtol * P.rtol * bb;
+  double rr = bb, pq = 0.0, rz = 0.0;
+  int iters = 0, breakdown = 0;
+  bool run = (bb > thresh) && P.maxit > 0;
+  if (run) {
+    ic0_apply(grid, Q.ic, P.r, Q.z);
+    double a1 = 0.0;
+    for (int i = blk * 256 + tid; i < n; i += stride) {
+      const double zi = Q.z[i];
+      P.p[i] = zi;
+      a1 = fma(P.r[i], zi, a1);
+    }
+    const double s1 = block_sum_256(a1, sm);
+    if (tid == 0) partB[blk] = s1;
+    grid.sync();
+    rz = block_total(partB, G, sm, &bc);
+    grid.sync();
+  }
+  while (run) {
+    {  // q = H p, p.q
+      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, 0, P.col16, P.s16);
+      const double bs = block_sum_256(loc, sm);
+      if (tid == 0) partA[blk] = bs;
+    }
+    grid.sync();
+    pq = block_total(partA, G, sm, &bc);
+    if (!(pq > 0.0)) {
+      breakdown = 1;
+      break;
+    }
+    const double alpha = rz / pq;
+    {  // x += alpha p, r -= alpha q, r.r
+      double a2 = 0.0;
+      for (int i = blk * 256 + tid; i < n; i += stride) {
+        P.x[i] = fma(alpha, P.p[i], P.x[i]);
+        const double ri = fma(-alpha, P.q[i], P.r[i]);
+        P.r[i] = ri;
+        a2 = fma(ri, ri, a2);
+      }
+      const double s2 = block_sum_256(a2, sm);
+      if (tid == 0) partC[blk] = s2;
+    }
+    grid.sync();
+    rr = block_total(partC, G, sm, &bc);
+    ++iters;
+    if (!(rr > thresh) || iters >= P.maxit) break;
+    ic0_apply(grid, Q.ic, P.r, Q.z);
+    {  // r.z
+      double a1 = 0.0;
+      for (int i = blk * 256 + tid; i < n; i += stride) a1 = fma(P.r[i], Q.z[i], a1);
+      const double s1 = block_sum_256(a1, sm);
+      if (tid == 0) partB[blk] = s1;
+    }
+    grid.sync();
+    const double rz_new = block_total(partB, G, sm, &bc);
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    for (int i = blk * 256 + tid; i < n; i += stride) P.p[i] = fma(beta, P.p[i], Q.z[i]);
+    grid.sync();
+  }
+  if (blk == 0 && tid == 0) {
+    PcgScalars* sc = P.sc;
+    sc->rz = rz;
+    sc->pq = pq;
+    sc->rr = rr;
+    sc->bb = bb;
+    sc->thresh = thresh;
+    sc->iters = iters;
+    sc->breakdown = breakdown;
+    sc->maxit = P.maxit;
+    sc->done = 1;
+  }
+}
+
+static IcView ic_view(Ic0Device* I) {
+  IcView V;
+  V.perm = I->perm.p;
+  V.color_ptr = I->color_ptr.p;
+  V.Lptr = I->Lptr.p;
+  V.Lcol = I->Lcol.p;
+  V.Uptr = I->Uptr.p;
+  V.Ucol = I->Ucol.p;
+  V.u_from = I->u_from.p;
+  V.a_pos = I->a_pos.p;
+  V.a_diag = I->a_diag.p;
+  V.Lval = I->Lval.p;
+  V.Uval = I->Uval.p;
+  V.invd = I->invd.p;
+  V.y = I->y.p;
+  V.zc = I->zc.p;
+  V.n = I->n;
+  V.ncolors = I->ncolors;
+  V.nz = I->nz;
+  return V;
+}
+
+static Ic0Device* ic0_ensure(spb_context* h) {
+  if (h->ic0) return (Ic0Device*)h->ic0;
+  Ic0Symbolic S;
+  ic0_symbolic(h->H, h->S, S);
+  Ic0Device* I = new Ic0Device;
+  h->ic0 = I;
+  cudaStream_t st = h->stream;
+  I->n = S.n;
+  I->ncolors = S.ncolors;
+  I->nz = (int64_t)S.Lcol.size();
+  SPB_CUDA(I->perm.upload(S.perm, st));
+  SPB_CUDA(I->color_ptr.upload(S.color_ptr, st));
+  SPB_CUDA(I->Lptr.upload(S.Lptr, st));
+  SPB_CUDA(I->Lcol.upload(S.Lcol, st));
+  SPB_CUDA(I->Uptr.upload(S.Uptr, st));
+  SPB_CUDA(I->Ucol.upload(S.Ucol, st));
+  SPB_CUDA(I->u_from.upload(S.u_from, st));
+  SPB_CUDA(I->a_pos.upload(S.a_pos, st));
+  SPB_CUDA(I->a_diag.upload(S.a_diag, st));
+  SPB_CUDA(I->Lval.alloc((size_t)std::max<int64_t>(1, I->nz)));
+  SPB_CUDA(I->Uval.alloc((size_t)std::max<int64_t>(1, I->nz)));
+  SPB_CUDA(I->invd.alloc(I->n));
+  SPB_CUDA(I->y.alloc(I->n));
+  SPB_CUDA(I->zc.alloc(I->n));
+  SPB_CUDA(I->z.alloc(I->n));
+  SPB_CUDA(I->flags.alloc(1));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  return I;
+}
+
+void ic0_release(spb_context* h) {
+  delete (Ic0Device*)h->ic0;
+  h->ic0 = nullptr;
+}
+
+spb_status ic0_factorize(spb_context* h) {
+  if (h->n == 0) return SPB_OK;
+  Ic0Device* I = ic0_ensure(h);
+  cudaStream_t st = h->stream;
+  int occ = 0;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ic0_factor_kernel, 256, 0));
+  const int G = std::max(1, std::min((h->n + 255) / 256, h->num_sms * std::max(1, occ)));
+  IcView V = ic_view(I);
+  const double* hv = h->d_hval.p;
+  int* fl = I->flags.p;
+  void* args[] = {&V, &hv, &fl};
+  SPB_CUDA(cudaMemsetAsync(I->flags.p, 0, sizeof(int), st));
+  stage_begin(h, ST_FACTOR);
+  SPB_CUDA(cudaLaunchCooperativeKernel((void*)ic0_factor_kernel, dim3(G), dim3(256), args, 0, st));
+  stage_end(h, ST_FACTOR, 1);
+  return SPB_OK;
+}
+
+spb_status pcg_ic0_solve(spb_context* h, const double* d_b, double* d_x, int* iters) {
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  if (iters) *iters = 0;
+  if (n == 0) return SPB_OK;
+  Ic0Device* I = (Ic0Device*)h->ic0;
+  if (!I) throw StateFail{"IC(0) solve without a factorisation"};
+  ensure_pcg_buffers(h);
+  SPB_CUDA(h->d_r.alloc(n));
+  SPB_CUDA(h->d_p.alloc(n));
+  SPB_CUDA(h->d_q.alloc(n));
+  const int nslices = (n + 31) / 32;
+  if (h->occ_ic == 0) {
+    int occ = 0;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_ic0_persistent_kernel, 256, 0));
+    h->occ_ic = std::max(1, occ);
+  }
+  const int G = std::max(1, std::min((nslices + 7) / 8, h->num_sms * h->occ_ic));
+  IcPcgParams Q;
+  PcgParams& P = Q.pc;
+  P.slice_off = h->d_slice_off.p;
+  P.col = h->d_sell_col.p;
+  P.col16 = h->pcg_col16 ? h->d_sell_col16.p : nullptr;
+  P.s16 = h->d_slice16.p;
+  P.rowlen = h->d_rowlen.p;
+  P.hval = h->d_hval.p;
+  P.b = d_b;
+  P.dinv = nullptr;
+  P.x = d_x;
+  P.r = h->d_r.p;
+  P.p = h->d_p.p;
+  P.q = h->d_q.p;
+  P.partial = h->d_partial.p;
+  P.sc = h->d_sc.p;
+  P.n = n;
+  P.nslices = nslices;
+  P.maxit = h->pcg_maxit;
+  P.rtol = h->pcg_rtol;
+  P.pin_fraction = 0.0;
+  Q.ic = ic_view(I);
+  Q.z = I->z.p;
+  void* args[] = {&Q};
+  stage_begin(h, ST_PCG);
+  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_ic0_persistent_kernel, dim3(G), dim3(256), args, 0, st));
+  stage_end(h, ST_PCG, 1);
+  SPB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaMemcpyAsync(&I->breakdowns, I->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
   h->pcg_last_iters = h->h_sc->iters;
   if (iters) *iters = h->h_sc->iters;
   if (h->h_sc->breakdown) return SPB_NOT_SPD;

@@ -250,6 +250,8 @@ struct spb_context {
   void* lm_ws = nullptr;  // spb::LmWorkspace*, owned (lm.cu)
   spb::Timing timing;
   void* chol = nullptr;  // spb::CholeskyState*, owned (cholesky.cu)
+  void* ic0 = nullptr;   // spb::Ic0Device*, owned (pcg.cu)
+  int occ_ic = 0;
 };
 
 namespace spb {
@@ -287,6 +289,11 @@ void dist_release(spb_context* h);
 spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* iters);
 // sum of squares of a vector whose entries are split across ranks (allreduce of the local sums)
 void dev_squared_norm_global(spb_context* h, const double* d_v, int64_t len, double* host_out);
+
+// pcg.cu: multicolour IC(0) preconditioner + IC(0)-PCG
+spb_status ic0_factorize(spb_context* h);
+spb_status pcg_ic0_solve(spb_context* h, const double* d_b, double* d_x, int* iters);
+void ic0_release(spb_context* h);
 
 // cholesky.cu
 spb_status chol_factorize(spb_context* h);

@@ -114,3 +114,68 @@ def test_not_spd_is_reported(spb):
     x, it, st = ls.handle.solve(np.array([1.0, -1.0, 0.5])) if ok else (None, 0, spb.capi.SPB_NOT_SPD)
     assert (not ok) or st == spb.capi.SPB_NOT_SPD
     ls.handle.close()
+
+
+@pytest.mark.parametrize("case", ["random", "lf", "rosenbrock", "dense"])
+def test_ic0_pcg_step_matches_llt_and_needs_fewer_iterations(spb, orc, case):
+    rng = np.random.default_rng(7)
+    if case == "random":
+        m, n = 6000, 2500
+        colptr, rowidx, vals = random_jacobian(rng, m, n, 5, cover_cols=True)
+    elif case == "lf":
+        J = orc.lf_matrix(48, 2, 20211)
+        colptr, rowidx, vals = J.csc()
+        m, n = J.shape
+    elif case == "rosenbrock":
+        nb = 200
+        m = n = 2 * nb
+        xx = rng.standard_normal(n) * 5
+        colptr = (2 * np.arange(n + 1)).astype(np.int32)
+        rowidx = (np.repeat(2 * np.arange(nb), 4) + np.tile([0, 1, 0, 1], nb)).astype(np.int32)
+        vals = np.empty(4 * nb)
+        vals[0::4] = -50.0 * xx[0::2]
+        vals[1::4] = -1.0
+        vals[2::4] = 25.0
+        vals[3::4] = 0.0
+    else:
+        m, n = 300, 40
+        A = rng.standard_normal((m, n))
+        import scipy.sparse as sps
+        S = sps.csc_matrix(A)
+        S.sort_indices()
+        colptr, rowidx, vals = S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data
+    E = rng.standard_normal(m)
+    h = spb.Handle(0)
+    h.analyze(m, n, colptr, rowidx)
+    h.assemble(vals, E, 0.01)
+    J = orc.from_csc(m, n, colptr, rowidx, vals)
+    D, _ = orc.damp_build(J, 0.01)
+    xref = orc.LLT(orc.ata(D), 1).solve(orc.jt_vec_neg(J, E))
+    h.set_solver(spb.SOLVER_PCG_JACOBI, 1e-13, 10000)
+    assert h.factorize()
+    xj, itj, stj = h.solve()
+    h.set_solver(spb.SOLVER_PCG_IC0, 1e-13, 10000)
+    assert h.factorize()
+    xi, iti, sti = h.solve()
+    assert sti == 0 and stj == 0
+    assert np.linalg.norm(xi - xref) <= STEP_RTOL * np.linalg.norm(xref)
+    assert iti <= itj  # a block-diagonal / dense H is solved (almost) exactly by IC(0)
+    if case in ("lf", "random"):
+        assert iti < 0.6 * itj
+    # deterministic
+    xi2, iti2, _ = h.solve()
+    assert iti2 == iti and (xi2 == xi).all()
+    h.close()
+
+
+def test_lm_with_ic0_matches_oracle(spb, orc):
+    h = spb.Handle(0)
+    prob = spb.BuiltinProblem(h, "lf", g=32, rows_mult=2, seed=20211)
+    ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_IC0)
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), 100)
+    ret = lm.solve(True)
+    ref = orc.lm_solve("lf", iparam0=32, iparam1=2, maxIterations=100)
+    assert ret == ref.ret and lm.currIter == ref.currIter and lm.exit_path == ref.exit_path
+    assert np.linalg.norm(lm.x - ref.x) <= 1e-10 * np.linalg.norm(ref.x)
+    h.close()

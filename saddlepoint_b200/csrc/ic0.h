@@ -13,6 +13,12 @@ struct Ic0Symbolic {
   std::vector<int64_t> a_diag;  // H storage position of every diagonal entry
   std::vector<int> Uptr, Ucol;  // U = L^T (strict), CSR
   std::vector<int> u_from;      // U slot -> L slot
+  // triangular-solve storage: sliced ELL (slice height 32) over the permuted rows, like H's SpMV layout
+  struct Sell {
+    std::vector<int64_t> slice_off;  // nslices+1
+    std::vector<int> col, rowlen;    // padded columns (padding: 0, never read thanks to rowlen), n
+    std::vector<int> pos_of_slot;    // CSR slot -> storage position
+  } Ls, Us;
 };
 
 void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I);
@@ -21,6 +27,9 @@ struct Ic0Device {
   int n = 0, ncolors = 0;
   int64_t nz = 0;
   DevBuf<int> perm, color_ptr, Lptr, Lcol, Uptr, Ucol, u_from;
+  DevBuf<int64_t> Ls_off, Us_off;
+  DevBuf<int> Ls_col, Ls_len, Ls_pos, Us_col, Us_len, Us_pos;
+  DevBuf<double> Ls_val, Us_val;
   DevBuf<int64_t> a_pos, a_diag;
   DevBuf<double> Lval, Uval, invd, y, zc, z;
   DevBuf<int> flags;  // [0]: number of pivots that had to fall back to the unmodified diagonal

@@ -84,6 +84,30 @@ void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I) {
         I.u_from[d] = t;
       }
   }
+  // sliced-ELL copies for the triangular solves (warp == 32 consecutive permuted rows)
+  auto build = [n](const std::vector<int>& ptr, const std::vector<int>& col, Ic0Symbolic::Sell& S) {
+    const int ns = (n + 31) / 32;
+    S.slice_off.assign((size_t)ns + 1, 0);
+    S.rowlen.resize(n);
+    for (int i = 0; i < n; ++i) S.rowlen[i] = ptr[(size_t)i + 1] - ptr[i];
+    for (int s = 0; s < ns; ++s) {
+      int w = 0;
+      for (int i = s * 32; i < std::min(n, s * 32 + 32); ++i) w = std::max(w, S.rowlen[i]);
+      S.slice_off[(size_t)s + 1] = S.slice_off[s] + (int64_t)w * 32;
+    }
+    S.col.assign((size_t)S.slice_off[ns], 0);
+    S.pos_of_slot.resize(col.size());
+    for (int i = 0; i < n; ++i) {
+      const int64_t base = S.slice_off[i >> 5] + (i & 31);
+      int k = 0;
+      for (int t = ptr[i]; t < ptr[(size_t)i + 1]; ++t, ++k) {
+        S.col[(size_t)(base + (int64_t)k * 32)] = col[t];
+        S.pos_of_slot[t] = (int)(base + (int64_t)k * 32);
+      }
+    }
+  };
+  build(I.Lptr, I.Lcol, I.Ls);
+  build(I.Uptr, I.Ucol, I.Us);
 }
 
 }  // namespace spb

@@ -644,12 +644,21 @@ struct IcView {
   const int* Lptr;
   const int* Lcol;
   const int* Uptr;
-  const int* Ucol;
   const int* u_from;
   const int64_t* a_pos;
   const int64_t* a_diag;
-  double* Lval;
-  double* Uval;
+  double* Lval;  // CSR values of the factor (row-contiguous: what the numeric factorisation wants)
+  // sliced-ELL copies of L and U = L^T (what the triangular solves want)
+  const int64_t* Ls_off;
+  const int* Ls_col;
+  const int* Ls_len;
+  const int* Ls_pos;
+  double* Ls_val;
+  const int64_t* Us_off;
+  const int* Us_col;
+  const int* Us_len;
+  const int* Us_pos;
+  double* Us_val;
   double* invd;
   double* y;
   double* zc;
@@ -657,67 +666,170 @@ struct IcView {
   int64_t nz;
 };
 
+// Numeric IC(0), colours ascending, ONE WARP PER ROW: the lanes hold the row's entries; for each
+// entry (i,j) in ascending j the lanes intersect the finished part of row i with row j (row j is
+// streamed through shuffles), a warp reduction gives the sparse dot, lane p keeps L_ij.  Rows
+// longer than 32 entries are walked by lane 0 (dense rows; rare).
 __global__ void __launch_bounds__(256) ic0_factor_kernel(IcView V, const double* __restrict__ hval, int* __restrict__ flags) {
   cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
   const int gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
   for (int c = 0; c < V.ncolors; ++c) {
     const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
-    for (int i = r0 + gtid; i < r1; i += gstride) {
-      const int s = V.Lptr[i], e = V.Lptr[i + 1];
-      for (int p = s; p < e; ++p) {
-        const int j = V.Lcol[p];
-        double acc = hval[V.a_pos[p]];
-        int a = s, b = V.Lptr[j];
-        const int eb = V.Lptr[j + 1];
-        while (a < p && b < eb) {  // sparse dot of the finished parts of rows i and j
-          const int ca = V.Lcol[a], cb = V.Lcol[b];
-          if (ca == cb) {
-            acc -= V.Lval[a] * V.Lval[b];
-            ++a;
-            ++b;
-          } else if (ca < cb) {
-            ++a;
-          } else {
-            ++b;
+    for (int i = r0 + gwarp; i < r1; i += nwarps) {
+      const int s = V.Lptr[i], ni = V.Lptr[i + 1] - s;
+      const double d = hval[V.a_diag[i]];
+      double ds;
+      if (ni <= 32) {
+        const int ci = lane < ni ? V.Lcol[s + lane] : -1;
+        double li = 0.0;                       // L(i, ci), final once its turn has passed
+        const double ai = lane < ni ? hval[V.a_pos[s + lane]] : 0.0;
+        // extents of every partner row in one round trip, then the partner rows are software
+        // pipelined: row j(p+1) is in flight while row j(p) is intersected
+        int bsl = 0, njl = 0;
+        double idl = 0.0;
+        if (lane < ni) {
+          bsl = V.Lptr[ci];
+          njl = V.Lptr[ci + 1] - bsl;
+          idl = V.invd[ci];
+        }
+        int bs = __shfl_sync(0xffffffffu, bsl, 0), nj = __shfl_sync(0xffffffffu, njl, 0);
+        int cb = lane < nj ? V.Lcol[bs + lane] : -2;
+        double vb = lane < nj ? V.Lval[bs + lane] : 0.0;
+        for (int p = 0; p < ni; ++p) {
+          int bs2 = 0, nj2 = 0, cb2 = -2;
+          double vb2 = 0.0;
+          if (p + 1 < ni) {
+            bs2 = __shfl_sync(0xffffffffu, bsl, p + 1);
+            nj2 = __shfl_sync(0xffffffffu, njl, p + 1);
+            cb2 = lane < nj2 ? V.Lcol[bs2 + lane] : -2;
+            vb2 = lane < nj2 ? V.Lval[bs2 + lane] : 0.0;
+          }
+          double contrib = 0.0;
+          for (int b0 = 0; b0 < nj; b0 += 32) {  // stream row j through the warp, 32 entries at a time
+            if (b0 > 0) {
+              cb = b0 + lane < nj ? V.Lcol[bs + b0 + lane] : -2;
+              vb = b0 + lane < nj ? V.Lval[bs + b0 + lane] : 0.0;
+            }
+            const int cnt = min(32, nj - b0);
+            for (int t = 0; t < cnt; ++t) {
+              const int cbt = __shfl_sync(0xffffffffu, cb, t);
+              const double vbt = __shfl_sync(0xffffffffu, vb, t);
+              if (lane < p && cbt == ci) contrib = fma(li, vbt, contrib);
+            }
+          }
+          contrib = warp_sum(contrib);
+          const double aij = __shfl_sync(0xffffffffu, ai, p);
+          const double idj = __shfl_sync(0xffffffffu, idl, p);
+          const double lij = (aij - contrib) * idj;
+          if (lane == p) li = lij;
+          bs = bs2;
+          nj = nj2;
+          cb = cb2;
+          vb = vb2;
+        }
+        if (lane < ni) V.Lval[s + lane] = li;
+        ds = d - warp_sum(li * li);
+      } else {
+        ds = d;
+        if (lane == 0) {
+          for (int p = s; p < s + ni; ++p) {
+            const int j = V.Lcol[p];
+            double acc = hval[V.a_pos[p]];
+            int a = s, b = V.Lptr[j];
+            const int eb = V.Lptr[j + 1];
+            while (a < p && b < eb) {
+              const int ca = V.Lcol[a], cb = V.Lcol[b];
+              if (ca == cb) {
+                acc -= V.Lval[a] * V.Lval[b];
+                ++a;
+                ++b;
+              } else if (ca < cb) {
+                ++a;
+              } else {
+                ++b;
+              }
+            }
+            V.Lval[p] = acc * V.invd[j];
+            ds -= V.Lval[p] * V.Lval[p];
           }
         }
-        V.Lval[p] = acc * V.invd[j];
+        ds = __shfl_sync(0xffffffffu, ds, 0);
       }
-      const double d = hval[V.a_diag[i]];
-      double ds = d;
-      for (int p = s; p < e; ++p) ds -= V.Lval[p] * V.Lval[p];
-      if (!(ds > 0.0)) {  // IC(0) breakdown on a non-M-matrix: keep the unmodified diagonal for this row
-        ds = d;
-        atomicAdd(flags, 1);
+      if (lane == 0) {
+        if (!(ds > 0.0)) {  // IC(0) breakdown on a non-M-matrix: keep the unmodified diagonal for this row
+          ds = d;
+          atomicAdd(flags, 1);
+        }
+        V.invd[i] = 1.0 / sqrt(ds);
       }
-      V.invd[i] = 1.0 / sqrt(ds);
     }
     grid.sync();
   }
-  for (int64_t t = gtid; t < V.nz; t += gstride) V.Uval[t] = V.Lval[V.u_from[t]];
+  // values into the triangular-solve layouts
+  for (int64_t t = gtid; t < V.nz; t += gstride) {
+    V.Ls_val[V.Ls_pos[t]] = V.Lval[t];
+    V.Us_val[V.Us_pos[t]] = V.Lval[V.u_from[t]];
+  }
 }
 
-// z = P^T (L L^T)^-1 P r ; every phase ends with a grid barrier
-__device__ __forceinline__ void ic0_apply(cg::grid_group& grid, const IcView& V, const double* r, double* z) {
-  const int gtid = blockIdx.x * 256 + threadIdx.x, gstride = gridDim.x * 256;
-  for (int c = 0; c < V.ncolors; ++c) {
-    const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
-    for (int i = r0 + gtid; i < r1; i += gstride) {
-      double s = r[V.perm[i]];
-      for (int p = V.Lptr[i]; p < V.Lptr[i + 1]; ++p) s -= __ldcs(V.Lval + p) * V.y[__ldcs(V.Lcol + p)];
-      V.y[i] = s * V.invd[i];
+// one colour phase of a triangular solve: warp == slice of 32 permuted rows, lane == row
+template <bool FORWARD>
+__device__ __forceinline__ void ic0_phase(const IcView& V, int r0, int r1, const double* r, double* z) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
+  const int64_t* soff = FORWARD ? V.Ls_off : V.Us_off;
+  const int* scol = FORWARD ? V.Ls_col : V.Us_col;
+  const int* slen = FORWARD ? V.Ls_len : V.Us_len;
+  const double* sval = FORWARD ? V.Ls_val : V.Us_val;
+  const double* src = FORWARD ? V.y : V.zc;  // solved entries of earlier phases
+  for (int slice = (r0 >> 5) + gwarp; slice <= ((r1 - 1) >> 5); slice += nwarps) {
+    const int i = slice * 32 + lane;
+    const bool mine = i >= r0 && i < r1;
+    const int64_t off = soff[slice];
+    const int len = mine ? slen[i] : 0;
+    const int width = __reduce_max_sync(0xffffffffu, len);
+    const int* cp = scol + off + lane;
+    const double* vp = sval + off + lane;
+    double s = 0.0;
+    int k = 0;
+    for (; k + 4 <= width; k += 4) {
+      const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32), c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
+      const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32), v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
+      if (k + 0 < len) s = fma(v0, src[c0], s);
+      if (k + 1 < len) s = fma(v1, src[c1], s);
+      if (k + 2 < len) s = fma(v2, src[c2], s);
+      if (k + 3 < len) s = fma(v3, src[c3], s);
     }
+    for (; k < width; ++k) {
+      const int c0 = __ldcs(cp + k * 32);
+      const double v0 = __ldcs(vp + k * 32);
+      if (k < len) s = fma(v0, src[c0], s);
+    }
+    if (mine) {
+      if (FORWARD) {
+        V.y[i] = (r[V.perm[i]] - s) * V.invd[i];
+      } else {
+        const double v = (V.y[i] - s) * V.invd[i];
+        V.zc[i] = v;
+        z[V.perm[i]] = v;
+      }
+    }
+  }
+}
+
+// z = P^T (L L^T)^-1 P r ; every colour phase ends with a grid barrier (1.6 us each on B200 at
+// 4 blocks/SM, scripts/micro/gridsync_bench.cu).  Measured and rejected: prefetching the next
+// phase's slice across the barrier, into L2 (no change) or into registers (slower: the register
+// cost halves the occupancy the SpMV phase needs).
+__device__ __forceinline__ void ic0_apply(cg::grid_group& grid, const IcView& V, const double* r, double* z) {
+  for (int c = 0; c < V.ncolors; ++c) {
+    ic0_phase<true>(V, V.color_ptr[c], V.color_ptr[c + 1], r, z);
     grid.sync();
   }
   for (int c = V.ncolors - 1; c >= 0; --c) {
-    const int r0 = V.color_ptr[c], r1 = V.color_ptr[c + 1];
-    for (int i = r0 + gtid; i < r1; i += gstride) {
-      double s = V.y[i];
-      for (int p = V.Uptr[i]; p < V.Uptr[i + 1]; ++p) s -= __ldcs(V.Uval + p) * V.zc[__ldcs(V.Ucol + p)];
-      const double v = s * V.invd[i];
-      V.zc[i] = v;
-      z[V.perm[i]] = v;
-    }
+    ic0_phase<false>(V, V.color_ptr[c], V.color_ptr[c + 1], r, z);
     grid.sync();
   }
 }
@@ -835,12 +947,20 @@ static IcView ic_view(Ic0Device* I) {
   V.Lptr = I->Lptr.p;
   V.Lcol = I->Lcol.p;
   V.Uptr = I->Uptr.p;
-  V.Ucol = I->Ucol.p;
   V.u_from = I->u_from.p;
   V.a_pos = I->a_pos.p;
   V.a_diag = I->a_diag.p;
   V.Lval = I->Lval.p;
-  V.Uval = I->Uval.p;
+  V.Ls_off = I->Ls_off.p;
+  V.Ls_col = I->Ls_col.p;
+  V.Ls_len = I->Ls_len.p;
+  V.Ls_pos = I->Ls_pos.p;
+  V.Ls_val = I->Ls_val.p;
+  V.Us_off = I->Us_off.p;
+  V.Us_col = I->Us_col.p;
+  V.Us_len = I->Us_len.p;
+  V.Us_pos = I->Us_pos.p;
+  V.Us_val = I->Us_val.p;
   V.invd = I->invd.p;
   V.y = I->y.p;
   V.zc = I->zc.p;
@@ -865,16 +985,28 @@ static Ic0Device* ic0_ensure(spb_context* h) {
   SPB_CUDA(I->Lptr.upload(S.Lptr, st));
   SPB_CUDA(I->Lcol.upload(S.Lcol, st));
   SPB_CUDA(I->Uptr.upload(S.Uptr, st));
-  SPB_CUDA(I->Ucol.upload(S.Ucol, st));
   SPB_CUDA(I->u_from.upload(S.u_from, st));
   SPB_CUDA(I->a_pos.upload(S.a_pos, st));
   SPB_CUDA(I->a_diag.upload(S.a_diag, st));
+  SPB_CUDA(I->Ls_off.upload(S.Ls.slice_off, st));
+  SPB_CUDA(I->Ls_col.upload(S.Ls.col, st));
+  SPB_CUDA(I->Ls_len.upload(S.Ls.rowlen, st));
+  SPB_CUDA(I->Ls_pos.upload(S.Ls.pos_of_slot, st));
+  SPB_CUDA(I->Us_off.upload(S.Us.slice_off, st));
+  SPB_CUDA(I->Us_col.upload(S.Us.col, st));
+  SPB_CUDA(I->Us_len.upload(S.Us.rowlen, st));
+  SPB_CUDA(I->Us_pos.upload(S.Us.pos_of_slot, st));
   SPB_CUDA(I->Lval.alloc((size_t)std::max<int64_t>(1, I->nz)));
-  SPB_CUDA(I->Uval.alloc((size_t)std::max<int64_t>(1, I->nz)));
+  SPB_CUDA(I->Ls_val.alloc(std::max<size_t>(1, S.Ls.col.size())));
+  SPB_CUDA(I->Us_val.alloc(std::max<size_t>(1, S.Us.col.size())));
+  SPB_CUDA(cudaMemsetAsync(I->Ls_val.p, 0, std::max<size_t>(1, S.Ls.col.size()) * sizeof(double), st));
+  SPB_CUDA(cudaMemsetAsync(I->Us_val.p, 0, std::max<size_t>(1, S.Us.col.size()) * sizeof(double), st));
   SPB_CUDA(I->invd.alloc(I->n));
   SPB_CUDA(I->y.alloc(I->n));
   SPB_CUDA(I->zc.alloc(I->n));
   SPB_CUDA(I->z.alloc(I->n));
+  SPB_CUDA(cudaMemsetAsync(I->y.p, 0, (size_t)I->n * sizeof(double), st));
+  SPB_CUDA(cudaMemsetAsync(I->zc.p, 0, (size_t)I->n * sizeof(double), st));
   SPB_CUDA(I->flags.alloc(1));
   SPB_CUDA(cudaStreamSynchronize(st));
   return I;

@@ -41,6 +41,7 @@ struct CholDevice {
   };
   std::vector<std::vector<Group>> groups;
   bool factored = false;
+  bool smem_attr_set = false;  // per device context, so per handle (not a process-wide static)
   int* h_fail = nullptr;
 };
 
@@ -625,11 +626,10 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
   chol_permute_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_b, D->perm.p, D->ywork.p, n, 0);
   ++nl;
   const size_t smem = (size_t)(C.max_r + 32) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!D->smem_attr_set) {
     SPB_CUDA(cudaFuncSetAttribute(chol_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SPB_CUDA(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    D->smem_attr_set = true;
   }
   for (int l = 0; l < C.nlevels; ++l) {
     for (const CholDevice::Group& G : D->groups[l]) {

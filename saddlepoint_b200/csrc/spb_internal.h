@@ -207,15 +207,11 @@ struct spb_context {
   spb::DevBuf<int> d_Jcolptr, d_Jrow;
   spb::DevBuf<uint16_t> d_rec16;
   spb::DevBuf<uint32_t> d_rec32;
-  spb::DevBuf<uint16_t> d_grp_slot, d_low_rank, d_low_rank_up;
-  spb::DevBuf<int> d_chunk_slot, d_chunk_npairs, d_chunk_stage_ptr, d_stage_cols, d_stage_off, d_colchunk, d_nup1;
-  spb::DevBuf<uint8_t> d_chunk_staged;
+  spb::DevBuf<int> d_colchunk, d_nup1;
   spb::DevBuf<spb::ChunkDesc> d_chunk_desc;
   spb::DevBuf<spb::StageEntry> d_stage_ent;
   spb::DevBuf<spb::SlotMeta> d_slot_meta;
-  spb::DevBuf<uint16_t> d_slot_il, d_slot_jl;
   spb::DevBuf<uint32_t> d_slot_start;  // (start << 16) | count, in processing order
-  spb::DevBuf<int64_t> d_chunk_rec;
   // device: H in SpMV layout
   spb::DevBuf<int> d_sell_col, d_rowlen;
   spb::DevBuf<uint16_t> d_sell_col16;

@@ -792,15 +792,35 @@ __device__ __forceinline__ void ic0_phase(const IcView& V, int r0, int r1, const
     const int width = __reduce_max_sync(0xffffffffu, len);
     const int* cp = scol + off + lane;
     const double* vp = sval + off + lane;
+    // independent of the row data: issue now so the perm -> r chain overlaps the factor stream
+    const int orig = mine ? V.perm[i] : 0;
+    const double dg = mine ? V.invd[i] : 0.0;
+    const double rhs = mine ? (FORWARD ? r[orig] : V.y[i]) : 0.0;
     double s = 0.0;
     int k = 0;
+    for (; k + 8 <= width; k += 8) {  // eight entries in flight per lane: two round trips per 8, not per 4
+      int c[8];
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        c[u] = __ldcs(cp + (k + u) * 32);
+        v[u] = __ldcs(vp + (k + u) * 32);
+      }
+      double g[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g[u] = src[c[u]];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + u < len) s = fma(v[u], g[u], s);
+    }
     for (; k + 4 <= width; k += 4) {
       const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32), c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
       const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32), v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
-      if (k + 0 < len) s = fma(v0, src[c0], s);
-      if (k + 1 < len) s = fma(v1, src[c1], s);
-      if (k + 2 < len) s = fma(v2, src[c2], s);
-      if (k + 3 < len) s = fma(v3, src[c3], s);
+      const double g0 = src[c0], g1 = src[c1], g2 = src[c2], g3 = src[c3];
+      if (k + 0 < len) s = fma(v0, g0, s);
+      if (k + 1 < len) s = fma(v1, g1, s);
+      if (k + 2 < len) s = fma(v2, g2, s);
+      if (k + 3 < len) s = fma(v3, g3, s);
     }
     for (; k < width; ++k) {
       const int c0 = __ldcs(cp + k * 32);
@@ -809,11 +829,11 @@ __device__ __forceinline__ void ic0_phase(const IcView& V, int r0, int r1, const
     }
     if (mine) {
       if (FORWARD) {
-        V.y[i] = (r[V.perm[i]] - s) * V.invd[i];
+        V.y[i] = (rhs - s) * dg;
       } else {
-        const double v = (V.y[i] - s) * V.invd[i];
+        const double v = (rhs - s) * dg;
         V.zc[i] = v;
-        z[V.perm[i]] = v;
+        z[orig] = v;
       }
     }
   }

@@ -19,6 +19,8 @@
 //    exit on a device flag, and the host only polls a pinned mirror once per batch.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include <cooperative_groups.h>
 
@@ -173,6 +175,9 @@ void dev_invert_diag(spb_context* h) {
 // never displaces the PCG vectors from L2.  PIN=true: L2 evict_last policy -- the persistent PCG
 // kernel re-reads the same H every iteration, so a fixed leading part of every block's slice
 // range is kept resident in the 126 MB L2 across iterations and only the rest comes from HBM.
+#ifndef SPB_SPMV_UNROLL8
+#define SPB_SPMV_UNROLL8 1
+#endif
 template <bool PIN>
 __device__ __forceinline__ int ld_h_i32(const int* p, uint64_t pol) {
   if (!PIN) return __ldcs(p);
@@ -209,6 +214,22 @@ __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_o
   const int rbase = row - 32768;
   double acc = 0.0;
   int k = 0;
+#if SPB_SPMV_UNROLL8
+  for (; k + 8 <= width; k += 8) {  // eight entries in flight per lane
+    int c[8];
+    double v[8], xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      c[u] = C16 ? rbase + (int)__ldcs(cp16 + (k + u) * 32) : ld_h_i32<PIN>(cp + (k + u) * 32, pol);
+      v[u] = ld_h_f64<PIN>(vp + (k + u) * 32, pol);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = NC ? __ldg(x + c[u]) : x[c[u]];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (k + u < len) acc = fma(v[u], xv[u], acc);
+  }
+#endif
   for (; k + 4 <= width; k += 4) {
     int c0, c1, c2, c3;
     if (C16) {
@@ -321,6 +342,33 @@ __device__ __forceinline__ double block_total(const double* part, int count, dou
   return r;
 }
 
+// two reductions finalised in one pass (one L2 round trip, one set of block barriers)
+__device__ __forceinline__ void block_total2(const double* partA, const double* partB, int count, double* sm2, double* bc2,
+                                             double& outA, double& outB) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) {
+    a += __ldcg(partA + i);
+    b += __ldcg(partB + i);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    sm2[threadIdx.x >> 5] = a;
+    sm2[8 + (threadIdx.x >> 5)] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const double* src = sm2 + 8 * threadIdx.x;
+    double r = src[0];
+    for (int w = 1; w < 8; ++w) r += src[w];
+    bc2[threadIdx.x] = r;
+  }
+  __syncthreads();
+  outA = bc2[0];
+  outB = bc2[1];
+  __syncthreads();
+}
+
 struct PcgParams {
   const int64_t* slice_off;
   const int* col;
@@ -339,13 +387,29 @@ struct PcgParams {
   int n, nslices, maxit;
   double rtol;
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
+  unsigned long long* phase_ns;  // debug (SPB_PCG_TIMING=1): per block, 9 accumulated phase durations; else null
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// phase stopwatch of thread 0 of every block; compiled in, but one uniform null test when off
+#define SPB_TICK(k)                                          \
+  if (P.phase_ns && tid == 0) {                              \
+    const unsigned long long now_ = global_ns();             \
+    P.phase_ns[(size_t)blk * 9 + (k)] += now_ - tick_;       \
+    tick_ = now_;                                            \
+  }
 
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[8];
   __shared__ double bc;
+  __shared__ double sm2[16];
+  __shared__ double bc2[2];
   const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
   const int n = P.n;
   const int stride = G * 256;
@@ -375,13 +439,14 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
     }
   }
   grid.sync();
-  double rz = block_total(partB, G, sm, &bc);
-  const double bb = block_total(partC, G, sm, &bc);
+  double rz, bb;
+  block_total2(partB, partC, G, sm2, bc2, rz, bb);
   const double thresh = P.rtol * P.rtol * bb;
   double rr = bb, pq = 0.0;
   int iters = 0, breakdown = 0;
   bool run = (bb > thresh) && P.maxit > 0;
   grid.sync();  // partB/partC are about to be reused
+  unsigned long long tick_ = P.phase_ns ? global_ns() : 0ull;
   while (run) {
     // phase 1: q = H p, partial p.q
     {
@@ -389,17 +454,44 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
       const double bs = block_sum_256(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
+    SPB_TICK(0)
     grid.sync();
+    SPB_TICK(1)
     pq = block_total(partA, G, sm, &bc);
+    SPB_TICK(2)
     if (!(pq > 0.0)) {  // not SPD (or NaN)
       breakdown = 1;
       break;
     }
     const double alpha = rz / pq;
-    // phase 2: x += alpha p, r -= alpha q, partial r.z and r.r
+    // phase 2: x += alpha p, r -= alpha q, partial r.z and r.r  (four elements' loads in flight per thread:
+    // the vectors live in L2, the loop is latency- not bandwidth-bound)
     {
       double a1 = 0.0, a2 = 0.0;
-      for (int i = blk * 256 + tid; i < n; i += stride) {
+      int i = blk * 256 + tid;
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        double pv[4], qv[4], xv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          pv[u] = P.p[j];
+          qv[u] = P.q[j];
+          xv[u] = P.x[j];
+          rv[u] = P.r[j];
+          dv[u] = P.dinv[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          P.x[j] = fma(alpha, pv[u], xv[u]);
+          const double ri = fma(-alpha, qv[u], rv[u]);
+          P.r[j] = ri;
+          const double z = ri * dv[u];
+          a1 = fma(ri, z, a1);
+          a2 = fma(ri, ri, a2);
+        }
+      }
+      for (; i < n; i += stride) {
         P.x[i] = fma(alpha, P.p[i], P.x[i]);
         const double ri = fma(-alpha, P.q[i], P.r[i]);
         P.r[i] = ri;
@@ -414,16 +506,36 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
         partC[blk] = s2;
       }
     }
+    SPB_TICK(3)
     grid.sync();
-    const double rz_new = block_total(partB, G, sm, &bc);
-    rr = block_total(partC, G, sm, &bc);
+    SPB_TICK(4)
+    double rz_new;
+    block_total2(partB, partC, G, sm2, bc2, rz_new, rr);
+    SPB_TICK(5)
     const double beta = rz_new / rz;
     rz = rz_new;
     ++iters;
     if (!(rr > thresh) || iters >= P.maxit) break;
     // phase 3: p = dinv*r + beta p
-    for (int i = blk * 256 + tid; i < n; i += stride) P.p[i] = fma(beta, P.p[i], P.r[i] * P.dinv[i]);
+    {
+      int i = blk * 256 + tid;
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        double pv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          pv[u] = P.p[j];
+          rv[u] = P.r[j];
+          dv[u] = P.dinv[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) P.p[i + u * stride] = fma(beta, pv[u], rv[u] * dv[u]);
+      }
+      for (; i < n; i += stride) P.p[i] = fma(beta, P.p[i], P.r[i] * P.dinv[i]);
+    }
+    SPB_TICK(6)
     grid.sync();
+    SPB_TICK(7)
   }
   if (blk == 0 && tid == 0) {
     PcgScalars* sc = P.sc;
@@ -588,12 +700,38 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
       const double h_bytes = 12.0 * (double)h->S.padded;
       P.pin_fraction = h_bytes > 0 ? std::min(1.0, std::max(0.0, h->pcg_pin_mb * 1048576.0 / h_bytes)) : 0.0;
     }
+    static const bool phase_timing = getenv("SPB_PCG_TIMING") && atoi(getenv("SPB_PCG_TIMING")) > 0;
+    DevBuf<unsigned long long> d_phase;
+    P.phase_ns = nullptr;
+    if (phase_timing) {
+      SPB_CUDA(d_phase.alloc((size_t)G * 9));
+      SPB_CUDA(cudaMemsetAsync(d_phase.p, 0, sizeof(unsigned long long) * (size_t)G * 9, st));
+      P.phase_ns = d_phase.p;
+    }
     void* args[] = {&P};
     stage_begin(h, ST_PCG);
     SPB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(256), args, 0, st));
     stage_end(h, ST_PCG, 1);
     SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     SPB_CUDA(cudaStreamSynchronize(st));
+    if (phase_timing) {  // debug print: per-iteration mean over blocks (and min/max over blocks) of every phase, in us
+      std::vector<unsigned long long> t((size_t)G * 9);
+      SPB_CUDA(cudaMemcpy(t.data(), d_phase.p, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+      static const char* names[8] = {"spmv", "sync1", "total1", "update", "sync2", "total2", "direction", "sync3"};
+      const double it = std::max(1, h->h_sc->iters);
+      fprintf(stderr, "[spb pcg timing] iters=%d G=%d us/iteration mean(min..max over blocks):", h->h_sc->iters, G);
+      for (int k = 0; k < 8; ++k) {
+        double sum = 0, lo = 1e30, hi = 0;
+        for (int b = 0; b < G; ++b) {
+          const double v = (double)t[(size_t)b * 9 + k] / it * 1e-3;
+          sum += v;
+          lo = std::min(lo, v);
+          hi = std::max(hi, v);
+        }
+        fprintf(stderr, " %s=%.2f(%.2f..%.2f)", names[k], sum / G, lo, hi);
+      }
+      fprintf(stderr, "\n");
+    }
     h->pcg_last_iters = h->h_sc->iters;
     if (iters) *iters = h->h_sc->iters;
     if (h->h_sc->breakdown) return SPB_NOT_SPD;

@@ -99,6 +99,15 @@ spb_status spb_get_damping(spb_handle h, double* d, int mem);
  * callers that keep the reference's LMSolver.h unchanged and pass dampJ^T*dampJ themselves.
  * The pattern is analysed on first use and whenever it changes. */
 spb_status spb_set_matrix(spb_handle h, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* vals, int mem);
+/* Legacy LinearSolver concept used by GNSolver / SLSolver / EigenSingleSolveWrapper:
+ * LS->analyze(HRows, HCols[, symmetric]) (GNSolver.h:131, SLSolver.h:123, EigenSolverWrapper.h:118)
+ * and LS->factorize(HVals[, symmetric]) (GNSolver.h:169, SLSolver.h:159, EigenSolverWrapper.h:119).
+ * The matrix is a triplet list (duplicates are summed in insertion order); symmetric != 0 means
+ * only entries with row <= col are listed and are mirrored.  spb_analyze_triplets does all
+ * pattern work once; spb_factorize_triplets takes one value per triplet, builds H on the
+ * device and factorises it (SPB_NOT_SPD <=> the reference's `false`); spb_solve follows. */
+spb_status spb_analyze_triplets(spb_handle h, int32_t n, int64_t nnz, const int32_t* rows, const int32_t* cols, int symmetric);
+spb_status spb_factorize_triplets(spb_handle h, const double* vals, int mem);
 /* Replaces solver.compute(A) + info()==Success (EigenSolverWrapper.h:58-59): numeric
  * factorisation of the current H.  SPB_NOT_SPD <=> the reference's `false`. */
 spb_status spb_factorize(spb_handle h);

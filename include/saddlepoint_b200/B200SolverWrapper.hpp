@@ -6,6 +6,9 @@
 //   analyze(JPattern)    EigenSolverWrapper.h:30   (takes J's pattern; also analyze_pattern)
 //   factorize(A)         EigenSolverWrapper.h:54   (explicit symmetric matrix, both triangles)
 //   solve(rhs, x)        EigenSolverWrapper.h:72   (vector) / :62 (columns of a matrix)
+// and the legacy triplet overloads the GN / SL solvers and EigenSingleSolveWrapper call:
+//   analyze(HRows, HCols[, symmetric])   GNSolver.h:131, SLSolver.h:123, EigenSolverWrapper.h:118
+//   factorize(HVals[, symmetric])        GNSolver.h:169, SLSolver.h:159, EigenSolverWrapper.h:119
 // A caller that keeps the reference's own LMSolver.h can plug this class in unchanged: the
 // product dampJ^T*dampJ it passes to factorize() is uploaded and factorised on the GPU.
 // SaddlePoint::LMSolver in this directory goes further and never forms that product on the
@@ -14,10 +17,19 @@
 #define SADDLEPOINT_B200_SOLVER_WRAPPER_HPP
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 
 #include "../saddlepoint_b200.h"
 
 namespace SaddlePoint {
+
+namespace detail {
+template <class T, class = void>
+struct has_outer_index : std::false_type {};
+template <class T>
+struct has_outer_index<T, std::void_t<decltype(std::declval<const T&>().outerIndexPtr())>> : std::true_type {};
+}  // namespace detail
 
 class B200SolverWrapper {
  public:
@@ -42,11 +54,30 @@ class B200SolverWrapper {
     return analyze(JPattern);
   }
 
-  template <class SparseMat>
-  bool factorize(const SparseMat& A) {
-    spb_status s = spb_set_matrix(h_, (int32_t)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), SPB_HOST);
-    if (s != SPB_OK) return false;
-    return spb_factorize(h_) == SPB_OK;
+  // legacy: the matrix itself as triplets; symmetric == true lists row <= col only (mirrored here)
+  template <class IndexVec>
+  bool analyze(const IndexVec& HRows, const IndexVec& HCols, bool symmetric = false) {
+    if (HRows.size() != HCols.size()) return false;
+    int32_t n = 0;
+    for (long t = 0; t < (long)HRows.size(); ++t) {
+      if (HRows.data()[t] + 1 > n) n = HRows.data()[t] + 1;
+      if (HCols.data()[t] + 1 > n) n = HCols.data()[t] + 1;
+    }
+    return spb_analyze_triplets(h_, n, (int64_t)HRows.size(), HRows.data(), HCols.data(), symmetric ? 1 : 0) == SPB_OK;
+  }
+
+  // A sparse matrix (anything with outerIndexPtr()): the explicit symmetric matrix, both triangles.
+  // A dense vector: legacy factorize(HVals[, symmetric]), one value per analysed triplet.
+  template <class MatOrVals>
+  bool factorize(const MatOrVals& A, bool symmetric = false) {
+    (void)symmetric;  // fixed at analyze(HRows, HCols, symmetric), as in the legacy wrapper's callers
+    if constexpr (detail::has_outer_index<MatOrVals>::value) {
+      spb_status s = spb_set_matrix(h_, (int32_t)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), SPB_HOST);
+      if (s != SPB_OK) return false;
+      return spb_factorize(h_) == SPB_OK;
+    } else {
+      return spb_factorize_triplets(h_, A.data(), SPB_HOST) == SPB_OK;
+    }
   }
 
   template <class Vec>

@@ -58,6 +58,8 @@ SYMBOLS = [
     ("spb_get_rhs", C.c_int, [vp, vp, C.c_int]),
     ("spb_get_damping", C.c_int, [vp, vp, C.c_int]),
     ("spb_set_matrix", C.c_int, [vp, C.c_int32, vp, vp, vp, C.c_int]),
+    ("spb_analyze_triplets", C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, C.c_int]),
+    ("spb_factorize_triplets", C.c_int, [vp, vp, C.c_int]),
     ("spb_factorize", C.c_int, [vp]),
     ("spb_solve", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("spb_factor_info", C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

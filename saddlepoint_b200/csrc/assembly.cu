@@ -496,6 +496,26 @@ void gather_h_values(spb_context* h, double* d_out) {
   SPB_CUDA(cudaGetLastError());
 }
 
+// Legacy triplet interface: every H entry (CSC order) is the sum of its triplets in insertion order,
+// the way Eigen's setFromTriplets accumulates duplicates [Eigen-upstream]; one thread per entry.
+__global__ void __launch_bounds__(256) sum_triplets_kernel(const int64_t* __restrict__ ptr, const int* __restrict__ src,
+                                                           const double* __restrict__ vals, int64_t nnz, double* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (q >= nnz) return;
+  const int64_t a = ptr[q], b = ptr[q + 1];
+  double s = a < b ? vals[src[a]] : 0.0;
+  for (int64_t t = a + 1; t < b; ++t) s = __dadd_rn(s, vals[src[t]]);
+  out[q] = s;
+}
+
+void sum_triplets(spb_context* h, const double* d_trip_vals, double* d_csc_vals) {
+  const int64_t nnz = h->H.nnz();
+  if (nnz == 0) return;
+  sum_triplets_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, h->stream>>>(h->d_trip_ptr.p, h->d_trip_src.p, d_trip_vals, nnz, d_csc_vals);
+  h->launches++;
+  SPB_CUDA(cudaGetLastError());
+}
+
 void scatter_h_values(spb_context* h, const double* d_in) {
   ensure_pos_of_slot(h);
   int64_t nnz = h->H.nnz();

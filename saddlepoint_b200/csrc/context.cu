@@ -1,5 +1,6 @@
 // context.cu -- handle lifetime, error plumbing, per-stage CUDA-event timing, and the
 // granular C ABI (analyze / assemble / factorize / solve / reductions).
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -173,6 +174,7 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
     SPB_CUDA(cudaSetDevice(h->device));
     validate_csc(m, n, colptr, rowidx);
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+    h->trip_nnz = -1;
     h->pcg_last_iters = 0;
     chol_release(h);
     ic0_release(h);
@@ -270,49 +272,125 @@ spb_status spb_get_damping(spb_handle h, double* d, int mem) {
   return copy_out(h, h->d_dvec.p, d, (size_t)h->n, mem);
 }
 
+// Installs an explicit symmetric H pattern (CSC, both triangles, full diagonal) on the handle:
+// SpMV layout, diagonal positions; invalidates everything derived from a previous pattern.
+static void install_explicit_pattern(spb_handle h, int32_t n, const int32_t* colptr, const int32_t* rowidx, uint64_t fp) {
+  h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+  h->trip_nnz = -1;
+  chol_release(h);
+  ic0_release(h);
+  h->n = n;
+  h->m = 0;
+  h->nnzJ = 0;
+  HPattern& H = h->H;
+  H.n = n;
+  H.colptr.assign(colptr, colptr + n + 1);
+  H.rowidx.assign(rowidx, rowidx + colptr[n]);
+  H.nup1.assign(n, 0);
+  for (int j = 0; j < n; ++j) {
+    int up = 0, prev = -1;
+    bool diag = false;
+    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+      int i = rowidx[q];
+      if (i < 0 || i >= n || i <= prev) throw ArgFail{"matrix pattern must have ascending in-range row indices"};
+      prev = i;
+      if (i <= j) ++up;
+      if (i == j) diag = true;
+    }
+    if (!diag) throw ArgFail{"matrix must have a structurally full diagonal"};
+    H.nup1[j] = up;
+  }
+  build_sell(h->H, h->S);
+  upload_h_layout(h);
+  h->h_fingerprint = fp;
+  h->have_h = true;
+}
+
 spb_status spb_set_matrix(spb_handle h, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* vals, int mem) {
   if (!h || !vals) return SPB_ERR_ARG;
   return guarded(h, [&]() {
     SPB_CUDA(cudaSetDevice(h->device));
     validate_csc(n, n, colptr, rowidx);
     uint64_t fp = pattern_fingerprint(n, n, colptr, rowidx);
-    if (!(h->have_h && !h->analyzed && h->n == n && h->h_fingerprint == fp)) {
-      // new explicit pattern: must be structurally symmetric with a full diagonal
-      h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
-      chol_release(h);
-      ic0_release(h);
-      h->n = n;
-      h->m = 0;
-      h->nnzJ = 0;
-      HPattern& H = h->H;
-      H.n = n;
-      H.colptr.assign(colptr, colptr + n + 1);
-      H.rowidx.assign(rowidx, rowidx + colptr[n]);
-      H.nup1.assign(n, 0);
-      for (int j = 0; j < n; ++j) {
-        int up = 0, prev = -1;
-        bool diag = false;
-        for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
-          int i = rowidx[q];
-          if (i < 0 || i >= n || i <= prev) throw ArgFail{"matrix pattern must have ascending in-range row indices"};
-          prev = i;
-          if (i <= j) ++up;
-          if (i == j) diag = true;
-        }
-        if (!diag) throw ArgFail{"matrix must have a structurally full diagonal"};
-        H.nup1[j] = up;
-      }
-      build_sell(h->H, h->S);
-      upload_h_layout(h);
-      h->h_fingerprint = fp;
-      h->have_h = true;
-    }
+    // new explicit pattern: must be structurally symmetric with a full diagonal
+    if (!(h->have_h && !h->analyzed && h->trip_nnz < 0 && h->n == n && h->h_fingerprint == fp)) install_explicit_pattern(h, n, colptr, rowidx, fp);
     size_t nnz = (size_t)h->H.nnz();
     const double* dv = to_device(h, vals, nnz, mem, h->d_vec_stage);
     scatter_h_values(h, dv);
     SPB_CUDA(cudaStreamSynchronize(h->stream));
     return SPB_OK;
   });
+}
+
+// Legacy LinearSolver concept (GNSolver.h:131,169; SLSolver.h:123,159; EigenSolverWrapper.h:118-119):
+// analyze(I, J, symmetric) takes the matrix as triplets -- with symmetric != 0 only entries on or above
+// the diagonal, which are mirrored -- and factorize(S, symmetric) takes one value per triplet;
+// duplicates are summed in insertion order.  The symbolic work (pattern, triplet -> entry map,
+// SpMV layout, and on first factorize the ordering/supernodes) is done once per pattern.
+spb_status spb_analyze_triplets(spb_handle h, int32_t n, int64_t nnz, const int32_t* rows, const int32_t* cols, int symmetric) {
+  if (!h || n < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols)) || nnz > 0x7fffffffLL) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    SPB_CUDA(cudaSetDevice(h->device));
+    // entry list: (column, row, source); a mirrored copy carries the same source
+    struct Ent {
+      int col, row, src;
+    };
+    std::vector<Ent> ent;
+    ent.reserve((size_t)nnz * (symmetric ? 2 : 1));
+    for (int64_t t = 0; t < nnz; ++t) {
+      const int i = rows[t], j = cols[t];
+      if (i < 0 || i >= n || j < 0 || j >= n) throw ArgFail{"triplet index out of range"};
+      if (symmetric && i > j) throw ArgFail{"symmetric triplets must lie on or above the diagonal (row <= col)"};
+      ent.push_back({j, i, (int)t});
+      if (symmetric && i != j) ent.push_back({i, j, (int)t});
+    }
+    // stable: duplicates keep their insertion order
+    std::stable_sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) { return a.col != b.col ? a.col < b.col : a.row < b.row; });
+    std::vector<int32_t> colptr((size_t)n + 1, 0), rowidx;
+    std::vector<int64_t> tptr;
+    std::vector<int> tsrc(ent.size());
+    for (size_t e = 0; e < ent.size(); ++e) {
+      if (e == 0 || ent[e].col != ent[e - 1].col || ent[e].row != ent[e - 1].row) {
+        rowidx.push_back(ent[e].row);
+        tptr.push_back((int64_t)e);
+        colptr[(size_t)ent[e].col + 1]++;
+      }
+      tsrc[e] = ent[e].src;
+    }
+    tptr.push_back((int64_t)ent.size());
+    for (int j = 0; j < n; ++j) colptr[(size_t)j + 1] += colptr[j];
+    if (!symmetric) {  // the solvers need a structurally symmetric pattern
+      for (int j = 0; j < n; ++j)
+        for (int q = colptr[j]; q < colptr[(size_t)j + 1]; ++q) {
+          const int i = rowidx[q];
+          if (i == j) continue;
+          if (!std::binary_search(rowidx.begin() + colptr[i], rowidx.begin() + colptr[(size_t)i + 1], j))
+            throw ArgFail{"triplet pattern is not structurally symmetric"};
+        }
+    }
+    install_explicit_pattern(h, n, colptr.data(), rowidx.data(), pattern_fingerprint(n, n, colptr.data(), rowidx.data()));
+    SPB_CUDA(h->d_trip_ptr.upload(tptr, h->stream));
+    SPB_CUDA(h->d_trip_src.upload(tsrc, h->stream));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    h->trip_nnz = nnz;
+    return SPB_OK;
+  });
+}
+
+spb_status spb_factorize_triplets(spb_handle h, const double* vals, int mem) {
+  if (!h || !vals) return SPB_ERR_ARG;
+  spb_status st = guarded(h, [&]() {
+    if (h->trip_nnz < 0 || !h->have_h) throw StateFail{"spb_factorize_triplets before spb_analyze_triplets"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    const double* dv = to_device(h, vals, (size_t)h->trip_nnz, mem, h->d_vec_stage2);
+    SPB_CUDA(h->d_vec_stage.alloc((size_t)h->H.nnz()));
+    sum_triplets(h, dv, h->d_vec_stage.p);
+    scatter_h_values(h, h->d_vec_stage.p);
+    if (mem == SPB_HOST) SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+  if (st != SPB_OK) return st;
+  return spb_factorize(h);
 }
 
 spb_status spb_factorize(spb_handle h) {

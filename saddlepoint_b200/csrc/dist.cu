@@ -172,6 +172,7 @@ spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int
   return guarded_dist(h, [&]() {
     SPB_CUDA(cudaSetDevice(h->device));
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
+    h->trip_nnz = -1;
     h->pcg_last_iters = 0;
     chol_release(h);
     ic0_release(h);

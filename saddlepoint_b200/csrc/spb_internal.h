@@ -195,6 +195,10 @@ struct spb_context {
   bool factor_valid = false;
   uint64_t fingerprint = 0;   // of the J pattern
   uint64_t h_fingerprint = 0; // of an explicitly set H pattern
+  // legacy triplet interface (spb_analyze_triplets): CSC entry q of H sums d_trip_src[d_trip_ptr[q] .. d_trip_ptr[q+1])
+  int64_t trip_nnz = -1;      // number of input triplets; -1 = no triplet analysis on this handle
+  spb::DevBuf<int64_t> d_trip_ptr;
+  spb::DevBuf<int> d_trip_src;
   int m = 0, n = 0;
   int64_t nnzJ = 0;
   spb::HPattern H;            // host copy kept for export and for the Cholesky symbolic phase
@@ -262,7 +266,8 @@ void upload_h_layout(spb_context* h);
 void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double lambda, double* foo_host);
 void ensure_pos_of_slot(spb_context* h);
 void gather_h_values(spb_context* h, double* d_out);   // CSC order
-void scatter_h_values(spb_context* h, const double* d_in);  // CSC order -> storage (+ hdiag)
+void scatter_h_values(spb_context* h, const double* d_in);
+void sum_triplets(spb_context* h, const double* d_trip_vals, double* d_csc_vals);  // insertion-order sums per H entry  // CSC order -> storage (+ hdiag)
 
 // blas1.cu
 void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);

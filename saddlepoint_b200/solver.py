@@ -172,6 +172,24 @@ class Handle:
         self._check(self.L.spb_set_matrix(self.h, n, pc, pr, pv, mv))
         self.n = n
 
+    def analyze_triplets(self, n, rows, cols, symmetric=False):
+        """Legacy LS->analyze(HRows, HCols, symmetric) (GNSolver.h:131, SLSolver.h:123)."""
+        rows, pr = _i32(rows)
+        cols, pc = _i32(cols)
+        if rows.shape != cols.shape:
+            raise ValueError("rows and cols must have the same length")
+        self._check(self.L.spb_analyze_triplets(self.h, n, rows.size, pr, pc, int(bool(symmetric))))
+        self.n = n
+        self._trip_nnz = rows.size
+
+    def factorize_triplets(self, vals):
+        """Legacy LS->factorize(HVals, symmetric) (GNSolver.h:169, SLSolver.h:159): one value per triplet."""
+        pv, mv, kv = _ptr(vals)
+        if len(vals) != getattr(self, "_trip_nnz", -1):
+            raise ValueError("one value per analysed triplet is required")
+        st = self._check(self.L.spb_factorize_triplets(self.h, pv, mv), allow=(SPB_NOT_SPD,))
+        return st == SPB_OK
+
     def factorize(self):
         """True on success, False iff the matrix is not positive definite (the reference's bool)."""
         st = self._check(self.L.spb_factorize(self.h), allow=(SPB_NOT_SPD,))
@@ -258,16 +276,31 @@ class B200SolverWrapper:
         self.handle.set_solver(solver, pcg_rtol, pcg_maxit)
         self.last_iters = 0
 
-    def analyze(self, JPattern):
-        """analyze(const SparseMatrix<int>& JPattern) (EigenSolverWrapper.h:30): J's pattern."""
+    def analyze(self, JPattern, HCols=None, symmetric=False, n=None):
+        """analyze(const SparseMatrix<int>& JPattern) (EigenSolverWrapper.h:30): J's pattern.
+
+        Legacy overload analyze(HRows, HCols, symmetric) (GNSolver.h:131, SLSolver.h:123): the matrix
+        itself as triplets; n defaults to max index + 1."""
+        if HCols is not None:
+            rows = np.asarray(JPattern, np.int32)
+            cols = np.asarray(HCols, np.int32)
+            if n is None:
+                n = int(max(rows.max(initial=-1), cols.max(initial=-1))) + 1
+            self.handle.analyze_triplets(n, rows, cols, symmetric)
+            return True
         m, n, colptr, rowidx, _ = _as_csc(JPattern)
         self.handle.analyze(m, n, colptr, rowidx)
         return True
 
     analyze_pattern = analyze
 
-    def factorize(self, A):
-        """factorize(SparseMatrix<double> A) (EigenSolverWrapper.h:54): explicit symmetric matrix."""
+    def factorize(self, A, symmetric=None):
+        """factorize(SparseMatrix<double> A) (EigenSolverWrapper.h:54): explicit symmetric matrix.
+
+        Legacy overload factorize(HVals, symmetric) (GNSolver.h:169, SLSolver.h:159): a 1-D value
+        array, one per triplet given to analyze(HRows, HCols, symmetric)."""
+        if not hasattr(A, "tocsc") and np.ndim(A) == 1:
+            return self.handle.factorize_triplets(A if _is_torch_cuda(A) else np.ascontiguousarray(A, np.float64))
         n, _, colptr, rowidx, vals = _as_csc(A)
         self.handle.set_matrix(n, colptr, rowidx, vals)
         return self.handle.factorize()

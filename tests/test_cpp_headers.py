@@ -9,6 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = "/tmp/spb_rosenbrock_gpu"
+EXE_GN = "/tmp/spb_gn_legacy_gpu"
 
 
 def _compile(spb):
@@ -19,9 +20,45 @@ def _compile(spb):
     subprocess.check_call(cmd)
 
 
+def _compile_gn(spb):
+    spb.capi.load()
+    lib = os.path.join(ROOT, "saddlepoint_b200", "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "gauss_newton_legacy.cpp"), "-L" + lib, "-lsaddlepoint_b200", "-Wl,-rpath," + lib, "-o", EXE_GN]
+    subprocess.check_call(cmd)
+
+
 def test_headers_compile_and_link(spb):
     _compile(spb)
     assert os.path.exists(EXE)
+    _compile_gn(spb)
+    assert os.path.exists(EXE_GN)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,solver", [(1000, 0), (1000, 1), (30000, 2)])
+def test_legacy_triplet_concept_gauss_newton(spb, n, solver):
+    """GNSolver.h:131,169,175 call sequence (analyze(HRows,HCols,true) / factorize(HVals,true) / solve)
+    on the Broyden tridiagonal system; the root is checked against an independent Newton solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    _compile_gn(spb)
+    out = subprocess.run([EXE_GN, str(n), str(solver)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    mres = re.search(r"RESULT iterations=(\d+) energy=(\S+) x0=(\S+) xmid=(\S+) xlast=(\S+)", out.stdout)
+    assert mres, out.stdout[-500:]
+    x = -np.ones(n)
+    for _ in range(50):
+        lo = np.concatenate([[0.0], x[:-1]])
+        hi = np.concatenate([x[1:], [0.0]])
+        f = (3 - 2 * x) * x - lo - 2 * hi + 1
+        if f @ f < 1e-28:
+            break
+        Jm = sp.diags([-np.ones(n - 1), 3 - 4 * x, -2 * np.ones(n - 1)], [-1, 0, 1], format="csc")
+        x = x + spla.spsolve(Jm, -f)
+    assert float(mres.group(2)) < 1e-20 and int(mres.group(1)) < 20
+    for g, want in ((3, x[0]), (4, x[n // 2]), (5, x[-1])):
+        assert abs(float(mres.group(g)) - want) <= 1e-10 * abs(want)
 
 
 @pytest.mark.gpu

@@ -179,3 +179,77 @@ def test_lm_with_ic0_matches_oracle(spb, orc):
     assert ret == ref.ret and lm.currIter == ref.currIter and lm.exit_path == ref.exit_path
     assert np.linalg.norm(lm.x - ref.x) <= 1e-10 * np.linalg.norm(ref.x)
     h.close()
+
+
+def _gn_triplets(rng, m, n, k):
+    """The legacy GN flow (GNSolver.h:44-95 in spirit): J by row-sorted triplets, J^T J by one
+    upper-triangle triplet per product of two entries of a residual row (duplicates galore)."""
+    colptr, rowidx, vals = random_jacobian(rng, m, n, k, cover_cols=True)
+    J = sp.csc_matrix((vals, rowidx, colptr), shape=(m, n)).tocsr()
+    J.sort_indices()
+    hr, hc, hv = [], [], []
+    for r in range(m):
+        cols = J.indices[J.indptr[r]:J.indptr[r + 1]]
+        v = J.data[J.indptr[r]:J.indptr[r + 1]]
+        for a in range(len(cols)):
+            for b in range(len(cols)):
+                if cols[b] >= cols[a]:
+                    hr.append(cols[a])
+                    hc.append(cols[b])
+                    hv.append(v[a] * v[b])
+    # a small diagonal shift keeps the matrix safely positive definite
+    for j in range(n):
+        hr.append(j)
+        hc.append(j)
+        hv.append(0.05)
+    return np.array(hr, np.int32), np.array(hc, np.int32), np.array(hv, np.float64)
+
+
+@pytest.mark.parametrize("solver", [0, 1, 2])
+def test_legacy_triplet_interface_matches_oracle(handle, spb, orc, solver):
+    """spb_analyze_triplets / spb_factorize_triplets: H bit-exact against the oracle's
+    setFromTriplets restatement (duplicates summed in insertion order, upper triangle mirrored),
+    steps within 1e-10 of its SimplicialLLT."""
+    rng = np.random.default_rng(40 + solver)
+    n = 700
+    hr, hc, hv = _gn_triplets(rng, 2100, n, 4)
+    handle.set_solver(solver, 1e-13, 10000)
+    handle.analyze_triplets(n, hr, hc, symmetric=True)
+    assert handle.factorize_triplets(hv)
+    # oracle: the same triplets with the strict upper part mirrored, in the same insertion order per entry
+    off = hr != hc
+    H = orc.from_triplets(n, n, np.concatenate([hr, hc[off]]), np.concatenate([hc, hr[off]]), np.concatenate([hv, hv[off]]))
+    p, i, x = H.csc()
+    hp, hi = handle.h_pattern()
+    assert np.array_equal(hp, p) and np.array_equal(hi, i)
+    assert np.array_equal(handle.h_values(), x)  # bit-exact
+    b = rng.standard_normal(n)
+    xs, _, st = handle.solve(b)
+    assert st == 0
+    F = orc.LLT(H, 1)
+    assert F.ok
+    xref = F.solve(b)
+    assert np.linalg.norm(xs - xref) <= STEP_RTOL * np.linalg.norm(xref)
+    # new values, same pattern: no re-analysis needed; a non-SPD matrix reports false
+    hv2 = hv * rng.uniform(0.5, 1.5)
+    assert handle.factorize_triplets(hv2)
+    xs2, _, _ = handle.solve(b)
+    assert np.linalg.norm(xs2 * (hv2[0] / hv[0]) - xref) <= 1e-9 * np.linalg.norm(xref)
+    if solver == 0:
+        assert not handle.factorize_triplets(-hv)
+
+
+def test_legacy_triplet_interface_rejects_bad_input(handle, spb):
+    with pytest.raises(spb.SpbError):
+        handle.analyze_triplets(3, [1, 0], [0, 1], symmetric=True)  # below the diagonal in symmetric mode
+    with pytest.raises(spb.SpbError):
+        handle.analyze_triplets(3, [0, 1, 2, 0], [0, 1, 2, 1], symmetric=False)  # not structurally symmetric
+    with pytest.raises(spb.SpbError):
+        handle.analyze_triplets(3, [0, 1], [0, 1], symmetric=True)  # missing diagonal entry
+    # unsymmetric listing of a symmetric matrix, python wrapper overloads
+    ls = spb.B200SolverWrapper(handle=handle, solver=spb.SOLVER_CHOLESKY)
+    assert ls.analyze([0, 1, 2, 0, 1], [0, 1, 2, 1, 0], False)
+    assert ls.factorize(np.array([4.0, 5.0, 6.0, 1.0, 1.0]))
+    x = ls.solve(np.array([1.0, 2.0, 3.0]))
+    A = np.array([[4.0, 1, 0], [1, 5.0, 0], [0, 0, 6.0]])
+    np.testing.assert_allclose(x, np.linalg.solve(A, [1.0, 2.0, 3.0]), rtol=1e-13)

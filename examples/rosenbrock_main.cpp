@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "saddlepoint_b200/LMSolver.hpp"
+#include "saddlepoint_b200/check_traits.hpp"
 
 typedef SaddlePoint::B200SolverWrapper LinearSolver;
 typedef SaddlePoint::shim::Vector Vec;
@@ -62,6 +63,13 @@ int main(int argc, char* argv[]) {
   SaddlePoint::DiagonalDamping<RosenbrockTraits> dTraits(0.01);
   SaddlePoint::LMSolver<LinearSolver, RosenbrockTraits, SaddlePoint::DiagonalDamping<RosenbrockTraits> > lmSolver;
   slTraits.init(blocks);
+  if (argc > 3) {  // gradient check first, as one does after coding a traits class (check_traits.h:17)
+    Vec xc;
+    slTraits.initial_solution(xc);
+    spb_check_result chk = SaddlePoint::check_traits(slTraits, xc, lSolver);
+    std::printf("CHECK max=%.17g discrepancies=%lld colors=%d evaluations=%d\n", chk.max_diff, (long long)chk.discrepancies, chk.ncolors,
+                chk.evaluations);
+  }
   lmSolver.init(&lSolver, &slTraits, &dTraits, 1000);
   bool ret = lmSolver.solve(true);
   std::printf("RESULT ret=%d currIter=%d factorizations=%d energy=%.17g lambda=%.17g x0=%.17g x1=%.17g\n", (int)ret, lmSolver.currIter,

@@ -179,6 +179,26 @@ void spb_lm_default_options(spb_lm_options* o);
 spb_status spb_lm_solve(spb_handle h, const spb_traits* traits, const spb_lm_options* opt, spb_lm_result* res,
                         double* x_out, int x_mem, double* trace, int32_t trace_cap, int32_t* trace_len);
 
+/* ---- check_traits (check_traits.h:19-83) on the GPU -------------------------------------- */
+/* Compares the traits' Jacobian at x with central finite differences (step 10e-5, entries with
+ * |FE| <= 10e-7 dropped, discrepancies counted above 10e-7 -- the reference's constants when the
+ * arguments are 0).  The reference perturbs one unknown at a time (2*xSize evaluations); here
+ * columns that share no residual row are perturbed together, 2*ncolors evaluations.  A response in
+ * a row that has no entry in any perturbed column is a derivative missing from the declared
+ * pattern and is reported separately (outside_*). */
+typedef struct {
+  double max_diff;        /* max |FE - J| over the pattern ("Maximum gradient difference")      */
+  int32_t max_row, max_col; /* its location (first in column-major order)                        */
+  int64_t discrepancies;  /* entries with |FE - J| > tol                                        */
+  double outside_max;     /* largest |FE| response outside the declared pattern                 */
+  int64_t outside_count;  /* such responses above tol (row, colour) pairs                       */
+  int32_t ncolors;
+  int32_t evaluations;    /* objective evaluations used                                          */
+} spb_check_result;
+/* x: xSize values (mem); fe_vals (optional, host): nnz(J) finite-difference values in CSC order. */
+spb_status spb_check_traits(spb_handle h, const spb_traits* traits, const double* x, int mem, double step, double tol,
+                            spb_check_result* out, double* fe_vals);
+
 /* ---- built-in device-resident benchmark traits --------------------------- */
 typedef struct spb_problem* spb_problem_t;
 /* "LF": sparse analogue of benchmark/linear_function: g x g torus, m=rows_mult*n,

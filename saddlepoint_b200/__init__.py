@@ -4,7 +4,7 @@ The numeric work lives in libsaddlepoint_b200.so (CUDA, sm_100a); see include/sa
 """
 from . import capi
 from .capi import SOLVER_CHOLESKY, SOLVER_PCG_IC0, SOLVER_PCG_JACOBI, SpbError
-from .solver import B200SolverWrapper, BuiltinProblem, DiagonalDamping, Handle, LMSolver
+from .solver import B200SolverWrapper, BuiltinProblem, DiagonalDamping, Handle, LMSolver, check_traits
 
-__all__ = ["capi", "Handle", "B200SolverWrapper", "DiagonalDamping", "LMSolver", "BuiltinProblem", "SpbError",
+__all__ = ["capi", "Handle", "B200SolverWrapper", "DiagonalDamping", "LMSolver", "BuiltinProblem", "SpbError", "check_traits",
            "SOLVER_CHOLESKY", "SOLVER_PCG_JACOBI", "SOLVER_PCG_IC0"]

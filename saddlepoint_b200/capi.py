@@ -27,6 +27,11 @@ class Traits(C.Structure):
                 ("pre_iteration", PRE_CB), ("post_iteration", POST_CB)]
 
 
+class CheckResult(C.Structure):
+    _fields_ = [("max_diff", C.c_double), ("max_row", C.c_int32), ("max_col", C.c_int32), ("discrepancies", C.c_int64),
+                ("outside_max", C.c_double), ("outside_count", C.c_int64), ("ncolors", C.c_int32), ("evaluations", C.c_int32)]
+
+
 class LMOptions(C.Structure):
     _fields_ = [("maxIterations", C.c_int32), ("funcTolerance", C.c_double), ("fooTolerance", C.c_double),
                 ("lambda0", C.c_double), ("verbose", C.c_int32), ("dedupe_evaluations", C.c_int32),
@@ -67,6 +72,8 @@ SYMBOLS = [
     ("spb_inf_norm", C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double)]),
     ("spb_spmv", C.c_int, [vp, vp, vp, C.c_int]),
     ("spb_lm_default_options", None, [C.POINTER(LMOptions)]),
+    ("spb_check_traits", C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.c_double, vp, vp]),
+    ("spb_check_traits", C.c_int, [vp, C.POINTER(Traits), vp, C.c_int, C.c_double, C.c_double, C.POINTER(CheckResult), vp]),
     ("spb_lm_solve", C.c_int, [vp, C.POINTER(Traits), C.POINTER(LMOptions), C.POINTER(LMResult), vp, C.c_int, vp,
                                C.c_int32, C.POINTER(C.c_int32)]),
     ("spb_problem_lf", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(vp)]),

@@ -22,6 +22,9 @@ struct Ic0Symbolic {
 };
 
 void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I);
+// Greedy distance-1 colouring of H's graph in natural order; returns the number of colours.
+// Columns of J with one colour share no residual row (H = J^T J structurally).
+int greedy_coloring(const HPattern& H, std::vector<int>& color);
 
 struct Ic0Device {
   int n = 0, ncolors = 0;

@@ -14,11 +14,10 @@
 
 namespace spb {
 
-void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I) {
+int greedy_coloring(const HPattern& H, std::vector<int>& color) {
   const int n = H.n;
-  I.n = n;
-  // greedy colouring in natural order
-  std::vector<int> color(n, -1), mark;
+  color.assign(n, -1);
+  std::vector<int> mark;
   int ncolors = 0;
   for (int v = 0; v < n; ++v) {
     mark.assign((size_t)ncolors + 1, 0);
@@ -31,6 +30,15 @@ void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I) {
     color[v] = c;
     if (c == ncolors) ++ncolors;
   }
+  return ncolors;
+}
+
+void ic0_symbolic(const HPattern& H, const SellLayout& S, Ic0Symbolic& I) {
+  const int n = H.n;
+  I.n = n;
+  // greedy colouring in natural order
+  std::vector<int> color;
+  const int ncolors = greedy_coloring(H, color);
   I.ncolors = ncolors;
   // order by (colour, index)
   I.color_ptr.assign((size_t)ncolors + 1, 0);

@@ -13,11 +13,13 @@
 // iteration.  With dedupe_evaluations the three redundant objective evaluations per
 // iteration (LMSolver.h:154 and DiagonalDamping.h:58-61 re-evaluate points whose residuals
 // are already known bit-for-bit) are skipped; the trajectory is unchanged.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
 
+#include "ic0.h"
 #include "spb_internal.h"
 
 using namespace spb;
@@ -310,3 +312,192 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
 }
 
 }  // extern "C"
+
+// ---- check_traits ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) perturb_kernel(const double* __restrict__ x, const int* __restrict__ color, int c, double step, int n,
+                                                      double* __restrict__ xp, double* __restrict__ xm) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const double vh = color[j] == c ? step : 0.0;  // CurrSolution +- vh (check_traits.h:49-52)
+  xp[j] = x[j] + vh;
+  xm[j] = x[j] - vh;
+}
+// one thread per column of colour c: FE values of its entries, and a stamp on every row it covers
+__global__ void __launch_bounds__(256) fe_gather_kernel(const int* __restrict__ cols_of_color, int count, const int* __restrict__ colptr,
+                                                        const int* __restrict__ rowidx, const double* __restrict__ Ep,
+                                                        const double* __restrict__ Em, double step, int stamp, double* __restrict__ fe,
+                                                        int* __restrict__ covered) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= count) return;
+  const int j = cols_of_color[t];
+  for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+    const int r = rowidx[q];
+    fe[q] = (Ep[r] - Em[r]) / (2 * step);  // check_traits.h:54
+    covered[r] = stamp;
+  }
+}
+// rows no perturbed column touches must not respond; out[0] = count above tol, out[1] = max (as ordered bits)
+__global__ void __launch_bounds__(256) fe_outside_kernel(const double* __restrict__ Ep, const double* __restrict__ Em, double step, double tol,
+                                                         const int* __restrict__ covered, int stamp, int m, unsigned long long* out) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= m || covered[r] == stamp) return;
+  const double v = fabs((Ep[r] - Em[r]) / (2 * step));
+  if (v > tol) atomicAdd(out, 1ull);
+  if (v > 0.0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like their bits
+}
+// diff = (|fe| > tol ? fe : 0) - J ; per block: max |diff| with the smallest position, count above tol
+__global__ void __launch_bounds__(256) fe_compare_kernel(const double* __restrict__ fe, const double* __restrict__ Jv, int64_t nnz, double tol,
+                                                         double* __restrict__ blk_max, long long* __restrict__ blk_pos,
+                                                         unsigned long long* __restrict__ count) {
+  __shared__ double smax[256];
+  __shared__ long long spos[256];
+  double best = -1.0;
+  long long bpos = -1;
+  unsigned long long cnt = 0;
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * 256) {
+    const double f = fabs(fe[q]) > tol ? fe[q] : 0.0;  // check_traits.h:56-57
+    const double d = fabs(f - Jv[q]);
+    if (d > tol) ++cnt;
+    if (d > best) {  // NaN never wins, like the reference's `maxcoeff<abs(value)`
+      best = d;
+      bpos = q;
+    }
+  }
+  smax[threadIdx.x] = best;
+  spos[threadIdx.x] = bpos;
+  if (cnt) atomicAdd(count, cnt);
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double o = smax[threadIdx.x + s];
+      const long long op = spos[threadIdx.x + s];
+      if (o > smax[threadIdx.x] || (o == smax[threadIdx.x] && op >= 0 && (spos[threadIdx.x] < 0 || op < spos[threadIdx.x]))) {
+        smax[threadIdx.x] = o;
+        spos[threadIdx.x] = op;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    blk_max[blockIdx.x] = smax[0];
+    blk_pos[blockIdx.x] = spos[0];
+  }
+}
+}  // namespace
+
+extern "C" spb_status spb_check_traits(spb_handle h, const spb_traits* T, const double* x, int mem, double step, double tol,
+                                       spb_check_result* out, double* fe_vals) {
+  if (!h || !T || !x || !out || !T->objective_jacobian) return SPB_ERR_ARG;
+  if (T->row_end > T->row_begin) return SPB_ERR_ARG;  // whole problems only
+  memset(out, 0, sizeof(*out));
+  if (step <= 0.0) step = 10e-5;
+  if (tol <= 0.0) tol = 10e-7;
+  try {
+    cudaGetLastError();
+    SPB_CUDA(cudaSetDevice(h->device));
+    const int n = T->xSize, m = T->ESize;
+    int same = 0;
+    spb_pattern_matches(h, m, n, T->colptr, T->rowidx, &same);
+    if (!same || h->partitioned) {
+      spb_status s = spb_analyze(h, m, n, T->colptr, T->rowidx);
+      if (s != SPB_OK) return s;
+    }
+    cudaStream_t st = h->stream;
+    const int64_t nnzJ = h->nnzJ;
+    if (!h->lm_ws) h->lm_ws = new LmWorkspace;
+    LmWorkspace& W = *(LmWorkspace*)h->lm_ws;
+    W.pattern_version = 0;  // the check may have re-analysed: the next LM solve re-validates its pattern
+    Evaluator ev{h, T, n, m, nnzJ, W.hx, W.hE, W.hJ};
+    ev.init();
+    // columns grouped by colour
+    std::vector<int> color;
+    const int ncolors = greedy_coloring(h->H, color);
+    std::vector<int> cptr((size_t)ncolors + 1, 0), cols(n);
+    for (int j = 0; j < n; ++j) cptr[(size_t)color[j] + 1]++;
+    for (int c = 0; c < ncolors; ++c) cptr[(size_t)c + 1] += cptr[c];
+    {
+      std::vector<int> cur(cptr.begin(), cptr.end() - 1);
+      for (int j = 0; j < n; ++j) cols[cur[color[j]]++] = j;
+    }
+    DevBuf<int> d_color, d_cols, d_cov;
+    DevBuf<double> d_x0, d_xp, d_xm, d_Ep, d_Em, d_E, d_Jv, d_fe, d_bmax;
+    DevBuf<long long> d_bpos;
+    DevBuf<unsigned long long> d_cnt;
+    SPB_CUDA(d_color.upload(color, st));
+    SPB_CUDA(d_cols.upload(cols, st));
+    SPB_CUDA(d_cov.alloc(std::max(m, 1)));
+    SPB_CUDA(cudaMemsetAsync(d_cov.p, 0xff, sizeof(int) * (size_t)std::max(m, 1), st));
+    SPB_CUDA(d_x0.alloc(std::max(n, 1)));
+    SPB_CUDA(d_xp.alloc(std::max(n, 1)));
+    SPB_CUDA(d_xm.alloc(std::max(n, 1)));
+    SPB_CUDA(d_Ep.alloc(std::max(m, 1)));
+    SPB_CUDA(d_Em.alloc(std::max(m, 1)));
+    SPB_CUDA(d_E.alloc(std::max(m, 1)));
+    SPB_CUDA(d_Jv.alloc((size_t)std::max<int64_t>(nnzJ, 1)));
+    SPB_CUDA(d_fe.alloc((size_t)std::max<int64_t>(nnzJ, 1)));
+    SPB_CUDA(d_cnt.alloc(3));
+    SPB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 3 * sizeof(unsigned long long), st));
+    SPB_CUDA(cudaMemcpyAsync(d_x0.p, x, (size_t)n * sizeof(double), mem == SPB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    ev.eval(d_x0.p, d_E.p, d_Jv.p);  // check_traits.h:32
+    int evals = 1;
+    for (int c = 0; c < ncolors; ++c) {
+      const int count = cptr[(size_t)c + 1] - cptr[c];
+      if (n > 0) perturb_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_x0.p, d_color.p, c, step, n, d_xp.p, d_xm.p);
+      ev.eval(d_xp.p, d_Ep.p, nullptr);
+      ev.eval(d_xm.p, d_Em.p, nullptr);
+      evals += 2;
+      if (count > 0)
+        fe_gather_kernel<<<(count + 255) / 256, 256, 0, st>>>(d_cols.p + cptr[c], count, h->d_Jcolptr.p, h->d_Jrow.p, d_Ep.p, d_Em.p, step, c,
+                                                             d_fe.p, d_cov.p);
+      if (m > 0) fe_outside_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_Ep.p, d_Em.p, step, tol, d_cov.p, c, m, d_cnt.p);
+      h->launches += 3;
+      SPB_CUDA(cudaGetLastError());
+    }
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>((nnzJ + 255) / 256, 1184));
+    SPB_CUDA(d_bmax.alloc(G));
+    SPB_CUDA(d_bpos.alloc(G));
+    fe_compare_kernel<<<G, 256, 0, st>>>(d_fe.p, d_Jv.p, nnzJ, tol, d_bmax.p, d_bpos.p, d_cnt.p + 2);
+    h->launches++;
+    SPB_CUDA(cudaGetLastError());
+    std::vector<double> bmax(G);
+    std::vector<long long> bpos(G);
+    unsigned long long cnt[3];
+    SPB_CUDA(cudaMemcpyAsync(bmax.data(), d_bmax.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaMemcpyAsync(bpos.data(), d_bpos.p, sizeof(long long) * G, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    if (fe_vals && nnzJ > 0) SPB_CUDA(cudaMemcpyAsync(fe_vals, d_fe.p, sizeof(double) * (size_t)nnzJ, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    double best = -32767.0;  // check_traits.h:62
+    long long pos = -1;
+    for (int b = 0; b < G; ++b)
+      if (bpos[b] >= 0 && (bmax[b] > best || (bmax[b] == best && bpos[b] < pos))) {
+        best = bmax[b];
+        pos = bpos[b];
+      }
+    out->max_diff = best;
+    out->max_row = out->max_col = -1;
+    if (pos >= 0) {
+      out->max_row = T->rowidx[pos];
+      out->max_col = (int)(std::upper_bound(T->colptr, T->colptr + n + 1, (int32_t)pos) - T->colptr) - 1;
+    }
+    out->discrepancies = (int64_t)cnt[2];
+    out->outside_count = (int64_t)cnt[0];
+    long long bits = (long long)cnt[1];
+    double om;
+    memcpy(&om, &bits, sizeof(om));
+    out->outside_max = om;
+    out->ncolors = ncolors;
+    out->evaluations = evals;
+    return SPB_OK;
+  } catch (const CudaFail& e) {
+    h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
+    return SPB_ERR_CUDA;
+  } catch (const ArgFail& e) {
+    h->err = e.msg;
+    return SPB_ERR_ARG;
+  } catch (const StateFail& e) {
+    h->err = e.msg;
+    return SPB_ERR_STATE;
+  }
+}

@@ -327,6 +327,83 @@ class DiagonalDamping:
         self.currLambda = currLambda
 
 
+def _c_traits(ST):
+    """spb_traits for a Python SolverTraits object (host callbacks) or a built-in device problem.
+    Returns (traits, objects that must stay alive while the traits are in use)."""
+    keep = []
+    T = capi.Traits()
+    if hasattr(ST, "c_traits"):  # built-in device-resident problem
+        return ST.c_traits(), keep
+    x0 = np.ascontiguousarray(ST.initial_solution(), np.float64)
+    n, m = int(ST.xSize), int(ST.ESize)
+    if hasattr(ST, "colptr") and hasattr(ST, "rowidx"):  # traits that publish their fixed CSC pattern
+        colptr, rowidx = ST.colptr, ST.rowidx
+    else:
+        E0, J0 = ST.objective_jacobian(x0.copy(), True)
+        rows, cols, colptr, rowidx, _ = _as_csc(J0)
+    colptr, pc = _i32(colptr)
+    rowidx, pr = _i32(rowidx)
+    nnz = int(colptr[-1])
+    keep += [colptr, rowidx]
+
+    def _init(user, xp):
+        np.ctypeslib.as_array(xp, shape=(n,))[:] = x0
+
+    def _objjac(user, xp, Ep, Jp, stream):
+        x = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy()
+        E, J = ST.objective_jacobian(x, bool(Jp))
+        np.ctypeslib.as_array(C.cast(Ep, C.POINTER(C.c_double)), shape=(m,))[:] = E
+        if Jp:
+            vals = _as_csc(J)[4] if not isinstance(J, np.ndarray) else J
+            np.ctypeslib.as_array(C.cast(Jp, C.POINTER(C.c_double)), shape=(nnz,))[:] = vals
+
+    def _pre(user, xp):
+        if hasattr(ST, "pre_iteration"):
+            ST.pre_iteration(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy())
+
+    def _post(user, xp):
+        if hasattr(ST, "post_iteration"):
+            return int(bool(ST.post_iteration(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy())))
+        return 0
+
+    T.xSize, T.ESize = n, m
+    T.colptr, T.rowidx = pc, pr
+    T.pattern_version = 0
+    T.mem = SPB_HOST
+    T.initial_solution = capi.INIT_CB(_init)
+    T.objective_jacobian = capi.OBJJAC_CB(_objjac)
+    T.pre_iteration = capi.PRE_CB(_pre)
+    T.post_iteration = capi.POST_CB(_post)
+    keep += [T.initial_solution, T.objective_jacobian, T.pre_iteration, T.post_iteration]
+    return T, keep
+
+
+def check_traits(handle, ST, x, step=0.0, tol=0.0, return_fe=False, verbose=True):
+    """check_traits(Traits, CurrSolution) (check_traits.h:19-83) with column-coloured central
+    differences on the GPU library: 2*ncolors evaluations instead of 2*xSize.  Returns a dict
+    (max_diff, max_row, max_col, discrepancies, outside_max, outside_count, ncolors, evaluations
+    [, fe: finite-difference values in the Jacobian's CSC order])."""
+    T, keep = _c_traits(ST)
+    px, mx, kx = _ptr(x)
+    nnz = int(np.ctypeslib.as_array(C.cast(T.colptr, C.POINTER(C.c_int32)), shape=(T.xSize + 1,))[-1])
+    fe = np.empty(nnz, np.float64) if return_fe else None
+    R = capi.CheckResult()
+    if verbose:
+        print("WARNING: FE gradient checking, reducing performance!!!")
+        print("******************************************************")
+        print("Solution Size:", T.xSize)
+    st = handle.L.spb_check_traits(handle.h, C.byref(T), px, mx, step, tol, C.byref(R), C.c_void_p(fe.ctypes.data) if return_fe else None)
+    handle._check(st)
+    handle.m, handle.n = T.ESize, T.xSize
+    out = {k: getattr(R, k) for k, _ in capi.CheckResult._fields_}
+    if verbose:
+        print("Maximum gradient difference:", R.max_diff)
+        print("At Location: (%d,%d)" % (R.max_row, R.max_col))
+    if return_fe:
+        out["fe"] = fe
+    return out
+
+
 class LMSolver:
     """LMSolver<LinearSolver, SolverTraits, DampingTraits> (LMSolver.h:22-193).
 
@@ -354,53 +431,7 @@ class LMSolver:
     def solve(self, verbose, dedupe_evaluations=False, fixed_iterations=0, x_out=None):
         H = self.LS.handle
         L = H.L
-        keep = []
-        T = capi.Traits()
-        if hasattr(self.ST, "c_traits"):  # built-in device-resident problem
-            T = self.ST.c_traits()
-        else:
-            ST = self.ST
-            x0 = np.ascontiguousarray(ST.initial_solution(), np.float64)
-            n, m = int(ST.xSize), int(ST.ESize)
-            if hasattr(ST, "colptr") and hasattr(ST, "rowidx"):  # traits that publish their fixed CSC pattern
-                colptr, rowidx = ST.colptr, ST.rowidx
-            else:
-                E0, J0 = ST.objective_jacobian(x0.copy(), True)
-                rows, cols, colptr, rowidx, _ = _as_csc(J0)
-            colptr, pc = _i32(colptr)
-            rowidx, pr = _i32(rowidx)
-            nnz = int(colptr[-1])
-            keep += [colptr, rowidx]
-
-            def _init(user, xp):
-                np.ctypeslib.as_array(xp, shape=(n,))[:] = x0
-
-            def _objjac(user, xp, Ep, Jp, stream):
-                x = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy()
-                E, J = ST.objective_jacobian(x, bool(Jp))
-                np.ctypeslib.as_array(C.cast(Ep, C.POINTER(C.c_double)), shape=(m,))[:] = E
-                if Jp:
-                    vals = _as_csc(J)[4] if not isinstance(J, np.ndarray) else J
-                    np.ctypeslib.as_array(C.cast(Jp, C.POINTER(C.c_double)), shape=(nnz,))[:] = vals
-
-            def _pre(user, xp):
-                if hasattr(ST, "pre_iteration"):
-                    ST.pre_iteration(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy())
-
-            def _post(user, xp):
-                if hasattr(ST, "post_iteration"):
-                    return int(bool(ST.post_iteration(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,)).copy())))
-                return 0
-
-            T.xSize, T.ESize = n, m
-            T.colptr, T.rowidx = pc, pr
-            T.pattern_version = 0
-            T.mem = SPB_HOST
-            T.initial_solution = capi.INIT_CB(_init)
-            T.objective_jacobian = capi.OBJJAC_CB(_objjac)
-            T.pre_iteration = capi.PRE_CB(_pre)
-            T.post_iteration = capi.POST_CB(_post)
-            keep += [T.initial_solution, T.objective_jacobian, T.pre_iteration, T.post_iteration]
+        T, keep = _c_traits(self.ST)
         O = capi.LMOptions()
         L.spb_lm_default_options(C.byref(O))
         O.maxIterations = self.maxIterations

@@ -36,6 +36,18 @@ def test_headers_compile_and_link(spb):
 
 
 @pytest.mark.gpu
+def test_check_traits_header(spb):
+    _compile(spb)
+    out = subprocess.run([EXE, "200", "1", "check"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    mres = re.search(r"CHECK max=(\S+) discrepancies=(\d+) colors=(\d+) evaluations=(\d+)", out.stdout)
+    assert mres, out.stdout[-500:]
+    assert float(mres.group(1)) < 10e-7 and int(mres.group(2)) == 0 and int(mres.group(3)) == 2 and int(mres.group(4)) == 5
+    assert "WARNING: FE gradient checking, reducing performance!!!" in out.stdout
+    assert "Maximum gradient difference" in out.stdout and "RESULT ret=" in out.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,solver", [(1000, 0), (1000, 1), (30000, 2)])
 def test_legacy_triplet_concept_gauss_newton(spb, n, solver):
     """GNSolver.h:131,169,175 call sequence (analyze(HRows,HCols,true) / factorize(HVals,true) / solve)

@@ -24,8 +24,14 @@
 // needs k/32 sequential steps, not k.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "chol_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace spb {
 
@@ -41,6 +47,7 @@ struct CholDevice {
   };
   std::vector<std::vector<Group>> groups;
   bool factored = false;
+  int coop_occ = 0;            // co-resident CTAs per SM of the cooperative solve kernels
   bool smem_attr_set = false;  // per device context, so per handle (not a process-wide static)
   int* h_fail = nullptr;
 };
@@ -469,6 +476,303 @@ __global__ void __launch_bounds__(256) chol_bwd_step_kernel(const int* __restric
   }
 }
 
+// ---- cooperative solves: all block steps of a group of fronts in ONE persistent launch -------
+// A front with k pivots needs k/32 dependent block steps; as separate launches (above) every
+// step pays a launch plus a drain/fill tail (~10 us measured), which made the solve of the top
+// separators a 486-launch latency chain.  Here the steps are separated by grid barriers
+// (~1.5 us): every CTA recomputes the 32-entry block solution through the inverted diagonal
+// block (fixed summation order, so all CTAs hold the same bits) and updates its own 256 rows
+// (forward) or 256 earlier pivots (backward).  Used for groups with few and/or large fronts;
+// groups of many small fronts keep the one-CTA-per-front shared-memory kernels.
+struct CoopSolveArgs {
+  const int* fronts;
+  int count, max_k, max_r;
+  unsigned long long* phase_ns;  // debug stopwatch of CTA 0 (SPB_CHOL_TIMING=2), else null
+  int parts;  // CTAs sharing one front (each redoes the tile's small solve, then takes every parts-th row block)
+  const int *sn_k, *sn_r, *col0;
+  const int64_t *L_off, *W_off, *dinv_off;
+  const int *child_ptr, *child_idx;
+  const int64_t* rel_ptr;
+  const int* rel_idx;
+  const int64_t* struct_ptr;
+  const int* struct_idx;
+  const double *Lbuf, *Dinv;
+  double *Wbuf, *y;
+};
+
+__device__ __forceinline__ unsigned long long chol_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CHOL_TICK(k)                                        \
+  if (A.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) {  \
+    const unsigned long long now_ = chol_global_ns();       \
+    A.phase_ns[k] += now_ - tick_;                          \
+    tick_ = now_;                                           \
+  }
+constexpr int kCoopTile = 128;  // pivots per grid step: the tile's own triangular solve is redone by every CTA
+constexpr int kBlkPitch = 33;   // shared-memory pitch of a 32x32 block: conflict-free by rows and by columns
+constexpr int kBlkSize = kBlkPitch * 32;
+// shared memory of the cooperative solves: 4 inverted diagonal blocks + the 6 blocks below them
+constexpr size_t kCoopSmem = (size_t)(10 * kBlkSize) * sizeof(double);
+
+// Stage the tile's factor data (read-only) in shared memory with every load in flight at once:
+// Dinv blocks b = 0..3 at sm[b], block (bi, bj), bi > bj, of the tile's lower triangle at
+// sm[4 + bi(bi-1)/2 + bj]; element (i, t) of a block at t * kBlkPitch + i.
+__device__ __forceinline__ void coop_stage_tile(const double* __restrict__ P, const double* __restrict__ Dinv_f, int r, int kb, int nbt,
+                                                double* sm) {
+  const int tid = threadIdx.x, i = tid & 31, tq = tid >> 5;
+  const int nblk = (nbt + 31) >> 5;
+  // all (up to 40) loads of a thread are issued before the first store: one memory round trip, not ten
+  double dv[4][4], lv[6][4];
+#pragma unroll
+  for (int bq = 0; bq < 4; ++bq) {
+    const double* Di = Dinv_f + (int64_t)((kb >> 5) + bq) * 1024;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dv[bq][u] = bq < nblk ? Di[(tq * 4 + u) * 32 + i] : 0.0;
+  }
+#pragma unroll
+  for (int bi = 1; bi < 4; ++bi)
+#pragma unroll
+    for (int bj = 0; bj < bi; ++bj) {
+      const int row = bi * 32 + i;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        lv[bi * (bi - 1) / 2 + bj][u] = row < nbt ? P[(int64_t)(kb + bj * 32 + tq * 4 + u) * r + kb + row] : 0.0;
+    }
+  asm volatile("" ::: "memory");  // keep the loads above the stores (issue them back to back)
+#pragma unroll
+  for (int bq = 0; bq < 4; ++bq)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sm[bq * kBlkSize + (tq * 4 + u) * kBlkPitch + i] = dv[bq][u];
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sm[(4 + q) * kBlkSize + (tq * 4 + u) * kBlkPitch + i] = lv[q][u];
+}
+
+// L2 prefetch of the factor data of the tile at kb (read-only), issued before a grid barrier so the
+// staging loads after it are L2 hits
+__device__ __forceinline__ void coop_prefetch_tile(const double* __restrict__ P, const double* __restrict__ Dinv_f, int r, int kb, int nbt) {
+  const int tid = threadIdx.x;
+  const int nblk = (nbt + 31) >> 5;
+  // one 128-byte line per prefetch: Dinv blocks are 8 KB contiguous each, L columns nbt*8 bytes each
+  for (int q = tid; q < nblk * 64; q += 256) {
+    const double* a = Dinv_f + (int64_t)(kb >> 5) * 1024 + (int64_t)q * 16;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+  }
+  const int lines = (nbt * 8 + 127) / 128 + 1;
+  for (int q = tid; q < nbt * lines; q += 256) {
+    const int t = q / lines, ln = q - t * lines;
+    const double* a = P + (int64_t)(kb + t) * r + kb + ln * 16;
+    if (ln * 16 < nbt + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+  }
+}
+
+// out[0..32) = Dinv_blk * v  (TRANS: Dinv_blk^T * v) from the staged block, all 256 threads, fixed order
+template <bool TRANS>
+__device__ __forceinline__ void coop_diag_apply(const double* Dsm, const double* v, int nb, double (*part)[32], double* out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double sacc = 0.0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = warp * 4 + u;
+    if (!TRANS) {
+      if (t < nb) sacc += Dsm[t * kBlkPitch + lane] * v[t];  // lower-triangular block: zeros above the diagonal
+    } else {
+      if (t < nb && t >= lane) sacc += Dsm[lane * kBlkPitch + t] * v[t];
+    }
+  }
+  part[warp][lane] = sacc;
+  __syncthreads();
+  if (tid < 32) {
+    double r = part[0][tid];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) r += part[q][tid];
+    out[tid] = r;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) chol_fwd_coop_kernel(CoopSolveArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double tile_sm[];
+  __shared__ double part[8][32];
+  __shared__ double wloc[kCoopTile];
+  __shared__ double ys[kCoopTile];
+  __shared__ double red[4][64];
+  const int tid = threadIdx.x;
+  // gather: w = [y_pivots ; 0] + children's tails, children in a fixed order
+  for (int fi = blockIdx.x; fi < A.count; fi += gridDim.x) {
+    const int f = A.fronts[fi];
+    const int k = A.sn_k[f], r = A.sn_r[f], c0 = A.col0[f];
+    double* w = A.Wbuf + A.W_off[f];
+    for (int i = tid; i < r; i += 256) w[i] = i < k ? A.y[c0 + i] : 0.0;
+    __syncthreads();
+    for (int ci = A.child_ptr[f]; ci < A.child_ptr[f + 1]; ++ci) {
+      const int c = A.child_idx[ci];
+      const int ck = A.sn_k[c], cu = A.sn_r[c] - ck;
+      const double* tail = A.Wbuf + A.W_off[c] + ck;
+      const int* rel = A.rel_idx + A.rel_ptr[c];
+      for (int t = tid; t < cu; t += 256) w[rel[t]] += tail[t];
+      __syncthreads();
+    }
+  }
+  grid.sync();
+  const int items = A.count * A.parts;
+  unsigned long long tick_ = A.phase_ns ? chol_global_ns() : 0ull;
+  for (int kb = 0; kb < A.max_k; kb += kCoopTile) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int fi = item / A.parts, pt = item - fi * A.parts;
+      const int f = A.fronts[fi];
+      const int k = A.sn_k[f];
+      if (k <= kb) continue;
+      const int r = A.sn_r[f];
+      const int nbt = min(kCoopTile, k - kb);
+      if (pt > 0 && kb + nbt + pt * 64 >= r) continue;  // no rows for this part
+      double* w = A.Wbuf + A.W_off[f];
+      const double* P = A.Lbuf + A.L_off[f];
+      coop_stage_tile(P, A.Dinv + A.dinv_off[f], r, kb, nbt, tile_sm);
+      if (tid < nbt) wloc[tid] = w[kb + tid];
+      __syncthreads();
+      CHOL_TICK(0)
+      for (int sb = 0, bq = 0; sb < nbt; sb += 32, ++bq) {  // the tile's triangular solve, 32 pivots at a time
+        const int nb = min(32, nbt - sb);
+        coop_diag_apply<false>(tile_sm + bq * kBlkSize, wloc + sb, nb, part, ys + sb);
+        const int i = sb + 32 + tid;  // remaining pivots of the tile (the blocks below this one)
+        if (i < nbt) {
+          const int bi = i >> 5;
+          const double* blk = tile_sm + (4 + bi * (bi - 1) / 2 + bq) * kBlkSize + (i & 31);
+          double sv = wloc[i];
+#pragma unroll 8
+          for (int t = 0; t < 32; ++t) sv -= blk[t * kBlkPitch] * ys[sb + t];
+          wloc[i] = sv;
+        }
+        __syncthreads();
+      }
+      if (pt == 0 && tid < nbt) A.y[A.col0[f] + kb + tid] = ys[tid];
+      if (tid >= nbt && tid < kCoopTile) ys[tid] = 0.0;  // partial tile: the row update multiplies zeros there
+      __syncthreads();
+      CHOL_TICK(1)
+      // rows below the tile (later pivots and the tail): 64 rows at a time, four threads per row, each
+      // takes 32 of the tile's columns with all its loads in flight; partial sums meet in a fixed order
+      for (int row0 = kb + nbt + pt * 64; row0 < r; row0 += A.parts * 64) {
+        const int i = row0 + (tid & 63), cgp = tid >> 6;
+        double acc = 0.0;
+        const double wi = (tid < 64 && i < r) ? w[i] : 0.0;
+        if (i < r) {
+          const double* col = P + (int64_t)(kb + cgp * 32) * r + i;
+          const int tn = min(32, nbt - cgp * 32);
+          double lv[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) lv[t] = t < tn ? col[(int64_t)t * r] : 0.0;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) acc += lv[t] * ys[cgp * 32 + t];
+        }
+        red[cgp][tid & 63] = acc;
+        __syncthreads();
+        if (tid < 64 && i < r) w[i] = wi - (((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid]);
+        __syncthreads();
+      }
+      CHOL_TICK(2)
+      if (kb + kCoopTile < k) coop_prefetch_tile(P, A.Dinv + A.dinv_off[f], r, kb + kCoopTile, min(kCoopTile, k - kb - kCoopTile));
+    }
+    grid.sync();
+    CHOL_TICK(3)
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) chol_bwd_coop_kernel(CoopSolveArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double tile_sm[];
+  __shared__ double part[8][32];
+  __shared__ double wloc[kCoopTile];
+  __shared__ double xs[kCoopTile];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // w_piv = y_piv - L21^T x_struct : one warp per pivot column
+  {
+    const int ngroups = (A.max_k + 7) / 8;
+    for (int item = blockIdx.x; item < A.count * ngroups; item += gridDim.x) {
+      const int fi = item / ngroups, gq = item - fi * ngroups;
+      const int f = A.fronts[fi];
+      const int k = A.sn_k[f], r = A.sn_r[f];
+      const int j = gq * 8 + warp;
+      if (j >= k) continue;
+      const int* st = A.struct_idx + A.struct_ptr[f];
+      const double* col = A.Lbuf + A.L_off[f] + (int64_t)j * r;
+      double sacc = 0.0;
+      int i = k + lane;
+      for (; i + 96 < r; i += 128) {  // four independent loads (and gathers) in flight per lane
+        const double a0 = col[i], a1 = col[i + 32], a2 = col[i + 64], a3 = col[i + 96];
+        const double b0 = A.y[st[i - k]], b1 = A.y[st[i + 32 - k]], b2 = A.y[st[i + 64 - k]], b3 = A.y[st[i + 96 - k]];
+        sacc += a0 * b0;
+        sacc += a1 * b1;
+        sacc += a2 * b2;
+        sacc += a3 * b3;
+      }
+      for (; i < r; i += 32) sacc += col[i] * A.y[st[i - k]];
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) A.Wbuf[A.W_off[f] + j] = A.y[A.col0[f] + j] - sacc;
+    }
+  }
+  grid.sync();
+  const int items = A.count * A.parts;
+  for (int kb = ((A.max_k - 1) / kCoopTile) * kCoopTile; kb >= 0; kb -= kCoopTile) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int fi = item / A.parts, pt = item - fi * A.parts;
+      const int f = A.fronts[fi];
+      const int k = A.sn_k[f];
+      if (k <= kb) continue;
+      if (pt > 0 && pt * 32 >= kb) continue;  // no earlier pivot columns for this part
+      const int r = A.sn_r[f];
+      const int nbt = min(kCoopTile, k - kb);
+      double* w = A.Wbuf + A.W_off[f];
+      const double* P = A.Lbuf + A.L_off[f];
+      coop_stage_tile(P, A.Dinv + A.dinv_off[f], r, kb, nbt, tile_sm);
+      if (tid < nbt) wloc[tid] = w[kb + tid];
+      __syncthreads();
+      for (int bq = (nbt - 1) >> 5; bq >= 0; --bq) {  // the tile's own back substitution
+        const int sb = bq * 32;
+        const int nb = min(32, nbt - sb);
+        coop_diag_apply<true>(tile_sm + bq * kBlkSize, wloc + sb, nb, part, xs + sb);
+        if (tid < sb) {  // earlier pivots of the tile: w_j -= sum_t L[sb+t, j] x_t
+          const double* blk = tile_sm + (4 + bq * (bq - 1) / 2 + (tid >> 5)) * kBlkSize + (tid & 31) * kBlkPitch;
+          double sv = wloc[tid];
+#pragma unroll 8
+          for (int t = 0; t < 32; ++t)
+            if (t < nb) sv -= blk[t] * xs[sb + t];
+          wloc[tid] = sv;
+        }
+        __syncthreads();
+      }
+      if (pt == 0 && tid < nbt) A.y[A.col0[f] + kb + tid] = xs[tid];
+      // earlier pivots: w_j -= sum_t L[kb+t, j] * x_t -- 32 columns at a time, four per warp, the lanes
+      // across the tile's (consecutive) rows so every load is a full line and 16 are in flight per lane
+      for (int c = pt; c * 32 < kb; c += A.parts) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = c * 32 + warp * 4 + u;
+          if (j < kb) {
+            const double* col = P + (int64_t)j * r + kb;
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < kCoopTile / 32; ++q) {
+              const int t = lane + 32 * q;
+              if (t < nbt) acc += col[t] * xs[t];
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) w[j] -= acc;
+          }
+        }
+      }
+      __syncthreads();
+      if (kb > 0) coop_prefetch_tile(P, A.Dinv + A.dinv_off[f], r, kb - kCoopTile, kCoopTile);
+    }
+    grid.sync();
+  }
+}
+
 __global__ void chol_permute_kernel(const double* __restrict__ in, const int* __restrict__ perm, double* __restrict__ out, int n, int dir) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -566,7 +870,9 @@ spb_status chol_factorize(spb_context* h) {
       const int b = C.rank_ptr[rk], cnt = C.rank_ptr[(size_t)rk + 1] - b;
       for (int off = 0; off < cnt; off += 32768) {
         const int c = std::min(32768, cnt - off);
-        chol_extend_add_kernel<<<dim3(64, c), 256, 0, st>>>(D->rank_children.p + b + off, D->parent.p, D->sn_k.p, D->sn_r.p, D->L_off.p,
+        // enough CTAs to fill the GPU even when a rank has one or two (large) children
+        const int gx = std::max(16, std::min(2048, (h->num_sms * 16 + c - 1) / c));
+        chol_extend_add_kernel<<<dim3(gx, c), 256, 0, st>>>(D->rank_children.p + b + off, D->parent.p, D->sn_k.p, D->sn_r.p, D->L_off.p,
                                                             D->U_off.p, D->rel_ptr.p, D->rel_idx.p, D->Lbuf.p, D->Ubuf.p);
         ++nl;
       }
@@ -614,6 +920,52 @@ spb_status chol_factorize(spb_context* h) {
   return D->factored ? SPB_OK : SPB_NOT_SPD;
 }
 
+// cooperative solve of a group: large fronts (the shared-memory kernels cannot hold them) and
+// groups with too few fronts to fill the GPU with one CTA per front
+static bool use_coop(spb_context* h, const CholDevice::Group& G) {
+  static const int mode = getenv("SPB_CHOL_COOP") ? atoi(getenv("SPB_CHOL_COOP")) : 1;
+  if (mode == 0) return false;
+  return G.max_r > kBigFront || (G.count < 2 * h->num_sms && G.max_k > 64);
+}
+static CoopSolveArgs coop_args(spb_context* h, CholDevice* D, const CholDevice::Group& G) {
+  CoopSolveArgs A;
+  A.phase_ns = nullptr;
+  A.parts = std::max(1, std::min((2 * h->num_sms + G.count - 1) / G.count, (G.max_r + 63) / 64));
+  A.fronts = D->level_sn.p + G.begin;
+  A.count = G.count;
+  A.max_k = G.max_k;
+  A.max_r = G.max_r;
+  A.sn_k = D->sn_k.p;
+  A.sn_r = D->sn_r.p;
+  A.col0 = D->col0.p;
+  A.L_off = D->L_off.p;
+  A.W_off = D->W_off.p;
+  A.dinv_off = D->dinv_off.p;
+  A.child_ptr = D->child_ptr.p;
+  A.child_idx = D->child_idx.p;
+  A.rel_ptr = D->rel_ptr.p;
+  A.rel_idx = D->rel_idx.p;
+  A.struct_ptr = D->struct_ptr.p;
+  A.struct_idx = D->struct_idx.p;
+  A.Lbuf = D->Lbuf.p;
+  A.Dinv = D->Dinv.p;
+  A.Wbuf = D->Wbuf.p;
+  A.y = D->ywork.p;
+  return A;
+}
+static int coop_grid(spb_context* h, CholDevice* D, int items) {
+  if (D->coop_occ == 0) {
+    int a = 0, b = 0;
+    SPB_CUDA(cudaFuncSetAttribute(chol_fwd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    SPB_CUDA(cudaFuncSetAttribute(chol_bwd_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem));
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, chol_fwd_coop_kernel, 256, kCoopSmem));
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, chol_bwd_coop_kernel, 256, kCoopSmem));
+    D->coop_occ = std::max(1, std::min(a, b));
+  }
+  // barriers get slower with more CTAs: no more than the work can use, at most two per SM
+  return std::max(1, std::min(items, h->num_sms * std::min(2, D->coop_occ)));
+}
+
 spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
   if (h->n == 0) return SPB_OK;
   CholDevice* D = (CholDevice*)h->chol;
@@ -631,9 +983,59 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
     SPB_CUDA(cudaFuncSetAttribute(chol_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     D->smem_attr_set = true;
   }
+  static const bool dbg = getenv("SPB_CHOL_TIMING") && atoi(getenv("SPB_CHOL_TIMING")) > 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (dbg) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+  }
+  auto dbg_begin = [&]() {
+    if (dbg) cudaEventRecord(e0, st);
+  };
+  auto dbg_end = [&](const char* what, int l, const CholDevice::Group& G) {
+    if (!dbg) return;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[spb chol timing] %s level %d fronts %d max_k %d max_r %d coop %d: %.1f us\n", what, l, G.count, G.max_k, G.max_r,
+            (int)use_coop(h, G), ms * 1e3);
+  };
   for (int l = 0; l < C.nlevels; ++l) {
     for (const CholDevice::Group& G : D->groups[l]) {
       const int* list = D->level_sn.p + G.begin;
+      dbg_begin();
+      struct Scope {
+        decltype(dbg_end)& f;
+        int l;
+        const CholDevice::Group& G;
+        ~Scope() { f("fwd", l, G); }
+      } scope{dbg_end, l, G};
+      if (use_coop(h, G)) {
+        CoopSolveArgs A = coop_args(h, D, G);
+        static const bool dbg2 = getenv("SPB_CHOL_TIMING") && atoi(getenv("SPB_CHOL_TIMING")) > 1;
+        DevBuf<unsigned long long> d_ns;
+        if (dbg2) {
+          SPB_CUDA(d_ns.alloc(4));
+          SPB_CUDA(cudaMemsetAsync(d_ns.p, 0, 32, st));
+          A.phase_ns = d_ns.p;
+        }
+        struct Pr {
+          bool on; DevBuf<unsigned long long>& b; cudaStream_t st; int steps;
+          ~Pr() {
+            if (!on) return;
+            unsigned long long t[4];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, b.p, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[spb chol timing]   fwd CTA0 per tile step: stage %.2f solve %.2f rows %.2f sync %.2f us (%d steps)\n", t[0] * 1e-3 / steps,
+                    t[1] * 1e-3 / steps, t[2] * 1e-3 / steps, t[3] * 1e-3 / steps, steps);
+          }
+        } pr{dbg2, d_ns, st, (G.max_k + kCoopTile - 1) / kCoopTile};
+        void* args[] = {&A};
+        SPB_CUDA(cudaLaunchCooperativeKernel((void*)chol_fwd_coop_kernel, dim3(coop_grid(h, D, G.count * A.parts)), dim3(256), args, kCoopSmem, st));
+        ++nl;
+        continue;
+      }
       if (G.max_r > kBigFront) {
         chol_fwd_gather_kernel<<<G.count, 256, 0, st>>>(list, D->sn_k.p, D->sn_r.p, D->col0.p, D->W_off.p, D->child_ptr.p, D->child_idx.p,
                                                         D->rel_ptr.p, D->rel_idx.p, D->Wbuf.p, D->ywork.p);
@@ -657,6 +1059,20 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
   for (int l = C.nlevels - 1; l >= 0; --l) {
     for (const CholDevice::Group& G : D->groups[l]) {
       const int* list = D->level_sn.p + G.begin;
+      dbg_begin();
+      struct Scope {
+        decltype(dbg_end)& f;
+        int l;
+        const CholDevice::Group& G;
+        ~Scope() { f("bwd", l, G); }
+      } scope{dbg_end, l, G};
+      if (use_coop(h, G)) {
+        CoopSolveArgs A = coop_args(h, D, G);
+        void* args[] = {&A};
+        SPB_CUDA(cudaLaunchCooperativeKernel((void*)chol_bwd_coop_kernel, dim3(coop_grid(h, D, G.count * std::max(A.parts, (G.max_k + 7) / 8))), dim3(256), args, kCoopSmem, st));
+        ++nl;
+        continue;
+      }
       if (G.max_r > kBigFront) {
         chol_bwd_tail_kernel<<<dim3((G.max_k + 7) / 8, G.count), 256, 0, st>>>(list, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
                                                                               D->struct_ptr.p, D->struct_idx.p, D->Lbuf.p, D->Wbuf.p,

@@ -41,6 +41,7 @@ struct CholDevice {
   DevBuf<int64_t> L_off, U_off, W_off, struct_ptr, rel_ptr, dinv_off, a_src, a_dst;
   DevBuf<double> Lbuf, Ubuf, Wbuf, Dinv, ywork;
   DevBuf<int> fail;
+  DevBuf<long long> dbg;
   // per level: groups of fronts of similar size -> ranges in level_sn (fronts sorted by r inside a level)
   struct Group {
     int begin, count, max_k, max_r;
@@ -53,6 +54,7 @@ struct CholDevice {
 };
 
 // ---- small device helpers --------------------------------------------------------------
+__device__ __forceinline__ unsigned long long chol_global_ns();
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -167,6 +169,168 @@ __global__ void __launch_bounds__(128) chol_trsm_kernel(const int* __restrict__ 
     if (t < nb) P[(int64_t)(kb + t) * r + row] = v[t];
 }
 
+// ---- fused block step: Cholesky of the 32x32 diagonal block + the rows below it -------------
+// One launch per 32-column step instead of two (potrf32 -> trsm): every CTA of a front loads the
+// diagonal block and factors it itself (warp 0, one lane per row, ~4 us; the other warps fetch
+// their rows of the panel meanwhile), then solves its 128 rows against it.  All CTAs compute the
+// same bits.  The factored block is NOT written back in place -- other CTAs of the launch are
+// still reading the unfactored one -- and nothing downstream reads it: the solves apply the
+// diagonal blocks through their inverses, which the launch's extra CTA (blockIdx.x == gridDim.x-1)
+// computes and stores together with the failure flag.
+__device__ __forceinline__ void warp_potrf32(double (*S)[33], int nb, int lane, int* fail_flag, double* rdiag) {
+  // lane i keeps row i of the block in registers; columns are eliminated right-looking.  The
+  // finished column is published through shared memory (rdiag doubles as the buffer) and read back
+  // with broadcast 16-byte loads: a single warp issues shuffles far too slowly for the 496 column
+  // entries the updates need.  Rows/columns >= nb are identity padding.
+  // One rsqrt per column instead of sqrt + divide (both long software sequences in FP64 on the
+  // critical path): l_jj = d * rsqrt(d), l_ij = a_ij * rsqrt(d); rdiag[j] = 1/l_jj afterwards for
+  // the row solves, which multiply instead of dividing.
+  (void)nb;
+  __shared__ __align__(16) double colbuf[4][32];  // one per warp of the CTA
+  double* cb = colbuf[(threadIdx.x >> 5) & 3];
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
+  bool bad = false;
+  double myr = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    bad = bad || (d <= 0.0);  // NaN passes, like the reference's `if (d <= 0)`
+    const double rs = rsqrt(d);
+    if (lane == j) {
+      a[j] = d * rs;
+      myr = rs;
+    } else if (lane > j) {
+      a[j] = a[j] * rs;
+    }
+    cb[lane] = a[j];
+    __syncwarp();
+#pragma unroll
+    for (int c = (j + 1) & ~1; c < 32; c += 2) {
+      const double2 l2 = *reinterpret_cast<const double2*>(cb + c);
+      if (c > j && lane >= c) a[c] -= a[j] * l2.x;
+      if (lane >= c + 1) a[c + 1] -= a[j] * l2.y;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && bad) *fail_flag = 1;
+  rdiag[lane] = myr;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) S[lane][c] = a[c];
+}
+
+// Column `lane` of S^-1 (S lower triangular in shared memory) by forward substitution; the factor
+// entries are broadcast reads, the 32 solution entries live in registers.  out: 32x32 column-major.
+__device__ __forceinline__ void warp_inverse32(double (*S)[33], const double* rdiag, int lane, double* __restrict__ out) {
+  double x[32];
+#pragma unroll
+  for (int rw = 0; rw < 32; ++rw) {
+    double acc = (rw == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int t = 0; t < rw; ++t) acc -= S[rw][t] * x[t];  // x[t] == 0 for t < lane
+    x[rw] = rw >= lane ? acc * rdiag[rw] : 0.0;
+  }
+#pragma unroll
+  for (int rw = 0; rw < 32; ++rw) out[lane * 32 + rw] = x[rw];
+}
+
+// Throughput variant for levels with many fronts: one WARP per front factors the 32x32 diagonal
+// block at pivot offset kb in registers, writes it back and stores its inverse.
+__global__ void __launch_bounds__(128) chol_potrf32_warp_kernel(const int* __restrict__ fronts, int count, int kb, const int* __restrict__ sn_k,
+                                                                const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                                const int64_t* __restrict__ dinv_off, double* __restrict__ Lbuf,
+                                                                double* __restrict__ Dinv, int* __restrict__ fail) {
+  __shared__ double Sm[4][32][33];
+  __shared__ double Rd[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = blockIdx.x * 4 + warp;
+  if (fi >= count) return;
+  const int f = fronts[fi];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  double* D = Lbuf + L_off[f] + (int64_t)kb * r + kb;
+  double(*S)[33] = Sm[warp];
+  for (int c = 0; c < 32; ++c) S[lane][c] = (lane < nb && c < nb && lane >= c) ? D[(int64_t)c * r + lane] : (lane == c ? 1.0 : 0.0);
+  __syncwarp();
+  int bad = 0;
+  warp_potrf32(S, nb, lane, &bad, Rd[warp]);
+  if (lane == 0 && bad) *fail = 1;
+  __syncwarp();
+  for (int c = 0; c < nb; ++c)
+    if (lane < nb && lane >= c) D[(int64_t)c * r + lane] = S[lane][c];
+  warp_inverse32(S, Rd[warp], lane, Dinv + dinv_off[f] + (int64_t)(kb >> 5) * 1024);
+}
+
+__global__ void __launch_bounds__(128) chol_step_kernel(const int* __restrict__ fronts, int kb, const int* __restrict__ sn_k,
+                                                        const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                        const int64_t* __restrict__ dinv_off, double* __restrict__ Lbuf,
+                                                        double* __restrict__ Dinv, int* __restrict__ fail, long long* dbg) {
+  __shared__ double Dm[32][33];
+  __shared__ double Rd[32];
+  __shared__ int sfail;
+  const bool dbg_on = dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  if (dbg_on) {
+    dbg[0] = clock64();
+    dbg[5] = (long long)chol_global_ns();
+  }
+  const int f = fronts[blockIdx.y];
+  const int k = sn_k[f];
+  if (k <= kb) return;
+  const int r = sn_r[f];
+  const int nb = min(32, k - kb);
+  const int rb = kb + nb;
+  const bool inv_cta = blockIdx.x == gridDim.x - 1;
+  if (!inv_cta && (int64_t)blockIdx.x * 128 >= r - rb) return;
+  double* P = Lbuf + L_off[f];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sfail = 0;
+  // all global loads first (the diagonal block and this thread's row of the panel): one memory round
+  // trip; the row stays in flight while warp 0 factors the block
+  const int row = rb + blockIdx.x * 128 + tid;
+  const bool have_row = !inv_cta && row < r;
+  double dl[8], v[32];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = warp + 4 * u;
+    dl[u] = (lane < nb && c < nb && lane >= c) ? P[(int64_t)(kb + c) * r + kb + lane] : (lane == c ? 1.0 : 0.0);
+  }
+#pragma unroll
+  for (int t = 0; t < 32; ++t) v[t] = (have_row && t < nb) ? P[(int64_t)(kb + t) * r + row] : 0.0;
+  asm volatile("" ::: "memory");
+#pragma unroll
+  for (int u = 0; u < 8; ++u) Dm[lane][warp + 4 * u] = dl[u];
+  __syncthreads();
+  if (dbg_on) dbg[1] = clock64();
+  if (warp == 0) warp_potrf32(Dm, nb, lane, &sfail, Rd);
+  __syncthreads();
+  if (dbg_on) dbg[2] = clock64();
+  if (inv_cta) {
+    if (tid == 0 && sfail) *fail = 1;
+    // inverse: warp w computes columns w, w+4, ... of Dm^-1 by forward substitution, lane t holds x_t
+    if (warp == 0) warp_inverse32(Dm, Rd, lane, Dinv + dinv_off[f] + (int64_t)(kb >> 5) * 1024);
+    return;
+  }
+  if (!have_row) return;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const double xq = v[q] * Rd[q];
+    v[q] = xq;
+#pragma unroll
+    for (int t = q + 1; t < 32; ++t) v[t] -= xq * Dm[t][q];
+  }
+  if (dbg_on) dbg[3] = clock64();
+#pragma unroll
+  for (int t = 0; t < 32; ++t)
+    if (t < nb) P[(int64_t)(kb + t) * r + row] = v[t];
+  if (dbg_on) {
+    dbg[4] = clock64();
+    dbg[6] = (long long)chol_global_ns();
+  }
+}
+
 // C -= A_i * A_j^T on 64x64 tiles of the lower triangle, FP64 tensor cores (DMMA m8n8k4).
 // mode 0: pivot columns [ke, min(cend, k)) are updated with the factor columns [ka, ke) -- used
 //         twice: inside a 256-column panel (ka = kb, ke = kb+32, cend = panel end; K = 32) and once
@@ -180,8 +344,10 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
                                                         const int* __restrict__ sn_k,
                                                         const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
                                                         const int64_t* __restrict__ U_off, double* __restrict__ Lbuf,
-                                                        double* __restrict__ Ubuf) {
+                                                        double* __restrict__ Ubuf, long long* dbg) {
   __shared__ double As[2 * kSyrkKC * kSyrkLd], Bs[2 * kSyrkKC * kSyrkLd];
+  const bool dbg_on = dbg && blockIdx.x == 0 && blockIdx.y == gridDim.y - 1 && blockIdx.z == 0 && threadIdx.x == 0;
+  if (dbg_on) dbg[0] = clock64();
   const int f = fronts[blockIdx.z];
   const int k = sn_k[f], r = sn_r[f];
   double* P = Lbuf + L_off[f];
@@ -237,6 +403,7 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   const int nchunks = (K + kSyrkKC - 1) / kSyrkKC;
+  if (dbg_on) dbg[1] = clock64();
   stage_load(0, 0);
   for (int c = 0; c < nchunks; ++c) {
     const int st = c & 1;
@@ -264,6 +431,11 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
     }
     __syncthreads();
   }
+  if (dbg_on) dbg[2] = clock64();
+  // read-modify-write of the C tile in two passes (all 32 loads of a thread in flight, then the
+  // stores): written as `C[..] -= acc` the compiler must assume aliasing and serialises 32 memory
+  // round trips, which cost more than the K=32 main loop
+  double cv[4][4][2];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -272,8 +444,19 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
       for (int e = 0; e < 2; ++e) {
         const int i = ti * 64 + wy * 32 + p * 8 + lr;
         const int j = tj * 64 + wx * 32 + q * 8 + 2 * lk + e;
-        if (i < nrows && j < ncols && i >= j) C[(int64_t)j * ldc + i] -= acc[p][q][e];
+        cv[p][q][e] = (i < nrows && j < ncols && i >= j) ? C[(int64_t)j * ldc + i] : 0.0;
       }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = ti * 64 + wy * 32 + p * 8 + lr;
+        const int j = tj * 64 + wx * 32 + q * 8 + 2 * lk + e;
+        if (i < nrows && j < ncols && i >= j) C[(int64_t)j * ldc + i] = cv[p][q][e] - acc[p][q][e];
+      }
+  if (dbg_on) dbg[3] = clock64();
 }
 
 // ---- solves --------------------------------------------------------------------------------
@@ -854,6 +1037,7 @@ spb_status chol_factorize(spb_context* h) {
   cudaStream_t st = h->stream;
   const int ns = C.nsuper;
   if ((size_t)(C.max_r + 32) * sizeof(double) > 200 * 1024) throw ArgFail{"front too large for the triangular-solve kernels"};
+  static const bool fused_step = !(getenv("SPB_CHOL_FUSED") && atoi(getenv("SPB_CHOL_FUSED")) == 0);
   stage_begin(h, ST_FACTOR);
   int nl = 0;
   SPB_CUDA(cudaMemsetAsync(D->Lbuf.p, 0, (size_t)C.L_off[ns] * sizeof(double), st));
@@ -883,32 +1067,70 @@ spb_status chol_factorize(spb_context* h) {
       for (int ob = 0; ob < G.max_k; ob += kPanel) {
         const int oe = ob + kPanel;
         for (int kb = ob; kb < std::min(oe, G.max_k); kb += 32) {
-          chol_potrf32_kernel<<<G.count, 1024, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p,
-                                                        D->fail.p);
-          ++nl;
-          const int rows = G.max_r - kb - 1;
-          if (rows > 0) {
-            chol_trsm_kernel<<<dim3((rows + 127) / 128, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->Lbuf.p);
+          const int rows_below = std::max(0, G.max_r - kb - 1);
+          if (fused_step && (int64_t)((rows_below + 127) / 128 + 1) * G.count <= 2 * h->num_sms) {  // latency regime
+            const int rows = rows_below;
+            static const bool dbg3 = getenv("SPB_CHOL_TIMING") && atoi(getenv("SPB_CHOL_TIMING")) == 3;
+            long long* dbgp = nullptr;
+            if (dbg3 && G.count == 1 && kb == 0 && l == C.nlevels - 1) {
+              SPB_CUDA(D->dbg.alloc(8));
+              dbgp = D->dbg.p;
+            }
+            chol_step_kernel<<<dim3((rows + 127) / 128 + 1, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p,
+                                                                                    D->Lbuf.p, D->Dinv.p, D->fail.p, dbgp);
+            if (dbgp) {
+              long long t[8];
+              cudaStreamSynchronize(st);
+              cudaMemcpy(t, dbgp, sizeof(t), cudaMemcpyDeviceToHost);
+              fprintf(stderr, "[spb chol timing] step kernel root kb=0: load %lld potrf %lld trsm %lld store %lld cycles; total %lld cycles in %lld ns\n",
+                      t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[4] - t[0], t[6] - t[5]);
+            }
             ++nl;
+          } else {
+            if (fused_step)
+              chol_potrf32_warp_kernel<<<(G.count + 3) / 4, 128, 0, st>>>(list, G.count, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p,
+                                                                          D->Lbuf.p, D->Dinv.p, D->fail.p);
+            else
+              chol_potrf32_kernel<<<G.count, 1024, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->dinv_off.p, D->Lbuf.p, D->Dinv.p,
+                                                            D->fail.p);
+            ++nl;
+            const int rows = G.max_r - kb - 1;
+            if (rows > 0) {
+              chol_trsm_kernel<<<dim3((rows + 127) / 128, G.count), 128, 0, st>>>(list, kb, D->sn_k.p, D->sn_r.p, D->L_off.p, D->Lbuf.p);
+              ++nl;
+            }
           }
           if (kb + 32 < std::min(oe, G.max_k)) {  // narrow update, confined to the panel's columns
             const int nti = (G.max_r - kb - 32 + 63) / 64, ntj = (std::min(oe, G.max_k) - kb - 32 + 63) / 64;
+            static const bool dbg4 = getenv("SPB_CHOL_TIMING") && atoi(getenv("SPB_CHOL_TIMING")) == 4;
+            long long* dbgp = nullptr;
+            if (dbg4 && G.count == 1 && kb == 0 && l == C.nlevels - 1) {
+              SPB_CUDA(D->dbg.alloc(8));
+              dbgp = D->dbg.p;
+            }
             chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, kb, kb + 32, oe, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
-                                                                    D->Lbuf.p, D->Ubuf.p);
+                                                                    D->Lbuf.p, D->Ubuf.p, dbgp);
+            if (dbgp) {
+              long long t[8];
+              cudaStreamSynchronize(st);
+              cudaMemcpy(t, dbgp, sizeof(t), cudaMemcpyDeviceToHost);
+              fprintf(stderr, "[spb chol timing] narrow syrk root kb=0 grid (%d,%d): setup %lld mainloop %lld epilogue %lld cycles\n", ntj, nti,
+                      t[1] - t[0], t[2] - t[1], t[3] - t[2]);
+            }
             ++nl;
           }
         }
         if (oe < G.max_k) {  // everything right of the panel, once, with K = 256
           const int nti = (G.max_r - oe + 63) / 64, ntj = (G.max_k - oe + 63) / 64;
           chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, ob, oe, 0x7fffffff, D->sn_k.p, D->sn_r.p, D->L_off.p,
-                                                                  D->U_off.p, D->Lbuf.p, D->Ubuf.p);
+                                                                  D->U_off.p, D->Lbuf.p, D->Ubuf.p, nullptr);
           ++nl;
         }
       }
       const int umax = G.max_r;  // upper bound on u inside the group
       const int nt = (umax + 63) / 64;
       chol_syrk_kernel<<<dim3(nt, nt, G.count), 128, 0, st>>>(list, 1, 0, 0, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
-                                                             D->Ubuf.p);
+                                                             D->Ubuf.p, nullptr);
       ++nl;
     }
   }

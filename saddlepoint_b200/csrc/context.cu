@@ -1,6 +1,9 @@
 // context.cu -- handle lifetime, error plumbing, per-stage CUDA-event timing, and the
 // granular C ABI (analyze / assemble / factorize / solve / reductions).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -183,13 +186,24 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
     h->nnzJ = colptr[n];
     h->partitioned = false;
     h->m_global = m;
-    build_h_pattern(m, n, colptr, rowidx, h->H);
-    build_sell(h->H, h->S);
+    const bool timing = getenv("SPB_ANALYZE_TIMING") && atoi(getenv("SPB_ANALYZE_TIMING")) > 0;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!timing) return;
+      auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[spb analyze timing] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    };
     AssemblyPlan P;
-    build_assembly_plan(m, n, colptr, rowidx, h->H, P);
+    build_analysis(m, n, colptr, rowidx, h->H, h->S, P);
+    lap("host symbolic (pattern, SpMV layout, assembly plan)");
     upload_h_layout(h);
+    lap("upload H layout");
     upload_analysis(h, colptr, rowidx, P);
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+    lap("pack + upload assembly plan");
     h->fingerprint = pattern_fingerprint(m, n, colptr, rowidx);
+    lap("fingerprint");
     h->h_fingerprint = 0;
     h->analyzed = true;
     h->have_h = true;

@@ -144,6 +144,8 @@ struct SlotMeta {    // 8 bytes
 void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H);
 void build_sell(const HPattern& H, SellLayout& S);
 void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P);
+// the three above in one pass over a shared row view of J (multithreaded; SPB_HOST_THREADS)
+void build_analysis(int m, int n, const int* colptr, const int* rowidx, HPattern& H, SellLayout& S, AssemblyPlan& P);
 uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx);
 
 }  // namespace spb

@@ -9,7 +9,12 @@
 // position in column j) pairs of J entries that share a residual row, in ascending row
 // order -- the accumulation order of the reference's product.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 #include "spb_internal.h"
 
@@ -31,6 +36,63 @@ uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx)
 }
 
 namespace {
+// Host threads for the symbolic phase (SPB_HOST_THREADS overrides; 1 = serial).
+int host_threads() {
+  static const int t = [] {
+    const char* e = getenv("SPB_HOST_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(v, 32));
+  }();
+  return t;
+}
+// SPB_ANALYZE_TIMING=2: stderr stopwatch of the symbolic sub-phases
+struct Lap {
+  const char* who;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit Lap(const char* w) : who(w), on(getenv("SPB_ANALYZE_TIMING") && atoi(getenv("SPB_ANALYZE_TIMING")) > 1), t0(std::chrono::steady_clock::now()) {}
+  void operator()(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spb analyze timing]   %s: %s %.3f s (threads %d)\n", who, what, std::chrono::duration<double>(t1 - t0).count(), host_threads());
+    t0 = t1;
+  }
+};
+// Splits columns [0,n) into `parts` contiguous ranges of roughly equal weight (prefix sums in w, n+1 entries).
+template <class W>
+std::vector<int> split_columns(int n, const W* w, int parts) {
+  std::vector<int> cut((size_t)parts + 1, n);
+  cut[0] = 0;
+  const double total = (double)(w[n] - w[0]);
+  for (int p = 1; p < parts; ++p) {
+    const double target = (double)w[0] + total * p / parts;
+    cut[p] = (int)(std::lower_bound(w, w + n + 1, target, [](W a, double b) { return (double)a < b; }) - w);
+    cut[p] = std::max(cut[p], cut[p - 1]);
+    cut[p] = std::min(cut[p], n);
+  }
+  return cut;
+}
+// Runs fn(part) for part in [0,parts) on its own thread; rethrows the first exception.
+template <class F>
+void run_parts(int parts, F fn) {
+  if (parts <= 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err((size_t)parts);
+  for (int p = 0; p < parts; ++p)
+    th.emplace_back([&, p] {
+      try {
+        fn(p);
+      } catch (...) {
+        err[p] = std::current_exception();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
 // CSR view of the J pattern with, per entry, its position inside its CSC column.
 struct RowView {
   std::vector<int64_t> ptr;  // m+1
@@ -63,40 +125,91 @@ void build_row_view(int m, int n, const int* colptr, const int* rowidx, RowView&
 }
 }  // namespace
 
+namespace {
+void h_pattern_impl(int m, int n, const int* colptr, const int* rowidx, const RowView& R, HPattern& H);
+void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, const RowView& R, const HPattern& H, AssemblyPlan& P);
+}  // namespace
+
 void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H) {
   RowView R;
   build_row_view(m, n, colptr, rowidx, R);
+  h_pattern_impl(m, n, colptr, rowidx, R, H);
+}
+
+void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P) {
+  RowView R;
+  build_row_view(m, n, colptr, rowidx, R);
+  assembly_plan_impl(m, n, colptr, rowidx, R, H, P);
+}
+
+// pattern + SpMV layout + assembly plan with one shared row view (what spb_analyze runs)
+void build_analysis(int m, int n, const int* colptr, const int* rowidx, HPattern& H, SellLayout& S, AssemblyPlan& P) {
+  RowView R;
+  Lap lap("build_analysis");
+  build_row_view(m, n, colptr, rowidx, R);
+  lap("row view");
+  h_pattern_impl(m, n, colptr, rowidx, R, H);
+  build_sell(H, S);
+  lap("pattern + sell");
+  assembly_plan_impl(m, n, colptr, rowidx, R, H, P);
+  lap("plan");
+}
+
+namespace {
+void h_pattern_impl(int m, int n, const int* colptr, const int* rowidx, const RowView& R, HPattern& H) {
+  (void)m;
+  Lap lap("build_h_pattern");
   H.n = n;
   H.colptr.assign((size_t)n + 1, 0);
-  H.rowidx.clear();
-  H.rowidx.reserve((size_t)colptr[n] * 2);
   H.nup1.assign(n, 0);
-  std::vector<int> mark(n, -1), tmp;
-  for (int j = 0; j < n; ++j) {
-    tmp.clear();
-    mark[j] = j;  // the damping row makes the diagonal structural even for empty columns
-    tmp.push_back(j);
-    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
-      int r = rowidx[q];
-      for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
-        int i = R.col[t];
-        if (mark[i] != j) {
-          mark[i] = j;
-          tmp.push_back(i);
+  // column ranges are independent: one thread each, local row lists concatenated afterwards
+  const int parts = n >= 4096 ? host_threads() : 1;
+  const std::vector<int> cut = split_columns(n, colptr, parts);
+  std::vector<std::vector<int>> local((size_t)parts);
+  std::vector<int> collen(n, 0);
+  run_parts(parts, [&](int p) {
+    std::vector<int> mark(n, -1), tmp;
+    std::vector<int>& out = local[p];
+    out.reserve((size_t)(colptr[cut[p + 1]] - colptr[cut[p]]) * 2 + 16);
+    for (int j = cut[p]; j < cut[p + 1]; ++j) {
+      tmp.clear();
+      mark[j] = j;  // the damping row makes the diagonal structural even for empty columns
+      tmp.push_back(j);
+      for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+        int r = rowidx[q];
+        for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
+          int i = R.col[t];
+          if (mark[i] != j) {
+            mark[i] = j;
+            tmp.push_back(i);
+          }
         }
       }
+      std::sort(tmp.begin(), tmp.end());
+      int up = 0;
+      for (int i : tmp) {
+        if (i <= j) ++up;
+        out.push_back(i);
+      }
+      H.nup1[j] = up;
+      collen[j] = (int)tmp.size();
     }
-    std::sort(tmp.begin(), tmp.end());
-    int up = 0;
-    for (int i : tmp) {
-      if (i <= j) ++up;
-      H.rowidx.push_back(i);
-    }
-    H.nup1[j] = up;
-    if (H.rowidx.size() > (size_t)0x7fffffff) throw ArgFail{"H pattern exceeds int32 indexing"};
-    H.colptr[(size_t)j + 1] = (int)H.rowidx.size();
+  });
+  lap("columns");
+  int64_t total = 0;
+  for (int j = 0; j < n; ++j) {
+    total += collen[j];
+    if (total > (int64_t)0x7fffffff) throw ArgFail{"H pattern exceeds int32 indexing"};
+    H.colptr[(size_t)j + 1] = (int)total;
   }
+  H.rowidx.resize((size_t)total);
+  run_parts(parts, [&](int p) {
+    if (!local[p].empty()) memcpy(H.rowidx.data() + H.colptr[cut[p]], local[p].data(), local[p].size() * sizeof(int));
+    std::vector<int>().swap(local[p]);
+  });
+  lap("concatenate");
 }
+}  // namespace
 
 void build_sell(const HPattern& H, SellLayout& S) {
   int n = H.n;
@@ -130,9 +243,9 @@ void build_sell(const HPattern& H, SellLayout& S) {
   // rows past n in the last slice never load; their col16 entries stay at delta 0
 }
 
-void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, const HPattern& H, AssemblyPlan& P) {
-  RowView R;
-  build_row_view(m, n, colptr, rowidx, R);
+namespace {
+void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, const RowView& R, const HPattern& H, AssemblyPlan& P) {
+  Lap lap("build_assembly_plan");
   P.m = m;
   P.n = n;
   P.nnzJ = colptr[n];
@@ -162,52 +275,70 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       }
     }
   }
-  // pair stream
-  std::vector<int> where(n, -1);
+  lap("slots and ranks");
+  // pair stream: column ranges are independent -- one thread each builds its slice of the
+  // slot-major record stream, the slices are concatenated in column order
   struct Tmp {
     int slot, po, qo;
   };
-  std::vector<Tmp> tmp;
-  std::vector<int> cnt, start;
-  std::vector<uint32_t> colrecs;     // records of the current column, slot-major
   std::vector<int> slot_npairs(P.nslots, 0);
   // First pass materialises records per column into one big stream (slot-major); chunking
   // and 32-padding are applied in a second pass over slots.
   std::vector<uint32_t> stream;
-  stream.reserve((size_t)P.nnzJ * 4);
   const int pobits = P.rec_bits == 16 ? 7 : 15;
-  for (int j = 0; j < n; ++j) {
-    int s0 = P.low_colptr[j], s1 = P.low_colptr[(size_t)j + 1];
-    int ns = s1 - s0;
-    if (ns == 0) continue;
-    for (int s = s0; s < s1; ++s) where[P.low_row[s]] = s - s0;
-    tmp.clear();
-    cnt.assign(ns, 0);
-    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
-      int r = rowidx[q];
-      int qo = q - colptr[j];
-      for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
-        int i = R.col[t];
-        if (i <= j) continue;
-        int sl = where[i];
-        tmp.push_back({sl, R.pos_in_col[t], qo});
-        cnt[sl]++;
+  {
+    const int parts = n >= 4096 ? host_threads() : 1;
+    const std::vector<int> cut = split_columns(n, P.low_colptr.data(), parts);
+    std::vector<std::vector<uint32_t>> lstream((size_t)parts);
+    run_parts(parts, [&](int p) {
+      std::vector<int> where(n, -1);
+      std::vector<Tmp> tmp;
+      std::vector<int> cnt, start;
+      std::vector<uint32_t> colrecs;  // records of the current column, slot-major
+      std::vector<uint32_t>& out = lstream[p];
+      out.reserve((size_t)(colptr[cut[p + 1]] - colptr[cut[p]]) * 4 + 16);
+      for (int j = cut[p]; j < cut[p + 1]; ++j) {
+        int s0 = P.low_colptr[j], s1 = P.low_colptr[(size_t)j + 1];
+        int ns = s1 - s0;
+        if (ns == 0) continue;
+        for (int s = s0; s < s1; ++s) where[P.low_row[s]] = s - s0;
+        tmp.clear();
+        cnt.assign(ns, 0);
+        for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+          int r = rowidx[q];
+          int qo = q - colptr[j];
+          for (int64_t t = R.ptr[r]; t < R.ptr[(size_t)r + 1]; ++t) {
+            int i = R.col[t];
+            if (i <= j) continue;
+            int sl = where[i];
+            tmp.push_back({sl, R.pos_in_col[t], qo});
+            cnt[sl]++;
+          }
+        }
+        start.assign((size_t)ns + 1, 0);
+        for (int k = 0; k < ns; ++k) start[(size_t)k + 1] = start[k] + cnt[k];
+        colrecs.resize(tmp.size());
+        std::vector<int>& cur = cnt;  // reuse as cursor
+        for (int k = 0; k < ns; ++k) cur[k] = start[k];
+        for (const Tmp& e : tmp) {
+          int d = cur[e.slot]++;
+          uint32_t first = (d == start[e.slot]) ? 1u : 0u;
+          colrecs[d] = (first << (2 * pobits)) | ((uint32_t)e.po << pobits) | (uint32_t)e.qo;
+        }
+        for (int k = 0; k < ns; ++k) slot_npairs[s0 + k] = start[(size_t)k + 1] - start[k];
+        out.insert(out.end(), colrecs.begin(), colrecs.end());
+        for (int s = s0; s < s1; ++s) where[P.low_row[s]] = -1;
       }
-    }
-    start.assign((size_t)ns + 1, 0);
-    for (int k = 0; k < ns; ++k) start[(size_t)k + 1] = start[k] + cnt[k];
-    colrecs.resize(tmp.size());
-    std::vector<int>& cur = cnt;  // reuse as cursor
-    for (int k = 0; k < ns; ++k) cur[k] = start[k];
-    for (const Tmp& e : tmp) {
-      int d = cur[e.slot]++;
-      uint32_t first = (d == start[e.slot]) ? 1u : 0u;
-      colrecs[d] = (first << (2 * pobits)) | ((uint32_t)e.po << pobits) | (uint32_t)e.qo;
-    }
-    for (int k = 0; k < ns; ++k) slot_npairs[s0 + k] = start[(size_t)k + 1] - start[k];
-    stream.insert(stream.end(), colrecs.begin(), colrecs.end());
-    for (int s = s0; s < s1; ++s) where[P.low_row[s]] = -1;
+    });
+    std::vector<size_t> off((size_t)parts + 1, 0);
+    for (int p = 0; p < parts; ++p) off[(size_t)p + 1] = off[p] + lstream[p].size();
+    stream.resize(off[parts]);
+    run_parts(parts, [&](int p) {
+      if (!lstream[p].empty()) memcpy(stream.data() + off[p], lstream[p].data(), lstream[p].size() * sizeof(uint32_t));
+      std::vector<uint32_t>().swap(lstream[p]);
+    });
   }
+  lap("pair stream");
   P.npairs = (int64_t)stream.size();
   // Position of the mirror entry H(j,i) in row j, and compaction to the slots that actually
   // receive products.  With a full Jacobian every structural slot is active; under row
@@ -258,9 +389,15 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
   P.grp_slot.clear();
   P.rec16.clear();
   P.rec32.clear();
-  if (P.rec_bits == 16) P.rec16.reserve(stream.size() + stream.size() / 16);
-  else P.rec32.reserve(stream.size() + stream.size() / 16);
   {
+    // Phase A (sequential, light): chunk boundaries and stage lists.  Phase B (parallel over
+    // chunks): copy the records with their 32-padding, group -> slot map, per-slot start/count
+    // and the processing order.
+    struct Open {
+      int cs, s_end, np;
+      int64_t src;
+    };
+    std::vector<Open> chunks;
     std::vector<int> local_of(n, -1);   // column -> index in the current chunk's stage list
     std::vector<int> cur_list;          // stage list being built
     int64_t src = 0;                    // cursor in `stream`
@@ -277,9 +414,8 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
     auto close_chunk = [&](int s_end) {
       if (s_end == cs) return;
       const int np = c_np;
-      int64_t rec0 = P.rec_bits == 16 ? (int64_t)P.rec16.size() : (int64_t)P.rec32.size();
+      chunks.push_back({cs, s_end, np, src});
       P.chunk_slot.push_back(cs);
-      P.chunk_rec.push_back(rec0);
       P.chunk_npairs.push_back(np);
       P.chunk_stage_ptr.push_back((int)P.stage_cols.size());
       const bool staged = c_vals <= kStageVals && (int)cur_list.size() <= kStageCols;
@@ -292,29 +428,6 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
         off += (colptr[col + 1] - colptr[col] + a + 1) & ~1;
         local_of[col] = -1;
       }
-      int sl = -1;  // chunk-local slot of the record being copied
-      for (int t = 0; t < np; ++t) {
-        uint32_t rec = stream[(size_t)(src + t)];
-        if (rec >> (2 * pobits)) {
-          ++sl;
-          P.slot_start[(size_t)cs + sl] = (uint16_t)std::min(t, 65535);
-        }
-        if ((t & 31) == 0) P.grp_slot.push_back((uint16_t)sl);
-        if (P.rec_bits == 16) P.rec16.push_back((uint16_t)rec); else P.rec32.push_back(rec);
-      }
-      int pad = (32 - (np & 31)) & 31;
-      for (int t = 0; t < pad; ++t) {
-        if (P.rec_bits == 16) P.rec16.push_back(0); else P.rec32.push_back(0);
-      }
-      // processing order inside the chunk: slots sorted by descending pair count, so the 32
-      // slots a warp walks in lock step have (nearly) equal trip counts -- no divergence waste.
-      // Records stay slot-major; every slot carries its own (start, count).
-      for (int s = cs; s < s_end; ++s) {
-        P.slot_cnt[s] = (uint16_t)std::min(slot_npairs[s], 65535);
-        P.proc_perm[s] = s;
-      }
-      std::stable_sort(P.proc_perm.begin() + cs, P.proc_perm.begin() + s_end,
-                       [&](int a, int b) { return slot_npairs[a] > slot_npairs[b]; });
       src += np;
       cur_list.clear();
       cs = s_end;
@@ -359,7 +472,46 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
       }
     }
     close_chunk(P.nslots);
+    lap("chunk boundaries");
+    // record offsets (32-padded per chunk)
+    const int nch = (int)chunks.size();
+    P.chunk_rec.resize(nch);
+    int64_t total = 0;
+    for (int c = 0; c < nch; ++c) {
+      P.chunk_rec[c] = total;
+      total += ((int64_t)chunks[c].np + 31) & ~(int64_t)31;
+    }
+    if (P.rec_bits == 16) P.rec16.assign((size_t)total, 0); else P.rec32.assign((size_t)total, 0);
+    P.grp_slot.assign((size_t)(total / 32), 0);
+    const int parts = nch >= 64 ? host_threads() : 1;
+    run_parts(parts, [&](int p) {
+      const int c_begin = (int)((int64_t)nch * p / parts), c_end = (int)((int64_t)nch * (p + 1) / parts);
+      for (int c = c_begin; c < c_end; ++c) {
+        const Open& ch = chunks[c];
+        const int64_t rec0 = P.chunk_rec[c];
+        int sl = -1;  // chunk-local slot of the record being copied
+        for (int t = 0; t < ch.np; ++t) {
+          const uint32_t rec = stream[(size_t)(ch.src + t)];
+          if (rec >> (2 * pobits)) {
+            ++sl;
+            P.slot_start[(size_t)ch.cs + sl] = (uint16_t)std::min(t, 65535);
+          }
+          if ((t & 31) == 0) P.grp_slot[(size_t)(rec0 / 32 + t / 32)] = (uint16_t)sl;
+          if (P.rec_bits == 16) P.rec16[(size_t)(rec0 + t)] = (uint16_t)rec; else P.rec32[(size_t)(rec0 + t)] = rec;
+        }
+        // processing order inside the chunk: slots sorted by descending pair count, so the 32
+        // slots a warp walks in lock step have (nearly) equal trip counts -- no divergence waste.
+        // Records stay slot-major; every slot carries its own (start, count).
+        for (int sidx = ch.cs; sidx < ch.s_end; ++sidx) {
+          P.slot_cnt[sidx] = (uint16_t)std::min(slot_npairs[sidx], 65535);
+          P.proc_perm[sidx] = sidx;
+        }
+        std::stable_sort(P.proc_perm.begin() + ch.cs, P.proc_perm.begin() + ch.s_end,
+                         [&](int a2, int b2) { return slot_npairs[a2] > slot_npairs[b2]; });
+      }
+    });
   }
+  lap("chunking");
   P.chunk_slot.push_back(P.nslots);
   P.chunk_stage_ptr.push_back((int)P.stage_cols.size());
   // column kernel chunks: by entry count and column count
@@ -376,5 +528,6 @@ void build_assembly_plan(int m, int n, const int* colptr, const int* rowidx, con
   }
   P.colchunk.push_back(n);
 }
+}  // namespace
 
 }  // namespace spb

@@ -1,6 +1,9 @@
 // symbolic_api.cpp -- host-only entry points of the symbolic phase (no GPU needed): used by
 // the CPU test tier to check the pattern and the assembly plan's invariants.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "chol_internal.h"
@@ -71,12 +74,19 @@ spb_status spb_symbolic_chol_stats(int32_t m, int32_t n, const int32_t* colptr, 
 spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats) {
   if (!colptr || !stats || m < 0 || n < 0) return SPB_ERR_ARG;
   try {
+    const bool timing = getenv("SPB_ANALYZE_TIMING") && atoi(getenv("SPB_ANALYZE_TIMING")) > 0;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!timing) return;
+      auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[spb analyze timing] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    };
     HPattern H;
-    build_h_pattern(m, n, colptr, rowidx, H);
     SellLayout S;
-    build_sell(H, S);
     AssemblyPlan P;
-    build_assembly_plan(m, n, colptr, rowidx, H, P);
+    build_analysis(m, n, colptr, rowidx, H, S, P);
+    lap("build_analysis (pattern + SpMV layout + assembly plan)");
     int64_t bad = 0;
     const int pobits = P.rec_bits == 16 ? 7 : 15;
     const uint32_t mask = (1u << pobits) - 1u;

@@ -426,6 +426,7 @@ spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int m
   if (!h || !x || nrhs < 1) return SPB_ERR_ARG;
   return guarded(h, [&]() {
     if (!h->factor_valid) throw StateFail{"spb_solve before spb_factorize"};
+    h->solve_xx_valid = false;
     SPB_CUDA(cudaSetDevice(h->device));
     const size_t n = (size_t)h->n;
     int total_iters = 0;

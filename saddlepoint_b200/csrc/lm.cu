@@ -186,7 +186,13 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
     do {
       if (T->pre_iteration) T->pre_iteration(T->user, ev.view(d_prevx.p));
       // LMSolver.h:117-119 + DiagonalDamping rebuild + LMSolver.h:136's product, fused
-      run_assembly(h, d_Jv.p, d_E.p, lambda, &foo);
+      if (fixed) {
+        // no stop test consumes ||rhs||_inf before the solve: fetch it with the solve's own synchronisation
+        run_assembly(h, d_Jv.p, d_E.p, lambda, nullptr);
+        SPB_CUDA(cudaMemcpyAsync(h->h_scalar + 2, h->d_foo_bits.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      } else {
+        run_assembly(h, d_Jv.p, d_E.p, lambda, &foo);
+      }
       if (!fixed && foo < O->fooTolerance) {
         copy_vec(d_x.p, d_prevx.p);
         if (verbose) {
@@ -211,8 +217,13 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
         goto done;
       }
       if (ss != SPB_OK && ss != SPB_NOT_CONVERGED) return ss;
+      if (fixed) {
+        if (h->solver == SPB_SOLVER_CHOLESKY) SPB_CUDA(cudaStreamSynchronize(st));  // the PCG solves end with a synchronisation
+        foo = h->h_scalar[2];
+      }
       double dn2 = 0.0;
-      dev_squared_norm(h, d_dir.p, n, &dn2);
+      if (h->solve_xx_valid) dn2 = h->h_sc->xx;  // by-product of the persistent PCG kernel
+      else dev_squared_norm(h, d_dir.p, n, &dn2);
       const double dn = std::sqrt(dn2);
       if (!fixed && dn < O->funcTolerance) {
         copy_vec(d_x.p, d_prevx.p);

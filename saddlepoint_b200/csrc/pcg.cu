@@ -537,6 +537,19 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
     grid.sync();
     SPB_TICK(7)
   }
+  // ||x||^2 while everything is still on chip: the LM loop's direction-norm test (LMSolver.h:146)
+  double xx;
+  {
+    double a = 0.0;
+    for (int i = blk * 256 + tid; i < n; i += stride) {
+      const double v = P.x[i];
+      a = fma(v, v, a);
+    }
+    const double s1 = block_sum_256(a, sm);
+    if (tid == 0) partA[blk] = s1;
+    grid.sync();
+    xx = block_total(partA, G, sm, &bc);
+  }
   if (blk == 0 && tid == 0) {
     PcgScalars* sc = P.sc;
     sc->rz = rz;
@@ -547,6 +560,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
     sc->iters = iters;
     sc->breakdown = breakdown;
     sc->maxit = P.maxit;
+    sc->xx = xx;
     sc->done = 1;
   }
 }
@@ -733,6 +747,7 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
       fprintf(stderr, "\n");
     }
     h->pcg_last_iters = h->h_sc->iters;
+    h->solve_xx_valid = true;
     if (iters) *iters = h->h_sc->iters;
     if (h->h_sc->breakdown) return SPB_NOT_SPD;
     if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;

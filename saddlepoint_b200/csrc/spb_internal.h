@@ -163,6 +163,7 @@ struct PcgScalars {
   unsigned int ticket_a, ticket_b;
   int pad0, pad1;
   double red[4];  // local partial sums handed to ncclAllReduce by the distributed PCG
+  double xx;      // ||x||^2 of the solution, by-product of the persistent kernel (saves the LM loop a launch and a sync)
 };
 
 struct Timing {
@@ -197,6 +198,7 @@ struct spb_context {
   bool factor_valid = false;
   uint64_t fingerprint = 0;   // of the J pattern
   uint64_t h_fingerprint = 0; // of an explicitly set H pattern
+  bool solve_xx_valid = false; // the last spb_solve left ||x||^2 in h_sc->xx
   // legacy triplet interface (spb_analyze_triplets): CSC entry q of H sums d_trip_src[d_trip_ptr[q] .. d_trip_ptr[q+1])
   int64_t trip_nnz = -1;      // number of input triplets; -1 = no triplet analysis on this handle
   spb::DevBuf<int64_t> d_trip_ptr;

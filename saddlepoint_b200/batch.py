@@ -4,8 +4,14 @@ Every problem is a complete LMSolver::solve with its own lambda, acceptance and 
 problems finish after different iteration counts.  The batch is sharded in contiguous index blocks
 (one handle per GPU, no data-path collective); results are gathered at the end.  Inside a rank the
 problems run back to back on one handle: the Jacobian pattern of same-shaped problems is analysed
-once (pattern fingerprint), buffers are reused.
+once (pattern fingerprint), buffers are reused.  With workers > 1 the rank keeps that many handles
+(each with its own CUDA stream) and host threads: the problems are small (their persistent PCG
+kernels occupy a few dozen CTAs, their LM loops are latency- and host-bound), so several of them
+share the GPU; every problem still runs the unmodified per-problem loop, results are identical.
 """
+from concurrent.futures import ThreadPoolExecutor
+import threading
+
 import numpy as np
 
 from . import dist as sd
@@ -47,19 +53,40 @@ def solve_problem(handle, spec, solver=SOLVER_CHOLESKY, verbose=True):
     return out
 
 
-def solve_batch(nproblems, rank=0, world=1, handle=None, make_spec=c4_problem_spec, solver=SOLVER_CHOLESKY, dist=None, keep_x=False):
+def solve_batch(nproblems, rank=0, world=1, handle=None, make_spec=c4_problem_spec, solver=SOLVER_CHOLESKY, dist=None, keep_x=False,
+                workers=1):
     """Solve this rank's block of the batch; with world > 1 gather every rank's results."""
-    own = handle is None
-    handle = handle or Handle(0)
     lo, hi = sd.shard_range(nproblems, world, rank)
-    mine = []
-    for i in range(lo, hi):
-        r = solve_problem(handle, make_spec(i), solver)
+
+    def one(h, i):
+        r = solve_problem(h, make_spec(i), solver)
         if not keep_x:
             r["xnorm"] = float(np.linalg.norm(r.pop("x")))
-        mine.append((i, r))
-    if own:
-        handle.close()
+        return (i, r)
+
+    if workers <= 1:
+        own = handle is None
+        handle = handle or Handle(0)
+        mine = [one(handle, i) for i in range(lo, hi)]
+        if own:
+            handle.close()
+    else:
+        # one handle (and stream) per worker thread; ctypes releases the GIL inside the library
+        local = threading.local()
+        handles = []
+        lock = threading.Lock()
+
+        def task(i):
+            if not hasattr(local, "h"):
+                local.h = Handle(handle.device if handle is not None else 0)
+                with lock:
+                    handles.append(local.h)
+            return one(local.h, i)
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            mine = list(pool.map(task, range(lo, hi)))
+        for h in handles:
+            h.close()
     if world == 1:
         return [r for _, r in mine]
     return sd.merge_problem_results(sd.gather_objects(mine, dist))

@@ -163,7 +163,7 @@ void h_pattern_impl(int m, int n, const int* colptr, const int* rowidx, const Ro
   H.colptr.assign((size_t)n + 1, 0);
   H.nup1.assign(n, 0);
   // column ranges are independent: one thread each, local row lists concatenated afterwards
-  const int parts = n >= 4096 ? host_threads() : 1;
+  const int parts = std::max(1, std::min(host_threads(), n / 32768));  // small problems stay on the calling thread
   const std::vector<int> cut = split_columns(n, colptr, parts);
   std::vector<std::vector<int>> local((size_t)parts);
   std::vector<int> collen(n, 0);
@@ -287,7 +287,7 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
   std::vector<uint32_t> stream;
   const int pobits = P.rec_bits == 16 ? 7 : 15;
   {
-    const int parts = n >= 4096 ? host_threads() : 1;
+    const int parts = std::max(1, std::min(host_threads(), n / 32768));
     const std::vector<int> cut = split_columns(n, P.low_colptr.data(), parts);
     std::vector<std::vector<uint32_t>> lstream((size_t)parts);
     run_parts(parts, [&](int p) {
@@ -483,7 +483,7 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
     }
     if (P.rec_bits == 16) P.rec16.assign((size_t)total, 0); else P.rec32.assign((size_t)total, 0);
     P.grp_slot.assign((size_t)(total / 32), 0);
-    const int parts = nch >= 64 ? host_threads() : 1;
+    const int parts = std::max(1, std::min(host_threads(), nch / 256));
     run_parts(parts, [&](int p) {
       const int c_begin = (int)((int64_t)nch * p / parts), c_end = (int)((int64_t)nch * (p + 1) / parts);
       for (int c = c_begin; c < c_end; ++c) {

@@ -42,3 +42,16 @@ def test_sharded_blocks_cover_batch(spb):
     merged = __import__("saddlepoint_b200").dist.merge_problem_results(parts)
     assert len(merged) == 5
     h.close()
+
+
+def test_concurrent_workers_give_identical_results(spb):
+    """workers > 1: several handles/streams share the GPU; every problem's result is bit-identical to
+    the back-to-back run (the per-problem loop is untouched)."""
+    from saddlepoint_b200 import batch
+    spec = lambda i: batch.c4_problem_spec(i, n=900) if i % 2 else {"kind": "rosenbrock", "nblocks": 200, "x0": None, "maxIterations": 1000}
+    seq = batch.solve_batch(10, make_spec=spec, keep_x=True, solver=spb.SOLVER_PCG_JACOBI)
+    par = batch.solve_batch(10, make_spec=spec, keep_x=True, solver=spb.SOLVER_PCG_JACOBI, workers=4)
+    assert len(seq) == len(par) == 10
+    for a, b in zip(seq, par):
+        assert a["currIter"] == b["currIter"] and a["exit_path"] == b["exit_path"] and a["energy"] == b["energy"]
+        assert np.array_equal(a["x"], b["x"])

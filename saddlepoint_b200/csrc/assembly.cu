@@ -31,10 +31,13 @@
 //    emits rhs, d, sqrt(d)^2 onto the diagonal, the Jacobi diagonal, and a block max of
 //    |rhs| folded with atomicMax on the (non-negative) bit pattern.
 #include <algorithm>
+#include <cstdlib>
 
 #include "spb_internal.h"
 
 namespace spb {
+
+constexpr int64_t kSliceBaseMask = ((int64_t)1 << 48) - 1;  // StageEntry::slice_base: low 48 bits position, high 16 bits run length
 
 // ---- TMA (bulk async copy) helpers: global -> shared with mbarrier completion ------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,14 +132,14 @@ __global__ void __launch_bounds__(256, 8) assemble_pairs_kernel(const RecT* __re
       const StageEntry e = stage[st0 + t];
       s_src[t] = e.src;
       s_offlen[t] = ((unsigned)e.off << 16) | e.len;
-      s_sbase[t] = e.slice_base;
+      s_sbase[t] = e.slice_base & kSliceBaseMask;
       if (staged && bulk) {
-        // TMA: one bulk async copy per listed J column (its 16-byte-aligned window), issued by
-        // the thread that just read the entry, all completing on one mbarrier -- no per-element
-        // instructions, and the copy is in flight while the other loads of this phase land.
+        // TMA: one bulk async copy per RUN of consecutive listed J columns (16-byte-aligned window),
+        // issued by the thread that just read the run's head entry, all completing on one mbarrier
+        // -- no per-element instructions, and the copy is in flight while the other loads land.
+        const int run = (int)((uint64_t)e.slice_base >> 48);
         const int a = e.src & 1;
-        const int nal = ((int)e.len + a + 1) & ~1;
-        if (nal > 0) tma_bulk_g2s(sval + ((int)e.off - a), Jv + (e.src - a), (uint32_t)nal * 8u, &bar);
+        if (run > 0) tma_bulk_g2s(sval + ((int)e.off - a), Jv + (e.src - a), (uint32_t)run * 8u, &bar);
       }
     }
   }
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(256, 8) assemble_pairs_kernel(const RecT* __re
         const StageEntry ei = stage[st0 + mt.il], ej = stage[st0 + mt.jl];
         bx = ei.src;
         by = ej.src;
-        bi = ei.slice_base;
-        bj = ej.slice_base;
+        bi = ei.slice_base & kSliceBaseMask;
+        bj = ej.slice_base & kSliceBaseMask;
       }
       double acc;
       if (staged && one_tile) acc = slot_sum<RecT, POBITS, true>(srec, sval + bx, sval + by, beg[k], end[k]);
@@ -204,6 +207,148 @@ __global__ void __launch_bounds__(256, 8) assemble_pairs_kernel(const RecT* __re
       else acc = slot_sum<RecT, POBITS, false>(recs + rec0, Jv + bx, Jv + by, beg[k], end[k]);
       hval[bi + (int64_t)mt.rank * 32] = acc;
       hval[bj + (int64_t)mt.rank_up * 32] = acc;
+    }
+  }
+}
+
+// ---- pipelined variant: a persistent CTA walks a contiguous range of chunks --------------------
+// assemble_pairs_kernel above is one dependent chain per CTA (descriptor -> stage entries / records /
+// slot metadata -> TMA copies -> sums -> stores, ~3.5 us) and relies on 8 co-resident CTAs per SM to
+// hide it.  Here the chain is software-pipelined three chunks deep inside one CTA: while chunk k is
+// summed from shared-memory buffer k&1, the TMA copies of chunk k+1 are in flight into the other
+// buffer and the stage entries and slot metadata of chunk k+2 are on their way into registers; the
+// pair records follow one chunk behind through cp.async.  Used when every chunk is on the common
+// path (staged in shared memory, TMA-safe windows, one record tile, short stage list); the sums,
+// their order and the stores are the same code as above, so the results are the same bits.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+constexpr int kDescRing = 64;
+
+template <typename RecT, int POBITS>
+__global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const RecT* __restrict__ recs, const ChunkDesc* __restrict__ chunks,
+                                                                          int nchunks, const StageEntry* __restrict__ stage,
+                                                                          const SlotMeta* __restrict__ slots,
+                                                                          const uint32_t* __restrict__ slot_start,
+                                                                          const double* __restrict__ Jv, double* __restrict__ hval) {
+  __shared__ __align__(16) double sval[2][kStageVals];
+  __shared__ __align__(16) RecT srec[2][kPairTile];
+  __shared__ unsigned s_offlen[2][kStageCols];
+  __shared__ int64_t s_sbase[2][kStageCols];
+  __shared__ __align__(16) ChunkDesc ring[kDescRing];
+  __shared__ uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int c0 = (int)(((int64_t)nchunks * blockIdx.x) / gridDim.x);
+  const int nk = (int)(((int64_t)nchunks * (blockIdx.x + 1)) / gridDim.x) - c0;
+  if (nk <= 0) return;
+  constexpr int SPT = kSlotCap / 256;  // slots per thread
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+  }
+  // descriptors of the first kDescRing chunks of the range (refilled half a ring at a time below)
+  for (int t = tid; t < min(nk, kDescRing) * 2; t += 256)
+    reinterpret_cast<uint4*>(ring)[t] = reinterpret_cast<const uint4*>(chunks + c0)[t];
+  __syncthreads();
+
+  StageEntry eNext;          // this thread's stage entry of the chunk whose TMA copies are issued next
+  SlotMeta mCur[SPT], mNext[SPT], mNew[SPT];
+  uint32_t scCur[SPT], scNext[SPT], scNew[SPT];
+  eNext.src = 0;
+  eNext.off = eNext.len = 0;
+  eNext.slice_base = 0;
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {
+    mCur[q] = mNext[q] = mNew[q] = SlotMeta{0, 0, 0, 0};
+    scCur[q] = scNext[q] = scNew[q] = 0;
+  }
+  // loads of chunk k that depend only on its descriptor: stage entry and slot metadata into registers
+  auto load_meta = [&](int k, StageEntry& e, SlotMeta (&m)[SPT], uint32_t (&sc)[SPT]) {
+    const ChunkDesc& d = ring[k % kDescRing];
+    if (tid < d.nstage) e = stage[d.stage0 + tid];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+      const int t = tid + q * 256;
+      if (t < d.nslots) {
+        m[q] = slots[d.slot0 + t];
+        sc[q] = slot_start[d.slot0 + t];
+      }
+    }
+  };
+  auto load_recs = [&](int k) {  // pair records of chunk k -> srec[k&1], asynchronously (chunks are 32-record padded)
+    if (k < nk) {
+      const ChunkDesc& d = ring[k % kDescRing];
+      const int n16 = (d.npairs * (int)sizeof(RecT) + 15) / 16;
+      const char* src = reinterpret_cast<const char*>(recs + d.rec0);
+      char* dst = reinterpret_cast<char*>(srec[k & 1]);
+      for (int t = tid; t < n16; t += 256) cp_async16(dst + t * 16, src + t * 16);
+    }
+    cp_async_commit();
+  };
+  auto issue_tma = [&](int k, const StageEntry& e) {  // stage list of chunk k -> shared memory buffer k&1
+    const ChunkDesc& d = ring[k % kDescRing];
+    const int b = k & 1;
+    if (tid == 0) mbar_expect_tx(&bar[b], (uint32_t)d.stage_bytes);
+    if (tid < d.nstage) {
+      s_offlen[b][tid] = ((unsigned)e.off << 16) | e.len;
+      s_sbase[b][tid] = e.slice_base & kSliceBaseMask;
+      const int run = (int)((uint64_t)e.slice_base >> 48);  // this column heads a run of consecutive columns: one copy for all
+      const int a = e.src & 1;
+      if (run > 0) tma_bulk_g2s(sval[b] + ((int)e.off - a), Jv + (e.src - a), (uint32_t)run * 8u, &bar[b]);
+    }
+  };
+
+  // prologue: chunk 0 fully issued, chunk 1's metadata on its way
+  load_meta(0, eNext, mCur, scCur);
+  load_recs(0);
+  issue_tma(0, eNext);
+  if (nk > 1) load_meta(1, eNext, mNext, scNext);
+  load_recs(1);
+
+  for (int k = 0; k < nk; ++k) {
+    const int b = k & 1;
+    if (k + 1 < nk) issue_tma(k + 1, eNext);                          // buffer b^1 was released by the barrier closing iteration k-1
+    if (k + 2 < nk) load_meta(k + 2, eNext, mNew, scNew);             // consumed in iteration k+1 / k+2
+    mbar_wait(&bar[b], (uint32_t)((k >> 1) & 1));
+    asm volatile("cp.async.wait_group 1;" ::: "memory");               // records of chunk k (those of k+1 may still be in flight)
+    __syncthreads();
+    {
+      const ChunkDesc& d = ring[k % kDescRing];
+      const int ns = d.nslots, np = d.npairs;
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        const int t = tid + q * 256;
+        if (t < ns) {
+          const SlotMeta mt = mCur[q];
+          const int beg = (int)(scCur[q] >> 16);
+          const int end = ns == 1 ? np : beg + (int)(scCur[q] & 0xffffu);
+          const int bx = (int)(s_offlen[b][mt.il] >> 16), by = (int)(s_offlen[b][mt.jl] >> 16);
+          const int64_t bi = s_sbase[b][mt.il], bj = s_sbase[b][mt.jl];
+          const double acc = slot_sum<RecT, POBITS, true>(srec[b], sval[b] + bx, sval[b] + by, beg, end);
+          hval[bi + (int64_t)mt.rank * 32] = acc;
+          hval[bj + (int64_t)mt.rank_up * 32] = acc;
+        }
+      }
+    }
+    __syncthreads();  // buffer b (values, records, stage arrays) is free again
+    // descriptor ring: once half a ring has been consumed, refill it with the descriptors half a ring ahead
+    if ((k + 1) % (kDescRing / 2) == 0) {
+      const int base = k + 1 + kDescRing / 2;  // first chunk of the half being refilled
+      for (int t = tid; t < kDescRing; t += 256) {
+        const int kk = base + t / 2;
+        if (kk < nk) reinterpret_cast<uint4*>(ring)[(kk % kDescRing) * 2 + (t & 1)] = reinterpret_cast<const uint4*>(chunks + c0 + kk)[t & 1];
+      }
+      __syncthreads();
+    }
+    load_recs(k + 2);
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+      mCur[q] = mNext[q];
+      scCur[q] = scNext[q];
+      mNext[q] = mNew[q];
+      scNext[q] = scNew[q];
     }
   }
 }
@@ -370,6 +515,7 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
     // packed device forms: one descriptor per chunk, one entry per staged column, one record per slot
     const int nch = (int)P.chunk_npairs.size();
     std::vector<ChunkDesc> cd((size_t)nch);
+    bool fast = true;  // every chunk on the common path: the pipelined kernel applies
     for (int c = 0; c < nch; ++c) {
       cd[c].slot0 = P.chunk_slot[c];
       cd[c].nslots = P.chunk_slot[(size_t)c + 1] - P.chunk_slot[c];
@@ -384,23 +530,27 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
         for (int t = P.chunk_stage_ptr[c]; t < P.chunk_stage_ptr[(size_t)c + 1]; ++t) {
           const int col = P.stage_cols[t];
           const int start = colptr[col], len = colptr[col + 1] - start, a = start & 1;
-          const int nal = (len + a + 1) & ~1;
           if (len > 32) cd[c].flags |= 2;
-          if ((int64_t)start - a + nal > (int64_t)colptr[h->n]) inside = false;  // window would run past the value array
-          bytes += nal * 8;
+          const int run = P.stage_run[t];  // doubles of the bulk copy headed by this column (0: inside a run)
+          if (run > 0) {
+            if ((int64_t)start - a + run > (int64_t)colptr[h->n]) inside = false;  // window would run past the value array
+            bytes += run * 8;
+          }
         }
         if (inside) cd[c].flags |= 4;
         cd[c].stage_bytes = bytes;
       }
       cd[c].rec0 = P.chunk_rec[c];
+      if (!((cd[c].flags & 1) && (cd[c].flags & 4) && cd[c].npairs <= kPairTile && cd[c].nstage <= kStageCols)) fast = false;
     }
+    h->pairs_fast_path = fast;
     std::vector<StageEntry> se(P.stage_cols.size());
     for (size_t t = 0; t < se.size(); ++t) {
       const int col = P.stage_cols[t];
       se[t].src = colptr[col];
       se[t].off = (uint16_t)std::min(P.stage_off[t], 65535);
       se[t].len = (uint16_t)std::min(colptr[col + 1] - colptr[col], 65535);
-      se[t].slice_base = h->S.slice_off[col >> 5] + (col & 31);
+      se[t].slice_base = (h->S.slice_off[col >> 5] + (col & 31)) | ((int64_t)P.stage_run[t] << 48);
     }
     std::vector<SlotMeta> sm((size_t)P.nslots);
     std::vector<uint32_t> sc((size_t)P.nslots);
@@ -440,7 +590,22 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   }
   if (h->nchunks > 0) {
     const int bulk_ok = (((uintptr_t)d_Jv) & 15) == 0 ? 1 : 0;  // TMA bulk copies need a 16-byte aligned source
-    if (h->rec_bits == 16)
+    static const bool pipe_off = getenv("SPB_ASM_PIPELINE") && atoi(getenv("SPB_ASM_PIPELINE")) == 0;
+    if (bulk_ok && h->pairs_fast_path && !pipe_off) {
+      if (h->occ_pairs == 0) {
+        int occ = 0;
+        if (h->rec_bits == 16) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, 0));
+        else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, 0));
+        h->occ_pairs = std::max(1, occ);
+      }
+      const int G = std::max(1, std::min(h->nchunks, h->num_sms * h->occ_pairs));
+      if (h->rec_bits == 16)
+        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
+                                                                        h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv);
+      else
+        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
+                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv);
+    } else if (h->rec_bits == 16)
       assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
                                                                      h->d_slot_start.p, d_Jv, hv, bulk_ok);
     else

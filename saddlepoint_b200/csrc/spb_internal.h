@@ -101,6 +101,7 @@ struct AssemblyPlan {
   // stage list of chunk c: J columns [chunk_stage_ptr[c], chunk_stage_ptr[c+1]) of stage_cols, with their
   // offsets in the shared-memory value buffer; chunk_staged[c]==0: list too big, gather from global
   std::vector<int> chunk_stage_ptr, stage_cols, stage_off;
+  std::vector<uint16_t> stage_run;  // per stage entry: doubles of the bulk copy starting at this column's (aligned) window, 0 unless it heads a run of consecutive columns
   std::vector<uint8_t> chunk_staged;
   std::vector<uint16_t> slot_start;        // per slot: first record of the slot, relative to its chunk
   std::vector<uint16_t> slot_cnt;          // per slot: number of records (saturated; multi-tile slots are alone in their chunk)
@@ -132,10 +133,13 @@ struct ChunkDesc {   // 32 bytes
   int stage_bytes;         // sum of the 16-byte-aligned column windows (mbarrier expect_tx)
   int64_t rec0;
 };
-struct StageEntry {  // 16 bytes: one J column of a chunk's stage list
+struct StageEntry {  // 16 bytes: one J column of a chunk's stage list (ascending columns)
   int src;             // Jcolptr[col]
   uint16_t off, len;   // offset in the shared value buffer, column length
-  int64_t slice_base;  // slice_off[col>>5] + (col&31): storage position of H row `col`, entry 0
+  // slice_off[col>>5] + (col&31): storage position of H row `col`, entry 0 (low 48 bits); the high 16
+  // bits hold the length in doubles of the bulk copy that starts at this column when it heads a run
+  // of consecutive columns (0 otherwise)
+  int64_t slice_base;
 };
 struct SlotMeta {    // 8 bytes
   uint16_t il, jl, rank, rank_up;
@@ -198,6 +202,8 @@ struct spb_context {
   bool factor_valid = false;
   uint64_t fingerprint = 0;   // of the J pattern
   uint64_t h_fingerprint = 0; // of an explicitly set H pattern
+  bool pairs_fast_path = false; // every assembly chunk is on the common path (pipelined kernel)
+  int occ_pairs = 0;
   bool solve_xx_valid = false; // the last spb_solve left ||x||^2 in h_sc->xx
   // legacy triplet interface (spb_analyze_triplets): CSC entry q of H sums d_trip_src[d_trip_ptr[q] .. d_trip_ptr[q+1])
   int64_t trip_nnz = -1;      // number of input triplets; -1 = no triplet analysis on this handle

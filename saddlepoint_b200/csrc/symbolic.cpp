@@ -381,6 +381,7 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
   P.chunk_staged.clear();
   P.stage_cols.clear();
   P.stage_off.clear();
+  P.stage_run.clear();
   P.slot_il.assign(P.nslots, 0);
   P.slot_jl.assign(P.nslots, 0);
   P.slot_start.assign(P.nslots, 0);
@@ -420,13 +421,43 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
       P.chunk_stage_ptr.push_back((int)P.stage_cols.size());
       const bool staged = c_vals <= kStageVals && (int)cur_list.size() <= kStageCols;
       P.chunk_staged.push_back(staged ? 1 : 0);
-      int off = 0;
-      for (int col : cur_list) {
-        const int a = colptr[col] & 1;  // the column's window starts one element early when it is odd-aligned
-        P.stage_cols.push_back(col);
-        P.stage_off.push_back(off + a);
-        off += (colptr[col + 1] - colptr[col] + a + 1) & ~1;
-        local_of[col] = -1;
+      // The list is stored in ascending column order so that runs of consecutive J columns -- which
+      // are contiguous in the CSC value array -- are staged by ONE bulk copy each (the TMA unit is
+      // issue-rate bound on small copies: one copy per column was the assembly kernel's limit).
+      // A run's window starts 16-byte aligned (one element early when the head column is
+      // odd-aligned) and is padded to an even length; inside a run the columns are back to back.
+      {
+        std::vector<int> sorted(cur_list);
+        std::sort(sorted.begin(), sorted.end());
+        for (size_t t = 0; t < sorted.size(); ++t) local_of[sorted[t]] = (int)t;  // new local index
+        for (int s = cs; s < s_end; ++s) {  // slots recorded insertion-order indices: remap
+          P.slot_il[s] = (uint16_t)local_of[cur_list[P.slot_il[s]]];
+          P.slot_jl[s] = (uint16_t)local_of[cur_list[P.slot_jl[s]]];
+        }
+        int cur = 0, run_head = -1, run_len = 0;
+        auto close_run = [&]() {
+          if (run_head < 0) return;
+          const int padded = (run_len + 1) & ~1;
+          P.stage_run[(size_t)run_head] = (uint16_t)std::min(padded, 65535);
+          cur += padded;
+          run_head = -1;
+        };
+        for (size_t t = 0; t < sorted.size(); ++t) {
+          const int col = sorted[t];
+          const int len = colptr[col + 1] - colptr[col];
+          if (t == 0 || col != sorted[t - 1] + 1) {
+            close_run();
+            const int a = colptr[col] & 1;
+            run_head = (int)P.stage_cols.size();
+            run_len = a;
+          }
+          P.stage_cols.push_back(col);
+          P.stage_off.push_back(cur + run_len);
+          P.stage_run.push_back(0);
+          run_len += len;
+          local_of[col] = -1;
+        }
+        close_run();
       }
       src += np;
       cur_list.clear();

@@ -119,12 +119,29 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
       // stage list: every slot's (i, j) columns are in the chunk's list at the recorded local index,
       // offsets are the running sum of the listed columns' lengths, and the staged flag respects the caps
       const int st0 = P.chunk_stage_ptr[c], st1 = P.chunk_stage_ptr[c + 1];
-      int off = 0;
+      // ascending columns; runs of consecutive columns share one 16-byte-aligned, even-length window
+      int off = 0, run_len = 0, run_head = -1;
+      auto close_run = [&]() {
+        if (run_head < 0) return;
+        const int padded = (run_len + 1) & ~1;
+        if (P.stage_run[run_head] != padded) ++bad;
+        off += padded;
+        run_head = -1;
+      };
       for (int t = st0; t < st1; ++t) {
-        const int a = colptr[P.stage_cols[t]] & 1;  // 16-byte aligned windows (TMA bulk copies)
-        if (P.stage_off[t] != off + a) ++bad;
-        off += (colptr[P.stage_cols[t] + 1] - colptr[P.stage_cols[t]] + a + 1) & ~1;
+        const int col = P.stage_cols[t];
+        if (t > st0 && col <= P.stage_cols[t - 1]) ++bad;
+        if (t == st0 || col != P.stage_cols[t - 1] + 1) {
+          close_run();
+          run_head = t;
+          run_len = colptr[col] & 1;
+        } else if (P.stage_run[t] != 0) {
+          ++bad;
+        }
+        if (P.stage_off[t] != off + run_len) ++bad;
+        run_len += colptr[col + 1] - colptr[col];
       }
+      close_run();
       if (P.chunk_staged[c] && (off > kStageVals || st1 - st0 > kStageCols)) ++bad;
       for (int s = s0; s < s1; ++s) {
         int j = (int)(std::upper_bound(P.low_colptr.begin(), P.low_colptr.end(), s) - P.low_colptr.begin()) - 1;

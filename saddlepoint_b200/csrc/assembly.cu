@@ -31,6 +31,7 @@
 //    emits rhs, d, sqrt(d)^2 onto the diagonal, the Jacobi diagonal, and a block max of
 //    |rhs| folded with atomicMax on the (non-negative) bit pattern.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "spb_internal.h"
@@ -75,7 +76,27 @@ __device__ __forceinline__ double slot_sum(const RecT* rec, const double* vi, co
   double a = SMEM ? vi[(r >> POBITS) & MASK] : __ldg(vi + ((r >> POBITS) & MASK));
   double b = SMEM ? vj[r & MASK] : __ldg(vj + (r & MASK));
   double acc = __dmul_rn(a, b);
-  for (int q = beg + 1; q < end; ++q) {
+  int q = beg + 1;
+  // Four pairs at a time: records, then both operands of every pair, are loaded before the first
+  // dependent use, so the longest slot of a chunk (the CTA's critical path between two barriers)
+  // costs one shared-memory round trip per four pairs instead of two per pair.  The products are
+  // still added strictly left to right.
+  for (; q + 4 <= end; q += 4) {
+    const uint32_t r0 = (uint32_t)rec[q], r1 = (uint32_t)rec[q + 1], r2 = (uint32_t)rec[q + 2], r3 = (uint32_t)rec[q + 3];
+    const double a0 = SMEM ? vi[(r0 >> POBITS) & MASK] : __ldg(vi + ((r0 >> POBITS) & MASK));
+    const double a1 = SMEM ? vi[(r1 >> POBITS) & MASK] : __ldg(vi + ((r1 >> POBITS) & MASK));
+    const double a2 = SMEM ? vi[(r2 >> POBITS) & MASK] : __ldg(vi + ((r2 >> POBITS) & MASK));
+    const double a3 = SMEM ? vi[(r3 >> POBITS) & MASK] : __ldg(vi + ((r3 >> POBITS) & MASK));
+    const double b0 = SMEM ? vj[r0 & MASK] : __ldg(vj + (r0 & MASK));
+    const double b1 = SMEM ? vj[r1 & MASK] : __ldg(vj + (r1 & MASK));
+    const double b2 = SMEM ? vj[r2 & MASK] : __ldg(vj + (r2 & MASK));
+    const double b3 = SMEM ? vj[r3 & MASK] : __ldg(vj + (r3 & MASK));
+    acc = __dadd_rn(acc, __dmul_rn(a0, b0));
+    acc = __dadd_rn(acc, __dmul_rn(a1, b1));
+    acc = __dadd_rn(acc, __dmul_rn(a2, b2));
+    acc = __dadd_rn(acc, __dmul_rn(a3, b3));
+  }
+  for (; q < end; ++q) {
     r = (uint32_t)rec[q];
     a = SMEM ? vi[(r >> POBITS) & MASK] : __ldg(vi + ((r >> POBITS) & MASK));
     b = SMEM ? vj[r & MASK] : __ldg(vj + (r & MASK));
@@ -232,9 +253,18 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
                                                                           int nchunks, const StageEntry* __restrict__ stage,
                                                                           const SlotMeta* __restrict__ slots,
                                                                           const uint32_t* __restrict__ slot_start,
-                                                                          const double* __restrict__ Jv, double* __restrict__ hval) {
+                                                                          const double* __restrict__ Jv, double* __restrict__ hval,
+                                                                          long long* dbg) {
   __shared__ __align__(16) double sval[2][kStageVals];
   __shared__ __align__(16) RecT srec[2][kPairTile];
+  long long tk = 0, acc_t[6] = {0, 0, 0, 0, 0, 0};
+  const bool dbg_on = dbg && blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 64 || threadIdx.x == 224);
+#define ASM_TICK(i)                     \
+  if (dbg_on) {                         \
+    const long long now_ = clock64();   \
+    acc_t[i] += now_ - tk;              \
+    tk = now_;                          \
+  }
   __shared__ unsigned s_offlen[2][kStageCols];
   __shared__ int64_t s_sbase[2][kStageCols];
   __shared__ __align__(16) ChunkDesc ring[kDescRing];
@@ -307,13 +337,17 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
   if (nk > 1) load_meta(1, eNext, mNext, scNext);
   load_recs(1);
 
+  if (dbg_on) tk = clock64();
   for (int k = 0; k < nk; ++k) {
     const int b = k & 1;
     if (k + 1 < nk) issue_tma(k + 1, eNext);                          // buffer b^1 was released by the barrier closing iteration k-1
     if (k + 2 < nk) load_meta(k + 2, eNext, mNew, scNew);             // consumed in iteration k+1 / k+2
+    ASM_TICK(0)
     mbar_wait(&bar[b], (uint32_t)((k >> 1) & 1));
+    ASM_TICK(1)
     asm volatile("cp.async.wait_group 1;" ::: "memory");               // records of chunk k (those of k+1 may still be in flight)
     __syncthreads();
+    ASM_TICK(2)
     {
       const ChunkDesc& d = ring[k % kDescRing];
       const int ns = d.nslots, np = d.npairs;
@@ -332,7 +366,9 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
         }
       }
     }
+    ASM_TICK(3)
     __syncthreads();  // buffer b (values, records, stage arrays) is free again
+    ASM_TICK(4)
     // descriptor ring: once half a ring has been consumed, refill it with the descriptors half a ring ahead
     if ((k + 1) % (kDescRing / 2) == 0) {
       const int base = k + 1 + kDescRing / 2;  // first chunk of the half being refilled
@@ -350,7 +386,14 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
       mNext[q] = mNew[q];
       scNext[q] = scNew[q];
     }
+    ASM_TICK(5)
   }
+  if (dbg_on) {
+    long long* o = dbg + (threadIdx.x == 0 ? 0 : threadIdx.x == 64 ? 8 : 16);
+    for (int i = 0; i < 6; ++i) o[i] = acc_t[i];
+    o[6] = nk;
+  }
+#undef ASM_TICK
 }
 
 __device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
@@ -599,12 +642,29 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
         h->occ_pairs = std::max(1, occ);
       }
       const int G = std::max(1, std::min(h->nchunks, h->num_sms * h->occ_pairs));
+      static const bool asm_dbg = getenv("SPB_ASM_TIMING") && atoi(getenv("SPB_ASM_TIMING")) > 0;
+      static DevBuf<long long> dbg_buf;
+      long long* dbgp = nullptr;
+      if (asm_dbg) {
+        SPB_CUDA(dbg_buf.alloc(24));
+        dbgp = dbg_buf.p;
+      }
       if (h->rec_bits == 16)
         assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
-                                                                        h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv);
+                                                                        h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
       else
         assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
-                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv);
+                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
+      if (dbgp) {
+        long long tt[24];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(tt, dbgp, sizeof(tt), cudaMemcpyDeviceToHost);
+        for (int w = 0; w < 3; ++w) {
+          const long long* t = tt + 8 * w;
+          fprintf(stderr, "[spb asm timing] thread %d cycles/chunk over %lld chunks: issue+meta %lld mbar_wait %lld recs+sync %lld sums %lld sync %lld tail %lld\n",
+                  w == 0 ? 0 : w == 1 ? 64 : 224, t[6], t[0] / t[6], t[1] / t[6], t[2] / t[6], t[3] / t[6], t[4] / t[6], t[5] / t[6]);
+        }
+      }
     } else if (h->rec_bits == 16)
       assemble_pairs_kernel<uint16_t, 7><<<h->nchunks, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->d_stage_ent.p, h->d_slot_meta.p,
                                                                      h->d_slot_start.p, d_Jv, hv, bulk_ok);

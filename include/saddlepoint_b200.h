@@ -207,6 +207,15 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
 /* Extended Rosenbrock of benchmark/rosenbrock/main.cpp:11,47-62 over nblocks blocks;
  * x0: 2*nblocks host values or NULL for (-100,100) repeated (main.cpp:43). */
 spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out);
+/* Block structure of the seamless-integration Jacobian (SIInitialSolutionTraits.h:115-248):
+ * rows [0,m_lin): E = A x - b with a CONSTANT sparse A (n columns, CSC, host; the integration, closeness
+ * and constraint blocks with their weights folded in); rows [m_lin, m_lin+nbar): the injectivity barrier
+ * w_bar*(1/bar(t)-1), t = ((c.x n.y - c.y n.x)/vol)/s, of the four unknowns bar_idx[4r..4r+3] =
+ * (c.x, c.y, n.x, n.y) (:148-172), whose Jacobian entries (:216-233; 0, finite or inf) are the only values
+ * recomputed per evaluation.  x0: n start values.  The Jacobian pattern is the row-wise stack, CSC. */
+spb_status spb_problem_blocks(spb_handle h, int32_t n, int32_t m_lin, const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_vals,
+                              const double* b, int32_t nbar, const int32_t* bar_idx, const double* bar_vol, double s, double w_bar,
+                              const double* x0, spb_problem_t* out);
 spb_status spb_problem_traits(spb_problem_t p, spb_traits* out);
 spb_status spb_problem_destroy(spb_problem_t p);
 

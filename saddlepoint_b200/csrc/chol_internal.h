@@ -13,7 +13,12 @@ struct CholSymbolic {
   std::vector<int> struct_idx;         // rows below the pivot block (new numbering, ascending)
   std::vector<int> sn_parent, sn_level;
   std::vector<int> level_ptr, level_sn;  // supernodes grouped by level, leaves first
-  std::vector<int64_t> L_off, U_off, W_off;  // panel (r x k), update matrix (u x u), rhs work (r)
+  std::vector<int64_t> L_off, U_off, W_off;  // panel (r x k), update matrix (u x u, lifetime-packed: see U_total), rhs work (r)
+  // Update matrices live from their front's level to their parent's level only, so their storage is
+  // packed by lifetime into one arena (first fit): U_total doubles instead of the sum of all u^2.
+  int64_t U_total = 0, U_sum = 0;
+  std::vector<int> u_zero_ptr;        // nlevels+1: ranges to clear before level l's extend-add
+  std::vector<int64_t> u_zero_range;  // (offset, length) pairs
   std::vector<int64_t> a_src, a_dst;   // H storage position -> panel position (lower entries)
   std::vector<int64_t> rel_ptr;        // nsuper+1
   std::vector<int> rel_idx;            // child struct -> parent front local index

@@ -1017,7 +1017,7 @@ static CholDevice* ensure_symbolic(spb_context* h) {
   SPB_CUDA(D->a_src.upload(C.a_src, st));
   SPB_CUDA(D->a_dst.upload(C.a_dst, st));
   SPB_CUDA(D->Lbuf.alloc((size_t)C.L_off[ns]));
-  SPB_CUDA(D->Ubuf.alloc((size_t)std::max<int64_t>(1, C.U_off[ns])));
+  SPB_CUDA(D->Ubuf.alloc((size_t)std::max<int64_t>(1, C.U_total)));
   SPB_CUDA(D->Wbuf.alloc((size_t)C.W_off[ns]));
   SPB_CUDA(D->Dinv.alloc((size_t)C.dinv_off[ns]));
   SPB_CUDA(D->ywork.alloc((size_t)h->n));
@@ -1041,7 +1041,6 @@ spb_status chol_factorize(spb_context* h) {
   stage_begin(h, ST_FACTOR);
   int nl = 0;
   SPB_CUDA(cudaMemsetAsync(D->Lbuf.p, 0, (size_t)C.L_off[ns] * sizeof(double), st));
-  if (C.U_off[ns] > 0) SPB_CUDA(cudaMemsetAsync(D->Ubuf.p, 0, (size_t)C.U_off[ns] * sizeof(double), st));
   SPB_CUDA(cudaMemsetAsync(D->fail.p, 0, sizeof(int), st));
   {
     const int64_t cnt = (int64_t)D->a_src.n;
@@ -1049,6 +1048,9 @@ spb_status chol_factorize(spb_context* h) {
     ++nl;
   }
   for (int l = 0; l < C.nlevels; ++l) {
+    // the update matrices born at this level start from zero (their arena blocks are reused across levels)
+    for (int z = C.u_zero_ptr[l]; z < C.u_zero_ptr[(size_t)l + 1]; ++z)
+      SPB_CUDA(cudaMemsetAsync(D->Ubuf.p + C.u_zero_range[(size_t)2 * z], 0, (size_t)C.u_zero_range[(size_t)2 * z + 1] * sizeof(double), st));
     // extend-add, one launch per child rank
     for (int rk = C.level_rank_ptr[l]; rk < C.level_rank_ptr[(size_t)l + 1]; ++rk) {
       const int b = C.rank_ptr[rk], cnt = C.rank_ptr[(size_t)rk + 1] - b;

@@ -28,7 +28,7 @@ spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, c
 }
 
 // Cholesky symbolic phase on the host: stats[0..7] = nsuper, nlevels, nnz(L), max pivot block,
-// max front, flops (rounded), sum of update-matrix entries, structural violations (must be 0).
+// max front, flops (rounded), update-matrix arena size (entries), structural violations (must be 0).
 // perm (optional, n ints) receives the fill-reducing order.
 spb_status spb_symbolic_chol_stats(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats, int32_t* perm) {
   if (!colptr || !stats || m < 0 || n < 0) return SPB_ERR_ARG;
@@ -54,13 +54,29 @@ spb_status spb_symbolic_chol_stats(int32_t m, int32_t n, const int32_t* colptr, 
       }
     }
     if ((int64_t)C.a_src.size() != (H.nnz() + n) / 2) ++bad;
+    {
+      // update-matrix arena: blocks that are live at the same time must not overlap
+      struct Iv { int64_t off, len; int birth, death; };
+      std::vector<Iv> iv;
+      for (int s = 0; s < C.nsuper; ++s) {
+        const int64_t u = C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s];
+        if (u == 0) continue;
+        if (C.U_off[s] < 0 || C.U_off[s] + u * u > C.U_total) ++bad;
+        iv.push_back({C.U_off[s], u * u, C.sn_level[s], C.sn_parent[s] >= 0 ? C.sn_level[C.sn_parent[s]] : C.sn_level[s]});
+      }
+      std::sort(iv.begin(), iv.end(), [](const Iv& a, const Iv& b) { return a.off < b.off; });
+      // sweep: compare each block with the following ones that start before it ends
+      for (size_t a = 0; a < iv.size(); ++a)
+        for (size_t b = a + 1; b < iv.size() && iv[b].off < iv[a].off + iv[a].len; ++b)
+          if (iv[a].birth <= iv[b].death && iv[b].birth <= iv[a].death) ++bad;
+    }
     stats[0] = C.nsuper;
     stats[1] = C.nlevels;
     stats[2] = C.nnzL;
     stats[3] = C.max_k;
     stats[4] = C.max_r;
     stats[5] = (int64_t)C.flops;
-    stats[6] = C.U_off[C.nsuper];
+    stats[6] = C.U_total;  // arena size (lifetime-packed); C.U_sum is the sum of all update matrices
     stats[7] = bad;
     if (perm) memcpy(perm, C.perm.data(), sizeof(int32_t) * (size_t)n);
     return SPB_OK;

@@ -467,7 +467,8 @@ class LMSolver:
 
 
 class BuiltinProblem:
-    """Device-resident SolverTraits (spb_problem_*): the benchmark workloads evaluated on the GPU."""
+    """Device-resident SolverTraits (spb_problem_*): the benchmark workloads evaluated on the GPU.
+    kinds: lf | lf_rows | rosenbrock | blocks (A, b, bar_idx, bar_vol, s, w_bar, x0: see spb_problem_blocks)."""
 
     def __init__(self, handle, kind, **kw):
         self.handle = handle
@@ -483,6 +484,21 @@ class BuiltinProblem:
             if x0 is not None:
                 x0 = np.ascontiguousarray(x0, np.float64)
             st = L.spb_problem_rosenbrock(handle.h, kw["nblocks"], C.c_void_p(x0.ctypes.data) if x0 is not None else None, C.byref(p))
+        elif kind == "blocks":  # constant sparse block + barrier block (seamless-integration structure)
+            A = kw["A"].tocsc()
+            A.sort_indices()
+            n, m_lin = A.shape[1], A.shape[0]
+            Ap, pAp = _i32(A.indptr)
+            Ai, pAi = _i32(A.indices)
+            Av = np.ascontiguousarray(A.data, np.float64)
+            b = np.ascontiguousarray(kw["b"], np.float64)
+            bidx, pbi = _i32(np.asarray(kw["bar_idx"]).reshape(-1))
+            bvol = np.ascontiguousarray(kw["bar_vol"], np.float64).reshape(-1)
+            x0 = np.ascontiguousarray(kw["x0"], np.float64)
+            if b.size != m_lin or x0.size != n or bidx.size != 4 * bvol.size:
+                raise ValueError("blocks problem: inconsistent sizes")
+            st = L.spb_problem_blocks(handle.h, n, m_lin, pAp, pAi, C.c_void_p(Av.ctypes.data), C.c_void_p(b.ctypes.data), bvol.size, pbi,
+                                      C.c_void_p(bvol.ctypes.data), float(kw["s"]), float(kw["w_bar"]), C.c_void_p(x0.ctypes.data), C.byref(p))
         else:
             raise ValueError(kind)
         handle._check(st)

@@ -30,6 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def _label(g):
+    """BASELINE.json's name for the configuration quoted (C2) or the sizes of the other LF configs."""
+    return "LF-1M (C2)" if g == 1024 else ("LF-20M (C5 size, one GPU)" if g == 4472 else "LF (g=%d, not a BASELINE configuration)" % g)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -137,7 +142,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "LM iterations/s", "value": val, "unit": "iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "benchmark/linear_function LF-1M (C2): g=%d torus, n=%d, m=%d, nnzJ=%d" % (args.g, n, m, nnzJ)},
+            "config": {"workload": "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d" % (_label(args.g), args.g, n, m, nnzJ)},
             "cpu_baseline": info,
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -303,7 +308,7 @@ def run_ours(args):
         line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "benchmark/linear_function LF-1M (C2): g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (g, n, m, nnzJ, nnzH),
+                "config": {"workload": "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (_label(g), g, n, m, nnzJ, nnzH),
                            "per_gpu": "one independent problem per GPU (seed 20211+rank)", "solver": "%s rtol=%g" % (args.solver, args.pcg_rtol),
                            "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
                            "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s},

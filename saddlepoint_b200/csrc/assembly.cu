@@ -643,11 +643,10 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
       }
       const int G = std::max(1, std::min(h->nchunks, h->num_sms * h->occ_pairs));
       static const bool asm_dbg = getenv("SPB_ASM_TIMING") && atoi(getenv("SPB_ASM_TIMING")) > 0;
-      static DevBuf<long long> dbg_buf;
       long long* dbgp = nullptr;
       if (asm_dbg) {
-        SPB_CUDA(dbg_buf.alloc(24));
-        dbgp = dbg_buf.p;
+        SPB_CUDA(h->d_dbg.alloc(24));
+        dbgp = h->d_dbg.p;
       }
       if (h->rec_bits == 16)
         assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,

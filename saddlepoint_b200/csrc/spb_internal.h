@@ -202,6 +202,7 @@ struct spb_context {
   bool factor_valid = false;
   uint64_t fingerprint = 0;   // of the J pattern
   uint64_t h_fingerprint = 0; // of an explicitly set H pattern
+  spb::DevBuf<long long> d_dbg;  // debug stopwatch buffer (SPB_ASM_TIMING)
   bool pairs_fast_path = false; // every assembly chunk is on the common path (pipelined kernel)
   int occ_pairs = 0;
   bool solve_xx_valid = false; // the last spb_solve left ||x||^2 in h_sc->xx

@@ -207,6 +207,10 @@ spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t s
 /* Extended Rosenbrock of benchmark/rosenbrock/main.cpp:11,47-62 over nblocks blocks;
  * x0: 2*nblocks host values or NULL for (-100,100) repeated (main.cpp:43). */
 spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out);
+/* The LOCAL part of the LF problem for spb_dist_ring_halo: unknowns [col_begin, col_end) of the torus plus a
+ * halo of 2g on either side, and the residual rows based at the owned unknowns (same data as spb_problem_lf). */
+spb_status spb_problem_lf_cols(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t col_begin, int32_t col_end,
+                               spb_problem_t* out);
 /* Block structure of the seamless-integration Jacobian (SIInitialSolutionTraits.h:115-248):
  * rows [0,m_lin): E = A x - b with a CONSTANT sparse A (n columns, CSC, host; the integration, closeness
  * and constraint blocks with their weights folded in); rows [m_lin, m_lin+nbar): the injectivity barrier
@@ -226,6 +230,15 @@ spb_status spb_problem_destroy(spb_problem_t p);
 spb_status spb_comm_unique_id(void* id128);
 spb_status spb_comm_init(spb_handle h, const void* id128, int rank, int nranks);
 spb_status spb_comm_destroy(spb_handle h);
+/* Subdomain (halo) mode -- the scalable form: the handle holds only the LOCAL problem of its rank (analyse /
+ * assemble / solve with the local Jacobian whose columns are [halo ghosts of the left neighbour | owned
+ * unknowns | halo ghosts of the right neighbour], ranks on a ring; suits banded problems partitioned by
+ * unknown).  Nothing of size n is communicated: per PCG iteration one halo slab of p forward, one of q back
+ * (added on the owners in a fixed order) and two scalar allreduces; assembly exchanges the halo parts of
+ * rhs, d and diag(H).  own_begin must equal halo, own_end - own_begin >= 2*halo; halo = 0 switches it off.
+ * spb_assemble / spb_factorize / spb_solve / spb_lm_solve then work on local vectors (ghost entries of
+ * results are kept consistent); only SPB_SOLVER_PCG_JACOBI is supported in this mode. */
+spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, int32_t halo, int32_t left_rank, int32_t right_rank);
 /* Same GLOBAL Jacobian pattern on every rank; this rank owns residual rows [row_begin,row_end).
  * Afterwards spb_assemble takes the owned values only (global CSC order restricted to the owned
  * rows; see spb_local_pattern) and the owned slice of EVec; the partial H / rhs / d of all ranks

@@ -78,12 +78,14 @@ SYMBOLS = [
                                C.c_int32, C.POINTER(C.c_int32)]),
     ("spb_problem_lf", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(vp)]),
     ("spb_problem_rosenbrock", C.c_int, [vp, C.c_int32, vp, C.POINTER(vp)]),
+    ("spb_problem_lf_cols", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     ("spb_problem_blocks", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_double, C.c_double, vp, C.POINTER(vp)]),
     ("spb_problem_traits", C.c_int, [vp, C.POINTER(Traits)]),
     ("spb_problem_destroy", C.c_int, [vp]),
     ("spb_comm_unique_id", C.c_int, [vp]),
     ("spb_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("spb_comm_destroy", C.c_int, [vp]),
+    ("spb_dist_ring_halo", C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("spb_analyze_partitioned", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32]),
     ("spb_local_nnz", C.c_int, [vp, C.POINTER(C.c_int64)]),
     ("spb_local_pattern", C.c_int, [vp, vp, vp]),

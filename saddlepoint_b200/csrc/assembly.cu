@@ -511,6 +511,40 @@ __global__ void __launch_bounds__(256) apply_damping_kernel(const double* __rest
   }
 }
 
+// subdomain (halo) mode, after the halo sums of rhs, d and diag(H): on the OWNED unknowns the damping
+// fl(sqrt(d_j))^2 enters this rank's local H_jj (the neighbours' local copies of the entry stay
+// undamped: H = sum of the local matrices), the Jacobi diagonal becomes the full H_jj, and ||rhs||_inf
+// is taken over the owned entries (combined with an allreduce-max afterwards)
+__global__ void __launch_bounds__(256) halo_damping_kernel(const double* __restrict__ dvec, const double* __restrict__ rhs,
+                                                           const int* __restrict__ nup1, const int64_t* __restrict__ slice_off, int own_lo,
+                                                           int own_hi, double* __restrict__ hval, double* __restrict__ hdiag,
+                                                           unsigned long long* __restrict__ foo_bits) {
+  __shared__ double s_max[8];
+  const int j = own_lo + blockIdx.x * 256 + threadIdx.x;
+  double mymax = 0.0;
+  if (j < own_hi) {
+    const double sd = sqrt(dvec[j]);
+    const double dd = __dmul_rn(sd, sd);
+    const int64_t pd = slice_off[j >> 5] + (int64_t)(nup1[j] - 1) * 32 + (j & 31);
+    hval[pd] = __dadd_rn(hval[pd], dd);
+    hdiag[j] = __dadd_rn(hdiag[j], dd);
+    if (rhs) {
+      const double ag = fabs(rhs[j]);
+      if (ag > mymax) mymax = ag;
+    }
+  }
+  if (rhs) {
+    for (int o = 16; o > 0; o >>= 1) mymax = fmax(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mymax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mx = s_max[0];
+      for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
+      atomicMax(foo_bits, (unsigned long long)__double_as_longlong(mx));
+    }
+  }
+}
+
 __global__ void gather_vals_kernel(const double* __restrict__ hval, const int64_t* __restrict__ pos, int64_t nnz,
                                    double* __restrict__ out) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,7 +662,7 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     assemble_cols_kernel<<<h->ncolchunks, 256, 0, st>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda,
                                                         h->d_nup1.p, h->d_slice_off.p, hv, h->d_hdiag.p,
                                                         part ? h->d_rhs_part.p : h->d_rhs.p, part ? h->d_dvec_part.p : h->d_dvec.p,
-                                                        h->d_foo_bits.p, part ? 1 : 0);
+                                                        h->d_foo_bits.p, (part || h->halo_mode) ? 1 : 0);
     ++nl;
   }
   if (h->nchunks > 0) {
@@ -682,6 +716,22 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     apply_damping_kernel<<<(h->n + 255) / 256, 256, 0, st>>>(h->d_dvec.p, d_f ? h->d_rhs.p : nullptr, h->d_nup1.p, h->d_slice_off.p, h->n,
                                                              h->d_hval.p, h->d_hdiag.p, h->d_foo_bits.p);
     ++nl;
+  }
+  if (h->halo_mode && !part) {
+    if (h->n != h->own_hi + h->halo) throw StateFail{"halo description does not match the analysed local problem"};
+    // sums over the ranks that share an unknown: gradient, damping vector and diagonal travel as halo slabs
+    if (d_f) halo_reverse_add(h, h->d_rhs.p);
+    halo_reverse_add(h, h->d_dvec.p);
+    halo_reverse_add(h, h->d_hdiag.p);
+    const int own = h->own_hi - h->own_lo;
+    halo_damping_kernel<<<(own + 255) / 256, 256, 0, st>>>(h->d_dvec.p, d_f ? h->d_rhs.p : nullptr, h->d_nup1.p, h->d_slice_off.p, h->own_lo,
+                                                         h->own_hi, h->d_hval.p, h->d_hdiag.p, h->d_foo_bits.p);
+    ++nl;
+    if (d_f) {
+      dist_allreduce_max(h, (const double*)h->d_foo_bits.p, (double*)h->d_foo_bits.p, 1);  // non-negative doubles: bits order like values
+      halo_forward(h, h->d_rhs.p);
+    }
+    halo_forward(h, h->d_dvec.p);
   }
   SPB_CUDA(cudaGetLastError());
   stage_end(h, ST_ASSEMBLY, nl);

@@ -445,7 +445,9 @@ spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int m
         dx = h->d_x.p;
       }
       int it = 0;
-      spb_status s = h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx)
+      if (h->halo_mode && h->solver != SPB_SOLVER_PCG_JACOBI) throw StateFail{"subdomain (halo) mode supports SPB_SOLVER_PCG_JACOBI only"};
+      spb_status s = h->halo_mode ? pcg_solve_halo(h, db, dx, &it)
+                     : h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx)
                      : h->solver == SPB_SOLVER_PCG_IC0 ? pcg_ic0_solve(h, db, dx, &it)
                      : (h->nranks > 1 ? pcg_solve_dist(h, db, dx, &it) : pcg_solve(h, db, dx, &it));
       total_iters += it;

@@ -30,6 +30,8 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -37,6 +39,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8;  // ncclDataType_t::ncclDouble
 constexpr int kNcclSum = 0;      // ncclRedOp_t::ncclSum
+constexpr int kNcclMax = 2;      // ncclRedOp_t::ncclMax
 
 bool load_nccl(std::string& err) {
   if (g_nccl.lib) return true;
@@ -53,10 +56,12 @@ bool load_nccl(std::string& err) {
   g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
   g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
   g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
   g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
   g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.GroupStart ||
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
       !g_nccl.GroupEnd) {
     err = "libnccl is missing required symbols";
     return false;
@@ -94,6 +99,59 @@ void dist_allgather(spb_context* h, const double* send, double* recv, size_t cou
   }
   SPB_NCCL(g_nccl.AllGather(send, recv, count_per_rank, kNcclFloat64, h->comm, h->stream));
   h->collectives++;
+}
+
+void dist_allreduce_max(spb_context* h, const double* send, double* recv, size_t count) {
+  if (h->nranks <= 1) {
+    if (send != recv) SPB_CUDA(cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
+  SPB_NCCL(g_nccl.AllReduce(send, recv, count, kNcclFloat64, kNcclMax, h->comm, h->stream));
+  h->collectives++;
+}
+
+// ---- subdomain (halo) mode -------------------------------------------------------------------
+// The scalable form of the one-large-problem case: a rank owns a contiguous range of unknowns and
+// the residual rows based there, and analyses / assembles only its LOCAL J_g (owned + halo columns).
+// The normal matrix is never summed across ranks: H x = sum_g R_g^T (J_g^T J_g) R_g x, so one product
+// is  forward halo exchange of p  ->  local SpMV  ->  reverse exchange of the ghost rows of q, added
+// on their owners (left neighbour's contribution first: fixed order, deterministic).  Per PCG
+// iteration the traffic is two halo slabs each way plus two scalar allreduces, independent of n/ranks.
+// Exchanges are grouped ncclSend/ncclRecv on the handle's stream over NVLink.
+__global__ void halo_add_kernel(double* __restrict__ v, const double* __restrict__ from_left, const double* __restrict__ from_right,
+                                int own_lo, int own_hi, int halo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= halo) return;
+  v[own_lo + i] += from_left[i];          // the left neighbour's right-ghost rows are my first owned entries
+  v[own_hi - halo + i] += from_right[i];  // the right neighbour's left-ghost rows are my last owned entries
+}
+
+void halo_forward(spb_context* h, double* v) {
+  const size_t hl = (size_t)h->halo;
+  SPB_NCCL(g_nccl.GroupStart());
+  SPB_NCCL(g_nccl.Send(v + h->own_lo, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));          // my first owned -> left's right ghosts
+  SPB_NCCL(g_nccl.Send(v + h->own_hi - hl, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));    // my last owned  -> right's left ghosts
+  SPB_NCCL(g_nccl.Recv(v + h->own_hi, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));         // right ghosts <- right's first owned
+  SPB_NCCL(g_nccl.Recv(v, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));                      // left ghosts  <- left's last owned
+  SPB_NCCL(g_nccl.GroupEnd());
+  h->collectives++;
+}
+
+void halo_reverse_add(spb_context* h, double* v) {
+  const size_t hl = (size_t)h->halo;
+  SPB_CUDA(h->d_halo_tmp.alloc(2 * hl));
+  double* from_right = h->d_halo_tmp.p;
+  double* from_left = h->d_halo_tmp.p + hl;
+  SPB_NCCL(g_nccl.GroupStart());
+  SPB_NCCL(g_nccl.Send(v, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));                  // my left-ghost rows  -> left (its last owned)
+  SPB_NCCL(g_nccl.Send(v + h->own_hi, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));     // my right-ghost rows -> right (its first owned)
+  SPB_NCCL(g_nccl.Recv(from_right, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));
+  SPB_NCCL(g_nccl.Recv(from_left, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));
+  SPB_NCCL(g_nccl.GroupEnd());
+  halo_add_kernel<<<(h->halo + 255) / 256, 256, 0, h->stream>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
+  h->launches++;
+  h->collectives++;
+  SPB_CUDA(cudaGetLastError());
 }
 
 void dist_release(spb_context* h) {
@@ -153,6 +211,27 @@ spb_status spb_comm_init(spb_handle h, const void* id128, int rank, int nranks) 
     h->comm = comm;
     h->rank = rank;
     h->nranks = nranks;
+    return SPB_OK;
+  });
+}
+
+spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, int32_t halo, int32_t left_rank, int32_t right_rank) {
+  if (!h) return SPB_ERR_ARG;
+  return guarded_dist(h, [&]() {
+    if (halo == 0) {  // switch the mode off
+      h->halo_mode = false;
+      return SPB_OK;
+    }
+    if (!h->comm || h->nranks < 2) throw StateFail{"spb_dist_ring_halo needs a communicator of at least two ranks (spb_comm_init)"};
+    if (halo < 0 || own_begin != halo || own_end - own_begin < 2 * halo || left_rank < 0 || left_rank >= h->nranks || right_rank < 0 ||
+        right_rank >= h->nranks || left_rank == h->rank || right_rank == h->rank)
+      throw ArgFail{"bad halo description: local unknowns are [halo ghosts | owned (>= 2*halo) | halo ghosts], neighbours are other ranks"};
+    h->halo_mode = true;
+    h->halo = halo;
+    h->own_lo = own_begin;
+    h->own_hi = own_end;
+    h->left_rank = left_rank;
+    h->right_rank = right_rank;
     return SPB_OK;
   });
 }

@@ -223,6 +223,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       }
       double dn2 = 0.0;
       if (h->solve_xx_valid) dn2 = h->h_sc->xx;  // by-product of the persistent PCG kernel
+      else if (h->halo_mode) dev_squared_norm_global(h, d_dir.p + h->own_lo, h->own_hi - h->own_lo, &dn2);  // owned entries, summed over ranks
       else dev_squared_norm(h, d_dir.p, n, &dn2);
       const double dn = std::sqrt(dn2);
       if (!fixed && dn < O->funcTolerance) {

@@ -1459,6 +1459,82 @@ spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* i
   return SPB_OK;
 }
 
+// p.q over the owned range (after the reverse halo sum made q final there)
+__global__ void __launch_bounds__(256) range_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int lo, int hi,
+                                                        double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  double acc = 0.0;
+  for (int i = lo + blockIdx.x * 256 + threadIdx.x; i < hi; i += gridDim.x * 256) acc = fma(a[i], b[i], acc);
+  const double s = block_sum_256(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (take_ticket(&sc->ticket_a, gridDim.x) && threadIdx.x < 32) {
+    const double t = ordered_sum(partial, gridDim.x);
+    if (threadIdx.x == 0) sc->red[0] = t;
+  }
+}
+
+// Jacobi-PCG in subdomain (halo) mode: vectors are local ([ghosts | owned | ghosts]); one iteration is
+//   forward halo exchange of p -> q = H_loc p (all local rows) -> reverse halo sum of q -> p.q (owned) ->
+//   allreduce -> x, r, z updates (owned) -> allreduce (r.z, r.r) -> p update (owned).
+// Scalars come out of the same allreduce on every rank, so alpha, beta and the stop decision agree.
+spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters) {
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  if (iters) *iters = 0;
+  if (n == 0) return SPB_OK;
+  if (n != h->own_hi + h->halo) throw StateFail{"halo description does not match the analysed local problem"};
+  ensure_pcg_buffers(h);
+  SPB_CUDA(h->d_r.alloc(n));
+  SPB_CUDA(h->d_p.alloc(n));
+  SPB_CUDA(h->d_q.alloc(n));
+  double* p = h->d_p.p;
+  PcgScalars* sc = h->d_sc.p;
+  const int lo = h->own_lo, hi = h->own_hi;
+  const int gv = std::max(1, std::min((hi - lo + 255) / 256, h->num_sms * 8));
+  stage_begin(h, ST_PCG);
+  int nl = 0;
+  SPB_CUDA(cudaMemsetAsync(d_x, 0, (size_t)n * sizeof(double), st));
+  SPB_CUDA(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), st));
+  dist_init_kernel<<<gv, 256, 0, st>>>(d_b, h->d_dinv.p, d_x, h->d_r.p, p, lo, hi, h->d_partial.p, sc);
+  dist_allreduce_sum(h, sc->red, sc->red, 2);
+  dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 0, h->pcg_rtol, h->pcg_maxit);
+  nl += 2;
+  int launched = 0;
+  int batch = h->pcg_last_iters > 0 ? std::min(h->pcg_last_iters + 2, h->pcg_maxit) : 16;
+  for (;;) {
+    for (int k = 0; k < batch; ++k) {
+      halo_forward(h, p);
+      spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n,
+                                                            (n + 31) / 32, nullptr, nullptr);
+      halo_reverse_add(h, h->d_q.p);
+      range_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, lo, hi, h->d_partial.p, sc);
+      dist_allreduce_sum(h, sc->red, sc->red, 1);
+      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);
+      dist_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, lo, hi, h->d_partial.p, sc);
+      dist_allreduce_sum(h, sc->red, sc->red, 2);
+      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 2, 0.0, 0);
+      dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, lo, hi, sc);
+      nl += 7;
+    }
+    launched += batch;
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    if (h->h_sc->done) break;  // identical on every rank
+    batch = 4;
+    if (launched >= h->pcg_maxit + 64) break;
+  }
+  halo_forward(h, d_x);  // the ghost copies of the solution
+  stage_end(h, ST_PCG, nl);
+  SPB_CUDA(cudaStreamSynchronize(st));
+  h->pcg_last_iters = h->h_sc->iters;
+  if (iters) *iters = h->h_sc->iters;
+  if (h->h_sc->breakdown) return SPB_NOT_SPD;
+  if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
+  return SPB_OK;
+}
+
 void dev_squared_norm_global(spb_context* h, const double* d_v, int64_t len, double* host_out) {
   if (h->nranks <= 1) {
     dev_squared_norm(h, d_v, len, host_out);

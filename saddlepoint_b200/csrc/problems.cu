@@ -287,6 +287,116 @@ spb_status spb_problem_lf_rows(spb_handle h, int32_t g, int32_t rows_mult, uint6
   return build_lf(h, g, rows_mult, seed, row_begin, row_end, true, out);
 }
 
+// LF restricted to the unknowns [col_begin, col_end) of the torus and the residual rows based
+// there (rows b + k*n, k < rows_mult): the LOCAL problem of one rank in the subdomain formulation
+// (dist.cu, halo mode).  Local unknowns are numbered [ghosts of the left neighbour | owned |
+// ghosts of the right neighbour] with halo = 2g on either side (the 3x3 window reaches one torus
+// row up and down, and wraps around inside a row); the data are the same splitmix64 stream as the global problem, so the ranks
+// together hold exactly the rows of spb_problem_lf.
+spb_status spb_problem_lf_cols(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t col_begin, int32_t col_end,
+                               spb_problem_t* out) {
+  if (!h || !out || g < 3 || rows_mult < 1) return SPB_ERR_ARG;
+  const int64_t n = (int64_t)g * g;
+  const int halo = 2 * g;  // |linear offset| <= g + (g-1): one torus row up/down plus the wrap-around inside a row
+  const int64_t own = (int64_t)col_end - col_begin;
+  if (col_begin < 0 || col_end > n || own < 2 * halo || own + 2 * halo > n) return SPB_ERR_ARG;
+  if (own * rows_mult * 8 > 0x7fffffffLL) return SPB_ERR_ARG;
+  *out = nullptr;
+  spb_problem* P = new spb_problem;
+  try {
+    SPB_CUDA(cudaSetDevice(h->device));
+    P->h = h;
+    P->kind = 0;
+    const int nloc = (int)(own + 2 * halo), ml = (int)(own * rows_mult);
+    P->n = nloc;
+    P->m = P->m_global = ml;
+    P->x0.assign(nloc, 1.0);
+    std::vector<int> rc((size_t)ml * 8);
+    std::vector<double> rv((size_t)ml * 8);
+    static const int dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+    static const int dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    const int64_t shift = (int64_t)col_begin - halo;  // global column of local index 0 (mod n)
+    for (int k = 0; k < rows_mult; ++k)
+      for (int64_t b = col_begin; b < col_end; ++b) {
+        const int64_t gr = (int64_t)k * n + b;
+        const int lr = (int)(k * own + (b - col_begin));
+        const int y0 = (int)(b / g), x0 = (int)(b % g);
+        const uint64_t h0 = splitmix64_at(seed, (uint64_t)gr * 8);
+        const int drop = (int)(h0 & 7);
+        int* c = &rc[(size_t)lr * 8];
+        double* v = &rv[(size_t)lr * 8];
+        int64_t gc[8];
+        gc[0] = b;
+        v[0] = 2.0 + unit_pm1(h0);
+        int sidx = 1;
+        for (int q = 0; q < 8; ++q) {
+          if (q == drop) continue;
+          gc[sidx] = (int64_t)((y0 + dy[q] + g) % g) * g + (x0 + dx[q] + g) % g;
+          v[sidx] = unit_pm1(splitmix64_at(seed, (uint64_t)gr * 8 + sidx));
+          ++sidx;
+        }
+        for (int a = 0; a < 8; ++a) {
+          const int64_t lc = ((gc[a] - shift) % n + n) % n;
+          if (lc >= nloc) throw ArgFail{"LF window reaches outside the halo"};
+          c[a] = (int)lc;
+        }
+        // NOTE: the global problem sorts a row's entries by GLOBAL column before summing; a local
+        // renumbering that wraps around the torus could change that order, so sort by the global column
+        for (int a = 1; a < 8; ++a) {
+          const int64_t gcc = gc[a];
+          const int cc = c[a];
+          const double vv = v[a];
+          int q = a - 1;
+          while (q >= 0 && gc[q] > gcc) {
+            gc[q + 1] = gc[q];
+            c[q + 1] = c[q];
+            v[q + 1] = v[q];
+            --q;
+          }
+          gc[q + 1] = gcc;
+          c[q + 1] = cc;
+          v[q + 1] = vv;
+        }
+      }
+    P->colptr.assign((size_t)nloc + 1, 0);
+    for (size_t e = 0; e < rc.size(); ++e) P->colptr[(size_t)rc[e] + 1]++;
+    for (int j = 0; j < nloc; ++j) P->colptr[(size_t)j + 1] += P->colptr[j];
+    P->rowidx.resize(rc.size());
+    std::vector<double> cv(rc.size());
+    {
+      std::vector<int> cur(P->colptr.begin(), P->colptr.end() - 1);
+      for (int r = 0; r < ml; ++r)
+        for (int q = 0; q < 8; ++q) {
+          const int d = cur[rc[(size_t)r * 8 + q]]++;
+          P->rowidx[d] = r;
+          cv[d] = rv[(size_t)r * 8 + q];
+        }
+    }
+    P->nnzJ = (int64_t)ml * 8;
+    std::vector<int> ec((size_t)ml * 8);
+    std::vector<double> evv((size_t)ml * 8);
+    for (int r = 0; r < ml; ++r)
+      for (int q = 0; q < 8; ++q) {
+        ec[(size_t)q * ml + r] = rc[(size_t)r * 8 + q];
+        evv[(size_t)q * ml + r] = rv[(size_t)r * 8 + q];
+      }
+    SPB_CUDA(P->d_ell_col.upload(ec, h->stream));
+    SPB_CUDA(P->d_ell_val.upload(evv, h->stream));
+    SPB_CUDA(P->d_csc_val.upload(cv, h->stream));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (const CudaFail& e) {
+    h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
+    delete P;
+    return SPB_ERR_CUDA;
+  } catch (const ArgFail& e) {
+    h->err = e.msg;
+    delete P;
+    return SPB_ERR_ARG;
+  }
+  *out = P;
+  return SPB_OK;
+}
+
 spb_status spb_problem_rosenbrock(spb_handle h, int32_t nblocks, const double* x0, spb_problem_t* out) {
   if (!h || !out || nblocks < 1) return SPB_ERR_ARG;
   spb_problem* P = new spb_problem;

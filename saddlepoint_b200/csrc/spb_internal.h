@@ -205,6 +205,11 @@ struct spb_context {
   spb::DevBuf<long long> d_dbg;  // debug stopwatch buffer (SPB_ASM_TIMING)
   bool pairs_fast_path = false; // every assembly chunk is on the common path (pipelined kernel)
   int occ_pairs = 0;
+  // subdomain (halo) mode, dist.cu: this handle holds the LOCAL problem of one rank; local unknowns are
+  // [left ghosts | owned | right ghosts] on a ring of ranks
+  bool halo_mode = false;
+  int halo = 0, own_lo = 0, own_hi = 0, left_rank = 0, right_rank = 0;
+  spb::DevBuf<double> d_halo_tmp;  // 2*halo receive buffer of the reverse exchange
   bool solve_xx_valid = false; // the last spb_solve left ||x||^2 in h_sc->xx
   // legacy triplet interface (spb_analyze_triplets): CSC entry q of H sums d_trip_src[d_trip_ptr[q] .. d_trip_ptr[q+1])
   int64_t trip_nnz = -1;      // number of input triplets; -1 = no triplet analysis on this handle
@@ -296,6 +301,10 @@ void dist_group_begin(spb_context* h);
 void dist_group_end(spb_context* h);
 void dist_allreduce_sum(spb_context* h, const double* send, double* recv, size_t count);
 void dist_allgather(spb_context* h, const double* send, double* recv, size_t count_per_rank);
+void dist_allreduce_max(spb_context* h, const double* send, double* recv, size_t count);
+void halo_forward(spb_context* h, double* v);      // owners -> the neighbours' ghost copies
+void halo_reverse_add(spb_context* h, double* v);  // ghost contributions -> owners (+=, left neighbour first)
+spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters);
 void dist_release(spb_context* h);
 // pcg.cu: distributed Jacobi-PCG over a row partition of H (replicated H, partitioned vectors)
 spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* iters);

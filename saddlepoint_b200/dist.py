@@ -64,3 +64,16 @@ def local_values(global_colptr, global_rowidx, global_vals, row_begin, row_end):
     rows): what spb_assemble expects after spb_analyze_partitioned."""
     keep = (global_rowidx >= row_begin) & (global_rowidx < row_end)
     return np.ascontiguousarray(global_vals[keep])
+
+
+def column_partition(n, world, rank, halo):
+    """Contiguous block of unknowns of `rank` for the subdomain (halo) mode; every block holds at least
+    2*halo unknowns (the exchange slabs of the two neighbours must not overlap)."""
+    lo, hi = shard_range(n, world, rank)
+    if hi - lo < 2 * halo:
+        raise ValueError("too many ranks for this problem: a rank needs at least 2*halo = %d unknowns" % (2 * halo))
+    return lo, hi
+
+
+def ring_neighbours(world, rank):
+    return (rank - 1) % world, (rank + 1) % world

@@ -104,6 +104,10 @@ class Handle:
         self._check(self.L.spb_local_nnz(self.h, C.byref(nnz)))
         self.nnzJ = nnz.value
 
+    def ring_halo(self, own_begin, own_end, halo, left_rank, right_rank):
+        """Subdomain (halo) mode (spb_dist_ring_halo): this handle holds the local problem of its rank."""
+        self._check(self.L.spb_dist_ring_halo(self.h, own_begin, own_end, halo, left_rank, right_rank))
+
     def local_pattern(self):
         colptr = np.empty(self.n + 1, np.int32)
         rowidx = np.empty(self.nnzJ, np.int32)
@@ -478,6 +482,9 @@ class BuiltinProblem:
             st = L.spb_problem_lf(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), C.byref(p))
         elif kind == "lf_rows":  # row-partitioned LF: this rank owns residual rows [row_begin,row_end)
             st = L.spb_problem_lf_rows(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), kw["row_begin"], kw["row_end"],
+                                       C.byref(p))
+        elif kind == "lf_cols":  # local part of LF for the subdomain (halo) mode: owned unknowns [col_begin,col_end)
+            st = L.spb_problem_lf_cols(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), kw["col_begin"], kw["col_end"],
                                        C.byref(p))
         elif kind == "rosenbrock":
             x0 = kw.get("x0")

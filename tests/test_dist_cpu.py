@@ -72,3 +72,19 @@ def test_shard_helpers_single_process():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sd.merge_problem_results([[(0, "a")], [(2, "b")]])
+
+
+def test_column_partition_and_ring_for_the_halo_mode():
+    from saddlepoint_b200 import dist as sd
+    n, halo = 1000, 40
+    for world in (2, 3, 8):
+        blocks = [sd.column_partition(n, world, r, halo) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+        assert all(hi - lo >= 2 * halo for lo, hi in blocks)
+        for r in range(world):
+            left, right = sd.ring_neighbours(world, r)
+            assert sd.ring_neighbours(world, left)[1] == r and sd.ring_neighbours(world, right)[0] == r
+    import pytest
+    with pytest.raises(ValueError):
+        sd.column_partition(n, 16, 0, halo)  # 62 unknowns per rank < 2*halo

@@ -1,0 +1,74 @@
+"""GPU tier: subdomain (halo) mode of the one-large-problem case.  On one GPU: the local problems of a
+column partition are exactly the rows of the global LF problem (same bits), and the sum of the local
+normal matrices restricted to their owners equals the global one.  With >= 2 GPUs a torchrun job runs the
+real path (ncclSend/ncclRecv halo exchanges) against the single-GPU solve."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _eval(prob, x):
+    import torch
+    T = prob.c_traits()
+    m, n, colptr, rowidx = prob.pattern()
+    xd = torch.tensor(x, dtype=torch.float64, device="cuda")
+    Ed = torch.empty(m, dtype=torch.float64, device="cuda")
+    Jd = torch.empty(int(colptr[-1]), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    T.objective_jacobian(T.user, xd.data_ptr(), Ed.data_ptr(), Jd.data_ptr(), None)
+    torch.cuda.synchronize()
+    return Ed.cpu().numpy(), sp.csc_matrix((Jd.cpu().numpy(), rowidx, colptr), shape=(m, n))
+
+
+def test_local_problems_are_the_rows_of_the_global_problem(spb, handle):
+    from saddlepoint_b200 import dist as sd
+    g, world = 16, 3
+    n, halo = g * g, 2 * g
+    rng = np.random.default_rng(8)
+    xg = rng.standard_normal(n)
+    glob = spb.BuiltinProblem(handle, "lf", g=g, rows_mult=2, seed=20211)
+    Eg, Jg = _eval(glob, xg)
+    Jg = Jg.tocsr()
+    Hsum = sp.csr_matrix((n, n))
+    for rank in range(world):
+        cb, ce = sd.column_partition(n, world, rank, halo)
+        own = ce - cb
+        loc = spb.BuiltinProblem(handle, "lf_cols", g=g, rows_mult=2, seed=20211, col_begin=cb, col_end=ce)
+        assert loc.xSize == own + 2 * halo and loc.ESize == 2 * own
+        gidx = np.arange(cb - halo, ce + halo) % n          # global index of every local unknown
+        El, Jl = _eval(loc, xg[gidx])
+        rows_g = np.concatenate([np.arange(cb, ce), n + np.arange(cb, ce)])   # local row k*own + (b-cb)  <->  global k*n + b
+        assert np.array_equal(El, Eg[rows_g])                # same bits: same entries, same summation order
+        # local Jacobian scattered to global columns equals the global rows
+        P = sp.csr_matrix((np.ones(len(gidx)), (np.arange(len(gidx)), gidx)), shape=(len(gidx), n))
+        assert abs(Jl.tocsr() @ P - Jg[rows_g]).max() == 0.0
+        Hsum = Hsum + (P.T @ (Jl.T @ Jl) @ P)
+        loc.close()
+    Hglob = (Jg.T @ Jg).tocsr()
+    assert abs(Hsum - Hglob).max() <= 1e-12 * abs(Hglob).max()   # H = sum of the local normal matrices
+    glob.close()
+
+
+def test_halo_mode_needs_a_communicator(spb):
+    h = spb.Handle(0)
+    with pytest.raises(spb.SpbError):
+        h.ring_halo(5, 25, 5, 0, 0)
+    h.close()
+
+
+def test_two_gpu_halo_job():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "scripts", "halo_check.py"), "--g", "96"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "HALO_CHECK_OK" in out.stdout

@@ -128,6 +128,11 @@ __global__ void halo_add_kernel(double* __restrict__ v, const double* __restrict
 
 void halo_forward(spb_context* h, double* v) {
   const size_t hl = (size_t)h->halo;
+  if (h->nranks <= 1) {  // a single rank that is its own neighbour on the ring (test configuration)
+    SPB_CUDA(cudaMemcpyAsync(v + h->own_hi, v + h->own_lo, hl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SPB_CUDA(cudaMemcpyAsync(v, v + h->own_hi - hl, hl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
   SPB_NCCL(g_nccl.GroupStart());
   SPB_NCCL(g_nccl.Send(v + h->own_lo, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));          // my first owned -> left's right ghosts
   SPB_NCCL(g_nccl.Send(v + h->own_hi - hl, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));    // my last owned  -> right's left ghosts
@@ -142,6 +147,14 @@ void halo_reverse_add(spb_context* h, double* v) {
   SPB_CUDA(h->d_halo_tmp.alloc(2 * hl));
   double* from_right = h->d_halo_tmp.p;
   double* from_left = h->d_halo_tmp.p + hl;
+  if (h->nranks <= 1) {  // self ring: my right-ghost rows are contributions to my first owned entries, and vice versa
+    SPB_CUDA(cudaMemcpyAsync(from_left, v + h->own_hi, hl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SPB_CUDA(cudaMemcpyAsync(from_right, v, hl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    halo_add_kernel<<<(h->halo + 255) / 256, 256, 0, h->stream>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
+    h->launches++;
+    SPB_CUDA(cudaGetLastError());
+    return;
+  }
   SPB_NCCL(g_nccl.GroupStart());
   SPB_NCCL(g_nccl.Send(v, hl, kNcclFloat64, h->left_rank, h->comm, h->stream));                  // my left-ghost rows  -> left (its last owned)
   SPB_NCCL(g_nccl.Send(v + h->own_hi, hl, kNcclFloat64, h->right_rank, h->comm, h->stream));     // my right-ghost rows -> right (its first owned)
@@ -222,9 +235,11 @@ spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, 
       h->halo_mode = false;
       return SPB_OK;
     }
-    if (!h->comm || h->nranks < 2) throw StateFail{"spb_dist_ring_halo needs a communicator of at least two ranks (spb_comm_init)"};
+    // without a communicator only the self ring (left == right == 0: one rank that is its own neighbour) is possible
+    const bool self_ring = h->nranks <= 1 && left_rank == 0 && right_rank == 0;
+    if (!self_ring && (!h->comm || h->nranks < 2)) throw StateFail{"spb_dist_ring_halo needs a communicator of at least two ranks (spb_comm_init)"};
     if (halo < 0 || own_begin != halo || own_end - own_begin < 2 * halo || left_rank < 0 || left_rank >= h->nranks || right_rank < 0 ||
-        right_rank >= h->nranks || left_rank == h->rank || right_rank == h->rank)
+        right_rank >= h->nranks || (!self_ring && (left_rank == h->rank || right_rank == h->rank)))
       throw ArgFail{"bad halo description: local unknowns are [halo ghosts | owned (>= 2*halo) | halo ghosts], neighbours are other ranks"};
     h->halo_mode = true;
     h->halo = halo;

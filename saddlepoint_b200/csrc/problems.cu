@@ -299,7 +299,8 @@ spb_status spb_problem_lf_cols(spb_handle h, int32_t g, int32_t rows_mult, uint6
   const int64_t n = (int64_t)g * g;
   const int halo = 2 * g;  // |linear offset| <= g + (g-1): one torus row up/down plus the wrap-around inside a row
   const int64_t own = (int64_t)col_end - col_begin;
-  if (col_begin < 0 || col_end > n || own < 2 * halo || own + 2 * halo > n) return SPB_ERR_ARG;
+  // own == n: one rank that is its own neighbour on the ring (ghosts are second copies of owned unknowns)
+  if (col_begin < 0 || col_end > n || own < 2 * halo || (own + 2 * halo > n && own != n)) return SPB_ERR_ARG;
   if (own * rows_mult * 8 > 0x7fffffffLL) return SPB_ERR_ARG;
   *out = nullptr;
   spb_problem* P = new spb_problem;

@@ -59,8 +59,61 @@ def test_local_problems_are_the_rows_of_the_global_problem(spb, handle):
 def test_halo_mode_needs_a_communicator(spb):
     h = spb.Handle(0)
     with pytest.raises(spb.SpbError):
-        h.ring_halo(5, 25, 5, 0, 0)
+        h.ring_halo(5, 25, 5, 1, 1)   # other ranks as neighbours, but no communicator
+    with pytest.raises(spb.SpbError):
+        h.ring_halo(5, 12, 5, 0, 0)   # fewer than 2*halo owned unknowns
     h.close()
+
+
+@pytest.mark.parametrize("g", [24, 64])
+def test_self_ring_halo_mode_matches_the_plain_solve(spb, orc, g):
+    """One rank that is its own neighbour on the ring: the whole halo-mode code path (local problem with ghost
+    copies, halo sums in the assembly, halo exchanges in the PCG, LM loop on local vectors) with device copies
+    standing in for ncclSend/ncclRecv.  The result must agree with the ordinary single-handle solve."""
+    n, halo = g * g, 2 * g
+    h = spb.Handle(0)
+    loc = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=20211, col_begin=0, col_end=n)
+    assert loc.xSize == n + 2 * halo
+    h.ring_halo(halo, halo + n, halo, 0, 0)
+    lm = spb.LMSolver()
+    lm.init(spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, 1e-13, 10000), loc, spb.DiagonalDamping(0.01), 100)
+    ret = lm.solve(True, dedupe_evaluations=True)
+    x = lm.x
+    # ghosts are copies of their owners
+    assert np.array_equal(x[:halo], x[halo + n - halo:halo + n]) and np.array_equal(x[halo + n:], x[halo:2 * halo])
+    ref = orc.lm_solve("lf", iparam0=g, iparam1=2, seed=20211, maxIterations=100)
+    assert ret == ref.ret and lm.exit_path == ref.exit_path
+    assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
+    xo = x[halo:halo + n]
+    assert np.linalg.norm(xo - ref.x) <= 1e-10 * np.linalg.norm(ref.x)
+    assert abs(lm.energy - ref.energy) <= 1e-10 * max(abs(ref.energy), 1e-16 * ref.trace["prevEnergy2"][0])
+    assert lm.trace["foo"][0] == ref.trace["foo"][0] or abs(lm.trace["foo"][0] - ref.trace["foo"][0]) <= 1e-12 * ref.trace["foo"][0]
+    # granular: assembled gradient and damping (halo sums) against the plain handle
+    hp = spb.Handle(0)
+    glob = spb.BuiltinProblem(hp, "lf", g=g, rows_mult=2, seed=20211)
+    import torch
+    T = glob.c_traits()
+    m, nn, colptr, rowidx = glob.pattern()
+    xd = torch.ones(nn, dtype=torch.float64, device="cuda")
+    Ed = torch.empty(m, dtype=torch.float64, device="cuda")
+    Jd = torch.empty(int(colptr[-1]), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    T.objective_jacobian(T.user, xd.data_ptr(), Ed.data_ptr(), Jd.data_ptr(), None)
+    torch.cuda.synchronize()
+    hp.analyze(m, nn, colptr, rowidx)
+    hp.assemble(Jd, Ed, 0.01)
+    Tl = loc.c_traits()
+    ml, nl, lcp, lri = loc.pattern()
+    xl = torch.ones(nl, dtype=torch.float64, device="cuda")
+    El = torch.empty(ml, dtype=torch.float64, device="cuda")
+    Jl = torch.empty(int(lcp[-1]), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    Tl.objective_jacobian(Tl.user, xl.data_ptr(), El.data_ptr(), Jl.data_ptr(), None)
+    torch.cuda.synchronize()
+    h.assemble(Jl, El, 0.01)
+    np.testing.assert_allclose(h.rhs()[halo:halo + n], hp.rhs(), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(h.damping()[halo:halo + n], hp.damping(), rtol=1e-13, atol=1e-300)
+    loc.close(); glob.close(); h.close(); hp.close()
 
 
 def test_two_gpu_halo_job():

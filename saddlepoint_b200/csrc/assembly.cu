@@ -732,6 +732,7 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
       halo_forward(h, h->d_rhs.p);
     }
     halo_forward(h, h->d_dvec.p);
+    halo_forward(h, h->d_hdiag.p);  // the PCG updates the ghost copies of its vectors itself and needs their Jacobi diagonal
   }
   SPB_CUDA(cudaGetLastError());
   stage_end(h, ST_ASSEMBLY, nl);

@@ -167,6 +167,42 @@ void halo_reverse_add(spb_context* h, double* v) {
   SPB_CUDA(cudaGetLastError());
 }
 
+// Both directions in one exchange: afterwards v holds the FULL sum on the owned edges and on the
+// ghosts (same bits on both holders: a + b is commutative).  A rank sends each neighbour its
+// partials for the 2*halo entries they share -- [its ghost rows of that neighbour | its own edge rows
+// next to that neighbour] -- and adds what it receives.
+__global__ void halo_sum_both_kernel(double* __restrict__ v, const double* __restrict__ from_left, const double* __restrict__ from_right,
+                                     int own_lo, int own_hi, int halo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * halo) return;
+  // the shared band with the left neighbour is local [0, 2*halo) (ghosts, then my first owned); with the
+  // right neighbour local [own_hi - halo, own_hi + halo).  Both ranks pack a band in ascending global order.
+  v[i] += from_left[i];
+  v[own_hi - halo + i] += from_right[i];
+}
+
+void halo_sum_both(spb_context* h, double* v) {
+  const size_t hl = (size_t)h->halo, band = 2 * hl;
+  SPB_CUDA(h->d_halo_tmp.alloc(2 * band));
+  double* from_right = h->d_halo_tmp.p;
+  double* from_left = h->d_halo_tmp.p + band;
+  if (h->nranks <= 1) {  // self ring: the left band [0,2h) and the right band [own_hi-h, own_hi+h) are the same global entries
+    SPB_CUDA(cudaMemcpyAsync(from_left, v + h->own_hi - hl, band * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SPB_CUDA(cudaMemcpyAsync(from_right, v, band * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    SPB_NCCL(g_nccl.GroupStart());
+    SPB_NCCL(g_nccl.Send(v, band, kNcclFloat64, h->left_rank, h->comm, h->stream));                    // my view of the band shared with left
+    SPB_NCCL(g_nccl.Send(v + h->own_hi - hl, band, kNcclFloat64, h->right_rank, h->comm, h->stream));  // ... shared with right
+    SPB_NCCL(g_nccl.Recv(from_right, band, kNcclFloat64, h->right_rank, h->comm, h->stream));          // right's view of our band
+    SPB_NCCL(g_nccl.Recv(from_left, band, kNcclFloat64, h->left_rank, h->comm, h->stream));            // left's view of our band
+    SPB_NCCL(g_nccl.GroupEnd());
+    h->collectives++;
+  }
+  halo_sum_both_kernel<<<(int)((band + 255) / 256), 256, 0, h->stream>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
+  h->launches++;
+  SPB_CUDA(cudaGetLastError());
+}
+
 void dist_release(spb_context* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;

@@ -1474,9 +1474,79 @@ __global__ void __launch_bounds__(256) range_dot_kernel(const double* __restrict
   }
 }
 
+// vector phases of the halo-mode PCG: every local entry (ghosts included) is updated -- the ghost copies
+// are recomputed redundantly from identical inputs, so they stay bit-identical to their owners and p
+// never has to be exchanged -- while the dot products count the owned entries [lo, hi) only
+__global__ void __launch_bounds__(256) halo_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ p, int n, int lo, int hi,
+                                                        double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  double rz = 0.0, bb = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double bi = b[i];
+    const double z = bi * dinv[i];
+    x[i] = 0.0;
+    r[i] = bi;
+    p[i] = z;
+    if (i >= lo && i < hi) {
+      rz = fma(bi, z, rz);
+      bb = fma(bi, bi, bb);
+    }
+  }
+  const double s1 = block_sum_256(rz, sm);
+  const double s2 = block_sum_256(bb, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s1;
+    partial[gridDim.x + blockIdx.x] = s2;
+  }
+  if (take_ticket(&sc->ticket_b, gridDim.x) && threadIdx.x < 32) {
+    const double a = ordered_sum(partial, gridDim.x);
+    const double c = ordered_sum(partial + gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) {
+      sc->red[0] = a;
+      sc->red[1] = c;
+      sc->done = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_update_kernel(const double* __restrict__ dinv, const double* p, const double* __restrict__ q,
+                                                          double* __restrict__ x, double* __restrict__ r, int n, int lo, int hi,
+                                                          double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    if (i >= lo && i < hi) {
+      const double z = ri * dinv[i];
+      a1 = fma(ri, z, a1);
+      a2 = fma(ri, ri, a2);
+    }
+  }
+  const double s1 = block_sum_256(a1, sm);
+  const double s2 = block_sum_256(a2, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s1;
+    partial[gridDim.x + blockIdx.x] = s2;
+  }
+  if (take_ticket(&sc->ticket_b, gridDim.x) && threadIdx.x < 32) {
+    const double a = ordered_sum(partial, gridDim.x);
+    const double c = ordered_sum(partial + gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) {
+      sc->red[0] = a;
+      sc->red[1] = c;
+    }
+  }
+}
+
 // Jacobi-PCG in subdomain (halo) mode: vectors are local ([ghosts | owned | ghosts]); one iteration is
-//   forward halo exchange of p -> q = H_loc p (all local rows) -> reverse halo sum of q -> p.q (owned) ->
-//   allreduce -> x, r, z updates (owned) -> allreduce (r.z, r.r) -> p update (owned).
+//   q = H_loc p (all local rows) -> ONE halo exchange that leaves the full q on the owned edges and on the
+//   ghosts -> p.q (owned) -> allreduce -> x, r updates (all local entries) with r.z, r.r (owned) ->
+//   allreduce -> p update (all local entries).
 // Scalars come out of the same allreduce on every rank, so alpha, beta and the stop decision agree.
 spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters) {
   const int n = h->n;
@@ -1491,12 +1561,11 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
   double* p = h->d_p.p;
   PcgScalars* sc = h->d_sc.p;
   const int lo = h->own_lo, hi = h->own_hi;
-  const int gv = std::max(1, std::min((hi - lo + 255) / 256, h->num_sms * 8));
+  const int gv = std::max(1, std::min((n + 255) / 256, h->num_sms * 8));
   stage_begin(h, ST_PCG);
   int nl = 0;
-  SPB_CUDA(cudaMemsetAsync(d_x, 0, (size_t)n * sizeof(double), st));
-  SPB_CUDA(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), st));
-  dist_init_kernel<<<gv, 256, 0, st>>>(d_b, h->d_dinv.p, d_x, h->d_r.p, p, lo, hi, h->d_partial.p, sc);
+  // b and the Jacobi diagonal carry valid ghost copies (run_assembly exchanges them)
+  halo_init_kernel<<<gv, 256, 0, st>>>(d_b, h->d_dinv.p, d_x, h->d_r.p, p, n, lo, hi, h->d_partial.p, sc);
   dist_allreduce_sum(h, sc->red, sc->red, 2);
   dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 0, h->pcg_rtol, h->pcg_maxit);
   nl += 2;
@@ -1504,17 +1573,16 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
   int batch = h->pcg_last_iters > 0 ? std::min(h->pcg_last_iters + 2, h->pcg_maxit) : 16;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
-      halo_forward(h, p);
       spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n,
                                                             (n + 31) / 32, nullptr, nullptr);
-      halo_reverse_add(h, h->d_q.p);
+      halo_sum_both(h, h->d_q.p);
       range_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, lo, hi, h->d_partial.p, sc);
       dist_allreduce_sum(h, sc->red, sc->red, 1);
       dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);
-      dist_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, lo, hi, h->d_partial.p, sc);
+      halo_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, n, lo, hi, h->d_partial.p, sc);
       dist_allreduce_sum(h, sc->red, sc->red, 2);
       dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 2, 0.0, 0);
-      dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, lo, hi, sc);
+      dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, 0, n, sc);
       nl += 7;
     }
     launched += batch;
@@ -1525,9 +1593,7 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
     batch = 4;
     if (launched >= h->pcg_maxit + 64) break;
   }
-  halo_forward(h, d_x);  // the ghost copies of the solution
   stage_end(h, ST_PCG, nl);
-  SPB_CUDA(cudaStreamSynchronize(st));
   h->pcg_last_iters = h->h_sc->iters;
   if (iters) *iters = h->h_sc->iters;
   if (h->h_sc->breakdown) return SPB_NOT_SPD;

@@ -304,6 +304,11 @@ def run_ours(args):
         cpu["value"] = v
         cpu["unit"] = "iterations/s"
 
+    # ---- N > 1 extra (not the headline): ONE problem of config C5's size over all ranks, subdomain (halo) mode
+    one_problem = None
+    if world > 1 and not args.no_one_problem:
+        one_problem = one_problem_all_gpus(spb, dist, torch, local, rank, world, args)
+
     if rank == 0:
         line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -315,9 +320,55 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "direct_solver": direct}
+        if one_problem is not None:
+            line["one_problem_all_gpus"] = one_problem
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def one_problem_all_gpus(spb, dist, torch, local, rank, world, args, iters=3):
+    """Strong-scaling data point next to the (weak-scaling) headline: one LF problem of config C5's size
+    (g=4472, n ~ 20 M; the 1-GPU time of the same problem is in DESIGN.md) solved by all ranks together in
+    subdomain (halo) mode -- local analysis per rank, one halo exchange and two scalar allreduces per PCG
+    iteration over NVLink.  Never fails the bench line: errors are reported as a string."""
+    try:
+        from saddlepoint_b200 import dist as sd
+        g = args.one_problem_g
+        n = g * g
+        halo = 2 * g
+        h = spb.Handle(local, torch.cuda.current_stream().cuda_stream)
+        sd.attach_comm(h, dist)
+        cb, ce = sd.column_partition(n, world, rank, halo)
+        left, right = sd.ring_neighbours(world, rank)
+        prob = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=20214, col_begin=cb, col_end=ce)
+        h.ring_halo(halo, halo + (ce - cb), halo, left, right)
+        ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+        lm = spb.LMSolver()
+        lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
+        x = torch.empty(prob.xSize, dtype=torch.float64, device="cuda")
+        lm.solve(False, dedupe_evaluations=True, fixed_iterations=1, x_out=x)  # warm-up incl. the local analysis
+        analyze_s = lm.seconds_analyze
+        lm.DT.currLambda = 0.01
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lm.solve(False, dedupe_evaluations=True, fixed_iterations=iters, x_out=x)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = {"workload": "LF g=%d (n=%d, m=%d) as ONE problem over %d GPUs, subdomain (halo) mode" % (g, n, 2 * n, world),
+               "ms_per_lm_iteration": float(t.item()) / iters, "lm_iterations_per_s": iters / (float(t.item()) * 1e-3),
+               "pcg_iterations_per_lm_iteration": lm.linear_iterations / iters, "local_analysis_seconds": analyze_s,
+               "collectives": int(h.collective_count()), "scaling": "strong"}
+        prob.close()
+        h.close()
+        return out
+    except Exception as e:  # noqa: BLE001 -- an extra must not break the bench line
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def main():
@@ -331,6 +382,8 @@ def main():
     ap.add_argument("--solver", default="pcg_jacobi", choices=["pcg_jacobi", "pcg_ic0"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the supernodal-Cholesky timing block")
+    ap.add_argument("--no-one-problem", action="store_true", help="N>1: skip the one-problem-over-all-GPUs (halo mode) extra")
+    ap.add_argument("--one-problem-g", type=int, default=4472, help="torus size of that extra (config C5: 4472)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -181,29 +181,35 @@ __global__ void halo_sum_both_kernel(double* __restrict__ v, const double* __res
   v[own_hi - halo + i] += from_right[i];
 }
 
-void halo_sum_both(spb_context* h, double* v) {
+void halo_sum_both(spb_context* h, double* v, cudaStream_t st) {
+  if (!st) st = h->stream;
   const size_t hl = (size_t)h->halo, band = 2 * hl;
   SPB_CUDA(h->d_halo_tmp.alloc(2 * band));
   double* from_right = h->d_halo_tmp.p;
   double* from_left = h->d_halo_tmp.p + band;
   if (h->nranks <= 1) {  // self ring: the left band [0,2h) and the right band [own_hi-h, own_hi+h) are the same global entries
-    SPB_CUDA(cudaMemcpyAsync(from_left, v + h->own_hi - hl, band * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SPB_CUDA(cudaMemcpyAsync(from_right, v, band * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SPB_CUDA(cudaMemcpyAsync(from_left, v + h->own_hi - hl, band * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SPB_CUDA(cudaMemcpyAsync(from_right, v, band * sizeof(double), cudaMemcpyDeviceToDevice, st));
   } else {
     SPB_NCCL(g_nccl.GroupStart());
-    SPB_NCCL(g_nccl.Send(v, band, kNcclFloat64, h->left_rank, h->comm, h->stream));                    // my view of the band shared with left
-    SPB_NCCL(g_nccl.Send(v + h->own_hi - hl, band, kNcclFloat64, h->right_rank, h->comm, h->stream));  // ... shared with right
-    SPB_NCCL(g_nccl.Recv(from_right, band, kNcclFloat64, h->right_rank, h->comm, h->stream));          // right's view of our band
-    SPB_NCCL(g_nccl.Recv(from_left, band, kNcclFloat64, h->left_rank, h->comm, h->stream));            // left's view of our band
+    SPB_NCCL(g_nccl.Send(v, band, kNcclFloat64, h->left_rank, h->comm, st));                    // my view of the band shared with left
+    SPB_NCCL(g_nccl.Send(v + h->own_hi - hl, band, kNcclFloat64, h->right_rank, h->comm, st));  // ... shared with right
+    SPB_NCCL(g_nccl.Recv(from_right, band, kNcclFloat64, h->right_rank, h->comm, st));          // right's view of our band
+    SPB_NCCL(g_nccl.Recv(from_left, band, kNcclFloat64, h->left_rank, h->comm, st));            // left's view of our band
     SPB_NCCL(g_nccl.GroupEnd());
     h->collectives++;
   }
-  halo_sum_both_kernel<<<(int)((band + 255) / 256), 256, 0, h->stream>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
+  halo_sum_both_kernel<<<(int)((band + 255) / 256), 256, 0, st>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
   h->launches++;
   SPB_CUDA(cudaGetLastError());
 }
 
 void dist_release(spb_context* h) {
+  if (h->halo_ev_band) cudaEventDestroy(h->halo_ev_band);
+  if (h->halo_ev_done) cudaEventDestroy(h->halo_ev_done);
+  if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
+  h->halo_ev_band = h->halo_ev_done = nullptr;
+  h->halo_stream = nullptr;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
   h->nranks = 1;

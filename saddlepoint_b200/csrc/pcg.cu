@@ -1459,6 +1459,16 @@ spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* i
   return SPB_OK;
 }
 
+// y = H x over the slices [s_lo, s_hi) only (halo mode: band rows first, interior rows while the exchange runs)
+__global__ void __launch_bounds__(256) spmv_slices_kernel(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
+                                                          const int* __restrict__ rowlen, const double* __restrict__ hval,
+                                                          const double* __restrict__ x, double* __restrict__ y, int n, int s_lo, int s_hi) {
+  const int ns = s_hi - s_lo;
+  const int s_begin = s_lo + (int)(((int64_t)ns * blockIdx.x) / gridDim.x);
+  const int s_end = s_lo + (int)(((int64_t)ns * (blockIdx.x + 1)) / gridDim.x);
+  (void)spmv_range<true>(slice_off, col, rowlen, hval, x, y, n, s_begin, s_end);
+}
+
 // p.q over the owned range (after the reverse halo sum made q final there)
 __global__ void __launch_bounds__(256) range_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int lo, int hi,
                                                         double* __restrict__ partial, PcgScalars* sc) {
@@ -1562,6 +1572,23 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
   PcgScalars* sc = h->d_sc.p;
   const int lo = h->own_lo, hi = h->own_hi;
   const int gv = std::max(1, std::min((n + 255) / 256, h->num_sms * 8));
+  // slices [0, sb_lo) and [sb_hi, nslices) hold every row of the two exchanged bands; the rest is interior
+  const int nslices = (n + 31) / 32;
+  const int sb_lo = std::min(nslices, (2 * h->halo + 31) / 32), sb_hi = std::max(sb_lo, (h->own_hi - h->halo) / 32);
+  // Overlapping the exchange with the interior rows (band rows first, exchange on a second stream) is
+  // implemented but OFF by default: measured on 4 x B200 at C5 size it is slower (57.2 vs 53.7 ms per LM
+  // iteration) -- three SpMV launches, two events and a cross-stream wait cost more than the ~25 us of
+  // exchange latency they hide.  SPB_HALO_OVERLAP=1 enables it.
+  static const bool overlap_on = getenv("SPB_HALO_OVERLAP") && atoi(getenv("SPB_HALO_OVERLAP")) == 1;
+  const bool overlap = overlap_on && sb_hi - sb_lo >= 64;
+  const int occ = std::max(1, h->occ_spmv ? h->occ_spmv : 6);
+  const int gband = std::max(1, std::min((sb_lo + 7) / 8, h->num_sms * occ));
+  const int gint = std::max(1, std::min((sb_hi - sb_lo + 7) / 8, h->num_sms * occ));
+  if (overlap && !h->halo_stream) {
+    SPB_CUDA(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    SPB_CUDA(cudaEventCreateWithFlags(&h->halo_ev_band, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&h->halo_ev_done, cudaEventDisableTiming));
+  }
   stage_begin(h, ST_PCG);
   int nl = 0;
   // b and the Jacobi diagonal carry valid ghost copies (run_assembly exchanges them)
@@ -1573,9 +1600,23 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
   int batch = h->pcg_last_iters > 0 ? std::min(h->pcg_last_iters + 2, h->pcg_maxit) : 16;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
-      spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n,
-                                                            (n + 31) / 32, nullptr, nullptr);
-      halo_sum_both(h, h->d_q.p);
+      if (overlap) {
+        // the rows whose q takes part in the exchange first; the exchange then runs on its own stream while the
+        // interior rows are multiplied
+        spmv_slices_kernel<<<gband, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n, 0, sb_lo);
+        spmv_slices_kernel<<<gband, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n, sb_hi, nslices);
+        SPB_CUDA(cudaEventRecord(h->halo_ev_band, st));
+        SPB_CUDA(cudaStreamWaitEvent(h->halo_stream, h->halo_ev_band, 0));
+        halo_sum_both(h, h->d_q.p, h->halo_stream);
+        SPB_CUDA(cudaEventRecord(h->halo_ev_done, h->halo_stream));
+        spmv_slices_kernel<<<gint, 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n, sb_lo, sb_hi);
+        SPB_CUDA(cudaStreamWaitEvent(st, h->halo_ev_done, 0));
+        nl += 2;
+      } else {
+        spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n,
+                                                              (n + 31) / 32, nullptr, nullptr);
+        halo_sum_both(h, h->d_q.p);
+      }
       range_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, lo, hi, h->d_partial.p, sc);
       dist_allreduce_sum(h, sc->red, sc->red, 1);
       dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);

@@ -210,6 +210,8 @@ struct spb_context {
   bool halo_mode = false;
   int halo = 0, own_lo = 0, own_hi = 0, left_rank = 0, right_rank = 0;
   spb::DevBuf<double> d_halo_tmp;  // 2*halo receive buffer of the reverse exchange
+  cudaStream_t halo_stream = nullptr;  // the exchange of the PCG runs here, concurrently with the interior SpMV
+  cudaEvent_t halo_ev_band = nullptr, halo_ev_done = nullptr;
   bool solve_xx_valid = false; // the last spb_solve left ||x||^2 in h_sc->xx
   // legacy triplet interface (spb_analyze_triplets): CSC entry q of H sums d_trip_src[d_trip_ptr[q] .. d_trip_ptr[q+1])
   int64_t trip_nnz = -1;      // number of input triplets; -1 = no triplet analysis on this handle
@@ -304,7 +306,7 @@ void dist_allgather(spb_context* h, const double* send, double* recv, size_t cou
 void dist_allreduce_max(spb_context* h, const double* send, double* recv, size_t count);
 void halo_forward(spb_context* h, double* v);      // owners -> the neighbours' ghost copies
 void halo_reverse_add(spb_context* h, double* v);  // ghost contributions -> owners (+=, left neighbour first)
-void halo_sum_both(spb_context* h, double* v);     // one exchange: full sums on the owned edges AND on the ghosts
+void halo_sum_both(spb_context* h, double* v, cudaStream_t st = nullptr);  // one exchange: full sums on the owned edges AND on the ghosts
 spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters);
 void dist_release(spb_context* h);
 // pcg.cu: distributed Jacobi-PCG over a row partition of H (replicated H, partitioned vectors)

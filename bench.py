@@ -93,11 +93,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ncu --set full capture of pcg_persistent_kernel on LF-1M (profiles/r1b_ncu_raw_metrics.txt):
-# dram__bytes_read.sum + dram__bytes_write.sum = 25.06 GB + 0.34 GB for the 96-iteration solve of the
-# third LM iteration (6.458 ms) = 264.6 MB per PCG iteration: the 10-byte/entry H stream (FP64 value +
-# 16-bit column delta, 26.2 M padded entries); the PCG vectors never leave the 126 MB L2.
-NCU_DRAM_BYTES_PER_PCG_ITERATION = 25.394e9 / 96.0
+# ncu --set full capture of pcg_persistent_kernel on LF-1M (profiles/r1c_ncu_raw_metrics.txt, end of round 1):
+# dram__bytes_read.sum + dram__bytes_write.sum = 21.380 GB + 0.289 GB for an 81-iteration solve (5.31 ms)
+# = 267.5 MB per PCG iteration (r1b: 25.394 GB / 96 iterations = 264.6 MB): the 10-byte/entry H stream (FP64
+# value + 16-bit column delta, 26.2 M padded entries) plus the solve's first and last vector passes; the PCG
+# vectors never leave the 126 MB L2.
+NCU_DRAM_BYTES_PER_PCG_ITERATION = 21.669e9 / 81.0
 
 
 def lf_sizes(g):

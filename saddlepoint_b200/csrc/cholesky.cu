@@ -11,17 +11,23 @@
 //   1. scatter the H values into the panels (one launch for the whole matrix);
 //   2. extend-add the children's update matrices into the level's fronts, one launch per
 //      child rank so the summation order is fixed (deterministic) and conflict-free;
-//   3. blocked right-looking factorisation of the pivot columns, block size 32:
-//        potrf32 (one CTA per front; also inverts the 32x32 block for the solves)
-//        trsm    (one thread per row below the block)
-//        syrk    (trailing pivot columns; FP64 tensor cores, mma.sync m8n8k4 DMMA)
+//   3. blocked right-looking factorisation of the pivot columns, block size 32.  A block step is
+//        chol_step_kernel   few CTAs in the group (top separators, latency regime): every CTA factors the
+//                           32x32 diagonal block itself in one warp and solves its 128 rows -- one launch;
+//                           an extra CTA stores the inverted block for the solves
+//        chol_potrf32_warp_kernel + chol_trsm_kernel   thousands of fronts (leaf levels, throughput regime)
+//        chol_syrk_kernel   trailing pivot columns of the 256-column panel (K=32) and, once per panel,
+//                           everything right of it (K=256); FP64 tensor cores, mma.sync m8n8k4 DMMA
 //   4. U_s -= L21 L21^T in one K=k SYRK (DMMA), the bulk of the flops.
-// Only steps 3-syrk and 4 are tensor-core work; scatter/extend-add/solves are bandwidth or
-// latency kernels (north_star item 3).  tcgen05 has no FP64 path, so DMMA is the FP64
-// tensor instruction on sm_100a.
-// Solves: level-ordered; forward gathers children's tails in a fixed order inside the
-// parent's CTA, diagonal blocks are applied through their precomputed inverses so a front
-// needs k/32 sequential steps, not k.
+// Only the SYRKs are tensor-core work; scatter/extend-add/solves are bandwidth or latency kernels
+// (north_star item 3).  tcgen05 has no FP64 path, so DMMA is the FP64 tensor instruction on sm_100a.
+// Update matrices live in one arena packed by lifetime (chol_symbolic.cpp), cleared per level.
+// Solves: level-ordered.  Groups of many small fronts: one CTA per front, work vector in shared
+// memory, children's tails gathered in a fixed order.  Groups with few and/or large fronts: one
+// cooperative launch per group runs all its block steps separated by grid barriers (128-pivot tiles
+// staged in shared memory); diagonal blocks are applied through their precomputed inverses.
+// Debug stopwatches: SPB_CHOL_TIMING=1 (per group), 2 (inside the cooperative forward kernel),
+// 3 (fused step kernel), 4 (narrow SYRK).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

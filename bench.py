@@ -15,8 +15,9 @@ benchmark/linear_function: g x g torus, n = g^2 unknowns, m = 2n residuals, 8 nn
   roofline : the dominant kernel (the PCG's SpMV) re-timed per launch with CUDA events.
   cpu_baseline / --impl reference : the CPU oracle (Eigen restatement, 1 thread) on a bounded
           sample of the same workload.
-N>1: one process per GPU (torchrun), each rank solves its own independent LF problem (different
-seed): the "batches of independent problems split per GPU" sharding -- no data-path collective.
+N>1: one process per GPU (torchrun), each rank solves its own independent instance of the same LF
+configuration: the "batches of independent problems split per GPU" sharding -- no data-path collective;
+plus, as an extra key, ONE C5-size problem solved by all ranks together (subdomain / halo mode, NCCL).
 """
 import argparse
 import json
@@ -161,8 +162,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1 or os.environ.get("SPB_BENCH_FORCE_PG"):
+        dist.init_process_group(os.environ.get("SPB_BENCH_PG_BACKEND", "nccl"), **({"device_id": torch.device("cuda", local)} if os.environ.get("SPB_BENCH_PG_BACKEND", "nccl") == "nccl" else {}))
+        if os.environ.get("SPB_BENCH_FORCE_PG"):
+            dist.barrier()
     import saddlepoint_b200 as spb
 
     K, W, g = args.steps, max(args.warmup, 3), args.g
@@ -171,7 +174,9 @@ def run_ours(args):
     h = spb.Handle(local, stream)
     solver_id = spb.SOLVER_PCG_IC0 if args.solver == "pcg_ic0" else spb.SOLVER_PCG_JACOBI
     h.set_solver(solver_id, args.pcg_rtol, 10000)
-    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211 + rank)
+    # every rank solves its own instance of the SAME configuration (seed 20211): per-GPU work is identical, so the
+    # max-over-ranks time measures scaling and not the spread of PCG iteration counts between different problems
+    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
     ls = spb.B200SolverWrapper(h, solver_id, args.pcg_rtol, 10000)
     lm = spb.LMSolver()
     lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
@@ -326,7 +331,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (_label(g), g, n, m, nnzJ, nnzH),
-                           "per_gpu": "one independent problem per GPU (seed 20211+rank)", "solver": "%s rtol=%g" % (args.solver, args.pcg_rtol),
+                           "per_gpu": "one independent problem per GPU (every rank its own instance of the same configuration, seed 20211)", "solver": "%s rtol=%g" % (args.solver, args.pcg_rtol),
                            "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
                            "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s,
                            "lm_bodies_per_solve": BODIES_PER_SOLVE},

@@ -181,7 +181,7 @@ __global__ void halo_sum_both_kernel(double* __restrict__ v, const double* __res
   v[own_hi - halo + i] += from_right[i];
 }
 
-void halo_sum_both(spb_context* h, double* v, cudaStream_t st) {
+void halo_sum_both(spb_context* h, double* v, cudaStream_t st, bool add) {
   if (!st) st = h->stream;
   const size_t hl = (size_t)h->halo, band = 2 * hl;
   SPB_CUDA(h->d_halo_tmp.alloc(2 * band));
@@ -199,6 +199,7 @@ void halo_sum_both(spb_context* h, double* v, cudaStream_t st) {
     SPB_NCCL(g_nccl.GroupEnd());
     h->collectives++;
   }
+  if (!add) return;  // the caller folds the additions into its next kernel (d_halo_tmp: [from_right | from_left])
   halo_sum_both_kernel<<<(int)((band + 255) / 256), 256, 0, st>>>(v, from_left, from_right, h->own_lo, h->own_hi, h->halo);
   h->launches++;
   SPB_CUDA(cudaGetLastError());

@@ -1553,6 +1553,96 @@ __global__ void __launch_bounds__(256) halo_update_kernel(const double* __restri
   }
 }
 
+// Fused phases of the halo-mode PCG (four launches per iteration: SpMV, this dot, update, direction).
+// The dot kernel first completes q on the two exchanged bands (received partials added in place), the update
+// kernel derives alpha from the allreduced p.q itself, and the LAST block of the direction kernel (ticket)
+// commits rz, rr, the iteration count and the stop flag -- all blocks have read the old rz by then.
+__global__ void __launch_bounds__(256) halo_dot_kernel(const double* __restrict__ p, double* __restrict__ q,
+                                                       const double* __restrict__ from_left, const double* __restrict__ from_right, int n,
+                                                       int lo, int hi, int halo, double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  const int rb = hi - halo;  // first entry of the band shared with the right neighbour
+  double acc = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    double qi = q[i];
+    if (i < 2 * halo) {
+      qi += from_left[i];
+      q[i] = qi;
+    } else if (i >= rb) {
+      qi += from_right[i - rb];
+      q[i] = qi;
+    }
+    if (i >= lo && i < hi) acc = fma(p[i], qi, acc);
+  }
+  const double s = block_sum_256(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (take_ticket(&sc->ticket_a, gridDim.x) && threadIdx.x < 32) {
+    const double t = ordered_sum(partial, gridDim.x);
+    if (threadIdx.x == 0) sc->red[0] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_update2_kernel(const double* __restrict__ dinv, const double* p, const double* __restrict__ q,
+                                                           double* __restrict__ x, double* __restrict__ r, int n, int lo, int hi,
+                                                           double* __restrict__ partial, PcgScalars* sc) {
+  __shared__ double sm[8];
+  if (sc->done) return;
+  const double pq = sc->red[0];  // allreduced p.q; overwritten only by the last block of this kernel, after every block read it
+  const bool bad = !(pq > 0.0);  // not SPD (or NaN)
+  const double alpha = bad ? 0.0 : sc->rz / pq;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->pq = pq;
+    sc->alpha = alpha;
+    if (bad) {
+      sc->breakdown = 1;
+      sc->done = 1;
+    }
+  }
+  if (bad) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    if (i >= lo && i < hi) {
+      const double z = ri * dinv[i];
+      a1 = fma(ri, z, a1);
+      a2 = fma(ri, ri, a2);
+    }
+  }
+  const double s1 = block_sum_256(a1, sm);
+  const double s2 = block_sum_256(a2, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s1;
+    partial[gridDim.x + blockIdx.x] = s2;
+  }
+  if (take_ticket(&sc->ticket_b, gridDim.x) && threadIdx.x < 32) {
+    const double a = ordered_sum(partial, gridDim.x);
+    const double c = ordered_sum(partial + gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) {
+      sc->red[0] = a;
+      sc->red[1] = c;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_direction2_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* p, int n,
+                                                              PcgScalars* sc) {
+  if (sc->done) return;
+  const double rz_new = sc->red[0], rr = sc->red[1];  // allreduced r.z and r.r
+  const double beta = rz_new / sc->rz;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) p[i] = fma(beta, p[i], r[i] * dinv[i]);
+  if (take_ticket(&sc->ticket_a, gridDim.x) && threadIdx.x == 0) {  // last block: everybody has read the old rz
+    sc->beta = beta;
+    sc->rz = rz_new;
+    sc->rr = rr;
+    const int it = sc->iters + 1;
+    sc->iters = it;
+    if (!(rr > sc->thresh) || it >= sc->maxit) sc->done = 1;
+  }
+}
+
 // Jacobi-PCG in subdomain (halo) mode: vectors are local ([ghosts | owned | ghosts]); one iteration is
 //   q = H_loc p (all local rows) -> ONE halo exchange that leaves the full q on the owned edges and on the
 //   ghosts -> p.q (owned) -> allreduce -> x, r updates (all local entries) with r.z, r.r (owned) ->
@@ -1581,6 +1671,7 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
   // exchange latency they hide.  SPB_HALO_OVERLAP=1 enables it.
   static const bool overlap_on = getenv("SPB_HALO_OVERLAP") && atoi(getenv("SPB_HALO_OVERLAP")) == 1;
   const bool overlap = overlap_on && sb_hi - sb_lo >= 64;
+  static const bool fused = !(getenv("SPB_HALO_FUSED") && atoi(getenv("SPB_HALO_FUSED")) == 0);  // four launches per iteration instead of eight
   const int occ = std::max(1, h->occ_spmv ? h->occ_spmv : 6);
   const int gband = std::max(1, std::min((sb_lo + 7) / 8, h->num_sms * occ));
   const int gint = std::max(1, std::min((sb_hi - sb_lo + 7) / 8, h->num_sms * occ));
@@ -1615,16 +1706,27 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
       } else {
         spmv_sell_kernel<false><<<spmv_grid(h), 256, 0, st>>>(h->d_slice_off.p, h->d_sell_col.p, h->d_rowlen.p, h->d_hval.p, p, h->d_q.p, n,
                                                               (n + 31) / 32, nullptr, nullptr);
-        halo_sum_both(h, h->d_q.p);
+        halo_sum_both(h, h->d_q.p, st, !fused);
       }
-      range_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, lo, hi, h->d_partial.p, sc);
-      dist_allreduce_sum(h, sc->red, sc->red, 1);
-      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);
-      halo_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, n, lo, hi, h->d_partial.p, sc);
-      dist_allreduce_sum(h, sc->red, sc->red, 2);
-      dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 2, 0.0, 0);
-      dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, 0, n, sc);
-      nl += 7;
+      if (fused && !overlap) {
+        const double* from_right = h->d_halo_tmp.p;
+        const double* from_left = h->d_halo_tmp.p + 2 * (size_t)h->halo;
+        halo_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, from_left, from_right, n, lo, hi, h->halo, h->d_partial.p, sc);
+        dist_allreduce_sum(h, sc->red, sc->red, 1);
+        halo_update2_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, n, lo, hi, h->d_partial.p, sc);
+        dist_allreduce_sum(h, sc->red, sc->red, 2);
+        halo_direction2_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, n, sc);
+        nl += 4;
+      } else {
+        range_dot_kernel<<<gv, 256, 0, st>>>(p, h->d_q.p, lo, hi, h->d_partial.p, sc);
+        dist_allreduce_sum(h, sc->red, sc->red, 1);
+        dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 1, 0.0, 0);
+        halo_update_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, p, h->d_q.p, d_x, h->d_r.p, n, lo, hi, h->d_partial.p, sc);
+        dist_allreduce_sum(h, sc->red, sc->red, 2);
+        dist_scalar_kernel<<<1, 1, 0, st>>>(sc, 2, 0.0, 0);
+        dist_direction_kernel<<<gv, 256, 0, st>>>(h->d_dinv.p, h->d_r.p, p, 0, n, sc);
+        nl += 7;
+      }
     }
     launched += batch;
     SPB_CUDA(cudaGetLastError());

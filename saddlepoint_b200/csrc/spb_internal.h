@@ -306,7 +306,7 @@ void dist_allgather(spb_context* h, const double* send, double* recv, size_t cou
 void dist_allreduce_max(spb_context* h, const double* send, double* recv, size_t count);
 void halo_forward(spb_context* h, double* v);      // owners -> the neighbours' ghost copies
 void halo_reverse_add(spb_context* h, double* v);  // ghost contributions -> owners (+=, left neighbour first)
-void halo_sum_both(spb_context* h, double* v, cudaStream_t st = nullptr);  // one exchange: full sums on the owned edges AND on the ghosts
+void halo_sum_both(spb_context* h, double* v, cudaStream_t st = nullptr, bool add = true);  // one exchange: full sums on the owned edges AND on the ghosts
 spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters);
 void dist_release(spb_context* h);
 // pcg.cu: distributed Jacobi-PCG over a row partition of H (replicated H, partitioned vectors)

@@ -1,3 +1,5 @@
+"""Reads bench.py JSON lines on stdin and prints one compact line each: value, ms/step, PCG iterations per step,
+us per PCG iteration, roofline fraction and the per-stage times.  Usage: python bench.py ... | python scripts/fmt_bench.py LABEL"""
 import sys,json
 for line in sys.stdin:
     if line.startswith("{"):

@@ -1,3 +1,6 @@
+"""Times the host symbolic phase (H pattern, SpMV layout, assembly plan; no GPU needed) on the LF pattern of a
+g x g torus.  SPB_HOST_THREADS=N and SPB_ANALYZE_TIMING=1|2 control threads and the stopwatch output.
+Usage: python scripts/symbolic_bench.py 1024"""
 import sys, time, ctypes as C, numpy as np
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sp_oracle as orc

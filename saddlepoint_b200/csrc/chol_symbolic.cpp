@@ -18,7 +18,13 @@
 // from the usual supernodal recurrence struct(s) = adj(cols(s)) U struct(children) above the
 // pivot block; the assembly-tree parent is the supernode owning min(struct(s)).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <exception>
 #include <numeric>
+#include <thread>
 
 #include "chol_internal.h"
 
@@ -28,26 +34,40 @@ namespace {
 
 constexpr int kLeaf = 48;
 
+// Nested dissection.  The recursion is a tree of independent subproblems (the two sides of a
+// separator share no edge), so the top of it runs on host threads: a region above kParallelMin
+// vertices is split by the calling thread, its first child handed to another thread (down to a
+// depth that matches the machine), the results concatenated in the serial algorithm's order
+// (first child, second child, separator) -- the ordering is identical to the single-threaded one.
+// `region` and `dist` are shared scratch arrays; a task only touches the entries of its own
+// vertices, except for reading region[] of neighbours, which is done with relaxed atomics (a
+// neighbour outside the region can never carry this region's id).
 struct NdBuilder {
   int n;
   const std::vector<int>& Ap;
   const std::vector<int>& Ai;
   std::vector<int> region;   // region id per vertex (current recursion owner)
   std::vector<int> dist;     // BFS scratch
-  std::vector<int> perm;     // output order (perm[new] = old)
-  std::vector<int> sn_col0;  // supernode boundaries in the new order
-  int next_region = 1;
+  std::atomic<int> next_region{1};
 
-  NdBuilder(int n_, const std::vector<int>& p, const std::vector<int>& i) : n(n_), Ap(p), Ai(i), region(n_, 0), dist(n_, -1) {
-    perm.reserve(n);
-    sn_col0.push_back(0);
-  }
+  struct Out {
+    std::vector<int> perm;      // order of this subproblem's vertices (perm[new] = old)
+    std::vector<int> sn_sizes;  // supernode sizes in that order
+    void emit(const std::vector<int>& verts) {
+      if (verts.empty()) return;
+      perm.insert(perm.end(), verts.begin(), verts.end());
+      sn_sizes.push_back((int)verts.size());
+    }
+    void append(Out&& o) {
+      perm.insert(perm.end(), o.perm.begin(), o.perm.end());
+      sn_sizes.insert(sn_sizes.end(), o.sn_sizes.begin(), o.sn_sizes.end());
+    }
+  };
 
-  void emit(const std::vector<int>& verts) {
-    if (verts.empty()) return;
-    for (int v : verts) perm.push_back(v);
-    sn_col0.push_back((int)perm.size());
-  }
+  NdBuilder(int n_, const std::vector<int>& p, const std::vector<int>& i) : n(n_), Ap(p), Ai(i), region(n_, 0), dist(n_, -1) {}
+
+  int region_of(int v) const { return __atomic_load_n(&region[v], __ATOMIC_RELAXED); }
+  void set_region(int v, int rid) { __atomic_store_n(&region[v], rid, __ATOMIC_RELAXED); }
 
   // BFS inside region `rid` from `src`; fills order (visit order) and dist; returns depth
   int bfs(int src, int rid, std::vector<int>& order) {
@@ -60,7 +80,7 @@ struct NdBuilder {
       depth = dist[v];
       for (int q = Ap[v]; q < Ap[v + 1]; ++q) {
         int w = Ai[q];
-        if (region[w] == rid && dist[w] < 0) {
+        if (region_of(w) == rid && dist[w] < 0) {
           dist[w] = dist[v] + 1;
           order.push_back(w);
         }
@@ -72,8 +92,80 @@ struct NdBuilder {
     for (int v : order) dist[v] = -1;
   }
 
-  void dissect(std::vector<int>& verts) {
-    // explicit stack to avoid deep recursion; each frame owns its vertex list
+  // One dissection step on `verts` (consumed).  Returns false when the region is a leaf (verts kept: emit it as
+  // one supernode); otherwise fills the two children A, B and the separator S (empty for a disconnected region).
+  bool split_step(std::vector<int>& verts, std::vector<int>& A, std::vector<int>& B, std::vector<int>& S) {
+    const int sz = (int)verts.size();
+    if (sz <= kLeaf) return false;
+    std::vector<int> order, order2;
+    const int rid = next_region.fetch_add(1, std::memory_order_relaxed);
+    for (int v : verts) set_region(v, rid);
+    // connected components
+    std::vector<std::vector<int>> comps;
+    for (int v : verts) {
+      if (dist[v] >= 0) continue;
+      bfs(v, rid, order);
+      comps.push_back(order);
+    }
+    for (int v : verts) dist[v] = -1;
+    if (comps.size() > 1) {
+      std::sort(comps.begin(), comps.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+      for (auto& c : comps) {
+        std::vector<int>& dst = A.size() <= B.size() ? A : B;
+        dst.insert(dst.end(), c.begin(), c.end());
+      }
+      std::vector<int>().swap(verts);
+      return true;  // no separator; the children are independent subtrees
+    }
+    // single component: pseudo-peripheral start (two sweeps), then median level cut
+    bfs(verts[0], rid, order);
+    int far = order.back();
+    clear_dist(order);
+    int depth = bfs(far, rid, order2);
+    if (depth < 2) {  // too shallow to cut: dense-ish block
+      clear_dist(order2);
+      return false;
+    }
+    std::vector<int> cnt(depth + 1, 0);
+    for (int v : order2) cnt[dist[v]]++;
+    // choose the level in the middle third (by cumulative size) with the fewest vertices
+    int best = -1;
+    {
+      int cum = 0;
+      for (int l = 0; l <= depth; ++l) {
+        int before = cum;
+        cum += cnt[l];
+        if (l == 0 || l == depth) continue;
+        int after = sz - cum;
+        if (before < sz / 4 || after < sz / 4) continue;
+        if (best < 0 || cnt[l] < cnt[best]) best = l;
+      }
+      if (best < 0) {  // fall back to the median level
+        cum = 0;
+        for (int l = 0; l <= depth; ++l) {
+          cum += cnt[l];
+          if (cum * 2 >= sz) {
+            best = std::min(std::max(l, 1), depth - 1);
+            break;
+          }
+        }
+      }
+    }
+    if (cnt[best] * 2 > sz) {  // separator would swallow the region
+      clear_dist(order2);
+      return false;
+    }
+    for (int v : order2) {
+      int d = dist[v];
+      (d < best ? A : d > best ? B : S).push_back(v);
+    }
+    clear_dist(order2);
+    std::vector<int>().swap(verts);
+    return true;
+  }
+
+  // serial dissection of one region (explicit stack: no deep recursion on path-like graphs)
+  void dissect_serial(std::vector<int>& verts, Out& out) {
     struct Frame {
       std::vector<int> verts;
       std::vector<int> sep;  // emitted after the children
@@ -81,97 +173,59 @@ struct NdBuilder {
     };
     std::vector<Frame> stack;
     stack.push_back({std::move(verts), {}, 0});
-    std::vector<int> order, order2;
     while (!stack.empty()) {
       Frame& F = stack.back();
       if (F.stage == 1) {  // children done: emit separator
-        emit(F.sep);
+        out.emit(F.sep);
         stack.pop_back();
         continue;
       }
       F.stage = 1;
-      const int sz = (int)F.verts.size();
-      if (sz <= kLeaf) {
-        emit(F.verts);
-        stack.pop_back();
-        continue;
-      }
-      const int rid = next_region++;
-      for (int v : F.verts) region[v] = rid;
-      // connected components
-      std::vector<std::vector<int>> comps;
-      for (int v : F.verts) {
-        if (dist[v] >= 0) continue;
-        bfs(v, rid, order);
-        comps.push_back(order);
-      }
-      for (int v : F.verts) dist[v] = -1;
-      if (comps.size() > 1) {
-        std::sort(comps.begin(), comps.end(), [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
-        std::vector<int> A, B;
-        for (auto& c : comps) {
-          std::vector<int>& dst = A.size() <= B.size() ? A : B;
-          dst.insert(dst.end(), c.begin(), c.end());
-        }
-        std::vector<int>().swap(F.verts);
-        // no separator; children become independent subtrees
-        stack.push_back({std::move(B), {}, 0});
-        stack.push_back({std::move(A), {}, 0});
-        continue;
-      }
-      // single component: pseudo-peripheral start (two sweeps), then median level cut
-      bfs(F.verts[0], rid, order);
-      int far = order.back();
-      clear_dist(order);
-      int depth = bfs(far, rid, order2);
-      if (depth < 2) {  // too shallow to cut: dense-ish block
-        clear_dist(order2);
-        emit(F.verts);
-        stack.pop_back();
-        continue;
-      }
-      std::vector<int> cnt(depth + 1, 0);
-      for (int v : order2) cnt[dist[v]]++;
-      // choose the level in the middle third (by cumulative size) with the fewest vertices
-      int best = -1;
-      {
-        int cum = 0;
-        for (int l = 0; l <= depth; ++l) {
-          int before = cum;
-          cum += cnt[l];
-          if (l == 0 || l == depth) continue;
-          int after = sz - cum;
-          if (before < sz / 4 || after < sz / 4) continue;
-          if (best < 0 || cnt[l] < cnt[best]) best = l;
-        }
-        if (best < 0) {  // fall back to the median level
-          cum = 0;
-          for (int l = 0; l <= depth; ++l) {
-            cum += cnt[l];
-            if (cum * 2 >= sz) {
-              best = std::min(std::max(l, 1), depth - 1);
-              break;
-            }
-          }
-        }
-      }
-      if (cnt[best] * 2 > sz) {  // separator would swallow the region
-        clear_dist(order2);
-        emit(F.verts);
-        stack.pop_back();
-        continue;
-      }
       std::vector<int> A, B, S;
-      for (int v : order2) {
-        int d = dist[v];
-        (d < best ? A : d > best ? B : S).push_back(v);
+      if (!split_step(F.verts, A, B, S)) {
+        out.emit(F.verts);
+        stack.pop_back();
+        continue;
       }
-      clear_dist(order2);
-      std::vector<int>().swap(F.verts);
       F.sep = std::move(S);
-      stack.push_back({std::move(B), {}, 0});
+      stack.push_back({std::move(B), {}, 0});  // note: invalidates F
       stack.push_back({std::move(A), {}, 0});
     }
+  }
+
+  static constexpr int kParallelMin = 20000;
+
+  // parallel top of the recursion
+  void dissect(std::vector<int>& verts, Out& out, int depth_left) {
+    if (depth_left <= 0 || (int)verts.size() < kParallelMin) {
+      dissect_serial(verts, out);
+      return;
+    }
+    std::vector<int> A, B, S;
+    if (!split_step(verts, A, B, S)) {
+      out.emit(verts);
+      return;
+    }
+    Out oa, ob;
+    std::exception_ptr err;
+    std::thread ta([&] {
+      try {
+        dissect(A, oa, depth_left - 1);
+      } catch (...) {
+        err = std::current_exception();
+      }
+    });
+    try {
+      dissect(B, ob, depth_left - 1);
+    } catch (...) {
+      ta.join();
+      throw;
+    }
+    ta.join();
+    if (err) std::rethrow_exception(err);
+    out.append(std::move(oa));
+    out.append(std::move(ob));
+    out.emit(S);
   }
 };
 
@@ -180,15 +234,35 @@ struct NdBuilder {
 void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
   const int n = H.n;
   C.n = n;
+  const bool timing = getenv("SPB_ANALYZE_TIMING") && atoi(getenv("SPB_ANALYZE_TIMING")) > 1;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spb analyze timing]   chol_symbolic: %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
   // ---- ordering + supernode partition
   {
     NdBuilder nd(n, H.colptr, H.rowidx);
     std::vector<int> all(n);
     std::iota(all.begin(), all.end(), 0);
-    nd.dissect(all);
-    C.perm = std::move(nd.perm);
-    C.sn_col0 = std::move(nd.sn_col0);
+    NdBuilder::Out out;
+    out.perm.reserve(n);
+    // 2^depth concurrent subtrees at the bottom of the parallel part: about twice the host threads
+    int depth = 0;
+    {
+      const char* e = getenv("SPB_HOST_THREADS");
+      int threads = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      threads = std::max(1, std::min(threads, 32));
+      while ((1 << depth) < 2 * threads && threads > 1) ++depth;
+    }
+    nd.dissect(all, out, depth);
+    C.perm = std::move(out.perm);
+    C.sn_col0.assign(1, 0);
+    for (int sz : out.sn_sizes) C.sn_col0.push_back(C.sn_col0.back() + sz);
   }
+  lap("nested dissection");
   if ((int)C.perm.size() != n) throw ArgFail{"internal: nested dissection lost vertices"};
   C.pinv.assign(n, 0);
   for (int k = 0; k < n; ++k) C.pinv[C.perm[k]] = k;
@@ -233,6 +307,7 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
       children[p].push_back(s);
     }
   }
+  lap("row structures");
   // ---- levels (leaves = 0)
   C.sn_level.assign(ns, 0);
   int nlevels = 0;
@@ -364,6 +439,7 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
     const int64_t u = C.struct_ptr[(size_t)s + 1] - C.struct_ptr[s];
     C.nnzL += k * (k + 1) / 2 + u * k;
   }
+  lap("levels, offsets, update-matrix arena");
   // ---- A scatter map: every lower entry (in the permuted order) of H -> position in its panel
   {
     const int64_t nlow = (H.nnz() + n) / 2;
@@ -426,6 +502,7 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
     for (int ch : children[s]) C.child_idx.push_back(ch);
     C.child_ptr[(size_t)s + 1] = (int)C.child_idx.size();
   }
+  lap("scatter and extend-add maps");
   C.dinv_off.assign((size_t)ns + 1, 0);
   for (int s = 0; s < ns; ++s) {
     const int64_t k = C.sn_col0[s + 1] - C.sn_col0[s];

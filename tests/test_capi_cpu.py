@@ -109,3 +109,45 @@ def test_symbolic_rejects_bad_patterns(spb):
     assert L.spb_symbolic_h_pattern(2, 1, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), None, None) == spb.capi.SPB_ERR_ARG
     rowidx = np.array([0, 5], np.int32)  # out of range
     assert L.spb_symbolic_h_pattern(2, 1, colptr.ctypes.data, rowidx.ctypes.data, C.byref(nnz), None, None) == spb.capi.SPB_ERR_ARG
+
+
+def test_symbolic_results_do_not_depend_on_the_thread_count():
+    """The threaded host phases (H pattern, pair stream, chunk packing; nested dissection over subtrees)
+    must produce exactly what the single-threaded run produces.  The thread count is latched per process,
+    so every count runs in its own interpreter and reports a digest."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from oracle import sp_oracle as orc
+orc.build()
+import saddlepoint_b200 as spb
+L = spb.capi.load()
+g = 224                                    # 50 176 unknowns: above both parallel thresholds
+A = orc.lf_matrix(g, 2, 20211)
+p, i, x = A.csc()
+n, m = g * g, 2 * g * g
+hsh = hashlib.sha256()
+nnz = C.c_int64(0)
+hp = np.zeros(n + 1, np.int32)
+assert L.spb_symbolic_h_pattern(m, n, p.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), C.byref(nnz), hp.ctypes.data_as(C.c_void_p), None) == 0
+hi = np.zeros(nnz.value, np.int32)
+assert L.spb_symbolic_h_pattern(m, n, p.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), C.byref(nnz), hp.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)) == 0
+hsh.update(hp.tobytes()); hsh.update(hi.tobytes())
+st = (C.c_int64 * 8)()
+assert L.spb_symbolic_plan_check(m, n, p.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), st) == 0 and st[7] == 0
+hsh.update(bytes(str(list(st)), "ascii"))
+perm = np.zeros(n, np.int32)
+assert L.spb_symbolic_chol_stats(m, n, p.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), st, perm.ctypes.data_as(C.c_void_p)) == 0 and st[7] == 0
+hsh.update(bytes(str(list(st)), "ascii")); hsh.update(perm.tobytes())
+print("DIGEST", hsh.hexdigest())
+''' % ROOT
+    digests = []
+    for threads in ("1", "5"):
+        env = dict(os.environ, SPB_HOST_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-2000:]
+        digests.append(re.search(r"DIGEST (\w+)", out.stdout).group(1))
+    assert digests[0] == digests[1]

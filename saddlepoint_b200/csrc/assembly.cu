@@ -575,6 +575,8 @@ void upload_h_layout(spb_context* h) {
   SPB_CUDA(h->d_hdiag.alloc(h->n));
   SPB_CUDA(h->d_rhs.alloc(h->n));
   SPB_CUDA(h->d_dvec.alloc(h->n));
+  // an assembly without residuals (no EVec, or zero residual rows) leaves the gradient untouched: it must read as zero
+  if (h->n > 0) SPB_CUDA(cudaMemsetAsync(h->d_rhs.p, 0, (size_t)h->n * sizeof(double), st));
   SPB_CUDA(cudaStreamSynchronize(st));
   std::vector<int>().swap(h->S.col);  // the big host copies are no longer needed
   std::vector<uint16_t>().swap(h->S.col16);
@@ -645,6 +647,33 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   }
   h->nchunks = (int)P.chunk_npairs.size();
   h->ncolchunks = (int)P.colchunk.size() - 1;
+  {
+    // for the streamed host path: how much of the J value array a chunk needs (its stage list's last column, plus
+    // the padding element of a bulk-copy window).  Chunks are launched in order of that need (a periodic problem's
+    // first chunks reference the last columns), so a second copy of the descriptors sorted by it is kept.
+    const int nch = h->nchunks;
+    std::vector<int64_t> need((size_t)nch, 0);
+    for (int c = 0; c < nch; ++c) {
+      int64_t nd = 0;
+      for (int t = P.chunk_stage_ptr[c]; t < P.chunk_stage_ptr[(size_t)c + 1]; ++t) nd = std::max<int64_t>(nd, (int64_t)colptr[P.stage_cols[t] + 1] + 1);
+      need[c] = std::min<int64_t>(nd, colptr[h->n]);
+    }
+    std::vector<int> order((size_t)nch);
+    for (int c = 0; c < nch; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return need[a] < need[b]; });
+    std::vector<ChunkDesc> sorted((size_t)nch);
+    std::vector<ChunkDesc> host_cd((size_t)nch);
+    SPB_CUDA(cudaMemcpy(host_cd.data(), h->d_chunk_desc.p, sizeof(ChunkDesc) * (size_t)nch, cudaMemcpyDeviceToHost));
+    h->chunk_need.assign((size_t)nch, 0);
+    for (int i = 0; i < nch; ++i) {
+      sorted[i] = host_cd[order[i]];
+      h->chunk_need[i] = need[order[i]];
+    }
+    SPB_CUDA(h->d_chunk_desc_sorted.upload(sorted, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    h->colchunk_host = P.colchunk;
+    h->Jcolptr_host.assign(colptr, colptr + h->n + 1);
+  }
   h->nslots = P.nslots;
   h->npairs = P.npairs;
   SPB_CUDA(h->d_foo_bits.alloc(1));
@@ -747,6 +776,109 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   }
   h->h_valid = true;
   h->factor_valid = false;
+}
+
+// spb_assemble from PINNED host memory: the J values are uploaded in parts on a copy stream and every part of
+// the assembly (column kernel chunks, pair kernel chunks) starts as soon as the values it reads have arrived,
+// so the 0.4 ms of assembly disappear behind the 2.4 ms PCIe transfer (C2) instead of following it.
+bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* host_f, double lambda, double* foo_host) {
+  constexpr int kParts = 8;
+  static const bool off = getenv("SPB_ASM_STREAMED") && atoi(getenv("SPB_ASM_STREAMED")) == 0;
+  if (off || !h->analyzed || h->partitioned || h->halo_mode || h->nchunks == 0 || !h->pairs_fast_path || h->nnzJ < (1 << 20)) return false;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_Jv) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      return false;  // pageable memory: the copy would not be asynchronous anyway
+    }
+  }
+  const int64_t nnzJ = h->nnzJ;
+  SPB_CUDA(h->d_Jv_stage.alloc((size_t)nnzJ));
+  if (host_f) SPB_CUDA(h->d_f_stage.alloc((size_t)h->m));
+  if ((((uintptr_t)h->d_Jv_stage.p) & 15) != 0) return false;
+  if (!h->copy_stream) {
+    SPB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : h->copy_ev) SPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&h->asm_done_ev, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->stream, cs = h->copy_stream;
+  double* dJ = h->d_Jv_stage.p;
+  // the staging buffers are still being read by the previous call's kernels
+  if (h->asm_done_recorded) SPB_CUDA(cudaStreamWaitEvent(cs, h->asm_done_ev, 0));
+  if (host_f) SPB_CUDA(cudaMemcpyAsync(h->d_f_stage.p, host_f, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, cs));
+  SPB_CUDA(cudaEventRecord(h->copy_ev[kParts], cs));
+  // part boundaries: whole J columns, about nnzJ/kParts values each
+  int colb[kParts + 1];
+  colb[0] = 0;
+  for (int k = 1; k < kParts; ++k) {
+    const int64_t target = nnzJ * k / kParts;
+    colb[k] = (int)(std::lower_bound(h->Jcolptr_host.begin(), h->Jcolptr_host.end(), (int)target) - h->Jcolptr_host.begin());
+    colb[k] = std::max(colb[k], colb[k - 1]);
+    colb[k] = std::min(colb[k], h->n);
+  }
+  colb[kParts] = h->n;
+  for (int k = 0; k < kParts; ++k) {
+    const int64_t v0 = h->Jcolptr_host[colb[k]], v1 = h->Jcolptr_host[colb[k + 1]];
+    if (v1 > v0) SPB_CUDA(cudaMemcpyAsync(dJ + v0, host_Jv + v0, (size_t)(v1 - v0) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    SPB_CUDA(cudaEventRecord(h->copy_ev[k], cs));
+  }
+  stage_begin(h, ST_ASSEMBLY);
+  int nl = 0;
+  const double* d_f = host_f ? h->d_f_stage.p : nullptr;
+  if (d_f) SPB_CUDA(cudaMemsetAsync(h->d_foo_bits.p, 0, sizeof(unsigned long long), st));
+  SPB_CUDA(cudaStreamWaitEvent(st, h->copy_ev[kParts], 0));
+  if (h->occ_pairs == 0) {
+    int occ = 0;
+    if (h->rec_bits == 16) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, 0));
+    else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, 0));
+    h->occ_pairs = std::max(1, occ);
+  }
+  int cc_done = 0, ch_done = 0;  // column-kernel chunks / pair-kernel chunks already launched
+  for (int k = 0; k < kParts; ++k) {
+    SPB_CUDA(cudaStreamWaitEvent(st, h->copy_ev[k], 0));
+    const int64_t have = h->Jcolptr_host[colb[k + 1]];  // J values [0, have) are on the device after this part
+    // column kernel: chunks whose columns are complete
+    int cc_end = cc_done;
+    while (cc_end < h->ncolchunks && h->colchunk_host[(size_t)cc_end + 1] <= colb[k + 1]) ++cc_end;
+    if (k == kParts - 1) cc_end = h->ncolchunks;
+    if (cc_end > cc_done) {
+      assemble_cols_kernel<<<cc_end - cc_done, 256, 0, st>>>(h->d_colchunk.p + cc_done, h->d_Jcolptr.p, h->d_Jrow.p, dJ, d_f, lambda, h->d_nup1.p,
+                                                            h->d_slice_off.p, h->d_hval.p, h->d_hdiag.p, h->d_rhs.p, h->d_dvec.p, h->d_foo_bits.p, 0);
+      ++nl;
+      cc_done = cc_end;
+    }
+    // pair kernel: chunks whose stage lists are complete
+    int ch_end = (int)(std::upper_bound(h->chunk_need.begin() + ch_done, h->chunk_need.end(), have) - h->chunk_need.begin());
+    if (k == kParts - 1) ch_end = h->nchunks;
+    if (ch_end > ch_done) {
+      const int cnt = ch_end - ch_done;
+      const int G = std::max(1, std::min(cnt, h->num_sms * h->occ_pairs));
+      if (h->rec_bits == 16)
+        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
+                                                                        h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
+      else
+        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
+                                                                         h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
+      ++nl;
+      ch_done = ch_end;
+    }
+  }
+  SPB_CUDA(cudaEventRecord(h->asm_done_ev, st));
+  h->asm_done_recorded = true;
+  SPB_CUDA(cudaGetLastError());
+  stage_end(h, ST_ASSEMBLY, nl);
+  if (foo_host) {
+    if (d_f) {
+      SPB_CUDA(cudaMemcpyAsync(h->h_scalar, h->d_foo_bits.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      SPB_CUDA(cudaStreamSynchronize(st));
+      *foo_host = h->h_scalar[0];
+    } else {
+      *foo_host = 0.0;
+    }
+  }
+  h->h_valid = true;
+  h->factor_valid = false;
+  return true;
 }
 
 void ensure_pos_of_slot(spb_context* h) {

@@ -146,6 +146,13 @@ spb_status spb_destroy(spb_handle h) {
     cudaEventDestroy(p.b);
   }
   for (auto e : h->timing.pool) cudaEventDestroy(e);
+  if (h->copy_stream) {
+    for (auto& e : h->copy_ev)
+      if (e) cudaEventDestroy(e);
+    if (h->asm_done_ev) cudaEventDestroy(h->asm_done_ev);
+    cudaStreamDestroy(h->copy_stream);
+    h->copy_stream = nullptr;
+  }
   if (h->h_sc) cudaFreeHost(h->h_sc);
   if (h->h_scalar) cudaFreeHost(h->h_scalar);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -258,6 +265,10 @@ spb_status spb_assemble(spb_handle h, const double* Jvals, const double* EVec, d
   return guarded(h, [&]() {
     if (!h->analyzed) throw StateFail{"spb_assemble before spb_analyze"};
     SPB_CUDA(cudaSetDevice(h->device));
+    if (mem == SPB_HOST && run_assembly_streamed(h, Jvals, EVec, lambda, foo)) {
+      SPB_CUDA(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+      return SPB_OK;
+    }
     const double* dJ = to_device(h, Jvals, (size_t)h->nnzJ, mem, h->d_Jv_stage);
     const double* dF = to_device(h, EVec, (size_t)h->m, mem, h->d_f_stage);
     run_assembly(h, dJ, dF, lambda, foo);

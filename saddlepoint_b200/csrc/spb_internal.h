@@ -223,6 +223,16 @@ struct spb_context {
   spb::SellLayout S;          // host: only slice_off/rowlen kept after upload
   int rec_bits = 16;
   int nchunks = 0, ncolchunks = 0, nslots = 0;
+  // streamed assembly from pinned host memory (spb_assemble, SPB_HOST): J is uploaded in parts on a copy stream
+  // while the parts already on the device are being assembled
+  std::vector<int64_t> chunk_need;   // per assembly chunk (in d_chunk_desc_sorted order): J values [0, need) must be on the device
+  spb::DevBuf<spb::ChunkDesc> d_chunk_desc_sorted;  // the chunk descriptors ordered by that need
+  std::vector<int> colchunk_host;    // column boundaries of the column-kernel chunks
+  std::vector<int> Jcolptr_host;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t asm_done_ev = nullptr;
+  bool asm_done_recorded = false;
   int64_t npairs = 0;
 
   // device: J pattern + assembly plan
@@ -282,6 +292,7 @@ void timing_flush(spb_context* h);
 void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, AssemblyPlan& P);
 void upload_h_layout(spb_context* h);
 void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double lambda, double* foo_host);
+bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* host_f, double lambda, double* foo_host);  // false: not applicable
 void ensure_pos_of_slot(spb_context* h);
 void gather_h_values(spb_context* h, double* d_out);   // CSC order
 void scatter_h_values(spb_context* h, const double* d_in);

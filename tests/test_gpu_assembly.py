@@ -190,3 +190,33 @@ def test_single_dense_row_and_single_column(handle, orc):
     # one unknown, many residuals: H is 1 x 1
     m = 500
     _check(handle, orc, m, 1, np.array([0, m], np.int32), np.arange(m, dtype=np.int32), rng.standard_normal(m), rng.standard_normal(m), 0.01)
+
+
+def test_streamed_host_assembly_equals_device_assembly(spb):
+    """spb_assemble from PINNED host memory uploads J in parts on a copy stream and assembles every part as soon
+    as its values are on the device; the result must be the same bits as the assembly from device buffers."""
+    import torch
+    h = spb.Handle(0)
+    g = 384  # nnzJ = 2.36 M: above the streaming threshold
+    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
+    m, n, colptr, rowidx = prob.pattern()
+    T = prob.c_traits()
+    xd = torch.ones(n, dtype=torch.float64, device="cuda")
+    Ed = torch.empty(m, dtype=torch.float64, device="cuda")
+    Jd = torch.empty(int(colptr[-1]), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    T.objective_jacobian(T.user, xd.data_ptr(), Ed.data_ptr(), Jd.data_ptr(), None)
+    torch.cuda.synchronize()
+    h.analyze(m, n, colptr, rowidx)
+    foo_dev = h.assemble(Jd, Ed, 0.01)
+    H_dev, g_dev, d_dev = h.h_values(), h.rhs(), h.damping()
+    Jh, Eh = Jd.cpu().pin_memory(), Ed.cpu().pin_memory()
+    for _ in range(2):  # twice: the second call reuses the staging buffers behind the first call's kernels
+        foo_host = h.assemble(Jh.numpy(), Eh.numpy(), 0.01)
+        assert foo_host == foo_dev
+        assert np.array_equal(h.h_values(), H_dev) and np.array_equal(h.rhs(), g_dev) and np.array_equal(h.damping(), d_dev)
+    # pageable host memory takes the plain path and gives the same result
+    foo_pg = h.assemble(Jd.cpu().numpy(), Ed.cpu().numpy(), 0.01)
+    assert foo_pg == foo_dev and np.array_equal(h.h_values(), H_dev)
+    prob.close()
+    h.close()

@@ -623,20 +623,28 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
       if (!((cd[c].flags & 1) && (cd[c].flags & 4) && cd[c].npairs <= kPairTile && cd[c].nstage <= kStageCols)) fast = false;
     }
     h->pairs_fast_path = fast;
+    // the per-entry packing loops run on the host threads (hundreds of millions of slots at C5 size)
     std::vector<StageEntry> se(P.stage_cols.size());
-    for (size_t t = 0; t < se.size(); ++t) {
-      const int col = P.stage_cols[t];
-      se[t].src = colptr[col];
-      se[t].off = (uint16_t)std::min(P.stage_off[t], 65535);
-      se[t].len = (uint16_t)std::min(colptr[col + 1] - colptr[col], 65535);
-      se[t].slice_base = (h->S.slice_off[col >> 5] + (col & 31)) | ((int64_t)P.stage_run[t] << 48);
-    }
     std::vector<SlotMeta> sm((size_t)P.nslots);
     std::vector<uint32_t> sc((size_t)P.nslots);
-    for (int pos = 0; pos < P.nslots; ++pos) {  // processing order (see symbolic.cpp)
-      const int s = P.proc_perm[pos];
-      sm[pos] = SlotMeta{P.slot_il[s], P.slot_jl[s], P.low_rank[s], P.low_rank_up[s]};
-      sc[pos] = ((uint32_t)P.slot_start[s] << 16) | P.slot_cnt[s];
+    {
+      const int parts = std::max(1, std::min(host_threads(), P.nslots / 262144));
+      const size_t nse = se.size();
+      run_parts(parts, [&](int p) {
+        for (size_t t = nse * p / parts; t < nse * (p + 1) / parts; ++t) {
+          const int col = P.stage_cols[t];
+          se[t].src = colptr[col];
+          se[t].off = (uint16_t)std::min(P.stage_off[t], 65535);
+          se[t].len = (uint16_t)std::min(colptr[col + 1] - colptr[col], 65535);
+          se[t].slice_base = (h->S.slice_off[col >> 5] + (col & 31)) | ((int64_t)P.stage_run[t] << 48);
+        }
+        const int64_t ns64 = P.nslots;
+        for (int64_t pos = ns64 * p / parts; pos < ns64 * (p + 1) / parts; ++pos) {  // processing order (see symbolic.cpp)
+          const int s = P.proc_perm[(size_t)pos];
+          sm[(size_t)pos] = SlotMeta{P.slot_il[s], P.slot_jl[s], P.low_rank[s], P.low_rank_up[s]};
+          sc[(size_t)pos] = ((uint32_t)P.slot_start[s] << 16) | P.slot_cnt[s];
+        }
+      });
     }
     SPB_CUDA(h->d_chunk_desc.upload(cd, st));
     SPB_CUDA(h->d_stage_ent.upload(se, st));

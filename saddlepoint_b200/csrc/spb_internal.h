@@ -4,7 +4,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/saddlepoint_b200.h"
@@ -144,6 +147,37 @@ struct StageEntry {  // 16 bytes: one J column of a chunk's stage list (ascendin
 struct SlotMeta {    // 8 bytes
   uint16_t il, jl, rank, rank_up;
 };
+
+// Host threads for the symbolic phase (SPB_HOST_THREADS overrides; 1 = serial).
+inline int host_threads() {
+  static const int t = [] {
+    const char* e = getenv("SPB_HOST_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(v, 32));
+  }();
+  return t;
+}
+// Runs fn(part) for part in [0,parts) on its own thread; rethrows the first exception.
+template <class F>
+inline void run_parts(int parts, F fn) {
+  if (parts <= 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err((size_t)parts);
+  for (int p = 0; p < parts; ++p)
+    th.emplace_back([&, p] {
+      try {
+        fn(p);
+      } catch (...) {
+        err[p] = std::current_exception();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
 
 void build_h_pattern(int m, int n, const int* colptr, const int* rowidx, HPattern& H);
 void build_sell(const HPattern& H, SellLayout& S);

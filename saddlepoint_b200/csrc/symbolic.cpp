@@ -36,15 +36,6 @@ uint64_t pattern_fingerprint(int m, int n, const int* colptr, const int* rowidx)
 }
 
 namespace {
-// Host threads for the symbolic phase (SPB_HOST_THREADS overrides; 1 = serial).
-int host_threads() {
-  static const int t = [] {
-    const char* e = getenv("SPB_HOST_THREADS");
-    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return std::max(1, std::min(v, 32));
-  }();
-  return t;
-}
 // SPB_ANALYZE_TIMING=2: stderr stopwatch of the symbolic sub-phases
 struct Lap {
   const char* who;
@@ -71,27 +62,6 @@ std::vector<int> split_columns(int n, const W* w, int parts) {
     cut[p] = std::min(cut[p], n);
   }
   return cut;
-}
-// Runs fn(part) for part in [0,parts) on its own thread; rethrows the first exception.
-template <class F>
-void run_parts(int parts, F fn) {
-  if (parts <= 1) {
-    fn(0);
-    return;
-  }
-  std::vector<std::thread> th;
-  std::vector<std::exception_ptr> err((size_t)parts);
-  for (int p = 0; p < parts; ++p)
-    th.emplace_back([&, p] {
-      try {
-        fn(p);
-      } catch (...) {
-        err[p] = std::current_exception();
-      }
-    });
-  for (auto& t : th) t.join();
-  for (auto& e : err)
-    if (e) std::rethrow_exception(e);
 }
 // CSR view of the J pattern with, per entry, its position inside its CSC column.
 struct RowView {
@@ -227,19 +197,24 @@ void build_sell(const HPattern& H, SellLayout& S) {
   S.col.assign((size_t)S.padded, 0);
   S.col16.assign((size_t)S.padded, 32768);
   S.slice16.assign((size_t)S.nslices, 1);
-  for (int r = 0; r < n; ++r) {
-    int64_t base = S.slice_off[r >> 5] + (r & 31);
-    int k = 0;
-    for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) {
-      const int c = H.rowidx[q];
-      S.col[(size_t)(base + (int64_t)k * 32)] = c;
-      const int d = c - r + 32768;
-      if (d < 0 || d > 65535) S.slice16[(size_t)(r >> 5)] = 0;
-      else S.col16[(size_t)(base + (int64_t)k * 32)] = (uint16_t)d;
+  // slices are independent: whole slices per host thread
+  const int parts = std::max(1, std::min(host_threads(), S.nslices / 4096));
+  run_parts(parts, [&](int p) {
+    const int r_begin = (int)((int64_t)S.nslices * p / parts) * 32, r_end = std::min(n, (int)((int64_t)S.nslices * (p + 1) / parts) * 32);
+    for (int r = r_begin; r < r_end; ++r) {
+      int64_t base = S.slice_off[r >> 5] + (r & 31);
+      int k = 0;
+      for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) {
+        const int c = H.rowidx[q];
+        S.col[(size_t)(base + (int64_t)k * 32)] = c;
+        const int d = c - r + 32768;
+        if (d < 0 || d > 65535) S.slice16[(size_t)(r >> 5)] = 0;
+        else S.col16[(size_t)(base + (int64_t)k * 32)] = (uint16_t)d;
+      }
+      int w = (int)((S.slice_off[(size_t)(r >> 5) + 1] - S.slice_off[r >> 5]) / 32);
+      for (; k < w; ++k) S.col[(size_t)(base + (int64_t)k * 32)] = r;  // padding: own row, delta 0
     }
-    int w = (int)((S.slice_off[(size_t)(r >> 5) + 1] - S.slice_off[r >> 5]) / 32);
-    for (; k < w; ++k) S.col[(size_t)(base + (int64_t)k * 32)] = r;  // padding: own row, delta 0
-  }
+  });
   // rows past n in the last slice never load; their col16 entries stay at delta 0
 }
 

@@ -556,11 +556,12 @@ __global__ void __launch_bounds__(256) chol_backward_kernel(const int* __restric
   for (int i = tid; i < k; i += 256) y[c0 + i] = w[i];
 }
 
-// ---- big fronts: one launch per 32-column block step, many CTAs per front -------------------
-// A front with thousands of rows cannot be swept by one CTA at memory speed; for those the work
-// vector lives in global memory (Wbuf) and every block step is a grid-wide launch: all CTAs
+// ---- big fronts, launch-per-step variant (fallback: SPB_CHOL_COOP=0) ---------------------------
+// A front with thousands of rows cannot be swept by one CTA at memory speed; here the work vector
+// lives in global memory (Wbuf) and every 32-column block step is a grid-wide launch: all CTAs
 // recompute the 32-entry block solution through the inverted diagonal block, each updates its own
-// 256 rows (forward) or 256 earlier pivots (backward).
+// 256 rows (forward) or 256 earlier pivots (backward).  Superseded by the cooperative kernels below
+// (1030 -> 58 launches per solve at C2); kept for A/B measurements.
 constexpr int kBigFront = 1536;
 
 __global__ void __launch_bounds__(256) chol_fwd_gather_kernel(const int* __restrict__ fronts, const int* __restrict__ sn_k,

@@ -247,6 +247,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
 constexpr int kDescRing = 64;
+template <typename RecT>
+constexpr size_t pipelined_smem_bytes() {
+  return sizeof(double) * 2 * kStageVals + sizeof(int64_t) * 2 * kStageCols + sizeof(ChunkDesc) * kDescRing + 16 + sizeof(unsigned) * 2 * kStageCols +
+         sizeof(RecT) * 2 * kPairTile;
+}
 
 template <typename RecT, int POBITS>
 __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const RecT* __restrict__ recs, const ChunkDesc* __restrict__ chunks,
@@ -255,8 +260,15 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
                                                                           const uint32_t* __restrict__ slot_start,
                                                                           const double* __restrict__ Jv, double* __restrict__ hval,
                                                                           long long* dbg) {
-  __shared__ __align__(16) double sval[2][kStageVals];
-  __shared__ __align__(16) RecT srec[2][kPairTile];
+  // dynamic shared memory (above the 48 KB static limit): two value buffers, two record buffers, two stage
+  // arrays, the descriptor ring and the two mbarriers -- see pipelined_smem_bytes()
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  double(*sval)[kStageVals] = reinterpret_cast<double(*)[kStageVals]>(pipe_smem);
+  int64_t(*s_sbase)[kStageCols] = reinterpret_cast<int64_t(*)[kStageCols]>(pipe_smem + sizeof(double) * 2 * kStageVals);
+  ChunkDesc* ring = reinterpret_cast<ChunkDesc*>(reinterpret_cast<unsigned char*>(s_sbase) + sizeof(int64_t) * 2 * kStageCols);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(ring) + sizeof(ChunkDesc) * kDescRing);
+  unsigned(*s_offlen)[kStageCols] = reinterpret_cast<unsigned(*)[kStageCols]>(reinterpret_cast<unsigned char*>(bar) + 16);
+  RecT(*srec)[kPairTile] = reinterpret_cast<RecT(*)[kPairTile]>(reinterpret_cast<unsigned char*>(s_offlen) + sizeof(unsigned) * 2 * kStageCols);
   long long tk = 0, acc_t[6] = {0, 0, 0, 0, 0, 0};
   const bool dbg_on = dbg && blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 64 || threadIdx.x == 224);
 #define ASM_TICK(i)                     \
@@ -265,10 +277,6 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
     acc_t[i] += now_ - tk;              \
     tk = now_;                          \
   }
-  __shared__ unsigned s_offlen[2][kStageCols];
-  __shared__ int64_t s_sbase[2][kStageCols];
-  __shared__ __align__(16) ChunkDesc ring[kDescRing];
-  __shared__ uint64_t bar[2];
   const int tid = threadIdx.x;
   const int c0 = (int)(((int64_t)nchunks * blockIdx.x) / gridDim.x);
   const int nk = (int)(((int64_t)nchunks * (blockIdx.x + 1)) / gridDim.x) - c0;
@@ -655,6 +663,7 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   }
   h->nchunks = (int)P.chunk_npairs.size();
   h->ncolchunks = (int)P.colchunk.size() - 1;
+  h->occ_pairs = 0;  // the record width may have changed: the pipelined kernel's instantiation (and its shared-memory opt-in) follows it
   {
     // for the streamed host path: how much of the J value array a chunk needs (its stage list's last column, plus
     // the padding element of a bulk-copy window).  Chunks are launched in order of that need (a periodic problem's
@@ -708,8 +717,13 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     if (bulk_ok && h->pairs_fast_path && !pipe_off) {
       if (h->occ_pairs == 0) {
         int occ = 0;
-        if (h->rec_bits == 16) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, 0));
-        else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, 0));
+        if (h->rec_bits == 16) {
+          SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_pipelined_kernel<uint16_t, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipelined_smem_bytes<uint16_t>()));
+          SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, pipelined_smem_bytes<uint16_t>()));
+        } else {
+          SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_pipelined_kernel<uint32_t, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipelined_smem_bytes<uint32_t>()));
+          SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, pipelined_smem_bytes<uint32_t>()));
+        }
         h->occ_pairs = std::max(1, occ);
       }
       const int G = std::max(1, std::min(h->nchunks, h->num_sms * h->occ_pairs));
@@ -720,10 +734,10 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
         dbgp = h->d_dbg.p;
       }
       if (h->rec_bits == 16)
-        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
+        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, pipelined_smem_bytes<uint16_t>(), st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
       else
-        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
+        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, pipelined_smem_bytes<uint32_t>(), st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
                                                                          h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
       if (dbgp) {
         long long tt[24];
@@ -837,8 +851,13 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
   SPB_CUDA(cudaStreamWaitEvent(st, h->copy_ev[kParts], 0));
   if (h->occ_pairs == 0) {
     int occ = 0;
-    if (h->rec_bits == 16) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, 0));
-    else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, 0));
+    if (h->rec_bits == 16) {
+      SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_pipelined_kernel<uint16_t, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipelined_smem_bytes<uint16_t>()));
+      SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint16_t, 7>, 256, pipelined_smem_bytes<uint16_t>()));
+    } else {
+      SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_pipelined_kernel<uint32_t, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipelined_smem_bytes<uint32_t>()));
+      SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assemble_pairs_pipelined_kernel<uint32_t, 15>, 256, pipelined_smem_bytes<uint32_t>()));
+    }
     h->occ_pairs = std::max(1, occ);
   }
   int cc_done = 0, ch_done = 0;  // column-kernel chunks / pair-kernel chunks already launched
@@ -862,10 +881,10 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
       const int cnt = ch_end - ch_done;
       const int G = std::max(1, std::min(cnt, h->num_sms * h->occ_pairs));
       if (h->rec_bits == 16)
-        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, 0, st>>>(h->d_rec16.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
+        assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, pipelined_smem_bytes<uint16_t>(), st>>>(h->d_rec16.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
                                                                         h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
       else
-        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, 0, st>>>(h->d_rec32.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
+        assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, pipelined_smem_bytes<uint32_t>(), st>>>(h->d_rec32.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
                                                                          h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
       ++nl;
       ch_done = ch_end;

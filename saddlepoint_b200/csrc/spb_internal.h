@@ -122,9 +122,9 @@ struct AssemblyPlan {
 };
 
 // tunables shared by host planning and kernels
-constexpr int kPairTile = 1024;   // products staged per tile
+constexpr int kPairTile = 2048;   // products staged per tile
 constexpr int kSlotCap = 512;     // strictly-lower slots per chunk
-constexpr int kStageVals = 2048;  // J values staged in shared memory per chunk
+constexpr int kStageVals = 3072;  // J values staged in shared memory per chunk
 constexpr int kStageCols = 192;   // J columns in a chunk's stage list
 constexpr int kEntTile = 2048;    // J entries staged per tile in the column kernel
 constexpr int kColCap = 512;      // columns per column-kernel chunk

@@ -162,10 +162,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1 or os.environ.get("SPB_BENCH_FORCE_PG"):
-        dist.init_process_group(os.environ.get("SPB_BENCH_PG_BACKEND", "nccl"), **({"device_id": torch.device("cuda", local)} if os.environ.get("SPB_BENCH_PG_BACKEND", "nccl") == "nccl" else {}))
-        if os.environ.get("SPB_BENCH_FORCE_PG"):
-            dist.barrier()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import saddlepoint_b200 as spb
 
     K, W, g = args.steps, max(args.warmup, 3), args.g

@@ -170,12 +170,13 @@ typedef struct {
   double energy, fooOptimality, lambda;
   int64_t linear_iterations; /* total PCG iterations                                      */
   double seconds_total, seconds_analyze;
+  int64_t unconverged_solves; /* PCG solves that hit maxit (the inexact direction is still used) */
 } spb_lm_result;
 
 void spb_lm_default_options(spb_lm_options* o);
 /* x_out: xSize values (host or device per x_mem).  trace (optional, host, 8 doubles per loop
  * body that reached the solve, at most trace_cap records): prevEnergy2,newEnergy2,lambda,
- * foo,dirnorm,accepted,lin_iters,reserved. */
+ * foo,dirnorm,accepted,lin_iters,linear solve not converged (0/1). */
 spb_status spb_lm_solve(spb_handle h, const spb_traits* traits, const spb_lm_options* opt, spb_lm_result* res,
                         double* x_out, int x_mem, double* trace, int32_t trace_cap, int32_t* trace_len);
 

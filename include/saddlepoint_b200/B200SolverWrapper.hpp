@@ -29,14 +29,35 @@ template <class T, class = void>
 struct has_outer_index : std::false_type {};
 template <class T>
 struct has_outer_index<T, std::void_t<decltype(std::declval<const T&>().outerIndexPtr())>> : std::true_type {};
+// dense arguments: a matrix type has rows()/cols() (Eigen::MatrixXd, and Eigen::VectorXd with cols()==1)
+template <class T, class = void>
+struct has_cols : std::false_type {};
+template <class T>
+struct has_cols<T, std::void_t<decltype(std::declval<const T&>().cols()), decltype(std::declval<const T&>().rows())>> : std::true_type {};
 }  // namespace detail
+
+// What the reference keeps in its public member `A` (EigenSolverWrapper.h:28; a host copy of the last matrix given
+// to factorize, used by solve() to size x): here the matrix lives on the device, `A` keeps its shape.
+struct FactorizedMatrixInfo {
+  long rows_ = 0, cols_ = 0, nnz_ = 0;
+  long rows() const { return rows_; }
+  long cols() const { return cols_; }
+  long nonZeros() const { return nnz_; }
+};
 
 class B200SolverWrapper {
  public:
-  explicit B200SolverWrapper(int solver = SPB_SOLVER_CHOLESKY, int device = 0, double pcg_rtol = 1e-13, int pcg_maxit = 10000) {
+  // the reference's public members (EigenSolverWrapper.h:26,28): `solver` is the GPU solver object standing in
+  // for the Eigen solver (the C-ABI handle; spb_* calls may be made on it directly), `A` the factorised matrix
+  spb_handle solver = nullptr;
+  FactorizedMatrixInfo A;
+
+  // default: the direct solver, the SimplicialLLT replacement (same default in the Python mirror)
+  explicit B200SolverWrapper(int solver_kind = SPB_SOLVER_CHOLESKY, int device = 0, double pcg_rtol = 1e-13, int pcg_maxit = 10000) {
     if (spb_create(device, nullptr, &h_) != SPB_OK)
       throw std::runtime_error("saddlepoint_b200: no CUDA device (there is no CPU fallback)");
-    spb_set_solver(h_, solver, pcg_rtol, pcg_maxit);
+    solver = h_;
+    spb_set_solver(h_, solver_kind, pcg_rtol, pcg_maxit);
   }
   ~B200SolverWrapper() { spb_destroy(h_); }
   B200SolverWrapper(const B200SolverWrapper&) = delete;
@@ -44,6 +65,8 @@ class B200SolverWrapper {
 
   spb_handle handle() const { return h_; }
   int last_iterations() const { return last_iters_; }
+  // status of the last factorize / solve call (solve() itself always returns true, like the reference's)
+  spb_status last_status() const { return last_status_; }
 
   template <class SparsePattern>
   bool analyze(const SparsePattern& JPattern) {
@@ -72,24 +95,43 @@ class B200SolverWrapper {
   bool factorize(const MatOrVals& A, bool symmetric = false) {
     (void)symmetric;  // fixed at analyze(HRows, HCols, symmetric), as in the legacy wrapper's callers
     if constexpr (detail::has_outer_index<MatOrVals>::value) {
-      spb_status s = spb_set_matrix(h_, (int32_t)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), SPB_HOST);
-      if (s != SPB_OK) return false;
-      return spb_factorize(h_) == SPB_OK;
+      last_status_ = spb_set_matrix(h_, (int32_t)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), SPB_HOST);
+      if (last_status_ != SPB_OK) return false;
+      this->A.rows_ = (long)A.rows();
+      this->A.cols_ = (long)A.cols();
+      this->A.nnz_ = (long)A.nonZeros();
+      last_status_ = spb_factorize(h_);
     } else {
-      return spb_factorize_triplets(h_, A.data(), SPB_HOST) == SPB_OK;
+      last_status_ = spb_factorize_triplets(h_, A.data(), SPB_HOST);
     }
+    return last_status_ == SPB_OK;
   }
 
-  template <class Vec>
-  bool solve(const Vec& rhs, Vec& x) {
-    x.resize(rhs.size());
-    spb_status s = spb_solve(h_, rhs.data(), x.data(), 1, SPB_HOST, &last_iters_);
-    (void)s;
-    return true;  // the reference's solve always returns true (EigenSolverWrapper.h:69,77)
+  // bool solve(const VectorXd& rhs, VectorXd& x) (EigenSolverWrapper.h:72-78) and
+  // bool solve(const MatrixXd& rhs, MatrixXd& x) (EigenSolverWrapper.h:62-70: one solve per column):
+  // a dense argument with rows()/cols() is taken column by column (column-major data()), anything else as
+  // one vector.  Always returns true like the reference; on a failed solve x is zero-filled and
+  // last_status() says why.
+  template <class Dense>
+  bool solve(const Dense& rhs, Dense& x) {
+    int nrhs = 1;
+    long len = 0;
+    if constexpr (detail::has_cols<Dense>::value) {
+      nrhs = (int)rhs.cols();
+      len = (long)rhs.rows();
+      x.resize(rhs.rows(), rhs.cols());
+    } else {
+      len = (long)rhs.size();
+      x.resize(rhs.size());
+    }
+    last_status_ = spb_solve(h_, rhs.data(), x.data(), nrhs, SPB_HOST, &last_iters_);
+    if (last_status_ != SPB_OK && last_status_ != SPB_NOT_CONVERGED)
+      for (long i = 0; i < len * nrhs; ++i) x.data()[i] = 0.0;
+    return true;  // EigenSolverWrapper.h:69,77
   }
-  // matrix right-hand side: nrhs columns, column-major, like the MatrixXd overload
+  // the same on raw column-major storage
   bool solve_columns(const double* rhs, int nrhs, double* x) {
-    spb_solve(h_, rhs, x, nrhs, SPB_HOST, &last_iters_);
+    last_status_ = spb_solve(h_, rhs, x, nrhs, SPB_HOST, &last_iters_);
     return true;
   }
   std::string last_error() const { return spb_last_error(h_); }
@@ -97,6 +139,7 @@ class B200SolverWrapper {
  private:
   spb_handle h_ = nullptr;
   int last_iters_ = 0;
+  spb_status last_status_ = SPB_OK;
 };
 
 }  // namespace SaddlePoint

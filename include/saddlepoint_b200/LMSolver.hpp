@@ -11,11 +11,17 @@
 // the host and are called through trampolines, everything else (gradient, damping, normal
 // matrix, factorize/solve, energies) is on the device.
 //
+// DampingTraits: the damping arithmetic (DiagonalDamping.h:31-43,58-68,73-85) is fused into the GPU assembly, so
+// only DT->currLambda is read (at solve entry) and written back (at exit); a user-supplied DampingTraits::update
+// with a different rule is NOT consulted -- use SaddlePoint::DiagonalDamping (or the reference's own LMSolver.h
+// with B200SolverWrapper as its LinearSolver) for custom damping policies.
+//
 // Type parameters VectorT / SparseT default to Eigen's when SPB_USE_EIGEN is defined, else to
 // the shims in SparseTypes.hpp; any type with Eigen's raw accessors works.
 #ifndef SADDLEPOINT_B200_LM_SOLVER_HPP
 #define SADDLEPOINT_B200_LM_SOLVER_HPP
 #include <cstring>
+#include <exception>
 #include <iostream>
 #include <stdexcept>
 #include <vector>
@@ -115,6 +121,10 @@ class LMSolver {
     spb_lm_result R;
     x.resize(ST->xSize);
     spb_status s = spb_lm_solve(LS->handle(), &T, &O, &R, x.data(), SPB_HOST, nullptr, 0, nullptr);
+    // Nothing is thrown across the C ABI: a failure inside a trampoline (the user's traits threw, or the Jacobian
+    // pattern changed mid-solve) is parked in the bridge, the loop is told to stop at its next post_iteration, and
+    // the exception continues from here, after spb_lm_solve has returned normally.
+    if (br.error) std::rethrow_exception(br.error);
     if (s != SPB_OK) throw std::runtime_error(std::string("spb_lm_solve failed: ") + spb_last_error(LS->handle()));
     energy = R.energy;
     fooOptimality = R.fooOptimality;
@@ -141,6 +151,22 @@ class LMSolver {
     VectorT E0;
     SparseT J0;
     bool first_pending = false;
+    std::exception_ptr error;  // first failure inside a trampoline; rethrown by solve() after the C call returns
+    template <class F>
+    void guarded(F&& f) {
+      if (error) return;
+      try {
+        f();
+      } catch (...) {
+        error = std::current_exception();
+      }
+    }
+    // same compressed pattern: sizes, nnz, outer and inner index arrays (not just the nonzero count)
+    static bool same_pattern(const SparseT& A, const SparseT& B) {
+      if (A.rows() != B.rows() || A.cols() != B.cols() || A.nonZeros() != B.nonZeros()) return false;
+      return std::memcmp(A.outerIndexPtr(), B.outerIndexPtr(), sizeof(int) * (size_t)(A.cols() + 1)) == 0 &&
+             std::memcmp(A.innerIndexPtr(), B.innerIndexPtr(), sizeof(int) * (size_t)A.nonZeros()) == 0;
+    }
     static void copy_in(VectorT& v, const double* p, long n) {
       v.resize(n);
       std::memcpy(v.data(), p, sizeof(double) * (size_t)n);
@@ -159,27 +185,42 @@ class LMSolver {
         std::memcpy(Jp, b->J0.valuePtr(), sizeof(double) * (size_t)b->J0.nonZeros());
         return;
       }
-      VectorT xv, E;
-      SparseT J;
-      copy_in(xv, xp, n);
-      ST->objective_jacobian(xv, E, J, Jp != nullptr);
-      std::memcpy(Ep, E.data(), sizeof(double) * (size_t)m);
-      if (Jp) {
-        if (J.nonZeros() != b->J0.nonZeros()) throw std::runtime_error("Jacobian pattern changed inside LMSolver::solve");
-        std::memcpy(Jp, J.valuePtr(), sizeof(double) * (size_t)J.nonZeros());
+      b->guarded([&] {
+        VectorT xv, E;
+        SparseT J;
+        copy_in(xv, xp, n);
+        ST->objective_jacobian(xv, E, J, Jp != nullptr);
+        if ((long)E.size() != m) throw std::runtime_error("objective_jacobian returned an EVec of the wrong size");
+        std::memcpy(Ep, E.data(), sizeof(double) * (size_t)m);
+        if (Jp) {
+          // the assembly plan belongs to the pattern analysed at solve() entry (the reference re-derives it every
+          // iteration, LMSolver.h:136; within one solve its benchmarks never change it)
+          if (!same_pattern(J, b->J0)) throw std::runtime_error("Jacobian pattern changed inside LMSolver::solve");
+          std::memcpy(Jp, J.valuePtr(), sizeof(double) * (size_t)J.nonZeros());
+        }
+      });
+      if (b->error) {  // keep the device work defined until the loop stops at post_iteration
+        std::memset(Ep, 0, sizeof(double) * (size_t)m);
+        if (Jp) std::memset(Jp, 0, sizeof(double) * (size_t)b->J0.nonZeros());
       }
     }
     static void pre_iteration(void* user, const double* xp) {
       Bridge* b = (Bridge*)user;
-      VectorT xv;
-      copy_in(xv, xp, b->self->ST->xSize);
-      b->self->ST->pre_iteration(xv);
+      b->guarded([&] {
+        VectorT xv;
+        copy_in(xv, xp, b->self->ST->xSize);
+        b->self->ST->pre_iteration(xv);
+      });
     }
     static int post_iteration(void* user, const double* xp) {
       Bridge* b = (Bridge*)user;
-      VectorT xv;
-      copy_in(xv, xp, b->self->ST->xSize);
-      return b->self->ST->post_iteration(xv) ? 1 : 0;
+      int stop = 0;
+      b->guarded([&] {
+        VectorT xv;
+        copy_in(xv, xp, b->self->ST->xSize);
+        stop = b->self->ST->post_iteration(xv) ? 1 : 0;
+      });
+      return b->error ? 1 : stop;  // a parked failure ends the loop here
     }
   };
 };

@@ -33,6 +33,29 @@ class Vector {
   std::vector<double> v_;
 };
 
+// Column-major dense matrix (stand-in for Eigen::MatrixXd in the matrix right-hand-side solve overload).
+class Matrix {
+ public:
+  Matrix() = default;
+  Matrix(long r, long c) : r_(r), c_(c), v_((size_t)(r * c), 0.0) {}
+  long rows() const { return r_; }
+  long cols() const { return c_; }
+  long size() const { return r_ * c_; }
+  void resize(long r, long c) {
+    r_ = r;
+    c_ = c;
+    v_.resize((size_t)(r * c));
+  }
+  double* data() { return v_.data(); }
+  const double* data() const { return v_.data(); }
+  double& operator()(long i, long j) { return v_[(size_t)(j * r_ + i)]; }
+  double operator()(long i, long j) const { return v_[(size_t)(j * r_ + i)]; }
+
+ private:
+  long r_ = 0, c_ = 0;
+  std::vector<double> v_;
+};
+
 struct Triplet {
   int r, c;
   double v;

@@ -23,8 +23,14 @@
 // and independent referees (numpy dense Cholesky, scipy.sparse products and splu).
 //
 // Built by oracle/Makefile with plain -O3 (no -march=native, no OpenMP), like the
-// reference's CMake Release build, single thread.
+// reference's CMake Release build, single thread.  One optional variant (solver_kind 3, used only by
+// bench.py's reference arm for context) runs the Jacobi-PCG twin and the normal-matrix product on a pool
+// of std::threads ("all the host cores"); every parity test uses the single-threaded code.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -200,6 +206,123 @@ static Csc ata(const Csc& A) {
     }
     H.p[j + 1] = (int)H.i.size();
   }
+  return H;
+}
+
+// ---- host thread pool (baseline variant only) -------------------------------------------
+class Pool {
+ public:
+  explicit Pool(int t) : T_(std::max(1, t)) {
+    for (int k = 1; k < T_; ++k) th_.emplace_back([this, k] { loop(k); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return T_; }
+  // runs f(t) for t in [0,T) (t = 0 on the calling thread) and waits for all of them
+  void run(const std::function<void(int)>& f) {
+    if (T_ == 1) {
+      f(0);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &f;
+      left_ = T_ - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return left_ == 0; });
+  }
+
+ private:
+  void loop(int k) {
+    long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* f;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        f = fn_;
+      }
+      (*f)(k);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--left_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int T_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  long gen_ = 0;
+  int left_ = 0;
+  bool stop_ = false;
+};
+static int g_threads = 1;  // spo_set_threads
+
+// ata() with the result columns split over the pool: per-entry arithmetic and order are those of ata()
+// (same bits); only the columns are computed concurrently.
+static Csc ata_threaded(const Csc& A, Pool& pool) {
+  Csc L = transpose(A);
+  const int n = A.cols, T = pool.size();
+  std::vector<std::vector<int>> pi(T);
+  std::vector<std::vector<double>> px(T);
+  std::vector<int> cnt(n, 0);
+  pool.run([&](int t) {
+    const int lo = (int)((int64_t)n * t / T), hi = (int)((int64_t)n * (t + 1) / T);
+    std::vector<char> mask(n, 0);
+    std::vector<double> acc(n, 0.0);
+    std::vector<int> idx;
+    for (int j = lo; j < hi; ++j) {
+      idx.clear();
+      for (int q = A.p[j]; q < A.p[j + 1]; ++q) {
+        const int k = A.i[q];
+        const double y = A.x[q];
+        for (int u = L.p[k]; u < L.p[k + 1]; ++u) {
+          const int i = L.i[u];
+          const double xv = L.x[u];
+          if (!mask[i]) {
+            mask[i] = 1;
+            acc[i] = xv * y;
+            idx.push_back(i);
+          } else {
+            acc[i] += xv * y;
+          }
+        }
+      }
+      std::sort(idx.begin(), idx.end());
+      for (int i : idx) {
+        pi[t].push_back(i);
+        px[t].push_back(acc[i]);
+        mask[i] = 0;
+      }
+      cnt[j] = (int)idx.size();
+    }
+  });
+  Csc H;
+  H.rows = H.cols = n;
+  H.p.assign(n + 1, 0);
+  for (int j = 0; j < n; ++j) H.p[j + 1] = H.p[j] + cnt[j];
+  H.i.resize(H.p[n]);
+  H.x.resize(H.p[n]);
+  pool.run([&](int t) {
+    const int lo = (int)((int64_t)n * t / T);
+    std::copy(pi[t].begin(), pi[t].end(), H.i.begin() + H.p[lo]);
+    std::copy(px[t].begin(), px[t].end(), H.x.begin() + H.p[lo]);
+  });
   return H;
 }
 
@@ -541,6 +664,75 @@ static PcgResult pcg_jacobi(const Csc& H, const double* b, double* x, double rto
   return R;
 }
 
+// The same recurrences with rows split over the pool (dot products: per-thread partials added in thread
+// order, so results differ from pcg_jacobi by rounding only).  Baseline variant, not used by parity tests.
+static PcgResult pcg_jacobi_threaded(const Csc& H, const double* b, double* x, double rtol, int maxit, Pool& pool) {
+  const int n = H.cols, T = pool.size();
+  std::vector<double> dinv(n, 1.0), r(b, b + n), z(n), p(n), q(n);
+  std::vector<double> s1(T), s2(T);
+  auto lo_of = [&](int t) { return (int)((int64_t)n * t / T); };
+  auto total = [&](const std::vector<double>& v) {
+    double a = 0.0;
+    for (double e : v) a += e;
+    return a;
+  };
+  pool.run([&](int t) {
+    double bb = 0.0, rz = 0.0;
+    for (int j = lo_of(t); j < lo_of(t + 1); ++j) {
+      for (int u = H.p[j]; u < H.p[j + 1]; ++u)
+        if (H.i[u] == j) dinv[j] = 1.0 / H.x[u];
+      x[j] = 0.0;
+      bb += b[j] * b[j];
+      z[j] = r[j] * dinv[j];
+      p[j] = z[j];
+      rz += r[j] * z[j];
+    }
+    s1[t] = bb;
+    s2[t] = rz;
+  });
+  const double bb = total(s1);
+  double rz = total(s2);
+  PcgResult R{0, 0.0};
+  if (bb == 0.0) return R;
+  const double thresh = rtol * rtol * bb;
+  double rr = bb;
+  while (R.iters < maxit && rr > thresh) {
+    pool.run([&](int t) {
+      double pq = 0.0;
+      for (int j = lo_of(t); j < lo_of(t + 1); ++j) {
+        double s = 0.0;
+        for (int u = H.p[j]; u < H.p[j + 1]; ++u) s += H.x[u] * p[H.i[u]];
+        q[j] = s;
+        pq += p[j] * s;
+      }
+      s1[t] = pq;
+    });
+    const double alpha = rz / total(s1);
+    pool.run([&](int t) {
+      double a = 0.0, c = 0.0;
+      for (int j = lo_of(t); j < lo_of(t + 1); ++j) {
+        x[j] += alpha * p[j];
+        r[j] -= alpha * q[j];
+        z[j] = r[j] * dinv[j];
+        a += r[j] * z[j];
+        c += r[j] * r[j];
+      }
+      s1[t] = a;
+      s2[t] = c;
+    });
+    const double rz_new = total(s1);
+    rr = total(s2);
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    pool.run([&](int t) {
+      for (int j = lo_of(t); j < lo_of(t + 1); ++j) p[j] = z[j] + beta * p[j];
+    });
+    ++R.iters;
+  }
+  R.relres = std::sqrt(rr / bb);
+  return R;
+}
+
 // ----------------------------------------------------------------------------------------
 // Benchmark problem definitions (the workloads), restated from the reference mains.
 static inline uint64_t splitmix64_at(uint64_t seed, uint64_t ctr) {
@@ -696,7 +888,7 @@ struct LMOptions {
   double fooTolerance = 10e-10;
   double lambda0 = 0.01;
   int verbose = 0;       // selects the quirk-A branch only; nothing is printed
-  int solver_kind = 0;   // 0 = LLT(AMD) faithful, 1 = Jacobi-PCG, 2 = LLT natural order
+  int solver_kind = 0;   // 0 = LLT(AMD) faithful, 1 = Jacobi-PCG, 2 = LLT natural order, 3 = Jacobi-PCG + product on g_threads host threads (baseline only)
   double pcg_rtol = 1e-13;
   int pcg_maxit = 10000;
 };
@@ -741,6 +933,9 @@ static void lm_solve(Traits& ST, const LMOptions& O, LMResult& R, bool keep_firs
   dampJ = damp_build(J, currLambda, nullptr);  // DT->init
   R.t_assembly += now_s() - t0;
   LLT F;
+  std::unique_ptr<Pool> pool;
+  if (O.solver_kind == 3) pool.reset(new Pool(g_threads));
+  const bool iterative = O.solver_kind == 1 || O.solver_kind == 3;
   auto add = [](const std::vector<double>& a, const std::vector<double>& b) {
     std::vector<double> c(a.size());
     for (size_t k = 0; k < a.size(); ++k) c[k] = a[k] + b[k];
@@ -757,13 +952,13 @@ static void lm_solve(Traits& ST, const LMOptions& O, LMResult& R, bool keep_firs
       if (verbose) { R.exit_path = 1; break; }
     }
     t0 = now_s();
-    Csc H = ata(dampJ);
+    Csc H = pool ? ata_threaded(dampJ, *pool) : ata(dampJ);
     R.t_assembly += now_s() - t0;
     if (keep_first && R.factorizations == 0) { R.firstH = H; R.first_rhs = rhs; }
     int lin_iters = 0;
     t0 = now_s();
     bool fok = true;
-    if (O.solver_kind != 1) {
+    if (!iterative) {
       llt_compute(H, O.solver_kind == 0 ? 1 : 0, F);
       fok = F.ok;
     }
@@ -771,10 +966,11 @@ static void lm_solve(Traits& ST, const LMOptions& O, LMResult& R, bool keep_firs
     R.factorizations++;
     if (!fok) { R.exit_path = 2; R.ret = 0; goto done; }
     t0 = now_s();
-    if (O.solver_kind != 1) {
+    if (!iterative) {
       llt_solve(F, rhs.data(), direction.data());
     } else {
-      PcgResult pr = pcg_jacobi(H, rhs.data(), direction.data(), O.pcg_rtol, O.pcg_maxit);
+      PcgResult pr = pool ? pcg_jacobi_threaded(H, rhs.data(), direction.data(), O.pcg_rtol, O.pcg_maxit, *pool)
+                          : pcg_jacobi(H, rhs.data(), direction.data(), O.pcg_rtol, O.pcg_maxit);
       lin_iters = pr.iters;
     }
     R.t_solve += now_s() - t0;
@@ -1001,6 +1197,9 @@ spo_lm_result* spo_lm_solve(const spo_lm_problem* P, const spo_lm_options* O) {
   return res;
 }
 void spo_lm_free(spo_lm_result* r) { delete r; }
+// host threads of the solver_kind 3 baseline variant (default 1)
+void spo_set_threads(int t) { g_threads = std::max(1, t); }
+int spo_get_threads() { return g_threads; }
 int spo_lm_ret(const spo_lm_result* r) { return r->R.ret; }
 int spo_lm_exit_path(const spo_lm_result* r) { return r->R.exit_path; }
 int spo_lm_curr_iter(const spo_lm_result* r) { return r->R.currIter; }

@@ -275,6 +275,11 @@ class LMResult:
             self._h = None
 
 
+def set_threads(t):
+    """Host threads of the solver_kind=3 baseline variant (threaded Jacobi-PCG + product); parity tests never use it."""
+    lib().spo_set_threads(int(t))
+
+
 def lm_solve(kind, iparam0=0, iparam1=0, seed=20211, x0=None, pattern=None, callback=None,
              maxIterations=100, funcTolerance=10e-10, fooTolerance=10e-10, lambda0=0.01,
              verbose=True, solver_kind=0, pcg_rtol=1e-13, pcg_maxit=10000, keep_first=False):

@@ -41,7 +41,8 @@ class LMOptions(C.Structure):
 class LMResult(C.Structure):
     _fields_ = [("ret", C.c_int32), ("exit_path", C.c_int32), ("currIter", C.c_int32), ("factorizations", C.c_int32),
                 ("energy", C.c_double), ("fooOptimality", C.c_double), ("lambda_", C.c_double),
-                ("linear_iterations", C.c_int64), ("seconds_total", C.c_double), ("seconds_analyze", C.c_double)]
+                ("linear_iterations", C.c_int64), ("seconds_total", C.c_double), ("seconds_analyze", C.c_double),
+                ("unconverged_solves", C.c_int64)]
 
 
 # every symbol include/saddlepoint_b200.h declares: (name, restype, argtypes)

@@ -77,6 +77,12 @@ static spb_status guarded(spb_handle h, F&& f) {
   } catch (const std::bad_alloc&) {
     if (h) h->err = "host allocation failed";
     return SPB_ERR_ARG;
+  } catch (const std::exception& e) {
+    if (h) h->err = std::string("internal error: ") + e.what();
+    return SPB_ERR_STATE;
+  } catch (...) {
+    if (h) h->err = "internal error (unknown exception)";
+    return SPB_ERR_STATE;
   }
 }
 
@@ -325,6 +331,15 @@ static void install_explicit_pattern(spb_handle h, int32_t n, const int32_t* col
     if (!diag) throw ArgFail{"matrix must have a structurally full diagonal"};
     H.nup1[j] = up;
   }
+  // Structural symmetry is required, not assumed: Eigen's SimplicialLLT reads the lower triangle only
+  // (EigenSolverWrapper.h:58), the SpMV and the PCG here read both, so an asymmetric pattern would give
+  // triangle-dependent answers.
+  for (int j = 0; j < n; ++j)
+    for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+      const int i = rowidx[q];
+      if (i == j) continue;
+      if (!std::binary_search(rowidx + colptr[i], rowidx + colptr[i + 1], j)) throw ArgFail{"matrix pattern is not structurally symmetric"};
+    }
   build_sell(h->H, h->S);
   upload_h_layout(h);
   h->h_fingerprint = fp;
@@ -457,7 +472,7 @@ spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int m
       }
       int it = 0;
       if (h->halo_mode && h->solver != SPB_SOLVER_PCG_JACOBI) throw StateFail{"subdomain (halo) mode supports SPB_SOLVER_PCG_JACOBI only"};
-      spb_status s = h->halo_mode ? pcg_solve_halo(h, db, dx, &it)
+      spb_status s = h->halo_mode ? ((h->peer && h->peer->ready) ? pcg_solve_halo_peer(h, db, dx, &it) : pcg_solve_halo(h, db, dx, &it))
                      : h->solver == SPB_SOLVER_CHOLESKY ? chol_solve(h, db, dx)
                      : h->solver == SPB_SOLVER_PCG_IC0 ? pcg_ic0_solve(h, db, dx, &it)
                      : (h->nranks > 1 ? pcg_solve_dist(h, db, dx, &it) : pcg_solve(h, db, dx, &it));

@@ -205,7 +205,107 @@ void halo_sum_both(spb_context* h, double* v, cudaStream_t st, bool add) {
   SPB_CUDA(cudaGetLastError());
 }
 
+// ---- peer-memory windows of the halo mode (used by pcg_peer.cu) ---------------------------------------------
+// One process per GPU: every rank allocates its window with cudaMalloc, exports it with cudaIpcGetMemHandle,
+// the 64-byte handles are all-gathered over the handle's communicator, and every rank maps all windows
+// (cudaIpcOpenMemHandle enables peer access over NVLink).  The fused kernel is used only if EVERY rank
+// mapped every window (one max-allreduce of a failure flag); otherwise all ranks keep the NCCL path.
+// A single rank that is its own neighbour (self ring; test configuration) maps nothing and uses its own window.
+void peer_window_release(spb_context* h) {
+  PeerState* S = h->peer;
+  if (!S) return;
+  for (size_t r = 0; r < S->peer.size(); ++r)
+    if (S->peer[r] && S->peer[r] != S->win) cudaIpcCloseMemHandle(S->peer[r]);
+  if (S->win) cudaFree(S->win);
+  delete S;
+  h->peer = nullptr;
+}
+
+void peer_window_setup(spb_context* h) {
+  peer_window_release(h);
+  const bool disabled = getenv("SPB_HALO_PEER") && atoi(getenv("SPB_HALO_PEER")) == 0;  // read at every setup: tests toggle it
+  if (disabled || !h->halo_mode) return;
+  const int R = std::max(1, h->nranks);
+  PeerState* S = new PeerState;
+  h->peer = S;
+  S->nranks = R;
+  S->rank = R > 1 ? h->rank : 0;
+  S->band = 2 * h->halo;
+  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  PeerLayout& L = S->L;
+  size_t off = 0;
+  L.flag_from_left = off;
+  off += 256;
+  L.flag_from_right = off;
+  off += 256;
+  L.abort_word = off;
+  off += 256;
+  L.slots = off;
+  off = align(off + sizeof(PeerSlot) * 2 * (size_t)R);
+  L.band_from_left = off;
+  off = align(off + sizeof(double) * 2 * (size_t)S->band);
+  L.band_from_right = off;
+  off = align(off + sizeof(double) * 2 * (size_t)S->band);
+  L.bytes = off;
+  cudaStream_t st = h->stream;
+  SPB_CUDA(cudaMalloc((void**)&S->win, L.bytes));
+  SPB_CUDA(cudaMemsetAsync(S->win, 0, L.bytes, st));
+  SPB_CUDA(S->d_ctl.alloc(1));
+  SPB_CUDA(cudaMemsetAsync(S->d_ctl.p, 0, sizeof(PeerCtl), st));
+  S->peer.assign((size_t)R, nullptr);
+  S->peer[(size_t)S->rank] = S->win;
+  double fail = 0.0;
+  if (R > 1) {
+    // exchange the IPC handles (64 bytes each) through the communicator
+    DevBuf<char> d_hnd;
+    DevBuf<double> d_flag;
+    SPB_CUDA(d_hnd.alloc((size_t)R * sizeof(cudaIpcMemHandle_t)));
+    SPB_CUDA(d_flag.alloc(1));
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, S->win);
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fail = 1.0;
+      memset(&mine, 0, sizeof(mine));
+    }
+    SPB_CUDA(cudaMemcpyAsync(d_hnd.p + (size_t)S->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    SPB_NCCL(g_nccl.AllGather(d_hnd.p + (size_t)S->rank * sizeof(mine), d_hnd.p, sizeof(mine), 0 /* ncclInt8 */, h->comm, st));
+    SPB_CUDA(cudaMemcpyAsync(all.data(), d_hnd.p, (size_t)R * sizeof(mine), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));  // also: every rank's window is zeroed before anybody can write into it
+    if (fail == 0.0) {
+      for (int r = 0; r < R; ++r) {
+        if (r == S->rank) continue;
+        void* ptr = nullptr;
+        e = cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          fail = 1.0;
+          break;
+        }
+        S->peer[(size_t)r] = (char*)ptr;
+      }
+    }
+    SPB_CUDA(cudaMemcpyAsync(d_flag.p, &fail, sizeof(double), cudaMemcpyHostToDevice, st));
+    SPB_NCCL(g_nccl.AllReduce(d_flag.p, d_flag.p, 1, kNcclFloat64, kNcclMax, h->comm, st));
+    SPB_CUDA(cudaMemcpyAsync(&fail, d_flag.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    h->collectives += 2;
+  } else {
+    SPB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (fail != 0.0) {  // some rank cannot map some window: everybody stays on the NCCL exchange
+    peer_window_release(h);
+    return;
+  }
+  std::vector<char*> pv(S->peer.begin(), S->peer.end());
+  SPB_CUDA(S->d_peer.upload(pv, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  S->ready = true;
+}
+
 void dist_release(spb_context* h) {
+  peer_window_release(h);
   if (h->halo_ev_band) cudaEventDestroy(h->halo_ev_band);
   if (h->halo_ev_done) cudaEventDestroy(h->halo_ev_done);
   if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
@@ -237,6 +337,12 @@ static spb_status guarded_dist(spb_handle h, F&& f) {
     return SPB_ERR_ARG;
   } catch (const StateFail& e) {
     if (h) h->err = e.msg;
+    return SPB_ERR_STATE;
+  } catch (const std::exception& e) {
+    if (h) h->err = std::string("internal error: ") + e.what();
+    return SPB_ERR_STATE;
+  } catch (...) {
+    if (h) h->err = "internal error (unknown exception)";
     return SPB_ERR_STATE;
   }
 }
@@ -276,6 +382,7 @@ spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, 
   return guarded_dist(h, [&]() {
     if (halo == 0) {  // switch the mode off
       h->halo_mode = false;
+      peer_window_release(h);
       return SPB_OK;
     }
     // without a communicator only the self ring (left == right == 0: one rank that is its own neighbour) is possible
@@ -290,6 +397,8 @@ spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, 
     h->own_hi = own_end;
     h->left_rank = left_rank;
     h->right_rank = right_rank;
+    SPB_CUDA(cudaSetDevice(h->device));
+    peer_window_setup(h);  // collective: every rank of the communicator calls spb_dist_ring_halo
     return SPB_OK;
   });
 }

@@ -211,6 +211,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       int lin_it = 0;
       spb_status ss = spb_solve(h, nullptr, d_dir.p, 1, SPB_DEVICE, &lin_it);
       R->linear_iterations += lin_it;
+      if (ss == SPB_NOT_CONVERGED) R->unconverged_solves++;
       if (ss == SPB_NOT_SPD) {  // PCG met p.Hp<=0: the iterative analogue of a failed factorisation
         exit_path = 2;
         ret = 0;
@@ -247,7 +248,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       if (trace && ntrace < trace_cap) {
         double* t = trace + (size_t)ntrace * 8;
         t[0] = prevEnergy2; t[1] = newEnergy2; t[2] = lambda; t[3] = foo; t[4] = dn; t[5] = accepted ? 1.0 : 0.0;
-        t[6] = (double)lin_it; t[7] = 0.0;
+        t[6] = (double)lin_it; t[7] = ss == SPB_NOT_CONVERGED ? 1.0 : 0.0;
         ++ntrace;
       }
       if (accepted) {
@@ -319,6 +320,12 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
     return SPB_ERR_ARG;
   } catch (const StateFail& e) {
     h->err = e.msg;
+    return SPB_ERR_STATE;
+  } catch (const std::exception& e) {  // e.g. bad_alloc, or an exception a C++ callback let escape: it stops here
+    h->err = std::string("exception inside the LM loop: ") + e.what();
+    return SPB_ERR_STATE;
+  } catch (...) {
+    h->err = "unknown exception inside the LM loop";
     return SPB_ERR_STATE;
   }
 }
@@ -510,6 +517,12 @@ extern "C" spb_status spb_check_traits(spb_handle h, const spb_traits* T, const 
     return SPB_ERR_ARG;
   } catch (const StateFail& e) {
     h->err = e.msg;
+    return SPB_ERR_STATE;
+  } catch (const std::exception& e) {  // e.g. bad_alloc, or an exception a C++ callback let escape: it stops here
+    h->err = std::string("exception inside the LM loop: ") + e.what();
+    return SPB_ERR_STATE;
+  } catch (...) {
+    h->err = "unknown exception inside the LM loop";
     return SPB_ERR_STATE;
   }
 }

@@ -204,6 +204,38 @@ struct PcgScalars {
   double xx;      // ||x||^2 of the solution, by-product of the persistent kernel (saves the LM loop a launch and a sync)
 };
 
+// ---- peer-memory exchange of the subdomain (halo) mode: dist.cu sets it up, pcg_peer.cu uses it --------------
+// Every rank owns one WINDOW of device memory that its neighbours (halo slabs) and all ranks (dot-product
+// slots) write directly over NVLink (CUDA IPC mappings); the layout is identical on every rank.
+struct PeerSlot {  // one rank's contribution to a fused all-to-all sum of up to three doubles
+  double v[3];
+  unsigned long long seq;  // round + 1 once v[] is complete
+};
+struct PeerLayout {  // byte offsets inside a window
+  size_t flag_from_left = 0, flag_from_right = 0;  // u64: number of band exchanges the neighbour has delivered
+  size_t abort_word = 0;                           // u32: a rank gave up waiting; everybody stops
+  size_t slots = 0;                                // PeerSlot[2][nranks]  (round parity)
+  size_t band_from_left = 0, band_from_right = 0;  // double[2][band]     (exchange parity)
+  size_t bytes = 0;
+};
+struct PeerCtl {  // local (not peer-visible) counters that persist across solves
+  unsigned long long band_seq;   // band exchanges completed so far
+  unsigned long long round;      // all-to-all rounds completed so far
+  unsigned long long sent_left;  // band rows written to the left / right neighbour so far (block tickets)
+  unsigned long long sent_right;
+  int failed, pad;
+};
+struct PeerState {
+  char* win = nullptr;         // own window (cudaMalloc; exported with cudaIpcGetMemHandle)
+  std::vector<char*> peer;     // windows of all ranks as mapped here (peer[rank] == win)
+  DevBuf<char*> d_peer;
+  DevBuf<PeerCtl> d_ctl;
+  PeerLayout L;
+  int band = 0, nranks = 1, rank = 0;
+  bool ready = false;   // every rank mapped every window: the fused kernel may be used
+  bool failed = false;  // a solve timed out waiting for a peer: the exchange state is lost
+};
+
 struct Timing {
   bool enabled = false;
   double ms[ST_COUNT] = {0};
@@ -301,6 +333,7 @@ struct spb_context {
   std::vector<int> local_colptr, local_rowidx;
   spb::DevBuf<double> d_hval_part, d_rhs_part, d_dvec_part, d_pfull, d_xfull;
   int64_t collectives = 0;
+  spb::PeerState* peer = nullptr;  // peer-memory windows of the halo mode (dist.cu), owned
 
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
@@ -353,6 +386,11 @@ void halo_forward(spb_context* h, double* v);      // owners -> the neighbours' 
 void halo_reverse_add(spb_context* h, double* v);  // ghost contributions -> owners (+=, left neighbour first)
 void halo_sum_both(spb_context* h, double* v, cudaStream_t st = nullptr, bool add = true);  // one exchange: full sums on the owned edges AND on the ghosts
 spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* iters);
+// pcg_peer.cu: the same solve as ONE persistent cooperative kernel per rank; halo slabs and dot products move
+// through the peer windows (PeerState) -- no NCCL call and no kernel boundary inside the solve
+spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, int* iters);
+void peer_window_setup(spb_context* h);    // collective over the handle's communicator (dist.cu)
+void peer_window_release(spb_context* h);
 void dist_release(spb_context* h);
 // pcg.cu: distributed Jacobi-PCG over a row partition of H (replicated H, partitioned vectors)
 spb_status pcg_solve_dist(spb_context* h, const double* d_b, double* d_x, int* iters);

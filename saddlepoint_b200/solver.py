@@ -275,7 +275,7 @@ def _as_csc(J):
 class B200SolverWrapper:
     """GPU LinearSolver concept (replaces EigenSolverWrapper<SimplicialLLT>, EigenSolverWrapper.h:23-79)."""
 
-    def __init__(self, handle=None, solver=capi.SOLVER_PCG_JACOBI, pcg_rtol=1e-13, pcg_maxit=10000, device=0):
+    def __init__(self, handle=None, solver=capi.SOLVER_CHOLESKY, pcg_rtol=1e-13, pcg_maxit=10000, device=0):
         self.handle = handle or Handle(device)
         self.handle.set_solver(solver, pcg_rtol, pcg_maxit)
         self.last_iters = 0
@@ -465,6 +465,7 @@ class LMSolver:
         self.exit_path = EXIT_PATHS.get(R.exit_path, R.exit_path)
         self.seconds_total = R.seconds_total
         self.seconds_analyze = R.seconds_analyze
+        self.unconverged_solves = R.unconverged_solves
         names = ["prevEnergy2", "newEnergy2", "lambda", "foo", "dirnorm", "accepted", "lin_iters"]
         self.trace = {nm: trace[: tlen.value, k].copy() for k, nm in enumerate(names)}
         return bool(R.ret)

@@ -10,6 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = "/tmp/spb_rosenbrock_gpu"
 EXE_GN = "/tmp/spb_gn_legacy_gpu"
+EXE_WC = "/tmp/spb_wrapper_concept_gpu"
 
 
 def _compile(spb):
@@ -28,11 +29,36 @@ def _compile_gn(spb):
     subprocess.check_call(cmd)
 
 
+def _compile_wc(spb):
+    spb.capi.load()
+    lib = os.path.join(ROOT, "saddlepoint_b200", "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "wrapper_concept.cpp"), "-L" + lib, "-lsaddlepoint_b200", "-Wl,-rpath," + lib, "-o", EXE_WC]
+    subprocess.check_call(cmd)
+
+
 def test_headers_compile_and_link(spb):
     _compile(spb)
     assert os.path.exists(EXE)
     _compile_gn(spb)
     assert os.path.exists(EXE_GN)
+    _compile_wc(spb)
+    assert os.path.exists(EXE_WC)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [0, 1])
+def test_linear_solver_concept_overloads_and_failures(spb, solver):
+    """EigenSolverWrapper.h:26-78 surface: solve(Vector), solve(Matrix), public solver / A; an asymmetric
+    pattern is refused; a Jacobian pattern that drifts inside LMSolver::solve (same nnz!) and a throwing
+    traits class surface as C++ exceptions after the C call returned, and the handle stays usable."""
+    _compile_wc(spb)
+    out = subprocess.run([EXE_WC, str(solver)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "RESULT failures=0" in out.stdout
+    assert "LM mode=1 threw=1 what=Jacobian pattern changed inside LMSolver::solve" in out.stdout
+    assert "LM mode=2 threw=1 what=traits failure" in out.stdout
+    assert "ASYMMETRIC refused=1" in out.stdout
 
 
 @pytest.mark.gpu

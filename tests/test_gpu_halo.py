@@ -65,11 +65,22 @@ def test_halo_mode_needs_a_communicator(spb):
     h.close()
 
 
+@pytest.fixture
+def peer_mode(request, monkeypatch):
+    """1: the fused persistent kernel with peer-memory windows (pcg_peer.cu; the default); 0: the launch-per-phase
+    path with NCCL / device-copy exchanges (pcg_solve_halo)."""
+    monkeypatch.setenv("SPB_HALO_PEER", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("peer_mode", [1, 0], indirect=True)
 @pytest.mark.parametrize("g", [24, 64])
-def test_self_ring_halo_mode_matches_the_plain_solve(spb, orc, g):
+def test_self_ring_halo_mode_matches_the_plain_solve(spb, orc, g, peer_mode):
     """One rank that is its own neighbour on the ring: the whole halo-mode code path (local problem with ghost
-    copies, halo sums in the assembly, halo exchanges in the PCG, LM loop on local vectors) with device copies
-    standing in for ncclSend/ncclRecv.  The result must agree with the ordinary single-handle solve."""
+    copies, halo sums in the assembly, halo exchanges in the PCG, LM loop on local vectors).  peer_mode 1 runs the
+    fused kernel against the rank's own window (band slabs, flags and dot-product slots all go through the same
+    loads/stores as over NVLink); peer_mode 0 the NCCL path with device copies standing in for ncclSend/ncclRecv.
+    The result must agree with the ordinary single-handle solve."""
     n, halo = g * g, 2 * g
     h = spb.Handle(0)
     loc = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=20211, col_begin=0, col_end=n)
@@ -114,6 +125,45 @@ def test_self_ring_halo_mode_matches_the_plain_solve(spb, orc, g):
     np.testing.assert_allclose(h.rhs()[halo:halo + n], hp.rhs(), rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(h.damping()[halo:halo + n], hp.damping(), rtol=1e-13, atol=1e-300)
     loc.close(); glob.close(); h.close(); hp.close()
+
+
+def test_fused_and_launch_per_phase_halo_solves_agree(spb, monkeypatch):
+    """Same local system, same right-hand side: the fused peer-window kernel and the launch-per-phase path must
+    take the same number of PCG iterations and agree on the step to rounding (they differ only in the order the
+    per-block partial dot products are added); consecutive fused solves reuse the windows (sequence numbers)."""
+    import torch
+    g = 48
+    n, halo = g * g, 2 * g
+    xs, its = [], []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SPB_HALO_PEER", mode)
+        h = spb.Handle(0)
+        loc = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=20211, col_begin=0, col_end=n)
+        h.ring_halo(halo, halo + n, halo, 0, 0)
+        h.set_solver(spb.SOLVER_PCG_JACOBI, 1e-13, 10000)
+        Tl = loc.c_traits()
+        ml, nl, lcp, lri = loc.pattern()
+        xl = torch.ones(nl, dtype=torch.float64, device="cuda")
+        El = torch.empty(ml, dtype=torch.float64, device="cuda")
+        Jl = torch.empty(int(lcp[-1]), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        Tl.objective_jacobian(Tl.user, xl.data_ptr(), El.data_ptr(), Jl.data_ptr(), None)
+        torch.cuda.synchronize()
+        h.analyze(ml, nl, lcp, lri)
+        for lam in (0.01, 1.0, 0.01):   # three solves on the same windows
+            h.assemble(Jl, El, lam)
+            h.factorize()
+            x, it, st = h.solve(None)
+            assert st == spb.capi.SPB_OK
+            xs.append(x)
+            its.append(it)
+        loc.close(); h.close()
+    for a, b, ia, ib in zip(xs[:3], xs[3:], its[:3], its[3:]):
+        assert abs(ia - ib) <= 1 and ia > 10
+        assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(b)
+        # ghosts are bit-identical copies of their owners in both paths
+        assert np.array_equal(a[:halo], a[n:halo + n]) and np.array_equal(a[halo + n:], a[halo:2 * halo])
+    assert np.linalg.norm(xs[0] - xs[2]) == 0.0   # deterministic: same system, same bits
 
 
 def test_two_gpu_halo_job():

@@ -5,19 +5,22 @@
 
 A *step* is one Levenberg-Marquardt loop body (LMSolver.h:110-188): fused assembly of
 rhs / ||rhs||_inf / damping / H, the damped sparse solve, the trial evaluation, acceptance and
-the lambda update.  Workload: config C2, "LF-1M" (sparse analogue of
-benchmark/linear_function: g x g torus, n = g^2 unknowns, m = 2n residuals, 8 nnz/row; g=1024).
-  value : steps/s with the traits evaluated on the device (inputs resident in HBM), K loop
-          bodies of one solve started at x0 (lambda follows the LM rule, stop tests off).
-  e2e   : the same hot path through the C ABI with HOST buffers -- every step uploads the
-          Jacobian values and the residual from pinned host memory, runs assemble + factorize +
-          solve, and downloads the step vector and ||rhs||_inf.
-  roofline : the dominant kernel (the PCG's SpMV) re-timed per launch with CUDA events.
-  cpu_baseline / --impl reference : the CPU oracle (Eigen restatement, 1 thread) on a bounded
-          sample of the same workload.
-N>1: one process per GPU (torchrun), each rank solves its own independent instance of the same LF
-configuration: the "batches of independent problems split per GPU" sharding -- no data-path collective;
-plus, as an extra key, ONE C5-size problem solved by all ranks together (subdomain / halo mode, NCCL).
+the lambda update.
+
+N = 1 -- config C2, "LF-1M" (sparse analogue of benchmark/linear_function: g x g torus, n = g^2 unknowns,
+m = 2n residuals, 8 nnz/row; g = 1024):
+  value : steps/s with the traits evaluated on the device (inputs resident in HBM), K loop bodies in solves of
+          5 bodies each started at x0 (lambda follows the LM rule, stop tests off).
+  e2e   : the same hot path through the C ABI with HOST buffers -- every step uploads the Jacobian values and
+          the residual from pinned host memory, runs assemble + factorize + solve, and downloads the step vector.
+  roofline : the dominant kernel (the persistent PCG solve) timed per launch with CUDA events.
+  cpu_baseline : the CPU oracle on a bounded sample of the same workload (measured at full size, not scaled).
+N > 1 -- config C5: ONE LF problem of g = 4472 (n ~ 20 M unknowns, m = 2n) solved by all ranks together
+(strong scaling; subdomain / halo mode: local analysis and assembly per rank, the PCG as one persistent kernel per
+rank with halo slabs and dot products exchanged through NVLink peer memory).  The line carries a CHECKED result:
+relative residual of the first step over all ranks, and the stop-test LM solve's iteration count / final energy
+compared with the one-GPU run of the same problem (profiles/r2_c5_expected.json).
+--impl reference : the reference's CPU path for the same configuration, measured on this host (see run_reference).
 """
 import argparse
 import json
@@ -30,10 +33,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+C2_G, C5_G = 1024, 4472
+C2_SEED, C5_SEED = 20211, 20214
+BODIES_PER_SOLVE = 5
+
 
 def _label(g):
     """BASELINE.json's name for the configuration quoted (C2) or the sizes of the other LF configs."""
-    return "LF-1M (C2)" if g == 1024 else ("LF-20M (C5 size, one GPU)" if g == 4472 else "LF (g=%d, not a BASELINE configuration)" % g)
+    return "LF-1M (C2)" if g == C2_G else ("LF-20M (C5)" if g == C5_G else "LF (g=%d, not a BASELINE configuration)" % g)
+
+
+def lf_sizes(g):
+    n = g * g
+    return n, 2 * n, 16 * n
+
+
+def workload_string(g):
+    n, m, nnzJ = lf_sizes(g)
+    return "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d" % (_label(g), g, n, m, nnzJ)
 
 
 def _peaks():
@@ -94,65 +111,147 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ncu --set full capture of pcg_persistent_kernel on LF-1M (profiles/r1c_ncu_raw_metrics.txt, end of round 1):
-# dram__bytes_read.sum + dram__bytes_write.sum = 21.380 GB + 0.289 GB for an 81-iteration solve (5.31 ms)
-# = 267.5 MB per PCG iteration (r1b: 25.394 GB / 96 iterations = 264.6 MB): the 10-byte/entry H stream (FP64
-# value + 16-bit column delta, 26.2 M padded entries) plus the solve's first and last vector passes; the PCG
-# vectors never leave the 126 MB L2.
-NCU_DRAM_BYTES_PER_PCG_ITERATION = 21.669e9 / 81.0
-
-
-def lf_sizes(g):
-    n = g * g
-    return n, 2 * n, 16 * n
+def _ncu_dram_bytes_per_pcg_iteration():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the persistent PCG kernel per PCG iteration, from the newest
+    committed `ncu --set full` capture of this kernel on LF-1M (profiles/*_pcg_traffic.json, written by
+    scripts/ncu_traffic.py from the .ncu-rep).  None if no capture is committed."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_pcg_traffic.json"))):
+        try:
+            best = json.load(open(p))
+            best["file"] = os.path.relpath(p, ROOT)
+        except Exception:
+            pass
+    return best
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference(args, sample_g=None, steps=None, warmup=None):
-    """The reference's own CPU path (oracle: Eigen restatement, SimplicialLLT with AMD, 1 thread)
-    on a bounded sample of the workload.  Returns (steps_per_s_scaled, info)."""
+# CPU reference (the oracle: Eigen restatement) -- MEASURED at the configuration's full size
+# ------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_pcg_measure(g, seed, bodies_target, threads, budget_s):
+    """K LM loop bodies of the reference loop (oracle lm_solve, LMSolver.h:86-191 restated) at the FULL size of
+    the configuration, in solves of 5 bodies started at x0 like the GPU arm, with the CPU twin of the GPU
+    algorithm as linear solver: conservative SpGEMM dampJ^T*dampJ + Jacobi-PCG rtol 1e-13.  threads > 1 runs the
+    product and the PCG on that many host threads (oracle solver_kind 3); 1 is the plain single-thread code."""
     from oracle import sp_oracle as orc
-    g_full = args.g
-    gs = sample_g or min(g_full, 160)
-    steps = steps or 2
-    warmup = 0 if warmup is None else warmup
-    n_s, m_s, _ = lf_sizes(gs)
-    t0 = time.time()
-    r = orc.lm_solve("lf", iparam0=gs, iparam1=2, seed=20211, maxIterations=max(0, warmup + steps - 1), funcTolerance=0.0,
-                     fooTolerance=0.0, verbose=False, solver_kind=0)
-    wall = time.time() - t0
-    bodies = max(1, r.factorizations)
-    per_iter = (r.times["assembly"] + r.times["factor"] + r.times["solve"]) / bodies
-    n_full = g_full * g_full
-    scale = n_s / float(n_full)  # linear extrapolation in the unknown count: optimistic for the CPU
-    info = {"kind": "port", "cores": 1,
-            "sample": "oracle (Eigen restatement: conservative SpGEMM + AMD + scalar up-looking LLT), LF g=%d (n=%d, 1/%.0f of the "
-                      "unknowns), %d loop bodies, assembly+factor+solve %.3f s/iteration, scaled linearly in n to g=%d "
-                      "(factorisation cost grows faster than n, so this over-states the CPU rate)" % (gs, n_s, 1.0 / scale, bodies, per_iter, g_full),
-            "seconds_per_iteration_sample": per_iter, "wall_s": wall,
-            "split_s": {k: v / bodies for k, v in r.times.items()}}
-    return (1.0 / per_iter) * scale, info
+    orc.set_threads(threads)
+    kind = 3 if threads > 1 else 1
+    done, secs, lin = 0, 0.0, 0.0
+    split = {"assembly": 0.0, "factor": 0.0, "solve": 0.0, "traits": 0.0}
+    t_start = time.time()
+    while done < bodies_target:
+        k = min(BODIES_PER_SOLVE, bodies_target - done)
+        r = orc.lm_solve("lf", iparam0=g, iparam1=2, seed=seed, maxIterations=k - 1, funcTolerance=0.0, fooTolerance=0.0, verbose=False,
+                         solver_kind=kind)
+        done += r.factorizations
+        secs += sum(r.times.values())
+        lin += float(r.trace["lin_iters"].sum())
+        for kk in split:
+            split[kk] += r.times[kk]
+        if time.time() - t_start > budget_s:
+            break
+    return {"bodies": done, "seconds": secs, "seconds_per_iteration": secs / max(1, done), "pcg_iterations_per_step": lin / max(1, done),
+            "split_s_per_iteration": {k: v / max(1, done) for k, v in split.items()}, "threads": threads, "wall_s": time.time() - t_start}
+
+
+def cpu_llt_samples(g_full, seed, budget_s):
+    """The reference's own linear solver -- SimplicialLLT: AMD + scalar up-looking LL^T (EigenSolverWrapper.h:58), 1 thread --
+    measured on growing sizes of the same workload until the budget is spent; fitted power law of the
+    factorisation time in n, and what it gives at the full size (flagged as extrapolated: the factorisation at the
+    full size is minutes per LM iteration)."""
+    import math
+    from oracle import sp_oracle as orc
+    pts = []
+    t_start = time.time()
+    for gs in (64, 96, 128, 160, 192, 224, 256, 320, 384, 448, 512):
+        if gs >= g_full:
+            break
+        if pts:
+            # predicted time of the next size from the last point (t ~ n^1.6), stop before blowing the budget
+            pred = pts[-1]["seconds"] * (gs * gs / float(pts[-1]["n"])) ** 1.6
+            if time.time() - t_start + pred > budget_s:
+                break
+        r = orc.lm_solve("lf", iparam0=gs, iparam1=2, seed=seed, maxIterations=0, funcTolerance=0.0, fooTolerance=0.0, verbose=False, solver_kind=0)
+        b = max(1, r.factorizations)
+        pts.append({"g": gs, "n": gs * gs, "seconds": sum(r.times.values()) / b, "factor_s": r.times["factor"] / b,
+                    "assembly_s": r.times["assembly"] / b, "solve_s": r.times["solve"] / b, "traits_s": r.times["traits"] / b})
+    out = {"solver": "SimplicialLLT restatement (AMD + scalar up-looking LL^T), 1 thread", "samples": pts}
+    if len(pts) >= 3:
+        xs = [math.log(p["n"]) for p in pts[-4:]]
+        ys = [math.log(max(p["factor_s"], 1e-9)) for p in pts[-4:]]
+        mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+        slope = sum((a - mx) * (b - my) for a, b in zip(xs, ys)) / max(1e-30, sum((a - mx) ** 2 for a in xs))
+        last = pts[-1]
+        scale = (g_full * g_full) / float(last["n"])
+        full = last["factor_s"] * scale ** slope + (last["assembly_s"] + last["solve_s"] + last["traits_s"]) * scale
+        out.update({"factor_time_exponent_in_n": slope, "largest_measured": {"g": last["g"], "seconds_per_iteration": last["seconds"]},
+                    "extrapolated": True, "extrapolated_seconds_per_iteration_at_full_size": full,
+                    "extrapolated_iterations_per_s_at_full_size": 1.0 / full})
+    return out
 
 
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path (the oracle port; Eigen is not in this
+    image so the reference itself cannot be built) on THIS host, at the full size of the configuration the GPU arm
+    runs (C2 at N=1, C5 at N>1), every step measured -- nothing is scaled.  The headline value uses all host
+    threads (threaded product + Jacobi-PCG twin); the single-thread run (the reference is single-threaded) and the
+    reference's own direct solver (SimplicialLLT, measured on smaller sizes + fitted exponent) are reported next to it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, info = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
-    n, m, nnzJ = lf_sizes(args.g)
-    info["value"] = val
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    g = args.g if world == 1 else args.one_problem_g
+    seed = C2_SEED if world == 1 else C5_SEED
+    T = host_threads()
+    budget = float(os.environ.get("SPB_REF_BUDGET_S", "150"))
+    main = cpu_pcg_measure(g, seed, max(1, args.steps), T, budget)
+    single = cpu_pcg_measure(g, seed, 2, 1, 40.0) if world == 1 else None
+    llt = cpu_llt_samples(g, seed, 45.0 if world == 1 else 20.0)
+    val = main["bodies"] / main["seconds"]
+    info = {"kind": "port", "cores": T, "value": val, "unit": "iterations/s",
+            "sample": "oracle LM loop (LMSolver.h:86-191 restated) at the FULL configuration (g=%d, n=%d): %d loop bodies measured in solves of %d "
+                      "from x0, conservative SpGEMM dampJ^T*dampJ + Jacobi-PCG rtol 1e-13 (CPU twin of the GPU algorithm) on %d host threads; "
+                      "nothing scaled or extrapolated" % (g, g * g, main["bodies"], BODIES_PER_SOLVE, T),
+            "measured": main, "single_thread": single, "reference_direct_solver": llt}
     line = {"impl": "reference", "metric": "LM iterations/s", "value": val, "unit": "iterations/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d" % (_label(args.g), args.g, n, m, nnzJ)},
+            "steps": args.steps, "steps_measured": main["bodies"], "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": False,
+            "config": {"workload": workload_string(g), "solver": "cpu pcg_jacobi rtol=1e-13, %d threads" % T,
+                       "lm_bodies_per_solve": BODIES_PER_SOLVE, "pcg_iterations_per_step": main["pcg_iterations_per_step"]},
             "cpu_baseline": info,
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
+def _timed(torch, dist, world, fn):
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -164,6 +263,48 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        run_c5(args, torch, dist, world, rank, local)
+        dist.destroy_process_group()
+    else:
+        run_c2(args, torch, dist, local)
+
+
+def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2):
+    peaks, peak_kind = _peaks()
+    # SURVEY 8(d): B_spmv = 12*nnzH + 4(n+1) + 8n + 8n bytes per product; a PCG iteration moves
+    # B_spmv + 10*8n (x, r, p, q, dinv reads/writes around the product)
+    b_spmv = 12 * nnzH_loc + 4 * (n_loc + 1) + 16 * n_loc
+    b_pcg = b_spmv + 80 * n_loc
+    total_ms = max(1e-9, sum(v[0] for v in stages.values()))
+    fused_ms, fused_launches = stages["pcg_fused"]
+    if fused_ms > 0:
+        kname = "pcg_sr_kernel (whole Jacobi-PCG solve: SpMV + vector updates + one reduction per iteration, one cooperative launch)"
+        k_ms, k_launches, k_bytes_total = fused_ms, fused_launches, b_pcg * max(1, lin_iters)
+    else:
+        kname = "spmv_sell_kernel<true> (PCG SpMV + p.q)"
+        k_ms, k_launches, k_bytes_total = stages["spmv"][0], max(1, lin_iters), b_spmv * max(1, lin_iters)
+    achieved = k_bytes_total / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    asm_ms, asm_launches = stages["assembly"]
+    b_asm = 12 * nnzJ_loc + 4 * (m_loc + 1) + 8 * m_loc + 8 * nnzH_loc + 16 * n_loc
+    cap = _ncu_dram_bytes_per_pcg_iteration() if (fused_ms > 0 and g_is_c2) else None
+    traffic = cap["dram_bytes_per_pcg_iteration"] * max(1, lin_iters) / max(1, k_launches) if cap else None
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
+            "bytes_per_launch": k_bytes_total / max(1, k_launches), "avg_launch_us": 1e3 * k_ms / max(1, k_launches),
+            "launches_timed": int(k_launches), "pcg_iterations_timed": lin_iters, "us_per_pcg_iteration": 1e3 * k_ms / max(1, lin_iters),
+            "share_of_step": k_ms / total_ms,
+            "assembly": {"achieved": b_asm * K / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0, "bytes_per_step": b_asm,
+                         "ms_per_step": asm_ms / K},
+            "stage_ms_per_step": {k: v[0] / K for k, v in stages.items()}}
+    if cap:
+        # the same launch measured on its real DRAM traffic (the H stream is 10 B/entry, the vectors stay in L2)
+        roof["traffic_source"] = cap.get("file")
+        roof["frac_on_measured_dram_bytes"] = (traffic / (1e3 * k_ms / max(1, k_launches) * 1e-6) / 1e9) / peaks["hbm_gbs"]
+    roof["assembly"]["frac"] = roof["assembly"]["achieved"] / peaks["hbm_gbs"]
+    return roof
+
+
+def run_c2(args, torch, dist, local):
     import saddlepoint_b200 as spb
 
     K, W, g = args.steps, max(args.warmup, 3), args.g
@@ -172,39 +313,15 @@ def run_ours(args):
     h = spb.Handle(local, stream)
     solver_id = spb.SOLVER_PCG_IC0 if args.solver == "pcg_ic0" else spb.SOLVER_PCG_JACOBI
     h.set_solver(solver_id, args.pcg_rtol, 10000)
-    # every rank solves its own instance of the SAME configuration (seed 20211): per-GPU work is identical, so the
-    # max-over-ranks time measures scaling and not the spread of PCG iteration counts between different problems
-    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
+    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=C2_SEED)
     ls = spb.B200SolverWrapper(h, solver_id, args.pcg_rtol, 10000)
     lm = spb.LMSolver()
     lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
     x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    # ---- device-resident run (value) -------------------------------------------------------
     # The LF problem is linear: LM converges after a handful of loop bodies and later bodies of the same solve
     # are cheap (the gradient is ~0, the PCG stops at once).  So that a step costs the same whatever --steps is,
-    # the solve is restarted from x0 every BODIES_PER_SOLVE loop bodies (the default --steps).
-    BODIES_PER_SOLVE = 5
-
+    # the solve is restarted from x0 every BODIES_PER_SOLVE loop bodies.
     def run_steps(k):
         iters = 0
         while k > 0:
@@ -217,15 +334,14 @@ def run_ours(args):
     run_steps(W)  # warm-up (+ one-time analysis)
     analyze_s = lm.seconds_analyze
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     l0 = h.launch_count()
     lin_box = []
-    ms = timed(lambda: lin_box.append(run_steps(K)))
+    ms = _timed(torch, dist, 1, lambda: lin_box.append(run_steps(K)))
     launches = h.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     lin_iters = int(lin_box[0])
-    value = world * K / (ms * 1e-3)
+    value = K / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel: same K steps, every launch bracketed by CUDA events
     h.stage_reset(True)
@@ -233,37 +349,9 @@ def run_ours(args):
     stages = h.stage_ms()
     h.stage_reset(False)
     nnzH = h.h_nnz()
-    peaks, peak_kind = _peaks()
-    # SURVEY 8(d): B_spmv = 12*nnzH + 4(n+1) + 8n + 8n bytes per product; a PCG iteration moves
-    # B_spmv + 10*8n (x, r, p, q, dinv reads/writes around the product)
-    b_spmv = 12 * nnzH + 4 * (n + 1) + 16 * n
-    b_pcg = b_spmv + 80 * n
-    total_ms = max(1e-9, sum(v[0] for v in stages.values()))
-    fused_ms, fused_launches = stages["pcg_fused"]
-    if fused_ms > 0:
-        kname = "pcg_persistent_kernel (whole Jacobi-PCG solve: SpMV + vector updates + reductions, one cooperative launch)"
-        k_ms, k_launches, k_bytes_total = fused_ms, fused_launches, b_pcg * max(1, lin_iters)
-    else:
-        kname = "spmv_sell_kernel<true> (PCG SpMV + p.q)"
-        k_ms, k_launches, k_bytes_total = stages["spmv"][0], max(1, lin_iters), b_spmv * max(1, lin_iters)
-    achieved = k_bytes_total / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    asm_ms, asm_launches = stages["assembly"]
-    b_asm = 12 * nnzJ + 4 * (m + 1) + 8 * m + 8 * nnzH + 16 * n
-    # DRAM bytes per launch from the committed ncu --set full capture (profiles/): per PCG iteration
-    # dram__bytes_read+write, scaled by this launch's iteration count; only valid for the g=1024 workload
-    traffic = NCU_DRAM_BYTES_PER_PCG_ITERATION * max(1, lin_iters) / max(1, k_launches) if (fused_ms > 0 and g == 1024) else None
-    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-            "bytes_per_launch": k_bytes_total / max(1, k_launches), "avg_launch_us": 1e3 * k_ms / max(1, k_launches),
-            "launches_timed": int(k_launches), "pcg_iterations_timed": lin_iters, "us_per_pcg_iteration": 1e3 * k_ms / max(1, lin_iters),
-            "share_of_step": k_ms / total_ms,
-            "assembly": {"achieved": b_asm * K / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0, "bytes_per_step": b_asm,
-                         "ms_per_step": asm_ms / K},
-            "stage_ms_per_step": {k: v[0] / K for k, v in stages.items()}}
-    roof["assembly"]["frac"] = roof["assembly"]["achieved"] / peaks["hbm_gbs"]
+    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G)
 
     # ---- e2e: the C-ABI hot path with HOST buffers (H2D + D2H inside the timed region) -------
-    mrows, ncols, colptr, rowidx = prob.pattern()
     Jv_host = torch.empty(nnzJ, dtype=torch.float64).pin_memory()
     E_host = torch.empty(m, dtype=torch.float64).pin_memory()
     dir_host = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -286,12 +374,14 @@ def run_ours(args):
             h.solve(None, out=dn_)
 
     e2e_steps(min(W, 3))
-    ms_e2e = timed(lambda: e2e_steps(K))
-    e2e_val = world * K / (ms_e2e * 1e-3)
+    ms_e2e = _timed(torch, dist, 1, lambda: e2e_steps(K))
+    e2e_val = K / (ms_e2e * 1e-3)
+    # the step just computed, checked: ||H dir - rhs|| / ||rhs||
+    relres = h.residual_check(dn_)
 
-    # ---- the direct path (supernodal Cholesky) on the same system, for the record (N=1 only) --
+    # ---- the direct path (supernodal Cholesky) on the same system, for the record --
     direct = None
-    if rank == 0 and world == 1 and not args.no_direct:
+    if not args.no_direct:
         h.set_solver(spb.SOLVER_CHOLESKY)
         h.assemble(Jn, En, 0.01)
         h.factorize()  # includes the one-time symbolic phase (ordering, supernodes, maps)
@@ -307,84 +397,188 @@ def run_ours(args):
         info = h.factor_info()
         direct = {"factor_ms": st2["factor"][0] / reps, "solve_ms": st2["trisolve"][0] / reps, "nnzL": info["nnzL"], "flops": info["flops"],
                   "factor_tflops_fp64": info["flops"] / (st2["factor"][0] / reps * 1e-3) / 1e12, "supernodes": info["nsuper"],
-                  "tree_levels": info["nlevels"],
-                  "note": "multifrontal LL^T, nested-dissection order; SYRK/GEMM on FP64 tensor cores (DMMA); LM steps/s with this "
-                          "solver = 1000/(assembly+factor+solve ms)"}
+                  "tree_levels": info["nlevels"], "relres_of_step": h.residual_check(dn_),
+                  "trisolve_gbs": 2 * 8 * info["nnzL"] / (st2["trisolve"][0] / reps * 1e-3) / 1e9,
+                  "note": "multifrontal LL^T, nested-dissection order; SYRK/GEMM on FP64 tensor cores (DMMA); the triangular solves are "
+                          "latency-bound (tree height), far below the HBM roofline; LM steps/s with this solver = 1000/(assembly+factor+solve ms)"}
         h.set_solver(solver_id, args.pcg_rtol, 10000)
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------
+    # ---- CPU baseline: bounded sample of the same workload, measured at full size -----------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cpu = cpu_reference(args)
-        cpu["value"] = v
-        cpu["unit"] = "iterations/s"
+    if not args.no_cpu_baseline:
+        T = host_threads()
+        mres = cpu_pcg_measure(g, C2_SEED, 3, T, 30.0)
+        cpu = {"kind": "port", "cores": T, "value": mres["bodies"] / mres["seconds"], "unit": "iterations/s",
+               "sample": "oracle LM loop at the full configuration (g=%d): %d loop bodies of one solve, conservative SpGEMM + Jacobi-PCG rtol 1e-13 "
+                         "(CPU twin of the GPU algorithm) on %d host threads; measured, not scaled.  `--impl reference` runs the full K steps, "
+                         "the single-thread variant and the reference's SimplicialLLT samples" % (g, mres["bodies"], T),
+               "measured": mres}
 
-    # ---- N > 1 extra (not the headline): ONE problem of config C5's size over all ranks, subdomain (halo) mode
-    one_problem = None
-    if world > 1 and not args.no_one_problem:
-        one_problem = one_problem_all_gpus(spb, dist, torch, local, rank, world, args)
+    line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_string(g) + ", nnzH=%d" % nnzH,
+                       "solver": "%s rtol=%g (single-reduction CG, one persistent kernel per solve)" % (args.solver, args.pcg_rtol),
+                       "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
+                       "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s,
+                       "lm_bodies_per_solve": BODIES_PER_SOLVE, "fixed_iterations": True,
+                       "dedupe_evaluations": "True: 2 objective evaluations per loop body instead of the reference's 5 (the 3 skipped ones "
+                                             "recompute bit-identical residuals, LMSolver.h:154 / DiagonalDamping.h:58-61)"},
+            "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
+                    "ms_per_step": ms_e2e / K, "relres_of_step": relres},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "direct_solver": direct}
+    print(json.dumps(line))
+
+
+def _c5_expected(g):
+    p = os.path.join(ROOT, "profiles", "r2_c5_expected.json")
+    if os.path.exists(p):
+        try:
+            e = json.load(open(p))
+            return e if e.get("g") == g else None
+        except Exception:
+            return None
+    return None
+
+
+def run_c5(args, torch, dist, world, rank, local):
+    """N > 1: ONE problem of config C5's size over all ranks (strong scaling), subdomain (halo) mode."""
+    import saddlepoint_b200 as spb
+    from saddlepoint_b200 import dist as sd
+
+    K, W, g = args.steps, max(args.warmup, 3), args.one_problem_g
+    n, m, nnzJ = lf_sizes(g)
+    halo = 2 * g
+    stream = torch.cuda.current_stream().cuda_stream
+    h = spb.Handle(local, stream)
+    sd.attach_comm(h, dist)
+    cb, ce = sd.column_partition(n, world, rank, halo)
+    own = ce - cb
+    left, right = sd.ring_neighbours(world, rank)
+    prob = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=C5_SEED, col_begin=cb, col_end=ce)
+    h.ring_halo(halo, halo + own, halo, left, right)
+    fused = h.peer_exchange_ready()
+    ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
+    x_dev = torch.empty(prob.xSize, dtype=torch.float64, device="cuda")
+
+    def run_steps(k):
+        iters = 0
+        while k > 0:
+            lm.DT.currLambda = 0.01
+            lm.solve(False, dedupe_evaluations=True, fixed_iterations=min(k, BODIES_PER_SOLVE), x_out=x_dev)
+            iters += int(lm.linear_iterations)
+            k -= BODIES_PER_SOLVE
+        return iters
+
+    run_steps(W)  # warm-up (+ the local analysis)
+    analyze_s = lm.seconds_analyze
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, c0 = h.launch_count(), h.collective_count()
+    lin_box = []
+    ms = _timed(torch, dist, world, lambda: lin_box.append(run_steps(K)))
+    launches = h.launch_count() - l0
+    collectives = h.collective_count() - c0
+    clocks = sampler.stop() if rank == 0 else None
+    lin_iters = int(lin_box[0])
+    value = K / (ms * 1e-3)  # ONE problem: whole-job LM iterations/s
+
+    h.stage_reset(True)
+    lin_iters_roof = run_steps(K)
+    stages = h.stage_ms()
+    h.stage_reset(False)
+    nnzH_loc = h.h_nnz()
+    roof = _roofline(h, stages, K, lin_iters_roof, prob.xSize, prob.ESize, int(prob.pattern()[2][-1]), nnzH_loc, False)
+    roof["note"] = "rank 0's kernel on its LOCAL system (n_loc=%d unknowns incl. ghosts) against one GPU's HBM peak" % prob.xSize
+
+    # ---- e2e: host buffers (this rank's local Jacobian values and residual), H2D + D2H inside the timed region
+    mloc, nloc, colptr, rowidx = prob.pattern()
+    nnzJ_loc = int(colptr[-1])
+    Jv_host = torch.empty(nnzJ_loc, dtype=torch.float64).pin_memory()
+    E_host = torch.empty(mloc, dtype=torch.float64).pin_memory()
+    dir_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    Tt = prob.c_traits()
+    xd = torch.ones(nloc, dtype=torch.float64, device="cuda")
+    Ed = torch.empty(mloc, dtype=torch.float64, device="cuda")
+    Jd = torch.empty(nnzJ_loc, dtype=torch.float64, device="cuda")
+    Tt.objective_jacobian(Tt.user, xd.data_ptr(), Ed.data_ptr(), Jd.data_ptr(), stream)
+    torch.cuda.synchronize()
+    Jv_host.copy_(Jd)
+    E_host.copy_(Ed)
+    del xd, Ed, Jd
+    Jn, En, dn_ = Jv_host.numpy(), E_host.numpy(), dir_host.numpy()
+
+    def e2e_steps(k):
+        for _ in range(k):
+            h.assemble(Jn, En, 0.01)
+            h.factorize()
+            h.solve(None, out=dn_)
+
+    e2e_steps(2)
+    ms_e2e = _timed(torch, dist, world, lambda: e2e_steps(K))
+    e2e_val = K / (ms_e2e * 1e-3)
+
+    # ---- the checked result -------------------------------------------------------------------------------
+    # (1) the step of the first LM body, as just computed through the host-buffer path: global relative residual
+    relres = h.residual_check(dn_)
+    # (2) the LM solve with the reference's stop tests on (LMSolver.h:123-129,147-152,164-168): iteration count, exit
+    #     path, final energy and checksums of x over the owned unknowns of all ranks
+    lm2 = spb.LMSolver()
+    lm2.init(ls, prob, spb.DiagonalDamping(0.01), 100)
+    ret = lm2.solve(True, dedupe_evaluations=True, x_out=x_dev)
+    xo = x_dev[halo:halo + own]
+    sums = torch.stack([xo.sum(), (xo * xo).sum()])
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    # ghosts must be bit-identical copies of their owners: exchange the edge slabs with torch and compare
+    lo_slab, hi_slab = x_dev[halo:2 * halo].contiguous(), x_dev[own:halo + own].contiguous()
+    from_right, from_left = torch.empty_like(lo_slab), torch.empty_like(hi_slab)
+    reqs = [dist.P2POp(dist.isend, lo_slab, left), dist.P2POp(dist.isend, hi_slab, right),
+            dist.P2POp(dist.irecv, from_right, right), dist.P2POp(dist.irecv, from_left, left)]
+    for r in dist.batch_isend_irecv(reqs):
+        r.wait()
+    ghosts_ok = bool((x_dev[:halo] == from_left).all()) and bool((x_dev[halo + own:] == from_right).all())
+    flag = torch.tensor([1 if ghosts_ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    check = {"relres_of_first_step": relres, "relres_ok": bool(relres <= 1e-12),
+             "lm_solve": {"ret": bool(ret), "currIter": int(lm2.currIter), "exit_path": int(lm2.exit_path), "factorizations": int(lm2.factorizations),
+                          "energy": float(lm2.energy), "x_sum": float(sums[0].item()), "x_sumsq": float(sums[1].item()),
+                          "pcg_iterations": int(lm2.linear_iterations)},
+             "ghost_copies_bit_identical": bool(int(flag.item()) == 1)}
+    exp = _c5_expected(g)
+    if exp:
+        e = exp["lm_solve"]
+        rel = lambda a, b: abs(a - b) / max(abs(b), 1e-300)
+        check["one_gpu_run"] = {"file": "profiles/r2_c5_expected.json", "currIter": e["currIter"], "exit_path": e["exit_path"], "energy": e["energy"],
+                                "ms_per_lm_iteration_one_gpu": exp.get("ms_per_lm_iteration")}
+        check["matches_one_gpu_run"] = bool(e["currIter"] == lm2.currIter and e["exit_path"] == lm2.exit_path and e["factorizations"] == lm2.factorizations
+                                            and rel(lm2.energy, e["energy"]) <= 1e-10 and rel(float(sums[1].item()), e["x_sumsq"]) <= 1e-10
+                                            and rel(float(sums[0].item()), e["x_sum"]) <= 1e-9)
+    else:
+        check["matches_one_gpu_run"] = None
 
     if rank == 0:
         line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "benchmark/linear_function %s: g=%d torus, n=%d, m=%d, nnzJ=%d, nnzH=%d" % (_label(g), g, n, m, nnzJ, nnzH),
-                           "per_gpu": "one independent problem per GPU (every rank its own instance of the same configuration, seed 20211)", "solver": "%s rtol=%g" % (args.solver, args.pcg_rtol),
-                           "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
-                           "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s,
-                           "lm_bodies_per_solve": BODIES_PER_SOLVE},
-                "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
+                "config": {"workload": workload_string(g) + " -- ONE problem over %d GPUs (strong scaling; N=1 runs config C2 instead, so the "
+                                                            "driver's N=1 value is another workload)" % world,
+                           "partition": "contiguous unknown ranges per rank + halo of 2g, local analysis/assembly per rank (subdomain mode)",
+                           "solver": "pcg_jacobi rtol=%g, single-reduction CG, one persistent kernel per rank per solve; exchange: %s"
+                                     % (args.pcg_rtol, "NVLink peer-memory windows (halo slabs + flag-in-word all-to-all of the dot products), no NCCL inside the solve"
+                                        if fused else "NCCL send/recv + allreduce (peer mapping unavailable)"),
+                           "l2": "inputs larger than L2 (local H %d MB per rank vs 126 MB L2)" % (12 * nnzH_loc // 2**20),
+                           "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time_per_rank": analyze_s,
+                           "lm_bodies_per_solve": BODIES_PER_SOLVE, "fixed_iterations": True, "dedupe_evaluations": True,
+                           "collectives_per_step_outside_the_solve": collectives / K},
+                "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ_loc + mloc) * world, "d2h_bytes_per_step": (8 * nloc + 8) * world,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "direct_solver": direct}
-        if one_problem is not None:
-            line["one_problem_all_gpus"] = one_problem
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": None, "check": check}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def one_problem_all_gpus(spb, dist, torch, local, rank, world, args, iters=3):
-    """Strong-scaling data point next to the (weak-scaling) headline: one LF problem of config C5's size
-    (g=4472, n ~ 20 M; the 1-GPU time of the same problem is in DESIGN.md) solved by all ranks together in
-    subdomain (halo) mode -- local analysis per rank, one halo exchange and two scalar allreduces per PCG
-    iteration over NVLink.  Never fails the bench line: errors are reported as a string."""
-    try:
-        from saddlepoint_b200 import dist as sd
-        g = args.one_problem_g
-        n = g * g
-        halo = 2 * g
-        h = spb.Handle(local, torch.cuda.current_stream().cuda_stream)
-        sd.attach_comm(h, dist)
-        cb, ce = sd.column_partition(n, world, rank, halo)
-        left, right = sd.ring_neighbours(world, rank)
-        prob = spb.BuiltinProblem(h, "lf_cols", g=g, rows_mult=2, seed=20214, col_begin=cb, col_end=ce)
-        h.ring_halo(halo, halo + (ce - cb), halo, left, right)
-        ls = spb.B200SolverWrapper(h, spb.SOLVER_PCG_JACOBI, args.pcg_rtol, 10000)
-        lm = spb.LMSolver()
-        lm.init(ls, prob, spb.DiagonalDamping(0.01), 100, funcTolerance=0.0, fooTolerance=0.0)
-        x = torch.empty(prob.xSize, dtype=torch.float64, device="cuda")
-        lm.solve(False, dedupe_evaluations=True, fixed_iterations=1, x_out=x)  # warm-up incl. the local analysis
-        analyze_s = lm.seconds_analyze
-        lm.DT.currLambda = 0.01
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lm.solve(False, dedupe_evaluations=True, fixed_iterations=iters, x_out=x)
-        e1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out = {"workload": "LF g=%d (n=%d, m=%d) as ONE problem over %d GPUs, subdomain (halo) mode" % (g, n, 2 * n, world),
-               "ms_per_lm_iteration": float(t.item()) / iters, "lm_iterations_per_s": iters / (float(t.item()) * 1e-3),
-               "pcg_iterations_per_lm_iteration": lm.linear_iterations / iters, "local_analysis_seconds": analyze_s,
-               "collectives": int(h.collective_count()), "scaling": "strong"}
-        prob.close()
-        h.close()
-        return out
-    except Exception as e:  # noqa: BLE001 -- an extra must not break the bench line
-        return {"error": "%s: %s" % (type(e).__name__, e)}
+    prob.close()
+    h.close()
 
 
 def main():
@@ -393,13 +587,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--g", type=int, default=1024)
+    ap.add_argument("--g", type=int, default=C2_G)
     ap.add_argument("--pcg-rtol", type=float, default=1e-13)
     ap.add_argument("--solver", default="pcg_jacobi", choices=["pcg_jacobi", "pcg_ic0"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the supernodal-Cholesky timing block")
-    ap.add_argument("--no-one-problem", action="store_true", help="N>1: skip the one-problem-over-all-GPUs (halo mode) extra")
-    ap.add_argument("--one-problem-g", type=int, default=4472, help="torus size of that extra (config C5: 4472)")
+    ap.add_argument("--one-problem-g", type=int, default=C5_G, help="N>1: torus size of the one problem solved by all ranks (config C5: 4472)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

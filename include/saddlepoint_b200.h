@@ -115,6 +115,10 @@ spb_status spb_factorize(spb_handle h);
  * column-major).  rhs==NULL means "use the assembled gradient". iters: PCG iterations or 0. */
 spb_status spb_solve(spb_handle h, const double* rhs, double* x, int nrhs, int mem, int* iters);
 
+/* ||H x - rhs|| / ||rhs|| with the assembled gradient and the current H, for checking a step returned by
+ * spb_solve (LMSolver.h:143).  Subdomain (halo) mode: a global number, identical on every rank. */
+spb_status spb_residual_check(spb_handle h, const double* x, int mem, double* relres);
+
 /* Size of the current Cholesky factor (after the first spb_factorize with SPB_SOLVER_CHOLESKY):
  * nnz(L) incl. supernodal fill, factorisation flops, supernode and tree-level counts. */
 spb_status spb_factor_info(spb_handle h, int64_t* nnzL, double* flops, int32_t* nsuper, int32_t* nlevels);
@@ -240,6 +244,10 @@ spb_status spb_comm_destroy(spb_handle h);
  * spb_assemble / spb_factorize / spb_solve / spb_lm_solve then work on local vectors (ghost entries of
  * results are kept consistent); only SPB_SOLVER_PCG_JACOBI is supported in this mode. */
 spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, int32_t halo, int32_t left_rank, int32_t right_rank);
+/* *ready = 1 if the halo mode's peer-memory exchange is in use: every rank mapped every rank's window (CUDA IPC over
+ * NVLink), so spb_solve runs the PCG as one persistent kernel per rank with the halo slabs and the dot products
+ * exchanged inside the kernel; 0: the ncclSend/ncclRecv + ncclAllReduce path (no peer access, or SPB_HALO_PEER=0). */
+spb_status spb_dist_peer_ready(spb_handle h, int* ready);
 /* Same GLOBAL Jacobian pattern on every rank; this rank owns residual rows [row_begin,row_end).
  * Afterwards spb_assemble takes the owned values only (global CSC order restricted to the owned
  * rows; see spb_local_pattern) and the owned slice of EVec; the partial H / rhs / d of all ranks

@@ -72,6 +72,7 @@ SYMBOLS = [
     ("spb_squared_norm", C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double)]),
     ("spb_inf_norm", C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(C.c_double)]),
     ("spb_spmv", C.c_int, [vp, vp, vp, C.c_int]),
+    ("spb_residual_check", C.c_int, [vp, vp, C.c_int, C.POINTER(C.c_double)]),
     ("spb_lm_default_options", None, [C.POINTER(LMOptions)]),
     ("spb_check_traits", C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.c_double, vp, vp]),
     ("spb_check_traits", C.c_int, [vp, C.POINTER(Traits), vp, C.c_int, C.c_double, C.c_double, C.POINTER(CheckResult), vp]),
@@ -87,6 +88,7 @@ SYMBOLS = [
     ("spb_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("spb_comm_destroy", C.c_int, [vp]),
     ("spb_dist_ring_halo", C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("spb_dist_peer_ready", C.c_int, [vp, C.POINTER(C.c_int)]),
     ("spb_analyze_partitioned", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32]),
     ("spb_local_nnz", C.c_int, [vp, C.POINTER(C.c_int64)]),
     ("spb_local_pattern", C.c_int, [vp, vp, vp]),

@@ -123,6 +123,7 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     h->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SPB_PCG_MULTI")) h->pcg_persistent = !(e[0] == '1');
     if (!prop.cooperativeLaunch) h->pcg_persistent = false;
+    if (const char* e = getenv("SPB_PCG_VARIANT")) h->pcg_single_reduction = !(e[0] == 'c');  // "classic": textbook recurrences
     if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
     if (const char* e = getenv("SPB_PCG_PIN_MB")) h->pcg_pin_mb = atof(e);
     if (const char* e = getenv("SPB_PCG_COL16")) h->pcg_col16 = e[0] != '0';
@@ -523,6 +524,50 @@ spb_status spb_spmv(spb_handle h, const double* x, double* y, int mem) {
     dev_spmv(h, dx, dy);
     if (mem == SPB_HOST) SPB_CUDA(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     SPB_CUDA(cudaStreamSynchronize(h->stream));
+    return SPB_OK;
+  });
+}
+
+// ||H x - rhs|| / ||rhs|| for the assembled gradient rhs and the current H: the check a caller (bench.py, tests)
+// runs on a step returned by spb_solve.  Subdomain (halo) mode: x carries valid ghost copies (as spb_solve
+// returns it), the product is completed across ranks by one halo exchange and both norms are sums over the owned
+// unknowns of all ranks, so every rank gets the same global number.
+namespace {
+__global__ void residual_diff_kernel(const double* __restrict__ y, const double* __restrict__ b, double* __restrict__ out, int64_t len) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) out[i] = y[i] - b[i];
+}
+}  // namespace
+spb_status spb_residual_check(spb_handle h, const double* x, int mem, double* relres) {
+  if (!h || !x || !relres) return SPB_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->h_valid || !h->analyzed) throw StateFail{"spb_residual_check needs an assembled system"};
+    SPB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n;
+    const double* dx = to_device(h, x, n, mem, h->d_vec_stage);
+    SPB_CUDA(h->d_vec_stage2.alloc(n));
+    double* dy = h->d_vec_stage2.p;
+    dev_spmv(h, dx, dy);
+    int lo = 0, hi = h->n;
+    if (h->halo_mode) {
+      halo_sum_both(h, dy);
+      lo = h->own_lo;
+      hi = h->own_hi;
+    }
+    const int64_t len = hi - lo;
+    if (len > 0) {
+      residual_diff_kernel<<<(int)std::min<int64_t>((len + 255) / 256, (int64_t)h->num_sms * 8), 256, 0, h->stream>>>(dy + lo, h->d_rhs.p + lo, dy + lo, len);
+      h->launches++;
+      SPB_CUDA(cudaGetLastError());
+    }
+    double rr = 0.0, bb = 0.0;
+    if (h->halo_mode) {
+      dev_squared_norm_global(h, dy + lo, len, &rr);
+      dev_squared_norm_global(h, h->d_rhs.p + lo, len, &bb);
+    } else {
+      dev_squared_norm(h, dy + lo, len, &rr);
+      dev_squared_norm(h, h->d_rhs.p + lo, len, &bb);
+    }
+    *relres = bb > 0.0 ? std::sqrt(rr / bb) : std::sqrt(rr);
     return SPB_OK;
   });
 }

@@ -403,6 +403,12 @@ spb_status spb_dist_ring_halo(spb_handle h, int32_t own_begin, int32_t own_end, 
   });
 }
 
+spb_status spb_dist_peer_ready(spb_handle h, int* ready) {
+  if (!h || !ready) return SPB_ERR_ARG;
+  *ready = (h->halo_mode && h->peer && h->peer->ready && !h->peer->failed) ? 1 : 0;
+  return SPB_OK;
+}
+
 spb_status spb_comm_destroy(spb_handle h) {
   if (!h) return SPB_ERR_ARG;
   cudaSetDevice(h->device);

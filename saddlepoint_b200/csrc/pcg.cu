@@ -489,6 +489,7 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
   SPB_CUDA(h->d_q.alloc(n));
   const int gv = vec_grid(h, n), gs = spmv_grid(h), nslices = (n + 31) / 32;
   PcgScalars* sc = h->d_sc.p;
+  if (h->pcg_persistent && h->pcg_single_reduction) return pcg_solve_sr(h, d_b, d_x, iters);
   if (h->pcg_persistent) {
     void* kern = h->pcg_minb >= 5 ? (void*)pcg_persistent_kernel<5> : (void*)pcg_persistent_kernel<4>;
     if (h->occ_pcg == 0) {

@@ -1,26 +1,36 @@
-// pcg_peer.cu -- the subdomain (halo) Jacobi-PCG of config C5 as ONE persistent cooperative kernel per
-// rank, fused with its collectives over NVLink peer memory (sm_100a, NVSwitch).
+// pcg_peer.cu -- Jacobi-preconditioned conjugate gradients as ONE persistent cooperative kernel with a SINGLE
+// reduction per iteration, on one GPU and -- fused with its collectives over NVLink peer memory -- on the ranks
+// of the subdomain (halo) mode of config C5 (sm_100a, NVSwitch).
 //
-// What it replaces: pcg_solve_halo (pcg.cu) runs an iteration as four kernel launches, a grouped
-// ncclSend/ncclRecv halo swap and two scalar ncclAllReduce calls -- at 8 ranks ~120 us of a 287 us iteration
-// is launch + NCCL latency, nothing of size n moves.  Here an iteration is three grid barriers and nothing
-// leaves the kernel:
-//   * the SpMV phase writes the rows of the two exchanged bands straight into the neighbours' windows
-//     (peer-mapped device memory, plain coalesced stores over NVLink) while it computes them; the blocks
-//     that own band rows process them first in program order, publish "band delivered" with a
-//     release-store on the neighbour once the last of them is done, and only then wait for the
-//     neighbour's slab -- so the transfer overlaps the interior rows of every other block;
-//   * dot products are combined by a flag+value all-to-all: block 0 writes this rank's partial (up to three
-//     doubles) into slot [rank] of every rank's window, every block polls its own window's slots and adds
-//     them in rank order, so all ranks (and all blocks) hold bit-identical alpha / beta / stop decisions;
-//   * vector updates run redundantly on the ghost entries from identical inputs, so p is never exchanged
-//     (same scheme as pcg_solve_halo).
-// Waiting is bounded: a spin that exceeds the timeout raises an abort word in every rank's window; the
-// kernels then leave at their next grid-uniform check and the solve returns SPB_ERR_STATE.
+// Recurrences: Chronopoulos & Gear's rearrangement of CG (u = M^-1 r, w = A u, s = A p kept by recurrence):
+//     gamma = (r,u), delta = (w,u), rr = (r,r)                      <- the only reduction
+//     beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old)
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = dinv r ; w = A u
+// Same iterates as textbook CG in exact arithmetic; on the LM systems of this repo the iteration counts are
+// identical and the solutions agree to 4e-16 (tests/test_gpu_solve.py).  An iteration is two phases and two grid
+// barriers (pcg_persistent_kernel in pcg.cu: three phases, three barriers, two reductions):
+//   A  per-row vector updates (every row is owned by the lane that multiplies it: lane == row of a 32-row slice)
+//   B  w = A u with the three dot products accumulated on the fly.
 //
-// Reference semantics kept: the solve stands in for EigenSolverWrapper::solve (EigenSolverWrapper.h:72-78) on
-// the damped normal matrix of LMSolver.h:136; acceptance (LMSolver.h:161-171) sees the same step as the
-// one-GPU solve to ~1e-16 relative (tests/test_gpu_halo.py, scripts/halo_check.py).
+// Multi-GPU (PEER = true).  pcg_solve_halo (pcg.cu) runs an iteration as four launches, a grouped
+// ncclSend/ncclRecv halo swap and two scalar ncclAllReduce calls: at 8 ranks ~120 us of a 287 us iteration is
+// launch + NCCL latency although nothing of size n moves.  Here nothing leaves the kernel:
+//   * the rows of the two exchanged bands are multiplied FIRST, spread over all warps of the grid, and written
+//     straight into the neighbours' windows (peer-mapped device memory: plain coalesced stores over NVLink); the
+//     block that completes a band publishes it with one release store on the neighbour.  The slab is in flight
+//     while the interior rows are multiplied; the neighbour's slab is added afterwards (q = mine + theirs: the
+//     owner and the ghost holder end up with the same bits, a + b being commutative);
+//   * the reduction is a flag-in-word all-to-all: block 0 writes this rank's three partial sums into slot [rank] of
+//     every rank's window as 8-byte words that carry 32 payload bits and the round tag (no fence, no separate
+//     flag), every block polls its own window and adds the slots in rank order: all blocks of all ranks hold
+//     bit-identical alpha / beta / stop decisions;
+//   * vector updates run redundantly on the ghost entries from identical inputs, so no vector is ever exchanged.
+// Waiting is bounded: a spin that exceeds the timeout raises an abort word in every rank's window; the kernels
+// leave at their next grid-uniform check and the solve returns SPB_ERR_STATE.
+//
+// Reference semantics kept: the solve stands in for EigenSolverWrapper::solve (EigenSolverWrapper.h:72-78) on the
+// damped normal matrix of LMSolver.h:136; a non-positive curvature is the iterative analogue of LLT's failed
+// pivot (EigenSolverWrapper.h:59), NaN systems return a NaN step.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,16 +50,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
   unsigned int v;
@@ -79,13 +89,20 @@ __device__ __noinline__ void peer_raise_abort_raw(char* const* peers, int nranks
 }
 __device__ __forceinline__ void peer_raise_abort(const PeerView& V) { peer_raise_abort_raw(V.peers, V.nranks, V.L.abort_word); }
 
-// spin until *addr >= want; false on abort / timeout (the caller carries on and reports at the next grid-uniform check)
-__device__ __noinline__ bool peer_wait_ge_raw(const unsigned long long* addr, unsigned long long want, const unsigned int* abort_w,
-                                              unsigned long long timeout_ns, char* const* peers, int nranks, size_t abort_off) {
+// Spin until pred(load(addr)); false on abort / timeout (the caller carries on and reports at the next grid-uniform
+// check).  MODE 0: acquire load, value >= want.  MODE 1: relaxed load, high 32 bits == want (flag-in-word).
+template <int MODE>
+__device__ __noinline__ bool peer_wait_raw(const unsigned long long* addr, unsigned long long want, unsigned long long* got,
+                                           const unsigned int* abort_w, unsigned long long timeout_ns, char* const* peers, int nranks,
+                                           size_t abort_off) {
   unsigned long long t0 = 0;
   unsigned int spins = 0;
   for (;;) {
-    if (ld_acquire_sys_u64(addr) >= want) return true;
+    const unsigned long long v = MODE == 0 ? ld_acquire_sys_u64(addr) : ld_relaxed_sys_u64(addr);
+    if (MODE == 0 ? (v >= want) : ((v >> 32) == want)) {
+      *got = v;
+      return true;
+    }
     if ((++spins & 63u) == 0) {
       if (ld_relaxed_sys_u32(abort_w)) return false;
       const unsigned long long now = peer_global_ns();
@@ -99,32 +116,51 @@ __device__ __noinline__ bool peer_wait_ge_raw(const unsigned long long* addr, un
   }
 }
 __device__ __forceinline__ bool peer_wait_ge(const PeerView& V, const unsigned long long* addr, unsigned long long want) {
-  return peer_wait_ge_raw(addr, want, (const unsigned int*)(V.win + V.L.abort_word), V.timeout_ns, V.peers, V.nranks, V.L.abort_word);
+  unsigned long long got;
+  return peer_wait_raw<0>(addr, want, &got, (const unsigned int*)(V.win + V.L.abort_word), V.timeout_ns, V.peers, V.nranks, V.L.abort_word);
 }
 
-// Sum of K doubles over all ranks.  Precondition: every block of this rank holds the same local values v[]
-// (finalised redundantly from the per-block partials).  `round` counts these calls since the windows were set up
-// and is the same number on every rank; slots are double-buffered by its parity (a rank can be at most one round
-// ahead of the slowest reader: posting round r+2 needs everybody's round r+1, which a rank posts only after all
-// its blocks have read round r).  Result: the sum in rank order -- the same bits in every block of every rank.
+// Sum of K <= 3 doubles over all ranks.  Precondition: every block of this rank holds the same local values v[]
+// (finalised redundantly from the per-block partials).  `round` counts these calls since the windows were set up and
+// is the same number on every rank; slots are double-buffered by its parity (a rank can be at most one round ahead
+// of the slowest reader: posting round r+2 needs everybody's round r+1, which a rank posts only after all its blocks
+// have read round r).  Result: the sum in rank order -- the same bits in every block of every rank.
 template <int K>
-__device__ __forceinline__ bool peer_allsum(const PeerView& V, unsigned long long round, double (&v)[K], double* bc /* shared, >= K */) {
+__device__ __forceinline__ bool peer_allsum(const PeerView& V, unsigned long long round, double (&v)[K], unsigned int* sh /* shared, nranks*2K */,
+                                            double* bc /* shared, K */) {
   const int tid = threadIdx.x;
   const int par = (int)(round & 1ull);
-  if (blockIdx.x == 0 && tid < V.nranks) {  // thread t delivers to rank t
-    PeerSlot* s = reinterpret_cast<PeerSlot*>(V.peers[tid] + V.L.slots) + (size_t)par * V.nranks + V.rank;
+  const unsigned long long tag = (round + 1) & 0xffffffffull;
+  const int nw = V.nranks * 2 * K;  // words to deliver / to collect
+  if (blockIdx.x == 0 && tid < nw) {  // thread t delivers word (t % 2K) to rank t / 2K
+    const int dst = tid / (2 * K), word = tid % (2 * K);
+    PeerSlot* s = reinterpret_cast<PeerSlot*>(V.peers[dst] + V.L.slots) + (size_t)par * V.nranks + V.rank;
+    double val = v[0];
 #pragma unroll
-    for (int k = 0; k < K; ++k) st_relaxed_sys_f64(&s->v[k], v[k]);
-    __threadfence_system();
-    st_release_sys_u64(&s->seq, round + 1);
+    for (int k = 1; k < K; ++k)
+      if ((word >> 1) == k) val = v[k];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+    const unsigned long long half = (word & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+    st_relaxed_sys_u64(&s->w[word], half | (tag << 32));
   }
   const PeerSlot* mine = reinterpret_cast<const PeerSlot*>(V.win + V.L.slots) + (size_t)par * V.nranks;
   int ok = 1;
-  if (tid < V.nranks) ok = peer_wait_ge(V, &mine[tid].seq, round + 1) ? 1 : 0;
+  if (tid < nw) {
+    const int src = tid / (2 * K), word = tid % (2 * K);
+    unsigned long long got = 0;
+    ok = peer_wait_raw<1>(&mine[src].w[word], tag, &got, (const unsigned int*)(V.win + V.L.abort_word), V.timeout_ns, V.peers, V.nranks,
+                          V.L.abort_word)
+             ? 1
+             : 0;
+    sh[tid] = (unsigned int)(got & 0xffffffffull);
+  }
   ok = __syncthreads_and(ok);
   if (tid < K) {
     double a = 0.0;
-    for (int r = 0; r < V.nranks; ++r) a += ld_relaxed_sys_f64(&mine[r].v[tid]);
+    for (int r = 0; r < V.nranks; ++r) {
+      const unsigned long long bits = (unsigned long long)sh[r * 2 * K + 2 * tid] | ((unsigned long long)sh[r * 2 * K + 2 * tid + 1] << 32);
+      a += __longlong_as_double((long long)bits);
+    }
     bc[tid] = a;
   }
   __syncthreads();
@@ -162,8 +198,28 @@ __device__ __forceinline__ void block_totals(const double* part, int G, double* 
   for (int k = 0; k < K; ++k) out[k] = bck[k];
   __syncthreads();
 }
+// K sums over a 256-thread block; results valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_sums(double (&v)[K], double* smk /* K*8 */) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) smk[k * 8 + (threadIdx.x >> 5)] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double r = smk[k * 8];
+      for (int w = 1; w < 8; ++w) r += smk[k * 8 + w];
+      v[k] = r;
+    }
+  }
+  __syncthreads();
+}
 
-struct HaloPcgParams {
+struct SrPcgParams {
   const int64_t* slice_off;
   const int* col;
   const uint16_t* col16;
@@ -174,309 +230,302 @@ struct HaloPcgParams {
   const double* dinv;
   double* x;
   double* r;
+  double* u;  // dinv * r
   double* p;
-  double* q;
-  double* partial;  // 7 * gridDim.x
+  double* s;  // H p (by recurrence)
+  double* w;  // H u
+  double* partial;  // 6 * gridDim.x
   PcgScalars* sc;
-  PeerCtl* ctl;
   int n, nslices, maxit;
   double rtol;
+  unsigned long long* phase_ns;  // debug (SPB_PCG_TIMING=1): per block, 8 accumulated phase durations; else null
+  // PEER only
+  PeerCtl* ctl;
   int lo, hi, halo;  // owned local range [lo, hi), ghosts [0, lo) and [hi, n)
   char* left;        // window of the left / right neighbour
   char* right;
   PeerView V;
-  unsigned long long* phase_ns;  // debug (SPB_PCG_TIMING=1): per block, 9 accumulated phase durations; else null
 };
 
 #define SPB_PTICK(k)                                         \
   if (P.phase_ns && tid == 0) {                              \
     const unsigned long long now_ = peer_global_ns();        \
-    P.phase_ns[(size_t)blk * 9 + (k)] += now_ - tick_;       \
+    P.phase_ns[(size_t)blk * 8 + (k)] += now_ - tick_;       \
     tick_ = now_;                                            \
   }
+// rows of band slice index k (0 <= k < nbs): the left band's slices first, then the right band's
+#define SPB_BAND_SLICE(k) ((k) < sbl ? (k) : sbr + ((k)-sbl))
 
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) pcg_halo_peer_kernel(HaloPcgParams P) {
+template <bool PEER>
+__global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[8];
   __shared__ double smk[32];
   __shared__ double bck[4];
+  __shared__ unsigned int shw[PEER ? 256 : 1];
+  __shared__ int band_cnt[2];
   const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int n = P.n, lo = P.lo, hi = P.hi;
-  const int stride = G * 256;
-  const PeerView& V = P.V;
-  // per-block partial arrays, G doubles each; a phase's sums are followed by its "a wait failed in this block" flag,
-  // summed with them and therefore seen identically by every block (the only place a lost peer may end the loop):
-  //   [0] p.q  [1] fail   |   [2] r.z  [3] r.r (init: b.b)  [4] fail   |   [5] x.x  [6] fail
-  // Phases that may overlap in time (a fast block writing its next partial while a slow one still sums the previous
-  // phase's) use different arrays.
+  const int n = P.n;
+  // per-block partial arrays, G doubles each:  [0] r.u  [1] w.u  [2] r.r  [3] "a wait failed in this block"  |  [4] x.x  [5] fail.
+  // The fail flags are summed with the dot products and therefore seen identically by every block: the only place a
+  // lost peer may end the loop.
   double* part = P.partial;
-  const int band = 2 * P.halo, rb = hi - P.halo;  // shared bands: local [0, band) with the left, [rb, n) with the right neighbour
-  const int s_begin = (int)(((int64_t)P.nslices * blk) / G);
-  const int s_end = (int)(((int64_t)P.nslices * (blk + 1)) / G);
-  const int r_begin = s_begin * 32, r_end = min(n, s_end * 32);
-  const int nL = max(0, min(r_end, band) - r_begin);  // this block's rows of the left / right band
-  const int nR = max(0, r_end - max(r_begin, rb));
-  // counters written by block 0 at the very end of the previous solve (before any grid barrier of this one)
-  unsigned long long seq = P.ctl->band_seq, round = P.ctl->round;
+  // ---- which slices are mine -------------------------------------------------------------------------------
+  // PEER: local rows [0, band) are shared with the left neighbour, [rb, n) with the right one (band = 2*halo).  The
+  // slices holding them ("band slices": [0, sbl) and [sbr, nslices)) are dealt round-robin to ALL warps of the grid
+  // and multiplied first; the interior slices [sbl, sbr) are split in contiguous block ranges.
+  const int lo = PEER ? P.lo : 0, hi = PEER ? P.hi : n;
+  const int band = PEER ? 2 * P.halo : 0, rb = PEER ? hi - P.halo : n;
+  const int sbl = PEER ? (band + 31) / 32 : 0, sbr = PEER ? rb / 32 : P.nslices;
+  const int nbs = sbl + (P.nslices - sbr);  // band slices
+  const int gw = blk * 8 + warp, GW = G * 8;
+  const int s_begin = sbl + (int)(((int64_t)(sbr - sbl) * blk) / G);
+  const int s_end = sbl + (int)(((int64_t)(sbr - sbl) * (blk + 1)) / G);
+  const bool block_has_band = PEER && (blk * 8 < nbs);
+  unsigned long long seq = 0, round = 0;
+  if (PEER) {  // counters written by block 0 at the very end of the previous solve (before any grid barrier of this one)
+    seq = P.ctl->band_seq;
+    round = P.ctl->round;
+  }
   double failed = 0.0;
+  bool lost = false;  // grid-uniform: some block of this rank gave up waiting
 
-  // init: r = b, p = z = dinv*r, x = 0 on every local entry (ghosts included); r.z and b.b over the owned ones
+  // ---- init: x = 0, r = b, u = dinv*b, p = s = 0 on every local row ----------------------------------------------
   {
-    double rz = 0.0, bb = 0.0;
-    for (int i = blk * 256 + tid; i < n; i += stride) {
-      const double bi = P.b[i];
-      const double z = bi * P.dinv[i];
-      P.x[i] = 0.0;
-      P.r[i] = bi;
-      P.p[i] = z;
-      if (i >= lo && i < hi) {
-        rz = fma(bi, z, rz);
-        bb = fma(bi, bi, bb);
+    auto init_row = [&](int row) {
+      if (row < n) {
+        const double bi = P.b[row];
+        P.x[row] = 0.0;
+        P.r[row] = bi;
+        P.u[row] = bi * P.dinv[row];
+        P.p[row] = 0.0;
+        P.s[row] = 0.0;
       }
-    }
-    const double s1 = block_sum_256(rz, sm);
-    const double s2 = block_sum_256(bb, sm);
-    if (tid == 0) {
-      part[2 * G + blk] = s1;
-      part[3 * G + blk] = s2;
-    }
+    };
+    if (PEER)
+      for (int k = gw; k < nbs; k += GW) init_row(SPB_BAND_SLICE(k) * 32 + lane);
+    for (int slice = s_begin + warp; slice < s_end; slice += 8) init_row(slice * 32 + lane);
   }
   grid.sync();
-  double rz, bb;
-  {
-    double t2[2];
-    block_totals<2>(part + (size_t)2 * G, G, smk, bck, t2);
-    if (!peer_allsum<2>(V, round++, t2, bck)) failed = 1.0;
-    rz = t2[0];
-    bb = t2[1];
-  }
-  const double thresh = P.rtol * P.rtol * bb;
-  double rr = bb, pq = 0.0;
+  double gam_old = 0.0, alpha = 0.0, bb = 0.0, thresh = 0.0, rr = 0.0, denom = 0.0;
   int iters = 0, breakdown = 0;
-  bool run = (bb > thresh) && P.maxit > 0;
-  bool lost = false;  // grid-uniform: some block of this rank gave up waiting
-  grid.sync();        // the partial arrays are about to be reused
   unsigned long long tick_ = P.phase_ns ? peer_global_ns() : 0ull;
-  while (run) {
-    // ---- phase 1: q = H_loc p on all local rows; band rows go to the neighbours as they are produced --------
-    double loc = 0.0;
-    {
-      const int par = (int)(seq & 1ull);
-      // my view of the left band lands in the left neighbour's "from right" buffer, and vice versa
-      double* const tl = reinterpret_cast<double*>(P.left + V.L.band_from_right) + (size_t)par * band;
-      double* const tr = reinterpret_cast<double*>(P.right + V.L.band_from_left) + (size_t)par * band;
-      for (int slice = s_begin + warp; slice < s_end; slice += 8) {
+  for (;;) {
+    // ---- phase B: w = H_loc u, with (r,u), (w,u), (r,r) over the owned rows -------------------------------------
+    double acc3[3] = {0.0, 0.0, 0.0};
+    const int par = (int)(seq & 1ull);
+    if (PEER) {
+      // band rows first: to memory and straight into the neighbours' windows (32 lanes = 256 contiguous bytes)
+      double* const tl = reinterpret_cast<double*>(P.left + P.V.L.band_from_right) + (size_t)par * band;  // my view of the left band -> left's "from right"
+      double* const tr = reinterpret_cast<double*>(P.right + P.V.L.band_from_left) + (size_t)par * band;
+      int nl = 0, nr = 0;
+      for (int k = gw; k < nbs; k += GW) {
+        const int slice = SPB_BAND_SLICE(k);
         const double acc = (P.col16 && P.s16[slice])
-                               ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.p, n, slice, lane, 0, P.col16)
-                               : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, n, slice, lane, 0, P.col16);
+                               ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16)
+                               : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16);
         const int row = slice * 32 + lane;
         if (row < n) {
-          P.q[row] = acc;
-          if (row < band) tl[row] = acc;                     // 32 lanes = 256 contiguous bytes over NVLink
+          P.w[row] = acc;
+          if (row < band) tl[row] = acc;
           else if (row >= rb) tr[row - rb] = acc;
-          else loc = fma(P.p[row], acc, loc);                // interior rows are all owned
         }
+        if (k < sbl) ++nl; else ++nr;
       }
-      SPB_PTICK(0)
-      if (nL + nR > 0) {
+      if (block_has_band) {
+        if (tid < 2) band_cnt[tid] = 0;
         __threadfence_system();  // this thread's slab stores are ordered before the ticket below
         __syncthreads();
+        if (lane == 0) {
+          if (nl) atomicAdd(&band_cnt[0], nl);
+          if (nr) atomicAdd(&band_cnt[1], nr);
+        }
+        __syncthreads();
         if (tid == 0) {
-          // the block that completes a band (all rows written by all blocks that share it) publishes it
-          if (nL > 0) {
-            const unsigned long long t = atomicAdd(&P.ctl->sent_left, (unsigned long long)nL) + (unsigned long long)nL;
-            if (t == (unsigned long long)band * (seq + 1)) {
+          // the block that completes a band (every slice of it written, by whichever blocks) publishes it
+          if (band_cnt[0] > 0) {
+            const unsigned long long t = atomicAdd(&P.ctl->sent_left, (unsigned long long)band_cnt[0]) + (unsigned long long)band_cnt[0];
+            if (t == (unsigned long long)sbl * (seq + 1)) {
               __threadfence_system();
-              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.left + V.L.flag_from_right), seq + 1);
+              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.left + P.V.L.flag_from_right), seq + 1);
             }
           }
-          if (nR > 0) {
-            const unsigned long long t = atomicAdd(&P.ctl->sent_right, (unsigned long long)nR) + (unsigned long long)nR;
-            if (t == (unsigned long long)band * (seq + 1)) {
+          if (band_cnt[1] > 0) {
+            const unsigned long long t = atomicAdd(&P.ctl->sent_right, (unsigned long long)band_cnt[1]) + (unsigned long long)band_cnt[1];
+            if (t == (unsigned long long)(P.nslices - sbr) * (seq + 1)) {
               __threadfence_system();
-              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.right + V.L.flag_from_left), seq + 1);
+              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.right + P.V.L.flag_from_left), seq + 1);
             }
           }
         }
-        // the neighbour's view of the same rows: q = mine + theirs (a + b is commutative: the owner and the ghost
-        // holder end up with the same bits)
+      }
+    }
+    SPB_PTICK(0)
+    for (int slice = s_begin + warp; slice < s_end; slice += 8) {
+      const double acc = (P.col16 && P.s16[slice])
+                             ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16)
+                             : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16);
+      const int row = slice * 32 + lane;
+      if (row < n) {
+        P.w[row] = acc;
+        const double ri = P.r[row], ui = P.u[row];  // interior rows are all owned
+        acc3[0] = fma(ri, ui, acc3[0]);
+        acc3[1] = fma(acc, ui, acc3[1]);
+        acc3[2] = fma(ri, ri, acc3[2]);
+      }
+    }
+    SPB_PTICK(1)
+    if (PEER) {
+      // the neighbours' views of the band rows have been in flight meanwhile: w = mine + theirs
+      if (block_has_band) {
         int ok = 1;
         if (tid == 0) {
-          if (nL > 0 && !peer_wait_ge(V, reinterpret_cast<const unsigned long long*>(V.win + V.L.flag_from_left), seq + 1)) ok = 0;
-          if (nR > 0 && !peer_wait_ge(V, reinterpret_cast<const unsigned long long*>(V.win + V.L.flag_from_right), seq + 1)) ok = 0;
+          if (!peer_wait_ge(P.V, reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.flag_from_left), seq + 1)) ok = 0;
+          if (!peer_wait_ge(P.V, reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.flag_from_right), seq + 1)) ok = 0;
         }
         ok = __syncthreads_and(ok);
         if (!ok) failed = 1.0;
-        const double* const fl = reinterpret_cast<const double*>(V.win + V.L.band_from_left) + (size_t)par * band;
-        const double* const fr = reinterpret_cast<const double*>(V.win + V.L.band_from_right) + (size_t)par * band;
-        if (nL > 0) {
-          const int e = min(r_end, band);
-          for (int i = r_begin + tid; i < e; i += 256) {
-            const double qi = P.q[i] + __ldcg(fl + i);
-            P.q[i] = qi;
-            if (i >= lo) loc = fma(P.p[i], qi, loc);
-          }
-        }
-        if (nR > 0) {
-          for (int i = max(r_begin, rb) + tid; i < r_end; i += 256) {
-            const double qi = P.q[i] + __ldcg(fr + (i - rb));
-            P.q[i] = qi;
-            if (i < hi) loc = fma(P.p[i], qi, loc);
+        const double* const fl = reinterpret_cast<const double*>(P.V.win + P.V.L.band_from_left) + (size_t)par * band;
+        const double* const fr = reinterpret_cast<const double*>(P.V.win + P.V.L.band_from_right) + (size_t)par * band;
+        for (int k = gw; k < nbs; k += GW) {
+          const int row = SPB_BAND_SLICE(k) * 32 + lane;
+          if (row < n) {
+            double wi = P.w[row];
+            if (row < band) {
+              wi += __ldcg(fl + row);
+              P.w[row] = wi;
+            } else if (row >= rb) {
+              wi += __ldcg(fr + (row - rb));
+              P.w[row] = wi;
+            }  // else: an interior row of a slice that straddles a band boundary
+            if (row >= lo && row < hi) {
+              const double ri = P.r[row], ui = P.u[row];
+              acc3[0] = fma(ri, ui, acc3[0]);
+              acc3[1] = fma(wi, ui, acc3[1]);
+              acc3[2] = fma(ri, ri, acc3[2]);
+            }
           }
         }
       }
       ++seq;
-      const double bs = block_sum_256(loc, sm);
-      if (tid == 0) {
-        part[blk] = bs;
-        part[G + blk] = failed;
-      }
     }
-    SPB_PTICK(1)
-    grid.sync();
+    block_sums<3>(acc3, smk);
+    if (tid == 0) {
+      part[blk] = acc3[0];
+      part[G + blk] = acc3[1];
+      part[2 * G + blk] = acc3[2];
+      if (PEER) part[3 * G + blk] = failed;
+    }
     SPB_PTICK(2)
-    {
-      double t[2];
-      block_totals<2>(part, G, smk, bck, t);
-      if (t[1] > 0.0) {
+    grid.sync();
+    SPB_PTICK(3)
+    double gam, delta;
+    if (PEER) {
+      double t[4];
+      block_totals<4>(part, G, smk, bck, t);
+      if (t[3] > 0.0) {
         lost = true;
         break;
       }
-      double v1[1] = {t[0]};
-      if (!peer_allsum<1>(V, round++, v1, bck)) failed = 1.0;
-      pq = v1[0];
-    }
-    SPB_PTICK(3)
-    if (!(pq > 0.0)) {  // not SPD (pq <= 0), or NaN in H (quirk H: the LLT would hand back a NaN step)
-      breakdown = (pq != pq) ? 2 : 1;
-      break;
-    }
-    const double alpha = rz / pq;
-    // ---- phase 2: x += alpha p, r -= alpha q on every local entry; r.z and r.r over the owned ones ---------
-    {
-      double a1 = 0.0, a2 = 0.0;
-      int i = blk * 256 + tid;
-      for (; i + 3 * stride < n; i += 4 * stride) {
-        double pv[4], qv[4], xv[4], rv[4], dv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = i + u * stride;
-          pv[u] = P.p[j];
-          qv[u] = P.q[j];
-          xv[u] = P.x[j];
-          rv[u] = P.r[j];
-          dv[u] = P.dinv[j];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = i + u * stride;
-          P.x[j] = fma(alpha, pv[u], xv[u]);
-          const double ri = fma(-alpha, qv[u], rv[u]);
-          P.r[j] = ri;
-          if (j >= lo && j < hi) {
-            const double z = ri * dv[u];
-            a1 = fma(ri, z, a1);
-            a2 = fma(ri, ri, a2);
-          }
-        }
-      }
-      for (; i < n; i += stride) {
-        P.x[i] = fma(alpha, P.p[i], P.x[i]);
-        const double ri = fma(-alpha, P.q[i], P.r[i]);
-        P.r[i] = ri;
-        if (i >= lo && i < hi) {
-          const double z = ri * P.dinv[i];
-          a1 = fma(ri, z, a1);
-          a2 = fma(ri, ri, a2);
-        }
-      }
-      const double s1 = block_sum_256(a1, sm);
-      const double s2 = block_sum_256(a2, sm);
-      if (tid == 0) {
-        part[2 * G + blk] = s1;
-        part[3 * G + blk] = s2;
-        part[4 * G + blk] = failed;
-      }
+      double v3[3] = {t[0], t[1], t[2]};
+      if (!peer_allsum<3>(P.V, round++, v3, shw, bck)) failed = 1.0;
+      gam = v3[0];
+      delta = v3[1];
+      rr = v3[2];
+    } else {
+      double t[3];
+      block_totals<3>(part, G, smk, bck, t);
+      gam = t[0];
+      delta = t[1];
+      rr = t[2];
     }
     SPB_PTICK(4)
-    grid.sync();
-    SPB_PTICK(5)
-    double rz_new;
-    {
-      double t[3];
-      block_totals<3>(part + (size_t)2 * G, G, smk, bck, t);
-      if (t[2] > 0.0) {
-        lost = true;
-        break;
-      }
-      double v2[2] = {t[0], t[1]};
-      if (!peer_allsum<2>(V, round++, v2, bck)) failed = 1.0;
-      rz_new = v2[0];
-      rr = v2[1];
+    double beta = 0.0;
+    if (iters == 0) {
+      bb = rr;  // r = b
+      thresh = P.rtol * P.rtol * bb;
+      if (!(bb > thresh) || P.maxit <= 0) break;  // zero (or NaN) right-hand side
+      denom = delta;
+    } else {
+      if (!(rr > thresh) || iters >= P.maxit) break;
+      beta = gam / gam_old;
+      denom = delta - beta * gam / alpha;  // = p.Hp of the new direction
     }
-    SPB_PTICK(6)
-    const double beta = rz_new / rz;
-    rz = rz_new;
-    ++iters;
-    if (!(rr > thresh) || iters >= P.maxit) break;
-    // ---- phase 3: p = dinv*r + beta p on every local entry --------------------------------------------------
+    if (!(denom > 0.0)) {  // not SPD (the iterative analogue of a failed pivot), or NaN in H (quirk H: NaN step)
+      breakdown = (denom != denom) ? 2 : 1;
+      break;
+    }
+    alpha = gam / denom;
+    gam_old = gam;
+    // ---- phase A: p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = dinv r on every local row ---------
     {
-      int i = blk * 256 + tid;
-      for (; i + 3 * stride < n; i += 4 * stride) {
-        double pv[4], rv[4], dv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = i + u * stride;
-          pv[u] = P.p[j];
-          rv[u] = P.r[j];
-          dv[u] = P.dinv[j];
+      auto update_row = [&](int row) {
+        if (row < n) {
+          const double ui = P.u[row], wi = P.w[row], pi = P.p[row], si = P.s[row], xi = P.x[row], ri = P.r[row], di = P.dinv[row];
+          const double pn = fma(beta, pi, ui);
+          const double sn = fma(beta, si, wi);
+          const double rn = fma(-alpha, sn, ri);
+          P.p[row] = pn;
+          P.s[row] = sn;
+          P.x[row] = fma(alpha, pn, xi);
+          P.r[row] = rn;
+          P.u[row] = rn * di;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) P.p[i + u * stride] = fma(beta, pv[u], rv[u] * dv[u]);
-      }
-      for (; i < n; i += stride) P.p[i] = fma(beta, P.p[i], P.r[i] * P.dinv[i]);
+      };
+      if (PEER)
+        for (int k = gw; k < nbs; k += GW) update_row(SPB_BAND_SLICE(k) * 32 + lane);
+      for (int slice = s_begin + warp; slice < s_end; slice += 8) update_row(slice * 32 + lane);
     }
-    SPB_PTICK(7)
+    ++iters;
+    SPB_PTICK(5)
     grid.sync();
-    SPB_PTICK(8)
+    SPB_PTICK(6)
   }
   // ---- epilogue: ||x||^2 over the owned entries of all ranks (LMSolver.h:146), NaN system => NaN step ----------
   const bool nan_system = (bb != bb) || breakdown == 2;
   double xx = 0.0;
   {
-    double a = 0.0;
-    for (int i = blk * 256 + tid; i < n; i += stride) {
-      double v = P.x[i];
-      if (nan_system) {
-        v = __longlong_as_double(0x7ff8000000000000LL);
-        P.x[i] = v;
+    double a1[1] = {0.0};
+    auto xx_row = [&](int row) {
+      if (row < n) {
+        double v = P.x[row];
+        if (nan_system) {
+          v = __longlong_as_double(0x7ff8000000000000LL);
+          P.x[row] = v;
+        }
+        if (row >= lo && row < hi) a1[0] = fma(v, v, a1[0]);
       }
-      if (i >= lo && i < hi) a = fma(v, v, a);
-    }
-    const double s1 = block_sum_256(a, sm);
+    };
+    if (PEER)
+      for (int k = gw; k < nbs; k += GW) xx_row(SPB_BAND_SLICE(k) * 32 + lane);
+    for (int slice = s_begin + warp; slice < s_end; slice += 8) xx_row(slice * 32 + lane);
+    block_sums<1>(a1, smk);
     // own arrays: a block that left the loop at a break may be followed by blocks still summing the loop's arrays
     if (tid == 0) {
-      part[5 * G + blk] = s1;
-      part[6 * G + blk] = failed;
+      part[4 * G + blk] = a1[0];
+      part[5 * G + blk] = failed;
     }
     grid.sync();
     double t2[2];
-    block_totals<2>(part + (size_t)5 * G, G, smk, bck, t2);
-    if (t2[1] > 0.0) lost = true;
-    if (!lost) {
-      double v1[1] = {t2[0]};
-      if (!peer_allsum<1>(V, round++, v1, bck)) lost = true;  // nothing follows: a late failure only marks the result
-      xx = v1[0];
+    block_totals<2>(part + (size_t)4 * G, G, smk, bck, t2);
+    xx = t2[0];
+    if (PEER) {
+      if (t2[1] > 0.0) lost = true;
+      if (!lost) {
+        double v1[1] = {t2[0]};
+        if (!peer_allsum<1>(P.V, round++, v1, shw, bck)) lost = true;  // nothing follows: a late failure only marks the result
+        xx = v1[0];
+      }
     }
   }
-  if (lost && tid == 0) peer_raise_abort(V);  // the other ranks must not wait for this one
-  if (lost) atomicExch(&P.ctl->failed, 1);
+  if (PEER && lost) {
+    if (tid == 0) peer_raise_abort(P.V);  // the other ranks must not wait for this one
+    atomicExch(&P.ctl->failed, 1);
+  }
   if (blk == 0 && tid == 0) {
     PcgScalars* sc = P.sc;
-    sc->rz = rz;
-    sc->pq = pq;
+    sc->rz = gam_old;
+    sc->pq = denom;
     sc->rr = rr;
     sc->bb = bb;
     sc->thresh = thresh;
@@ -485,9 +534,123 @@ __global__ void __launch_bounds__(256, MINB) pcg_halo_peer_kernel(HaloPcgParams 
     sc->maxit = P.maxit;
     sc->xx = xx;
     sc->done = 1;
-    P.ctl->band_seq = seq;
-    P.ctl->round = round;
+    if (PEER) {
+      P.ctl->band_seq = seq;
+      P.ctl->round = round;
+    }
   }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+template <bool PEER>
+static int sr_grid(spb_context* h, int nslices) {
+  static int occ_cached = 0;
+  if (occ_cached == 0) {
+    int occ = 0;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_sr_kernel<PEER>, 256, 0));
+    occ_cached = std::max(1, occ);
+  }
+  return std::max(1, std::min((nslices + 7) / 8, h->num_sms * std::min(occ_cached, 8)));
+}
+
+static void sr_common(spb_context* h, SrPcgParams& P, const double* d_b, double* d_x) {
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  {
+    const size_t need = (size_t)h->num_sms * 8 * 6 + 64;
+    if (h->d_partial.n < need + 8) SPB_CUDA(h->d_partial.alloc(need + 8));
+    if (!h->d_sc.p) {
+      SPB_CUDA(h->d_sc.alloc(1));
+      SPB_CUDA(cudaMemsetAsync(h->d_sc.p, 0, sizeof(PcgScalars), st));
+    }
+  }
+  SPB_CUDA(h->d_r.alloc(n));
+  SPB_CUDA(h->d_p.alloc(n));
+  SPB_CUDA(h->d_q.alloc(n));
+  SPB_CUDA(h->d_u.alloc(n));
+  SPB_CUDA(h->d_w.alloc(n));
+  P.slice_off = h->d_slice_off.p;
+  P.col = h->d_sell_col.p;
+  P.col16 = h->pcg_col16 ? h->d_sell_col16.p : nullptr;
+  P.s16 = h->d_slice16.p;
+  P.rowlen = h->d_rowlen.p;
+  P.hval = h->d_hval.p;
+  P.b = d_b;
+  P.dinv = h->d_dinv.p;
+  P.x = d_x;
+  P.r = h->d_r.p;
+  P.u = h->d_u.p;
+  P.p = h->d_p.p;
+  P.s = h->d_q.p;
+  P.w = h->d_w.p;
+  P.partial = h->d_partial.p;
+  P.sc = h->d_sc.p;
+  P.n = n;
+  P.nslices = (n + 31) / 32;
+  P.maxit = h->pcg_maxit;
+  P.rtol = h->pcg_rtol;
+  P.phase_ns = nullptr;
+  P.ctl = nullptr;
+  P.lo = 0;
+  P.hi = n;
+  P.halo = 0;
+  P.left = P.right = nullptr;
+  P.V = PeerView{nullptr, nullptr, PeerLayout{}, 0, 1, 0ull};
+}
+
+static void sr_print_phases(const char* tag, int rank, spb_context* h, const DevBuf<unsigned long long>& d_phase, int G) {
+  std::vector<unsigned long long> t((size_t)G * 8);
+  SPB_CUDA(cudaMemcpy(t.data(), d_phase.p, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+  static const char* names[7] = {"band_spmv+publish", "spmv", "band_fix+block_sums", "sync1", "totals+allsum", "update", "sync2"};
+  const double it = std::max(1, h->h_sc->iters + 1);
+  char line[1024];
+  int o = snprintf(line, sizeof(line), "[spb %s timing] rank=%d iters=%d G=%d us/iteration mean(min..max over blocks):", tag, rank, h->h_sc->iters, G);
+  for (int k = 0; k < 7; ++k) {
+    double sum = 0, lo = 1e30, hi = 0;
+    for (int b = 0; b < G; ++b) {
+      const double v = (double)t[(size_t)b * 8 + k] / it * 1e-3;
+      sum += v;
+      lo = std::min(lo, v);
+      hi = std::max(hi, v);
+    }
+    o += snprintf(line + o, sizeof(line) - (size_t)o, " %s=%.2f(%.2f..%.2f)", names[k], sum / G, lo, hi);
+  }
+  fprintf(stderr, "%s\n", line);
+}
+
+static spb_status sr_finish(spb_context* h, int* iters) {
+  h->pcg_last_iters = h->h_sc->iters;
+  h->solve_xx_valid = true;
+  if (iters) *iters = h->h_sc->iters;
+  if (h->h_sc->breakdown == 2 || h->h_sc->bb != h->h_sc->bb) return SPB_OK;  // NaN system: NaN step (quirk H)
+  if (h->h_sc->breakdown) return SPB_NOT_SPD;
+  if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
+  return SPB_OK;
+}
+
+spb_status pcg_solve_sr(spb_context* h, const double* d_b, double* d_x, int* iters) {
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  if (iters) *iters = 0;
+  if (n == 0) return SPB_OK;
+  SrPcgParams P;
+  sr_common(h, P, d_b, d_x);
+  const int G = sr_grid<false>(h, P.nslices);
+  static const bool phase_timing = getenv("SPB_PCG_TIMING") && atoi(getenv("SPB_PCG_TIMING")) > 0;
+  DevBuf<unsigned long long> d_phase;
+  if (phase_timing) {
+    SPB_CUDA(d_phase.alloc((size_t)G * 8));
+    SPB_CUDA(cudaMemsetAsync(d_phase.p, 0, sizeof(unsigned long long) * (size_t)G * 8, st));
+    P.phase_ns = d_phase.p;
+  }
+  void* args[] = {&P};
+  stage_begin(h, ST_PCG);
+  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_sr_kernel<false>, dim3(G), dim3(256), args, 0, st));
+  stage_end(h, ST_PCG, 1);
+  SPB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  if (phase_timing) sr_print_phases("pcg-sr", 0, h, d_phase, G);
+  return sr_finish(h, iters);
 }
 
 spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, int* iters) {
@@ -500,46 +663,10 @@ spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, i
   if (S->failed) throw StateFail{"an earlier solve lost a peer (exchange timed out): re-create the halo description"};
   if (n != h->own_hi + h->halo) throw StateFail{"halo description does not match the analysed local problem"};
   if (S->band != 2 * h->halo) throw StateFail{"peer windows were sized for another halo width"};
-  // partial arrays: 7 segments of G doubles
-  {
-    const size_t need = (size_t)h->num_sms * 8 * 7 + 64;
-    if (h->d_partial.n < need + 8) SPB_CUDA(h->d_partial.alloc(need + 8));
-    if (!h->d_sc.p) {
-      SPB_CUDA(h->d_sc.alloc(1));
-      SPB_CUDA(cudaMemsetAsync(h->d_sc.p, 0, sizeof(PcgScalars), st));
-    }
-  }
-  SPB_CUDA(h->d_r.alloc(n));
-  SPB_CUDA(h->d_p.alloc(n));
-  SPB_CUDA(h->d_q.alloc(n));
-  const int nslices = (n + 31) / 32;
-  static int occ_cached = 0;
-  if (occ_cached == 0) {
-    int occ = 0;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_halo_peer_kernel<4>, 256, 0));
-    occ_cached = std::max(1, occ);
-  }
-  const int G = std::max(1, std::min((nslices + 7) / 8, h->num_sms * std::min(occ_cached, 8)));
-  HaloPcgParams P;
-  P.slice_off = h->d_slice_off.p;
-  P.col = h->d_sell_col.p;
-  P.col16 = h->pcg_col16 ? h->d_sell_col16.p : nullptr;
-  P.s16 = h->d_slice16.p;
-  P.rowlen = h->d_rowlen.p;
-  P.hval = h->d_hval.p;
-  P.b = d_b;
-  P.dinv = h->d_dinv.p;
-  P.x = d_x;
-  P.r = h->d_r.p;
-  P.p = h->d_p.p;
-  P.q = h->d_q.p;
-  P.partial = h->d_partial.p;
-  P.sc = h->d_sc.p;
+  if (S->nranks * 6 > 256) throw StateFail{"the fused all-to-all supports at most 42 ranks"};
+  SrPcgParams P;
+  sr_common(h, P, d_b, d_x);
   P.ctl = S->d_ctl.p;
-  P.n = n;
-  P.nslices = nslices;
-  P.maxit = h->pcg_maxit;
-  P.rtol = h->pcg_rtol;
   P.lo = h->own_lo;
   P.hi = h->own_hi;
   P.halo = h->halo;
@@ -552,51 +679,28 @@ spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, i
   P.V.nranks = S->nranks;
   static const long timeout_ms = getenv("SPB_PEER_TIMEOUT_MS") ? std::max(1L, atol(getenv("SPB_PEER_TIMEOUT_MS"))) : 20000L;
   P.V.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+  const int G = sr_grid<true>(h, P.nslices);
   static const bool phase_timing = getenv("SPB_PCG_TIMING") && atoi(getenv("SPB_PCG_TIMING")) > 0;
   DevBuf<unsigned long long> d_phase;
-  P.phase_ns = nullptr;
   if (phase_timing) {
-    SPB_CUDA(d_phase.alloc((size_t)G * 9));
-    SPB_CUDA(cudaMemsetAsync(d_phase.p, 0, sizeof(unsigned long long) * (size_t)G * 9, st));
+    SPB_CUDA(d_phase.alloc((size_t)G * 8));
+    SPB_CUDA(cudaMemsetAsync(d_phase.p, 0, sizeof(unsigned long long) * (size_t)G * 8, st));
     P.phase_ns = d_phase.p;
   }
   void* args[] = {&P};
   stage_begin(h, ST_PCG);
-  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_halo_peer_kernel<4>, dim3(G), dim3(256), args, 0, st));
+  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_sr_kernel<true>, dim3(G), dim3(256), args, 0, st));
   stage_end(h, ST_PCG, 1);
   SPB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
   PeerCtl ctl;
   SPB_CUDA(cudaMemcpyAsync(&ctl, S->d_ctl.p, sizeof(PeerCtl), cudaMemcpyDeviceToHost, st));
   SPB_CUDA(cudaStreamSynchronize(st));
-  if (phase_timing) {
-    std::vector<unsigned long long> t((size_t)G * 9);
-    SPB_CUDA(cudaMemcpy(t.data(), d_phase.p, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
-    static const char* names[9] = {"spmv", "exchange", "sync1", "allsum1", "update", "sync2", "allsum2", "direction", "sync3"};
-    const double it = std::max(1, h->h_sc->iters);
-    fprintf(stderr, "[spb halo-peer timing] rank=%d iters=%d G=%d us/iteration mean(min..max over blocks):", S->rank, h->h_sc->iters, G);
-    for (int k = 0; k < 9; ++k) {
-      double sum = 0, lo = 1e30, hi = 0;
-      for (int b = 0; b < G; ++b) {
-        const double v = (double)t[(size_t)b * 9 + k] / it * 1e-3;
-        sum += v;
-        lo = std::min(lo, v);
-        hi = std::max(hi, v);
-      }
-      fprintf(stderr, " %s=%.2f(%.2f..%.2f)", names[k], sum / G, lo, hi);
-    }
-    fprintf(stderr, "\n");
-  }
+  if (phase_timing) sr_print_phases("halo-peer", S->rank, h, d_phase, G);
   if (ctl.failed) {
     S->failed = true;
     throw StateFail{"halo exchange timed out waiting for a peer rank (SPB_PEER_TIMEOUT_MS)"};
   }
-  h->pcg_last_iters = h->h_sc->iters;
-  h->solve_xx_valid = true;
-  if (iters) *iters = h->h_sc->iters;
-  if (h->h_sc->breakdown == 2 || h->h_sc->bb != h->h_sc->bb) return SPB_OK;  // NaN system: NaN step (quirk H)
-  if (h->h_sc->breakdown) return SPB_NOT_SPD;
-  if (h->h_sc->rr > h->h_sc->thresh) return SPB_NOT_CONVERGED;
-  return SPB_OK;
+  return sr_finish(h, iters);
 }
 
 }  // namespace spb

@@ -207,9 +207,11 @@ struct PcgScalars {
 // ---- peer-memory exchange of the subdomain (halo) mode: dist.cu sets it up, pcg_peer.cu uses it --------------
 // Every rank owns one WINDOW of device memory that its neighbours (halo slabs) and all ranks (dot-product
 // slots) write directly over NVLink (CUDA IPC mappings); the layout is identical on every rank.
-struct PeerSlot {  // one rank's contribution to a fused all-to-all sum of up to three doubles
-  double v[3];
-  unsigned long long seq;  // round + 1 once v[] is complete
+// One rank's contribution to a fused all-to-all sum of up to three doubles, in the flag-in-word form NCCL's LL
+// protocol uses: every 8-byte word carries 32 bits of payload and the 32-bit round tag, so a word is complete the
+// moment its tag matches (8-byte stores are atomic) and no fence or separate flag store is needed.
+struct PeerSlot {
+  unsigned long long w[8];  // w[2k], w[2k+1]: low / high half of value k; 64 bytes = one slot per (parity, source rank)
 };
 struct PeerLayout {  // byte offsets inside a window
   size_t flag_from_left = 0, flag_from_right = 0;  // u64: number of band exchanges the neighbour has delivered
@@ -319,7 +321,7 @@ struct spb_context {
   spb::DevBuf<double> d_hval, d_hdiag, d_dinv;
   // device: vectors
   spb::DevBuf<double> d_rhs, d_dvec, d_Jv_stage, d_f_stage, d_vec_stage, d_vec_stage2;
-  spb::DevBuf<double> d_r, d_p, d_q, d_x, d_partial;
+  spb::DevBuf<double> d_r, d_p, d_q, d_x, d_partial, d_u, d_w;
   spb::DevBuf<spb::PcgScalars> d_sc;
   spb::DevBuf<unsigned long long> d_foo_bits;
   spb::PcgScalars* h_sc = nullptr;      // pinned
@@ -337,6 +339,7 @@ struct spb_context {
 
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
+  bool pcg_single_reduction = true;  // the two-barrier Chronopoulos-Gear kernel (pcg_peer.cu); false: the three-barrier textbook kernel (pcg.cu)
   int occ_spmv = 0, occ_pcg = 0;
   bool pcg_col16 = true;       // persistent PCG reads 16-bit column deltas where a slice allows it
   double pcg_pin_mb = 0.0;     // MB of H the persistent PCG keeps in L2 (evict_last) across iterations
@@ -389,6 +392,8 @@ spb_status pcg_solve_halo(spb_context* h, const double* d_b, double* d_x, int* i
 // pcg_peer.cu: the same solve as ONE persistent cooperative kernel per rank; halo slabs and dot products move
 // through the peer windows (PeerState) -- no NCCL call and no kernel boundary inside the solve
 spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, int* iters);
+// pcg_peer.cu: the single-GPU solve with the same single-reduction kernel (no peers, no bands)
+spb_status pcg_solve_sr(spb_context* h, const double* d_b, double* d_x, int* iters);
 void peer_window_setup(spb_context* h);    // collective over the handle's communicator (dist.cu)
 void peer_window_release(spb_context* h);
 void dist_release(spb_context* h);

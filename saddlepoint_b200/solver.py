@@ -108,6 +108,12 @@ class Handle:
         """Subdomain (halo) mode (spb_dist_ring_halo): this handle holds the local problem of its rank."""
         self._check(self.L.spb_dist_ring_halo(self.h, own_begin, own_end, halo, left_rank, right_rank))
 
+    def peer_exchange_ready(self):
+        """True if the halo mode exchanges through NVLink peer-memory windows inside the PCG kernel (spb_dist_peer_ready)."""
+        r = C.c_int(0)
+        self._check(self.L.spb_dist_peer_ready(self.h, C.byref(r)))
+        return bool(r.value)
+
     def local_pattern(self):
         colptr = np.empty(self.n + 1, np.int32)
         rowidx = np.empty(self.nnzJ, np.int32)
@@ -214,6 +220,13 @@ class Handle:
         it = C.c_int(0)
         st = self._check(self.L.spb_solve(self.h, pr, po, nrhs, mo, C.byref(it)), allow=(SPB_NOT_SPD, SPB_NOT_CONVERGED))
         return out, it.value, st
+
+    def residual_check(self, x):
+        """||H x - rhs|| / ||rhs|| for the assembled system (global over ranks in halo mode)."""
+        p, m, k = _ptr(x)
+        out = C.c_double(0)
+        self._check(self.L.spb_residual_check(self.h, p, m, C.byref(out)))
+        return out.value
 
     def factor_info(self):
         nnzL, flops, ns, nl = C.c_int64(0), C.c_double(0), C.c_int32(0), C.c_int32(0)

@@ -22,7 +22,10 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "LM iterations/s" and d["unit"] == "iterations/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # measured at the size it names, nothing scaled
+    assert d["extrapolated"] is False and d["steps_measured"] >= 1 and d["cpu_baseline"]["measured"]["bodies"] == d["steps_measured"]
+    assert abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
                                                                           const SlotMeta* __restrict__ slots,
                                                                           const uint32_t* __restrict__ slot_start,
                                                                           const double* __restrict__ Jv, double* __restrict__ hval,
-                                                                          long long* dbg) {
+                                                                          long long* dbg, int strided) {
   // dynamic shared memory (above the 48 KB static limit): two value buffers, two record buffers, two stage
   // arrays, the descriptor ring and the two mbarriers -- see pipelined_smem_bytes()
   extern __shared__ __align__(16) unsigned char pipe_smem[];
@@ -278,8 +278,14 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
     tk = now_;                          \
   }
   const int tid = threadIdx.x;
-  const int c0 = (int)(((int64_t)nchunks * blockIdx.x) / gridDim.x);
-  const int nk = (int)(((int64_t)nchunks * (blockIdx.x + 1)) / gridDim.x) - c0;
+  // Which chunks this CTA walks.  strided: chunk blockIdx.x + k*gridDim.x -- at any moment the whole grid works on one
+  // window of ~gridDim.x consecutive chunks, so the J columns a chunk shares with its neighbours (and with the chunks
+  // one torus row further, for stencil-like problems) are re-read from L2, not from DRAM.  contiguous: a private range
+  // per CTA (the grid's working set is then spread over the whole J array and does not fit the 126 MB L2 at C2 size).
+  const int c0 = strided ? (int)blockIdx.x : (int)(((int64_t)nchunks * blockIdx.x) / gridDim.x);
+  const int cstep = strided ? (int)gridDim.x : 1;
+  const int nk = strided ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : (int)(((int64_t)nchunks * (blockIdx.x + 1)) / gridDim.x) - c0;
   if (nk <= 0) return;
   constexpr int SPT = kSlotCap / 256;  // slots per thread
   if (tid == 0) {
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
   }
   // descriptors of the first kDescRing chunks of the range (refilled half a ring at a time below)
   for (int t = tid; t < min(nk, kDescRing) * 2; t += 256)
-    reinterpret_cast<uint4*>(ring)[t] = reinterpret_cast<const uint4*>(chunks + c0)[t];
+    reinterpret_cast<uint4*>(ring)[t] = reinterpret_cast<const uint4*>(chunks + c0 + (int64_t)(t >> 1) * cstep)[t & 1];
   __syncthreads();
 
   StageEntry eNext;          // this thread's stage entry of the chunk whose TMA copies are issued next
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
       const int base = k + 1 + kDescRing / 2;  // first chunk of the half being refilled
       for (int t = tid; t < kDescRing; t += 256) {
         const int kk = base + t / 2;
-        if (kk < nk) reinterpret_cast<uint4*>(ring)[(kk % kDescRing) * 2 + (t & 1)] = reinterpret_cast<const uint4*>(chunks + c0 + kk)[t & 1];
+        if (kk < nk) reinterpret_cast<uint4*>(ring)[(kk % kDescRing) * 2 + (t & 1)] = reinterpret_cast<const uint4*>(chunks + c0 + (int64_t)kk * cstep)[t & 1];
       }
       __syncthreads();
     }
@@ -432,10 +438,30 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
   }
   for (int a = e0; a < e1 || a == e0; a += kEntTile) {
     const int b = min(e1, a + kEntTile);
-    for (int e = a + tid; e < b; e += 256) {
-      const double v = Jv[e];
-      sv[skew(e - a)] = v;
-      sf[skew(e - a)] = f ? __ldg(f + Jrow[e]) : 0.0;
+    {
+      // all of a thread's row indices first, then all residual gathers, then the stores: written as one loop the
+      // dependent chain Jrow -> f (a random access into an L2-resident vector) is paid once per element, eight
+      // times in a row
+      constexpr int EPT = kEntTile / 256;
+      double vv[EPT], ff[EPT];
+      int rr[EPT];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = a + tid + u * 256;
+        const bool ok = e < b;
+        vv[u] = ok ? Jv[e] : 0.0;
+        rr[u] = (ok && f) ? Jrow[e] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) ff[u] = rr[u] >= 0 ? __ldg(f + rr[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = a + tid + u * 256;
+        if (e < b) {
+          sv[skew(e - a)] = vv[u];
+          sf[skew(e - a)] = ff[u];
+        }
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -733,12 +759,13 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
         SPB_CUDA(h->d_dbg.alloc(24));
         dbgp = h->d_dbg.p;
       }
+      static const int strided = getenv("SPB_ASM_STRIDED") ? atoi(getenv("SPB_ASM_STRIDED")) : 1;
       if (h->rec_bits == 16)
         assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, pipelined_smem_bytes<uint16_t>(), st>>>(h->d_rec16.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
-                                                                        h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
+                                                                        h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp, strided);
       else
         assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, pipelined_smem_bytes<uint32_t>(), st>>>(h->d_rec32.p, h->d_chunk_desc.p, h->nchunks, h->d_stage_ent.p,
-                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp);
+                                                                         h->d_slot_meta.p, h->d_slot_start.p, d_Jv, hv, dbgp, strided);
       if (dbgp) {
         long long tt[24];
         cudaStreamSynchronize(st);
@@ -882,10 +909,10 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
       const int G = std::max(1, std::min(cnt, h->num_sms * h->occ_pairs));
       if (h->rec_bits == 16)
         assemble_pairs_pipelined_kernel<uint16_t, 7><<<G, 256, pipelined_smem_bytes<uint16_t>(), st>>>(h->d_rec16.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
-                                                                        h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
+                                                                        h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr, 1);
       else
         assemble_pairs_pipelined_kernel<uint32_t, 15><<<G, 256, pipelined_smem_bytes<uint32_t>(), st>>>(h->d_rec32.p, h->d_chunk_desc_sorted.p + ch_done, cnt, h->d_stage_ent.p,
-                                                                         h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr);
+                                                                         h->d_slot_meta.p, h->d_slot_start.p, dJ, h->d_hval.p, nullptr, 1);
       ++nl;
       ch_done = ch_end;
     }

@@ -291,15 +291,23 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
   bool lost = false;  // grid-uniform: some block of this rank gave up waiting
 
   // ---- init: x = 0, r = b, u = dinv*b, p = s = 0 on every local row ----------------------------------------------
+  // (r,u) and (r,r) of the NEXT reduction are accumulated where r and u are produced (here and in phase A) and
+  // carried in registers across the grid barrier; phase B only adds (w,u)
+  double acc_ru = 0.0, acc_rr = 0.0;
   {
     auto init_row = [&](int row) {
       if (row < n) {
         const double bi = P.b[row];
+        const double ui = bi * P.dinv[row];
         P.x[row] = 0.0;
         P.r[row] = bi;
-        P.u[row] = bi * P.dinv[row];
+        P.u[row] = ui;
         P.p[row] = 0.0;
         P.s[row] = 0.0;
+        if (row >= lo && row < hi) {
+          acc_ru = fma(bi, ui, acc_ru);
+          acc_rr = fma(bi, bi, acc_rr);
+        }
       }
     };
     if (PEER)
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
   unsigned long long tick_ = P.phase_ns ? peer_global_ns() : 0ull;
   for (;;) {
     // ---- phase B: w = H_loc u, with (r,u), (w,u), (r,r) over the owned rows -------------------------------------
-    double acc3[3] = {0.0, 0.0, 0.0};
+    double acc3[3] = {acc_ru, 0.0, acc_rr};
     const int par = (int)(seq & 1ull);
     if (PEER) {
       // band rows first: to memory and straight into the neighbours' windows (32 lanes = 256 contiguous bytes)
@@ -368,10 +376,7 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
       const int row = slice * 32 + lane;
       if (row < n) {
         P.w[row] = acc;
-        const double ri = P.r[row], ui = P.u[row];  // interior rows are all owned
-        acc3[0] = fma(ri, ui, acc3[0]);
-        acc3[1] = fma(acc, ui, acc3[1]);
-        acc3[2] = fma(ri, ri, acc3[2]);
+        acc3[1] = fma(acc, P.u[row], acc3[1]);  // interior rows are all owned
       }
     }
     SPB_PTICK(1)
@@ -398,12 +403,7 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
               wi += __ldcg(fr + (row - rb));
               P.w[row] = wi;
             }  // else: an interior row of a slice that straddles a band boundary
-            if (row >= lo && row < hi) {
-              const double ri = P.r[row], ui = P.u[row];
-              acc3[0] = fma(ri, ui, acc3[0]);
-              acc3[1] = fma(wi, ui, acc3[1]);
-              acc3[2] = fma(ri, ri, acc3[2]);
-            }
+            if (row >= lo && row < hi) acc3[1] = fma(wi, P.u[row], acc3[1]);
           }
         }
       }
@@ -458,6 +458,8 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
     alpha = gam / denom;
     gam_old = gam;
     // ---- phase A: p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = dinv r on every local row ---------
+    acc_ru = 0.0;
+    acc_rr = 0.0;
     {
       auto update_row = [&](int row) {
         if (row < n) {
@@ -465,11 +467,16 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
           const double pn = fma(beta, pi, ui);
           const double sn = fma(beta, si, wi);
           const double rn = fma(-alpha, sn, ri);
+          const double un = rn * di;
           P.p[row] = pn;
           P.s[row] = sn;
           P.x[row] = fma(alpha, pn, xi);
           P.r[row] = rn;
-          P.u[row] = rn * di;
+          P.u[row] = un;
+          if (row >= lo && row < hi) {
+            acc_ru = fma(rn, un, acc_ru);
+            acc_rr = fma(rn, rn, acc_rr);
+          }
         }
       };
       if (PEER)

@@ -73,3 +73,24 @@ def test_lm_converges_to_the_least_squares_solution(c2, spb):
     assert lm.currIter <= 10
     # first-order optimality of the linear least-squares problem at the returned x
     assert lm.trace["foo"][-1] < 1e-3 * lm.trace["foo"][0]
+
+
+def test_c2_assembly_is_bit_exact_against_the_oracle(c2, orc):
+    """The whole C2 normal matrix (25.9 M entries), gradient and damping vector against the oracle's restatement of
+    DiagonalDamping.h:31-43 + `dampJ.transpose()*dampJ` (LMSolver.h:136) + `-(J^T E)` (LMSolver.h:117): pattern and
+    values bit for bit at BASELINE's size (the oracle's sparse product takes seconds there, not minutes)."""
+    h, n, m = c2["h"], c2["n"], c2["m"]
+    foo = h.assemble(c2["Jv"], c2["E"], 0.01)
+    vals = c2["Jv"].cpu().numpy()
+    E = c2["E"].cpu().numpy()
+    J = orc.from_csc(m, n, c2["colptr"], c2["rowidx"], vals)
+    D, d = orc.damp_build(J, 0.01)
+    hp, hi, hx = orc.ata(D).csc()
+    cp, ri = h.h_pattern()
+    assert np.array_equal(cp, hp) and np.array_equal(ri, hi), "H pattern differs at C2 size"
+    hv = h.h_values()
+    bits = lambda a: np.ascontiguousarray(a, np.float64).view(np.uint64)
+    assert np.array_equal(bits(hv), bits(hx)), "H values not bit-exact at C2 size"
+    g = orc.jt_vec_neg(J, E)
+    assert np.array_equal(bits(h.rhs()), bits(g)) and np.array_equal(bits(h.damping()), bits(d))
+    assert foo == np.abs(g).max()

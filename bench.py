@@ -269,7 +269,7 @@ def run_ours(args):
         run_c2(args, torch, dist, local)
 
 
-def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2):
+def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2, fused_kernel):
     peaks, peak_kind = _peaks()
     # B_spmv = 12*nnzH + 4(n+1) + 8n + 8n bytes per product; a PCG iteration moves
     # B_spmv + 10*8n (x, r, p, q, dinv reads/writes around the product)
@@ -278,7 +278,7 @@ def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2
     total_ms = max(1e-9, sum(v[0] for v in stages.values()))
     fused_ms, fused_launches = stages["pcg_fused"]
     if fused_ms > 0:
-        kname = "pcg_sr_kernel (whole Jacobi-PCG solve: SpMV + vector updates + one reduction per iteration, one cooperative launch)"
+        kname = fused_kernel
         k_ms, k_launches, k_bytes_total = fused_ms, fused_launches, b_pcg * max(1, lin_iters)
     else:
         kname = "spmv_sell_kernel<true> (PCG SpMV + p.q)"
@@ -349,7 +349,10 @@ def run_c2(args, torch, dist, local):
     stages = h.stage_ms()
     h.stage_reset(False)
     nnzH = h.h_nnz()
-    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G)
+    sr = os.environ.get("SPB_PCG_VARIANT", "classic").startswith("s")
+    kname = ("pcg_sr_kernel<false> (whole Jacobi-PCG solve, single-reduction CG: SpMV + dots | vector updates, two grid barriers per iteration, one cooperative launch)"
+             if sr else "pcg_persistent_kernel<4> (whole Jacobi-PCG solve: SpMV + vector updates + reductions, one cooperative launch)")
+    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G, kname)
 
     # ---- e2e: the C-ABI hot path with HOST buffers (H2D + D2H inside the timed region) -------
     Jv_host = torch.empty(nnzJ, dtype=torch.float64).pin_memory()
@@ -418,7 +421,7 @@ def run_c2(args, torch, dist, local):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_string(g) + ", nnzH=%d" % nnzH,
-                       "solver": "%s rtol=%g (single-reduction CG, one persistent kernel per solve)" % (args.solver, args.pcg_rtol),
+                       "solver": "%s rtol=%g (one persistent cooperative kernel per solve)" % (args.solver, args.pcg_rtol),
                        "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
                        "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s,
                        "lm_bodies_per_solve": BODIES_PER_SOLVE, "fixed_iterations": True,
@@ -491,7 +494,9 @@ def run_c5(args, torch, dist, world, rank, local):
     stages = h.stage_ms()
     h.stage_reset(False)
     nnzH_loc = h.h_nnz()
-    roof = _roofline(h, stages, K, lin_iters_roof, prob.xSize, prob.ESize, int(prob.pattern()[2][-1]), nnzH_loc, False)
+    roof = _roofline(h, stages, K, lin_iters_roof, prob.xSize, prob.ESize, int(prob.pattern()[2][-1]), nnzH_loc, False,
+                     "pcg_sr_kernel<true> (whole halo-mode Jacobi-PCG solve of one rank: SpMV + in-kernel halo exchange + one all-to-all reduction per iteration)"
+                     if fused else "pcg_solve_halo launches (NCCL path)")
     roof["note"] = "rank 0's kernel on its LOCAL system (n_loc=%d unknowns incl. ghosts) against one GPU's HBM peak" % prob.xSize
 
     # ---- e2e: host buffers (this rank's local Jacobian values and residual), H2D + D2H inside the timed region
@@ -543,7 +548,7 @@ def run_c5(args, torch, dist, world, rank, local):
     flag = torch.tensor([1 if ghosts_ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     check = {"relres_of_first_step": relres, "relres_ok": bool(relres <= 1e-12),
-             "lm_solve": {"ret": bool(ret), "currIter": int(lm2.currIter), "exit_path": int(lm2.exit_path), "factorizations": int(lm2.factorizations),
+             "lm_solve": {"ret": bool(ret), "currIter": int(lm2.currIter), "exit_path": str(lm2.exit_path), "factorizations": int(lm2.factorizations),
                           "energy": float(lm2.energy), "x_sum": float(sums[0].item()), "x_sumsq": float(sums[1].item()),
                           "pcg_iterations": int(lm2.linear_iterations)},
              "ghost_copies_bit_identical": bool(int(flag.item()) == 1)}

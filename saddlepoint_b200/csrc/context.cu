@@ -123,7 +123,9 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     h->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SPB_PCG_MULTI")) h->pcg_persistent = !(e[0] == '1');
     if (!prop.cooperativeLaunch) h->pcg_persistent = false;
-    if (const char* e = getenv("SPB_PCG_VARIANT")) h->pcg_single_reduction = !(e[0] == 'c');  // "classic": textbook recurrences
+    // one GPU: the textbook three-phase kernel (pcg.cu) is the default -- measured 65.5 vs 69.3 us per iteration at C2;
+    // "sr" selects the single-reduction kernel (pcg_peer.cu), which the multi-GPU halo mode always uses
+    if (const char* e = getenv("SPB_PCG_VARIANT")) h->pcg_single_reduction = (e[0] == 's');
     if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
     if (const char* e = getenv("SPB_PCG_PIN_MB")) h->pcg_pin_mb = atof(e);
     if (const char* e = getenv("SPB_PCG_COL16")) h->pcg_col16 = e[0] != '0';

@@ -242,10 +242,10 @@ void peer_window_setup(spb_context* h) {
   off += 256;
   L.slots = off;
   off = align(off + sizeof(PeerSlot) * 2 * (size_t)R);
-  L.band_from_left = off;
-  off = align(off + sizeof(double) * 2 * (size_t)S->band);
+  L.band_from_left = off;  // two 8-byte words (payload half + tag) per double, two parities
+  off = align(off + sizeof(unsigned long long) * 2 * 2 * (size_t)S->band);
   L.band_from_right = off;
-  off = align(off + sizeof(double) * 2 * (size_t)S->band);
+  off = align(off + sizeof(unsigned long long) * 2 * 2 * (size_t)S->band);
   L.bytes = off;
   cudaStream_t st = h->stream;
   SPB_CUDA(cudaMalloc((void**)&S->win, L.bytes));

@@ -5,7 +5,7 @@
 // Recurrences: Chronopoulos & Gear's rearrangement of CG (u = M^-1 r, w = A u, s = A p kept by recurrence):
 //     gamma = (r,u), delta = (w,u), rr = (r,r)                      <- the only reduction
 //     beta = gamma/gamma_old, alpha = gamma / (delta - beta*gamma/alpha_old)
-//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = dinv r ; w = A u
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; u -= alpha dinv s (r = u/dinv is not stored) ; w = A u
 // Same iterates as textbook CG in exact arithmetic; on the LM systems of this repo the iteration counts are
 // identical and the solutions agree to 4e-16 (tests/test_gpu_solve.py).  An iteration is two phases and two grid
 // barriers (pcg_persistent_kernel in pcg.cu: three phases, three barriers, two reductions):
@@ -16,14 +16,14 @@
 // ncclSend/ncclRecv halo swap and two scalar ncclAllReduce calls: at 8 ranks ~120 us of a 287 us iteration is
 // launch + NCCL latency although nothing of size n moves.  Here nothing leaves the kernel:
 //   * the rows of the two exchanged bands are multiplied FIRST, spread over all warps of the grid, and written
-//     straight into the neighbours' windows (peer-mapped device memory: plain coalesced stores over NVLink); the
-//     block that completes a band publishes it with one release store on the neighbour.  The slab is in flight
-//     while the interior rows are multiplied; the neighbour's slab is added afterwards (q = mine + theirs: the
-//     owner and the ghost holder end up with the same bits, a + b being commutative);
-//   * the reduction is a flag-in-word all-to-all: block 0 writes this rank's three partial sums into slot [rank] of
-//     every rank's window as 8-byte words that carry 32 payload bits and the round tag (no fence, no separate
-//     flag), every block polls its own window and adds the slots in rank order: all blocks of all ranks hold
-//     bit-identical alpha / beta / stop decisions;
+//     straight into the neighbours' windows (peer-mapped device memory, coalesced stores over NVLink) as 8-byte words
+//     that carry 32 payload bits and the exchange tag: no fence, no "slab complete" flag, no ticket.  The slab is in
+//     flight while the interior rows are multiplied; afterwards every band row adds the neighbour's view as soon as
+//     its two words carry the tag (q = mine + theirs: the owner and the ghost holder end up with the same bits, a + b
+//     being commutative);
+//   * the reduction is an all-to-all in the same flag-in-word form: block 0 writes this rank's three partial sums into
+//     slot [rank] of every rank's window, every block polls its own window and adds the slots in rank order: all
+//     blocks of all ranks hold bit-identical alpha / beta / stop decisions;
 //   * vector updates run redundantly on the ghost entries from identical inputs, so no vector is ever exchanged.
 // Waiting is bounded: a spin that exceeds the timeout raises an abort word in every rank's window; the kernels
 // leave at their next grid-uniform check and the solve returns SPB_ERR_STATE.
@@ -229,8 +229,7 @@ struct SrPcgParams {
   const double* b;
   const double* dinv;
   double* x;
-  double* r;
-  double* u;  // dinv * r
+  double* u;  // dinv * r (the residual r itself is never stored)
   double* p;
   double* s;  // H p (by recurrence)
   double* w;  // H u
@@ -256,13 +255,12 @@ struct SrPcgParams {
 // rows of band slice index k (0 <= k < nbs): the left band's slices first, then the right band's
 #define SPB_BAND_SLICE(k) ((k) < sbl ? (k) : sbr + ((k)-sbl))
 
-template <bool PEER>
-__global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
+template <bool PEER, int MINB>
+__global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double smk[32];
   __shared__ double bck[4];
   __shared__ unsigned int shw[PEER ? 256 : 1];
-  __shared__ int band_cnt[2];
   const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int n = P.n;
@@ -300,7 +298,6 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
         const double bi = P.b[row];
         const double ui = bi * P.dinv[row];
         P.x[row] = 0.0;
-        P.r[row] = bi;
         P.u[row] = ui;
         P.p[row] = 0.0;
         P.s[row] = 0.0;
@@ -323,10 +320,13 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
     double acc3[3] = {acc_ru, 0.0, acc_rr};
     const int par = (int)(seq & 1ull);
     if (PEER) {
-      // band rows first: to memory and straight into the neighbours' windows (32 lanes = 256 contiguous bytes)
-      double* const tl = reinterpret_cast<double*>(P.left + P.V.L.band_from_right) + (size_t)par * band;  // my view of the left band -> left's "from right"
-      double* const tr = reinterpret_cast<double*>(P.right + P.V.L.band_from_left) + (size_t)par * band;
-      int nl = 0, nr = 0;
+      // band rows first: to memory and straight into the neighbours' windows.  Every double travels as two 8-byte words
+      // that carry 32 payload bits and the exchange tag (the flag-in-word form of NCCL's LL protocol): a word is complete
+      // the moment its tag matches, so the writer needs no fence, no "slab complete" flag and no block barrier, and the
+      // reader can take each row as soon as it has landed.  32 lanes write 512 contiguous bytes over NVLink.
+      unsigned long long* const tl = reinterpret_cast<unsigned long long*>(P.left + P.V.L.band_from_right) + (size_t)par * band * 2;  // my view of the left band -> left's "from right"
+      unsigned long long* const tr = reinterpret_cast<unsigned long long*>(P.right + P.V.L.band_from_left) + (size_t)par * band * 2;
+      const unsigned long long tagw = ((seq + 1) & 0xffffffffull) << 32;
       for (int k = gw; k < nbs; k += GW) {
         const int slice = SPB_BAND_SLICE(k);
         const double acc = (P.col16 && P.s16[slice])
@@ -335,35 +335,11 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
         const int row = slice * 32 + lane;
         if (row < n) {
           P.w[row] = acc;
-          if (row < band) tl[row] = acc;
-          else if (row >= rb) tr[row - rb] = acc;
-        }
-        if (k < sbl) ++nl; else ++nr;
-      }
-      if (block_has_band) {
-        if (tid < 2) band_cnt[tid] = 0;
-        __threadfence_system();  // this thread's slab stores are ordered before the ticket below
-        __syncthreads();
-        if (lane == 0) {
-          if (nl) atomicAdd(&band_cnt[0], nl);
-          if (nr) atomicAdd(&band_cnt[1], nr);
-        }
-        __syncthreads();
-        if (tid == 0) {
-          // the block that completes a band (every slice of it written, by whichever blocks) publishes it
-          if (band_cnt[0] > 0) {
-            const unsigned long long t = atomicAdd(&P.ctl->sent_left, (unsigned long long)band_cnt[0]) + (unsigned long long)band_cnt[0];
-            if (t == (unsigned long long)sbl * (seq + 1)) {
-              __threadfence_system();
-              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.left + P.V.L.flag_from_right), seq + 1);
-            }
-          }
-          if (band_cnt[1] > 0) {
-            const unsigned long long t = atomicAdd(&P.ctl->sent_right, (unsigned long long)band_cnt[1]) + (unsigned long long)band_cnt[1];
-            if (t == (unsigned long long)(P.nslices - sbr) * (seq + 1)) {
-              __threadfence_system();
-              st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.right + P.V.L.flag_from_left), seq + 1);
-            }
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(acc);
+          unsigned long long* dst = row < band ? tl + 2 * (size_t)row : (row >= rb ? tr + 2 * (size_t)(row - rb) : nullptr);
+          if (dst) {
+            st_relaxed_sys_u64(dst, (bits & 0xffffffffull) | tagw);
+            st_relaxed_sys_u64(dst + 1, (bits >> 32) | tagw);
           }
         }
       }
@@ -383,29 +359,27 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
     if (PEER) {
       // the neighbours' views of the band rows have been in flight meanwhile: w = mine + theirs
       if (block_has_band) {
-        int ok = 1;
-        if (tid == 0) {
-          if (!peer_wait_ge(P.V, reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.flag_from_left), seq + 1)) ok = 0;
-          if (!peer_wait_ge(P.V, reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.flag_from_right), seq + 1)) ok = 0;
-        }
-        ok = __syncthreads_and(ok);
-        if (!ok) failed = 1.0;
-        const double* const fl = reinterpret_cast<const double*>(P.V.win + P.V.L.band_from_left) + (size_t)par * band;
-        const double* const fr = reinterpret_cast<const double*>(P.V.win + P.V.L.band_from_right) + (size_t)par * band;
+        const unsigned long long* const fl = reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.band_from_left) + (size_t)par * band * 2;
+        const unsigned long long* const fr = reinterpret_cast<const unsigned long long*>(P.V.win + P.V.L.band_from_right) + (size_t)par * band * 2;
+        const unsigned long long tag = (seq + 1) & 0xffffffffull;
+        const unsigned int* const abort_w = reinterpret_cast<const unsigned int*>(P.V.win + P.V.L.abort_word);
+        int bad = 0;
         for (int k = gw; k < nbs; k += GW) {
           const int row = SPB_BAND_SLICE(k) * 32 + lane;
           if (row < n) {
             double wi = P.w[row];
-            if (row < band) {
-              wi += __ldcg(fl + row);
-              P.w[row] = wi;
-            } else if (row >= rb) {
-              wi += __ldcg(fr + (row - rb));
+            if (row < band || row >= rb) {
+              const unsigned long long* src = row < band ? fl + 2 * (size_t)row : fr + 2 * (size_t)(row - rb);
+              unsigned long long w0 = 0, w1 = 0;
+              if (!peer_wait_raw<1>(src, tag, &w0, abort_w, P.V.timeout_ns, P.V.peers, P.V.nranks, P.V.L.abort_word)) bad = 1;
+              if (!peer_wait_raw<1>(src + 1, tag, &w1, abort_w, P.V.timeout_ns, P.V.peers, P.V.nranks, P.V.L.abort_word)) bad = 1;
+              wi += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
               P.w[row] = wi;
             }  // else: an interior row of a slice that straddles a band boundary
             if (row >= lo && row < hi) acc3[1] = fma(wi, P.u[row], acc3[1]);
           }
         }
+        if (__syncthreads_or(bad)) failed = 1.0;
       }
       ++seq;
     }
@@ -463,15 +437,18 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
     {
       auto update_row = [&](int row) {
         if (row < n) {
-          const double ui = P.u[row], wi = P.w[row], pi = P.p[row], si = P.s[row], xi = P.x[row], ri = P.r[row], di = P.dinv[row];
+          const double ui = P.u[row], wi = P.w[row], pi = P.p[row], si = P.s[row], xi = P.x[row], di = P.dinv[row];
           const double pn = fma(beta, pi, ui);
           const double sn = fma(beta, si, wi);
-          const double rn = fma(-alpha, sn, ri);
-          const double un = rn * di;
+          // The residual itself is not stored: only its preconditioned form u = dinv r is kept (it is what the next product
+          // gathers), updated as u -= alpha dinv s; r = u / dinv is formed where the dot products need it.  One vector less
+          // to stream through L2 per iteration and one less dirty in it (ncu: the sixth read-write vector pushed 15 MB per
+          // iteration of write-backs into the H stream's DRAM time).
+          const double un = fma(-alpha * di, sn, ui);
+          const double rn = un / di;
           P.p[row] = pn;
           P.s[row] = sn;
           P.x[row] = fma(alpha, pn, xi);
-          P.r[row] = rn;
           P.u[row] = un;
           if (row >= lo && row < hi) {
             acc_ru = fma(rn, un, acc_ru);
@@ -549,12 +526,23 @@ __global__ void __launch_bounds__(256, 4) pcg_sr_kernel(SrPcgParams P) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
+// blocks per SM the kernel is compiled for: 4 (64 registers) or 3 (80 registers: the eight-deep unrolled loads of the
+// SpMV inner loop are then all issued before the first use); SPB_SR_MINB overrides
+static int sr_minb() {
+  static const int v = getenv("SPB_SR_MINB") ? atoi(getenv("SPB_SR_MINB")) : 3;
+  return v == 4 ? 4 : 3;
+}
+template <bool PEER>
+static void* sr_kernel_ptr() {
+  return sr_minb() == 4 ? (void*)pcg_sr_kernel<PEER, 4> : (void*)pcg_sr_kernel<PEER, 3>;
+}
 template <bool PEER>
 static int sr_grid(spb_context* h, int nslices) {
   static int occ_cached = 0;
   if (occ_cached == 0) {
     int occ = 0;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_sr_kernel<PEER>, 256, 0));
+    if (sr_minb() == 4) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_sr_kernel<PEER, 4>, 256, 0));
+    else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_sr_kernel<PEER, 3>, 256, 0));
     occ_cached = std::max(1, occ);
   }
   return std::max(1, std::min((nslices + 7) / 8, h->num_sms * std::min(occ_cached, 8)));
@@ -571,7 +559,6 @@ static void sr_common(spb_context* h, SrPcgParams& P, const double* d_b, double*
       SPB_CUDA(cudaMemsetAsync(h->d_sc.p, 0, sizeof(PcgScalars), st));
     }
   }
-  SPB_CUDA(h->d_r.alloc(n));
   SPB_CUDA(h->d_p.alloc(n));
   SPB_CUDA(h->d_q.alloc(n));
   SPB_CUDA(h->d_u.alloc(n));
@@ -585,7 +572,6 @@ static void sr_common(spb_context* h, SrPcgParams& P, const double* d_b, double*
   P.b = d_b;
   P.dinv = h->d_dinv.p;
   P.x = d_x;
-  P.r = h->d_r.p;
   P.u = h->d_u.p;
   P.p = h->d_p.p;
   P.s = h->d_q.p;
@@ -652,7 +638,7 @@ spb_status pcg_solve_sr(spb_context* h, const double* d_b, double* d_x, int* ite
   }
   void* args[] = {&P};
   stage_begin(h, ST_PCG);
-  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_sr_kernel<false>, dim3(G), dim3(256), args, 0, st));
+  SPB_CUDA(cudaLaunchCooperativeKernel(sr_kernel_ptr<false>(), dim3(G), dim3(256), args, 0, st));
   stage_end(h, ST_PCG, 1);
   SPB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
   SPB_CUDA(cudaStreamSynchronize(st));
@@ -696,7 +682,7 @@ spb_status pcg_solve_halo_peer(spb_context* h, const double* d_b, double* d_x, i
   }
   void* args[] = {&P};
   stage_begin(h, ST_PCG);
-  SPB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_sr_kernel<true>, dim3(G), dim3(256), args, 0, st));
+  SPB_CUDA(cudaLaunchCooperativeKernel(sr_kernel_ptr<true>(), dim3(G), dim3(256), args, 0, st));
   stage_end(h, ST_PCG, 1);
   SPB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
   PeerCtl ctl;

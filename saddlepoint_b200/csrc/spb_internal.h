@@ -214,17 +214,16 @@ struct PeerSlot {
   unsigned long long w[8];  // w[2k], w[2k+1]: low / high half of value k; 64 bytes = one slot per (parity, source rank)
 };
 struct PeerLayout {  // byte offsets inside a window
-  size_t flag_from_left = 0, flag_from_right = 0;  // u64: number of band exchanges the neighbour has delivered
+  size_t flag_from_left = 0, flag_from_right = 0;  // (reserved)
   size_t abort_word = 0;                           // u32: a rank gave up waiting; everybody stops
   size_t slots = 0;                                // PeerSlot[2][nranks]  (round parity)
-  size_t band_from_left = 0, band_from_right = 0;  // double[2][band]     (exchange parity)
+  size_t band_from_left = 0, band_from_right = 0;  // u64[2][band][2]: halo slabs, payload half + exchange tag per word (exchange parity)
   size_t bytes = 0;
 };
 struct PeerCtl {  // local (not peer-visible) counters that persist across solves
   unsigned long long band_seq;   // band exchanges completed so far
   unsigned long long round;      // all-to-all rounds completed so far
-  unsigned long long sent_left;  // band rows written to the left / right neighbour so far (block tickets)
-  unsigned long long sent_right;
+  unsigned long long reserved0, reserved1;
   int failed, pad;
 };
 struct PeerState {
@@ -339,7 +338,7 @@ struct spb_context {
 
   int pcg_last_iters = 0;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
-  bool pcg_single_reduction = true;  // the two-barrier Chronopoulos-Gear kernel (pcg_peer.cu); false: the three-barrier textbook kernel (pcg.cu)
+  bool pcg_single_reduction = false;  // the two-barrier Chronopoulos-Gear kernel (pcg_peer.cu); false: the three-barrier textbook kernel (pcg.cu)
   int occ_spmv = 0, occ_pcg = 0;
   bool pcg_col16 = true;       // persistent PCG reads 16-bit column deltas where a slice allows it
   double pcg_pin_mb = 0.0;     // MB of H the persistent PCG keeps in L2 (evict_last) across iterations

@@ -41,7 +41,7 @@ lm2 = spb.LMSolver()
 lm2.init(ls, prob, spb.DiagonalDamping(0.01), 100)
 ret = lm2.solve(True, dedupe_evaluations=True, x_out=x)
 out = {"g": g, "n": n, "seed": 20214, "gpus": 1, "ms_per_lm_iteration": ms, "pcg_iterations_per_step": pcg_per_step, "analysis_seconds": analyze_s,
-       "lm_solve": {"ret": bool(ret), "currIter": int(lm2.currIter), "exit_path": int(lm2.exit_path), "factorizations": int(lm2.factorizations),
+       "lm_solve": {"ret": bool(ret), "currIter": int(lm2.currIter), "exit_path": str(lm2.exit_path), "factorizations": int(lm2.factorizations),
                     "energy": float(lm2.energy), "x_sum": float(x.sum().item()), "x_sumsq": float((x * x).sum().item()),
                     "pcg_iterations": int(lm2.linear_iterations)}}
 os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -184,6 +184,7 @@ struct PcgParams {
   int n, nslices, maxit;
   double rtol;
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
+  int sweep;            // 1: slices dealt round-robin to the warps of the grid (see phase 1)
   unsigned long long* phase_ns;  // debug (SPB_PCG_TIMING=1): per block, 9 accumulated phase durations; else null
 };
 
@@ -250,7 +251,10 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
   while (run) {
     // phase 1: q = H p, partial p.q
     {
-      const double loc = spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, s_pin_end, P.col16, P.s16);
+      // sweep: at any moment the whole grid reads one contiguous window of the H stream (slice = global warp + k * warps)
+      // instead of one private range per block
+      const double loc = P.sweep ? spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, 0, P.nslices, 0, P.col16, P.s16, blk * 8 + (tid >> 5), G * 8)
+                                 : spmv_range<false>(P.slice_off, P.col, P.rowlen, P.hval, P.p, P.q, n, s_begin, s_end, s_pin_end, P.col16, P.s16);
       const double bs = block_sum_256(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
@@ -523,6 +527,8 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
       const double h_bytes = 12.0 * (double)h->S.padded;
       P.pin_fraction = h_bytes > 0 ? std::min(1.0, std::max(0.0, h->pcg_pin_mb * 1048576.0 / h_bytes)) : 0.0;
     }
+    static const int sweep = getenv("SPB_SPMV_SWEEP") ? atoi(getenv("SPB_SPMV_SWEEP")) : 1;
+    P.sweep = sweep;
     static const bool phase_timing = getenv("SPB_PCG_TIMING") && atoi(getenv("SPB_PCG_TIMING")) > 0;
     DevBuf<unsigned long long> d_phase;
     P.phase_ns = nullptr;
@@ -1057,6 +1063,7 @@ spb_status pcg_ic0_solve(spb_context* h, const double* d_b, double* d_x, int* it
   P.maxit = h->pcg_maxit;
   P.rtol = h->pcg_rtol;
   P.pin_fraction = 0.0;
+  P.sweep = 0;
   Q.ic = ic_view(I);
   Q.z = I->z.p;
   void* args[] = {&Q};

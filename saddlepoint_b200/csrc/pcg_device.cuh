@@ -164,12 +164,15 @@ template <bool NC>
 __device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
                                              const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
                                              double* y, int n, int s_begin, int s_end, int s_pin_end = 0,
-                                             const uint16_t* __restrict__ col16 = nullptr, const uint8_t* __restrict__ s16 = nullptr) {
+                                             const uint16_t* __restrict__ col16 = nullptr, const uint8_t* __restrict__ s16 = nullptr,
+                                             int first = -1, int step = 8) {
+  // default: the 8 warps of a block stride over the block's contiguous range [s_begin, s_end); first/step override
+  // the walk (sweep order: first = global warp index, step = warps in the grid, s_end = all slices)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double loc = 0.0;
   uint64_t pol = 0;
   if (s_pin_end > s_begin) pol = l2_evict_last_policy();
-  for (int slice = s_begin + warp; slice < s_end; slice += 8) {
+  for (int slice = first >= 0 ? first : s_begin + warp; slice < s_end; slice += step) {
     if (col16 && s16[slice]) loc += spmv_slice<NC, false, true>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
     else if (slice < s_pin_end) loc += spmv_slice<NC, true, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
     else loc += spmv_slice<NC, false, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);

@@ -236,6 +236,7 @@ struct SrPcgParams {
   double* partial;  // 6 * gridDim.x
   PcgScalars* sc;
   int n, nslices, maxit;
+  int sweep;  // 1: slices dealt round-robin to the warps of the grid; 0: contiguous block ranges
   double rtol;
   unsigned long long* phase_ns;  // debug (SPB_PCG_TIMING=1): per block, 8 accumulated phase durations; else null
   // PEER only
@@ -277,8 +278,21 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
   const int sbl = PEER ? (band + 31) / 32 : 0, sbr = PEER ? rb / 32 : P.nslices;
   const int nbs = sbl + (P.nslices - sbr);  // band slices
   const int gw = blk * 8 + warp, GW = G * 8;
-  const int s_begin = sbl + (int)(((int64_t)(sbr - sbl) * blk) / G);
-  const int s_end = sbl + (int)(((int64_t)(sbr - sbl) * (blk + 1)) / G);
+  // Interior slices: dealt round-robin to the warps of the grid, continuing the deal of the band slices (unit t of
+  // [band slices | interior slices] goes to warp t mod GW), so a warp that multiplied a band slice gets one interior
+  // slice less, and at any moment the whole grid reads one contiguous window of the H stream.  P.sweep == 0: contiguous
+  // private block ranges instead (the one-GPU kernel's layout).
+  int i_first, i_end, i_step;
+  if (P.sweep) {
+    const int t0 = gw >= nbs ? gw : gw + ((nbs - gw + GW - 1) / GW) * GW;  // this warp's first unit that is not a band slice
+    i_first = sbl + (t0 - nbs);
+    i_end = sbr;
+    i_step = GW;
+  } else {
+    i_first = sbl + (int)(((int64_t)(sbr - sbl) * blk) / G) + warp;
+    i_end = sbl + (int)(((int64_t)(sbr - sbl) * (blk + 1)) / G);
+    i_step = 8;
+  }
   const bool block_has_band = PEER && (blk * 8 < nbs);
   unsigned long long seq = 0, round = 0;
   if (PEER) {  // counters written by block 0 at the very end of the previous solve (before any grid barrier of this one)
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
     };
     if (PEER)
       for (int k = gw; k < nbs; k += GW) init_row(SPB_BAND_SLICE(k) * 32 + lane);
-    for (int slice = s_begin + warp; slice < s_end; slice += 8) init_row(slice * 32 + lane);
+    for (int slice = i_first; slice < i_end; slice += i_step) init_row(slice * 32 + lane);
   }
   grid.sync();
   double gam_old = 0.0, alpha = 0.0, bb = 0.0, thresh = 0.0, rr = 0.0, denom = 0.0;
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
       }
     }
     SPB_PTICK(0)
-    for (int slice = s_begin + warp; slice < s_end; slice += 8) {
+    for (int slice = i_first; slice < i_end; slice += i_step) {
       const double acc = (P.col16 && P.s16[slice])
                              ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16)
                              : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16);
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
       };
       if (PEER)
         for (int k = gw; k < nbs; k += GW) update_row(SPB_BAND_SLICE(k) * 32 + lane);
-      for (int slice = s_begin + warp; slice < s_end; slice += 8) update_row(slice * 32 + lane);
+      for (int slice = i_first; slice < i_end; slice += i_step) update_row(slice * 32 + lane);
     }
     ++iters;
     SPB_PTICK(5)
@@ -482,7 +496,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
     };
     if (PEER)
       for (int k = gw; k < nbs; k += GW) xx_row(SPB_BAND_SLICE(k) * 32 + lane);
-    for (int slice = s_begin + warp; slice < s_end; slice += 8) xx_row(slice * 32 + lane);
+    for (int slice = i_first; slice < i_end; slice += i_step) xx_row(slice * 32 + lane);
     block_sums<1>(a1, smk);
     // own arrays: a block that left the loop at a break may be followed by blocks still summing the loop's arrays
     if (tid == 0) {
@@ -583,6 +597,8 @@ static void sr_common(spb_context* h, SrPcgParams& P, const double* d_b, double*
   P.maxit = h->pcg_maxit;
   P.rtol = h->pcg_rtol;
   P.phase_ns = nullptr;
+  static const int sweep = getenv("SPB_SPMV_SWEEP") ? atoi(getenv("SPB_SPMV_SWEEP")) : 1;
+  P.sweep = sweep;
   P.ctl = nullptr;
   P.lo = 0;
   P.hi = n;

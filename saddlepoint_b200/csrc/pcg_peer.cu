@@ -624,7 +624,16 @@ static void sr_print_phases(const char* tag, int rank, spb_context* h, const Dev
     }
     o += snprintf(line + o, sizeof(line) - (size_t)o, " %s=%.2f(%.2f..%.2f)", names[k], sum / G, lo, hi);
   }
-  fprintf(stderr, "%s\n", line);
+  if (const char* dir = getenv("SPB_PCG_TIMING_DIR")) {  // one file per rank (the ranks' stderr lines interleave under torchrun)
+    char path[512];
+    snprintf(path, sizeof(path), "%s/pcg_timing_rank%d.txt", dir, rank);
+    if (FILE* f = fopen(path, "a")) {
+      fprintf(f, "%s\n", line);
+      fclose(f);
+    }
+  } else {
+    fprintf(stderr, "%s\n", line);
+  }
 }
 
 static spb_status sr_finish(spb_context* h, int* iters) {

@@ -127,6 +127,7 @@ spb_status spb_create(int device, void* stream, spb_handle* out) {
     // "sr" selects the single-reduction kernel (pcg_peer.cu), which the multi-GPU halo mode always uses
     if (const char* e = getenv("SPB_PCG_VARIANT")) h->pcg_single_reduction = (e[0] == 's');
     if (const char* e = getenv("SPB_PCG_MINB")) h->pcg_minb = atoi(e);
+    if (const char* e = getenv("SPB_PCG_RELAX")) h->pcg_relax_factor = atof(e);
     if (const char* e = getenv("SPB_PCG_PIN_MB")) h->pcg_pin_mb = atof(e);
     if (const char* e = getenv("SPB_PCG_COL16")) h->pcg_col16 = e[0] != '0';
     SPB_CUDA(cudaMallocHost((void**)&h->h_sc, sizeof(PcgScalars)));

@@ -74,6 +74,11 @@ __device__ __forceinline__ double ld_h_f64(const double* p, uint64_t pol) {
   asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   return v;
 }
+// the FP32 copy of the value stream (relaxed-precision products of the late PCG iterations): streaming loads only
+template <bool PIN>
+__device__ __forceinline__ double ld_h_f64(const float* p, uint64_t) {
+  return (double)__ldcs(p);
+}
 __device__ __forceinline__ uint64_t l2_evict_last_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -83,17 +88,21 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
 // C16: the slice's column indices are read from the 16-bit stream (column = row + delta - 32768),
 // 10 instead of 12 bytes per entry; slices with a delta that does not fit keep the 32-bit stream.
 // row sum of one lane's row of a slice (no store): acc = sum_k H(row, c_k) x[c_k], ascending k
-template <bool NC, bool PIN, bool C16>
+// VT: double (the assembled values) or float (their FP32 copy, see pcg.cu "relaxed-precision products").  W32: also
+// write the FP32 copy of every value read (VT = double only): the conversion rides on the solve's first product.
+template <bool NC, bool PIN, bool C16, typename VT = double, bool W32 = false>
 __device__ __forceinline__ double spmv_slice_acc(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
-                                                 const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
-                                                 int n, int slice, int lane, uint64_t pol, const uint16_t* __restrict__ col16) {
+                                                 const int* __restrict__ rowlen, const VT* __restrict__ hval, const double* x,
+                                                 int n, int slice, int lane, uint64_t pol, const uint16_t* __restrict__ col16,
+                                                 float* __restrict__ h32out = nullptr) {
   const int row = slice * 32 + lane;
   const int64_t off = slice_off[slice];
   const int width = (int)((slice_off[slice + 1] - off) >> 5);
   const int len = row < n ? rowlen[row] : 0;
   const int* cp = col + off + lane;
   const uint16_t* cp16 = col16 + off + lane;
-  const double* vp = hval + off + lane;
+  const VT* vp = hval + off + lane;
+  float* wp = W32 ? h32out + off + lane : nullptr;
   const int rbase = row - 32768;
   double acc = 0.0;
   int k = 0;
@@ -105,6 +114,10 @@ __device__ __forceinline__ double spmv_slice_acc(const int64_t* __restrict__ sli
     for (int u = 0; u < 8; ++u) {
       c[u] = C16 ? rbase + (int)__ldcs(cp16 + (k + u) * 32) : ld_h_i32<PIN>(cp + (k + u) * 32, pol);
       v[u] = ld_h_f64<PIN>(vp + (k + u) * 32, pol);
+    }
+    if (W32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) __stcs(wp + (k + u) * 32, (float)v[u]);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) xv[u] = NC ? __ldg(x + c[u]) : x[c[u]];
@@ -128,6 +141,12 @@ __device__ __forceinline__ double spmv_slice_acc(const int64_t* __restrict__ sli
     }
     const double v0 = ld_h_f64<PIN>(vp + (k + 0) * 32, pol), v1 = ld_h_f64<PIN>(vp + (k + 1) * 32, pol),
                  v2 = ld_h_f64<PIN>(vp + (k + 2) * 32, pol), v3 = ld_h_f64<PIN>(vp + (k + 3) * 32, pol);
+    if (W32) {
+      __stcs(wp + (k + 0) * 32, (float)v0);
+      __stcs(wp + (k + 1) * 32, (float)v1);
+      __stcs(wp + (k + 2) * 32, (float)v2);
+      __stcs(wp + (k + 3) * 32, (float)v3);
+    }
     const double x0 = NC ? __ldg(x + c0) : x[c0], x1 = NC ? __ldg(x + c1) : x[c1], x2 = NC ? __ldg(x + c2) : x[c2], x3 = NC ? __ldg(x + c3) : x[c3];
     if (k + 0 < len) acc = fma(v0, x0, acc);
     if (k + 1 < len) acc = fma(v1, x1, acc);
@@ -137,17 +156,19 @@ __device__ __forceinline__ double spmv_slice_acc(const int64_t* __restrict__ sli
   for (; k < width; ++k) {
     const int c0 = C16 ? rbase + (int)__ldcs(cp16 + k * 32) : ld_h_i32<PIN>(cp + k * 32, pol);
     const double v0 = ld_h_f64<PIN>(vp + k * 32, pol);
+    if (W32) __stcs(wp + k * 32, (float)v0);
     const double x0 = NC ? __ldg(x + c0) : x[c0];
     if (k < len) acc = fma(v0, x0, acc);
   }
   return acc;
 }
 
-template <bool NC, bool PIN, bool C16>
+template <bool NC, bool PIN, bool C16, typename VT = double, bool W32 = false>
 __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
-                                             const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
-                                             double* y, int n, int slice, int lane, uint64_t pol, const uint16_t* __restrict__ col16) {
-  const double acc = spmv_slice_acc<NC, PIN, C16>(slice_off, col, rowlen, hval, x, n, slice, lane, pol, col16);
+                                             const int* __restrict__ rowlen, const VT* __restrict__ hval, const double* x,
+                                             double* y, int n, int slice, int lane, uint64_t pol, const uint16_t* __restrict__ col16,
+                                             float* __restrict__ h32out = nullptr) {
+  const double acc = spmv_slice_acc<NC, PIN, C16, VT, W32>(slice_off, col, rowlen, hval, x, n, slice, lane, pol, col16, h32out);
   const int row = slice * 32 + lane;
   if (row < n) {
     y[row] = acc;
@@ -160,12 +181,12 @@ __device__ __forceinline__ double spmv_slice(const int64_t* __restrict__ slice_o
 // warps of a block stride over the range.  Returns this thread's share of x.y.
 // NC=true: x is immutable for the kernel's lifetime, gathers may use the non-coherent path.
 // Slices below s_pin_end are loaded with the L2 evict_last policy (see ld_h_*).
-template <bool NC>
+template <bool NC, typename VT = double, bool W32 = false>
 __device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_off, const int* __restrict__ col,
-                                             const int* __restrict__ rowlen, const double* __restrict__ hval, const double* x,
+                                             const int* __restrict__ rowlen, const VT* __restrict__ hval, const double* x,
                                              double* y, int n, int s_begin, int s_end, int s_pin_end = 0,
                                              const uint16_t* __restrict__ col16 = nullptr, const uint8_t* __restrict__ s16 = nullptr,
-                                             int first = -1, int step = 8) {
+                                             int first = -1, int step = 8, float* __restrict__ h32out = nullptr) {
   // default: the 8 warps of a block stride over the block's contiguous range [s_begin, s_end); first/step override
   // the walk (sweep order: first = global warp index, step = warps in the grid, s_end = all slices)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -173,9 +194,9 @@ __device__ __forceinline__ double spmv_range(const int64_t* __restrict__ slice_o
   uint64_t pol = 0;
   if (s_pin_end > s_begin) pol = l2_evict_last_policy();
   for (int slice = first >= 0 ? first : s_begin + warp; slice < s_end; slice += step) {
-    if (col16 && s16[slice]) loc += spmv_slice<NC, false, true>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
-    else if (slice < s_pin_end) loc += spmv_slice<NC, true, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
-    else loc += spmv_slice<NC, false, false>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16);
+    if (col16 && s16[slice]) loc += spmv_slice<NC, false, true, VT, W32>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16, h32out);
+    else if (slice < s_pin_end) loc += spmv_slice<NC, true, false, VT, W32>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16, h32out);
+    else loc += spmv_slice<NC, false, false, VT, W32>(slice_off, col, rowlen, hval, x, y, n, slice, lane, pol, col16, h32out);
   }
   return loc;
 }

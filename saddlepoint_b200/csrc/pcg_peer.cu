@@ -226,6 +226,8 @@ struct SrPcgParams {
   const uint8_t* s16;
   const int* rowlen;
   const double* hval;
+  float* hval32;     // FP32 copy of the value stream, or nullptr (always FP64)
+  double relax_tol;  // switch to it once ||r||/||b|| <= relax_tol
   const double* b;
   const double* dinv;
   double* x;
@@ -246,6 +248,20 @@ struct SrPcgParams {
   char* right;
   PeerView V;
 };
+
+// one row sum of w = H u; vmode 0: FP64 values, 1: FP64 values and write their FP32 copy (the solve's first product),
+// 2: the FP32 copy (relaxed-precision products once the residual is small; see PcgParams::hval32 in pcg.cu)
+__device__ __forceinline__ double sr_row_acc(const SrPcgParams& P, int vmode, int slice, int lane) {
+  const bool c16 = P.col16 && P.s16[slice];
+  if (vmode == 2)
+    return c16 ? spmv_slice_acc<false, false, true, float, false>(P.slice_off, P.col, P.rowlen, P.hval32, P.u, P.n, slice, lane, 0, P.col16)
+               : spmv_slice_acc<false, false, false, float, false>(P.slice_off, P.col, P.rowlen, P.hval32, P.u, P.n, slice, lane, 0, P.col16);
+  if (vmode == 1)
+    return c16 ? spmv_slice_acc<false, false, true, double, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, P.n, slice, lane, 0, P.col16, P.hval32)
+               : spmv_slice_acc<false, false, false, double, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, P.n, slice, lane, 0, P.col16, P.hval32);
+  return c16 ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, P.n, slice, lane, 0, P.col16)
+             : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, P.n, slice, lane, 0, P.col16);
+}
 
 #define SPB_PTICK(k)                                         \
   if (P.phase_ns && tid == 0) {                              \
@@ -328,10 +344,12 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
   grid.sync();
   double gam_old = 0.0, alpha = 0.0, bb = 0.0, thresh = 0.0, rr = 0.0, denom = 0.0;
   int iters = 0, breakdown = 0;
+  bool use32 = false;
   unsigned long long tick_ = P.phase_ns ? peer_global_ns() : 0ull;
   for (;;) {
     // ---- phase B: w = H_loc u, with (r,u), (w,u), (r,r) over the owned rows -------------------------------------
     double acc3[3] = {acc_ru, 0.0, acc_rr};
+    const int vmode = use32 ? 2 : ((P.hval32 && iters == 0) ? 1 : 0);
     const int par = (int)(seq & 1ull);
     if (PEER) {
       // band rows first: to memory and straight into the neighbours' windows.  Every double travels as two 8-byte words
@@ -343,9 +361,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
       const unsigned long long tagw = ((seq + 1) & 0xffffffffull) << 32;
       for (int k = gw; k < nbs; k += GW) {
         const int slice = SPB_BAND_SLICE(k);
-        const double acc = (P.col16 && P.s16[slice])
-                               ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16)
-                               : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16);
+        const double acc = sr_row_acc(P, vmode, slice, lane);
         const int row = slice * 32 + lane;
         if (row < n) {
           P.w[row] = acc;
@@ -360,9 +376,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
     }
     SPB_PTICK(0)
     for (int slice = i_first; slice < i_end; slice += i_step) {
-      const double acc = (P.col16 && P.s16[slice])
-                             ? spmv_slice_acc<false, false, true>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16)
-                             : spmv_slice_acc<false, false, false>(P.slice_off, P.col, P.rowlen, P.hval, P.u, n, slice, lane, 0, P.col16);
+      const double acc = sr_row_acc(P, vmode, slice, lane);
       const int row = slice * 32 + lane;
       if (row < n) {
         P.w[row] = acc;
@@ -436,6 +450,7 @@ __global__ void __launch_bounds__(256, MINB) pcg_sr_kernel(SrPcgParams P) {
       denom = delta;
     } else {
       if (!(rr > thresh) || iters >= P.maxit) break;
+      if (P.hval32 && rr <= P.relax_tol * P.relax_tol * bb) use32 = true;  // same bits in every block of every rank
       beta = gam / gam_old;
       denom = delta - beta * gam / alpha;  // = p.Hp of the new direction
     }
@@ -583,6 +598,13 @@ static void sr_common(spb_context* h, SrPcgParams& P, const double* d_b, double*
   P.s16 = h->d_slice16.p;
   P.rowlen = h->d_rowlen.p;
   P.hval = h->d_hval.p;
+  P.hval32 = nullptr;
+  P.relax_tol = 0.0;
+  if (h->pcg_relax_factor > 0.0) {
+    SPB_CUDA(h->d_hval32.alloc((size_t)h->S.padded));
+    P.hval32 = h->d_hval32.p;
+    P.relax_tol = std::min(1.0, h->pcg_rtol * h->pcg_relax_factor);
+  }
   P.b = d_b;
   P.dinv = h->d_dinv.p;
   P.x = d_x;

@@ -318,6 +318,7 @@ struct spb_context {
   spb::DevBuf<int64_t> d_slice_off;
   spb::DevBuf<int64_t> d_pos_of_slot;  // lazily built: CSC slot -> storage position
   spb::DevBuf<double> d_hval, d_hdiag, d_dinv;
+  spb::DevBuf<float> d_hval32;  // FP32 copy of the value stream (relaxed-precision products of the late PCG iterations)
   // device: vectors
   spb::DevBuf<double> d_rhs, d_dvec, d_Jv_stage, d_f_stage, d_vec_stage, d_vec_stage2;
   spb::DevBuf<double> d_r, d_p, d_q, d_x, d_partial, d_u, d_w;
@@ -337,6 +338,9 @@ struct spb_context {
   spb::PeerState* peer = nullptr;  // peer-memory windows of the halo mode (dist.cu), owned
 
   int pcg_last_iters = 0;
+  // relaxed-precision products: switch to the FP32 value stream once ||r||/||b|| <= pcg_rtol * pcg_relax_factor
+  // (1e6: 1e-7 at the default rtol 1e-13); 0 = always FP64.  SPB_PCG_RELAX overrides.
+  double pcg_relax_factor = 1e6;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
   bool pcg_single_reduction = false;  // the two-barrier Chronopoulos-Gear kernel (pcg_peer.cu); false: the three-barrier textbook kernel (pcg.cu)
   int occ_spmv = 0, occ_pcg = 0;

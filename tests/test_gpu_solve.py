@@ -303,3 +303,41 @@ def test_pcg_breakdown_and_nan_systems(spb):
     x1, it1, st1 = h.solve(b)
     assert st1 == spb.capi.SPB_OK and it1 == it0 and np.array_equal(x1, x0)
     h.close()
+
+
+@pytest.mark.parametrize("variant", ["classic", "sr"])
+def test_relaxed_precision_products_keep_the_step(spb, monkeypatch, variant):
+    """Late PCG iterations read the matrix values from an FP32 copy (inexact-Krylov relaxation: once ||r||/||b|| <= 1e-7
+    a product error of 6e-8 ||H|| is below what an rtol of 1e-13 allows).  Against the all-FP64 solve on the same system:
+    same iteration count (+-1), step within 1e-12 relative (north_star: 1e-10), true FP64 residual at the rtol level."""
+    import torch
+    monkeypatch.setenv("SPB_PCG_VARIANT", variant)
+    g = 160
+    out = {}
+    for relax in ("0", "1e6"):
+        monkeypatch.setenv("SPB_PCG_RELAX", relax)
+        h = spb.Handle(0)
+        prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
+        m, n, colptr, rowidx = prob.pattern()
+        T = prob.c_traits()
+        x = torch.ones(n, dtype=torch.float64, device="cuda")
+        E = torch.empty(m, dtype=torch.float64, device="cuda")
+        Jv = torch.empty(int(colptr[-1]), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        T.objective_jacobian(T.user, x.data_ptr(), E.data_ptr(), Jv.data_ptr(), None)
+        torch.cuda.synchronize()
+        h.set_solver(spb.SOLVER_PCG_JACOBI, 1e-13, 10000)
+        h.analyze(m, n, colptr, rowidx)
+        res = []
+        for lam in (0.01, 1e-4):
+            h.assemble(Jv, E, lam)
+            h.factorize()
+            d, it, st = h.solve(None)
+            assert st == spb.capi.SPB_OK
+            res.append((d.copy(), it, h.residual_check(d)))
+        out[relax] = res
+        prob.close(); h.close()
+    for (d0, it0, r0), (d1, it1, r1) in zip(out["0"], out["1e6"]):
+        assert abs(it0 - it1) <= 1 and it0 > 30
+        assert np.linalg.norm(d1 - d0) <= 1e-12 * np.linalg.norm(d0)
+        assert r0 <= 2e-13 and r1 <= 2e-13

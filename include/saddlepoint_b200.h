@@ -184,6 +184,19 @@ void spb_lm_default_options(spb_lm_options* o);
 spb_status spb_lm_solve(spb_handle h, const spb_traits* traits, const spb_lm_options* opt, spb_lm_result* res,
                         double* x_out, int x_mem, double* trace, int32_t trace_cap, int32_t* trace_len);
 
+typedef struct spb_problem* spb_problem_t;
+/* ---- many independent problems at once (config C4) ---------------------------------------------------------- */
+/* `traits` describes ONE block-diagonal problem made of `nproblems` independent problems of equal size: problem p owns
+ * unknowns [p*xSize/nproblems, (p+1)*xSize/nproblems) and residual rows [p*ESize/nproblems, ...); its Jacobian block may
+ * have its own pattern.  Every problem runs LMSolver::solve's loop (LMSolver.h:86-191, with dedupe_evaluations semantics)
+ * with its own lambda, acceptance, stop tests and exit path, but every stage is one launch over all problems: one fused
+ * assembly, one persistent PCG kernel with per-problem dot products and convergence, a device-side controller; finished
+ * problems are frozen while the others continue.  results: nproblems records; x_out: xSize values.  Jacobi-PCG only. */
+spb_status spb_lm_solve_batch(spb_handle h, const spb_traits* traits, int32_t nproblems, const spb_lm_options* opt, spb_lm_result* results,
+                              double* x_out, int x_mem);
+/* nproblems LF problems (seeds seed, seed+seed_stride, ...) as one block-diagonal problem for spb_lm_solve_batch */
+spb_status spb_problem_lf_batch(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t seed_stride, int32_t nproblems, spb_problem_t* out);
+
 /* ---- check_traits (check_traits.h:19-83) on the GPU -------------------------------------- */
 /* Compares the traits' Jacobian at x with central finite differences (step 10e-5, entries with
  * |FE| <= 10e-7 dropped, discrepancies counted above 10e-7 -- the reference's constants when the
@@ -205,7 +218,6 @@ spb_status spb_check_traits(spb_handle h, const spb_traits* traits, const double
                             spb_check_result* out, double* fe_vals);
 
 /* ---- built-in device-resident benchmark traits --------------------------- */
-typedef struct spb_problem* spb_problem_t;
 /* "LF": sparse analogue of benchmark/linear_function: g x g torus, m=rows_mult*n,
  * 8 nnz/row, counter-based splitmix64 data, f = A x - 1, x0 = 1. */
 spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, spb_problem_t* out);

@@ -53,6 +53,60 @@ def solve_problem(handle, spec, solver=SOLVER_CHOLESKY, verbose=True):
     return out
 
 
+EXIT = {1: "foo", 2: "factorize_failed", 3: "direction_small", 4: "func_tol", 5: "traits_stop", 6: "max_iter"}
+
+
+def solve_batch_fused(handle, indices, n=10000, seed=20213, verbose=True, keep_x=False, pcg_rtol=1e-13):
+    """The C4 problems `indices` (all Rosenbrock = even indices, or all LF = odd indices) as ONE block-diagonal
+    problem through spb_lm_solve_batch: one fused assembly, one persistent PCG kernel and one controller launch per
+    stage for all of them; per-problem lambda / acceptance / stop tests on the device.  Returns one dict per problem
+    (same keys as solve_problem)."""
+    import ctypes as C
+    from . import capi
+    from .solver import _c_traits
+    indices = list(indices)
+    B = len(indices)
+    kinds = {i % 2 for i in indices}
+    if len(kinds) != 1:
+        raise ValueError("a fused batch holds problems of one kind (even indices: Rosenbrock, odd: LF)")
+    if 0 in kinds:
+        specs = [c4_problem_spec(i, n=n, seed=seed) for i in indices]
+        nb = specs[0]["nblocks"]
+        prob = BuiltinProblem(handle, "rosenbrock", nblocks=nb * B, x0=np.concatenate([s["x0"] for s in specs]))
+        max_it = specs[0]["maxIterations"]
+    else:
+        stride = indices[1] - indices[0] if B > 1 else 1
+        if any(indices[k + 1] - indices[k] != stride for k in range(B - 1)):
+            raise ValueError("LF batch indices must be equally spaced")
+        spec0 = c4_problem_spec(indices[0], n=n, seed=seed)
+        prob = BuiltinProblem(handle, "lf_batch", g=spec0["g"], rows_mult=2, seed=spec0["seed"], seed_stride=stride, nproblems=B)
+        max_it = spec0["maxIterations"]
+    handle.set_solver(SOLVER_PCG_JACOBI, pcg_rtol, 10000)
+    T, keep = _c_traits(prob)
+    O = capi.LMOptions()
+    handle.L.spb_lm_default_options(C.byref(O))
+    O.maxIterations = max_it
+    O.verbose = int(bool(verbose))
+    O.dedupe_evaluations = 1
+    R = (capi.LMResult * B)()
+    x = np.empty(T.xSize, np.float64)
+    handle._check(handle.L.spb_lm_solve_batch(handle.h, C.byref(T), B, C.byref(O), R, C.c_void_p(x.ctypes.data), capi.SPB_HOST))
+    n_per = T.xSize // B
+    out = []
+    for p in range(B):
+        r = {"ret": bool(R[p].ret), "currIter": R[p].currIter, "factorizations": R[p].factorizations, "energy": R[p].energy,
+             "exit_path": EXIT.get(R[p].exit_path, R[p].exit_path), "lambda": R[p].lambda_, "linear_iterations": R[p].linear_iterations,
+             "seconds": R[p].seconds_total, "seconds_analyze": R[p].seconds_analyze}
+        xp = x[p * n_per:(p + 1) * n_per]
+        if keep_x:
+            r["x"] = xp.copy()
+        else:
+            r["xnorm"] = float(np.linalg.norm(xp))
+        out.append(r)
+    prob.close()
+    return out
+
+
 def solve_batch(nproblems, rank=0, world=1, handle=None, make_spec=c4_problem_spec, solver=SOLVER_CHOLESKY, dist=None, keep_x=False,
                 workers=1):
     """Solve this rank's block of the batch; with world > 1 gather every rank's results."""

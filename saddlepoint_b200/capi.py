@@ -79,6 +79,8 @@ SYMBOLS = [
     ("spb_lm_solve", C.c_int, [vp, C.POINTER(Traits), C.POINTER(LMOptions), C.POINTER(LMResult), vp, C.c_int, vp,
                                C.c_int32, C.POINTER(C.c_int32)]),
     ("spb_problem_lf", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(vp)]),
+    ("spb_problem_lf_batch", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
+    ("spb_lm_solve_batch", C.c_int, [vp, C.POINTER(Traits), C.c_int32, C.POINTER(LMOptions), C.POINTER(LMResult), vp, C.c_int]),
     ("spb_problem_rosenbrock", C.c_int, [vp, C.c_int32, vp, C.POINTER(vp)]),
     ("spb_problem_lf_cols", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     ("spb_problem_blocks", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_double, C.c_double, vp, C.POINTER(vp)]),

@@ -416,19 +416,22 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
     const int* __restrict__ colchunk, const int* __restrict__ Jcolptr, const int* __restrict__ Jrow,
     const double* __restrict__ Jv, const double* __restrict__ f, double lambda, const int* __restrict__ nup1,
     const int64_t* __restrict__ slice_off, double* __restrict__ hval, double* __restrict__ hdiag,
-    double* __restrict__ rhs, double* __restrict__ dvec, unsigned long long* __restrict__ foo_bits, int defer_damping) {
+    double* __restrict__ rhs, double* __restrict__ dvec, unsigned long long* __restrict__ foo_bits, int defer_damping,
+    const double* __restrict__ lam_vec, int lam_n_per) {
   __shared__ double sv[kEntTile + kEntTile / 16 + 1], sf[kEntTile + kEntTile / 16 + 1];
   __shared__ double s_max[8];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int j0 = colchunk[c], j1 = colchunk[c + 1];
   const int e0 = Jcolptr[j0], e1 = Jcolptr[j1];
   constexpr int CPT = kColCap / 256;  // columns per thread
-  double a_vf[CPT], a_d[CPT], a_vv[CPT];
+  double a_vf[CPT], a_d[CPT], a_vv[CPT], lam[CPT];
   bool started[CPT];
   int cs[CPT], ce[CPT];
 #pragma unroll
   for (int k = 0; k < CPT; ++k) {
     const int j = j0 + tid + k * 256;
+    // batched independent problems (block-diagonal Jacobian): every problem has its own lambda
+    lam[k] = (lam_vec && j < j1) ? lam_vec[j / lam_n_per] : lambda;
     a_vf[k] = 0.0;
     a_d[k] = 0.0;
     a_vv[k] = 0.0;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(256) assemble_cols_kernel(
       for (int e = lo; e < hi; ++e) {
         const double v = sv[skew(e - a)], fr = sf[skew(e - a)];
         a_vf[k] = __dadd_rn(a_vf[k], __dmul_rn(v, fr));              // tmp += v*f   (LMSolver.h:117)
-        a_d[k] = __dadd_rn(a_d[k], __dmul_rn(__dmul_rn(lambda, v), v));  // (lambda*v)*v (DiagonalDamping.h:35)
+        a_d[k] = __dadd_rn(a_d[k], __dmul_rn(__dmul_rn(lam[k], v), v));  // (lambda*v)*v (DiagonalDamping.h:35)
         const double vv = __dmul_rn(v, v);
         a_vv[k] = started[k] ? __dadd_rn(a_vv[k], vv) : vv;          // first product assigned, then added
         started[k] = true;
@@ -734,7 +737,7 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     assemble_cols_kernel<<<h->ncolchunks, 256, 0, st>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda,
                                                         h->d_nup1.p, h->d_slice_off.p, hv, h->d_hdiag.p,
                                                         part ? h->d_rhs_part.p : h->d_rhs.p, part ? h->d_dvec_part.p : h->d_dvec.p,
-                                                        h->d_foo_bits.p, (part || h->halo_mode) ? 1 : 0);
+                                                        h->d_foo_bits.p, (part || h->halo_mode) ? 1 : 0, h->d_lambda_vec, h->lambda_n_per);
     ++nl;
   }
   if (h->nchunks > 0) {
@@ -897,7 +900,7 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
     if (k == kParts - 1) cc_end = h->ncolchunks;
     if (cc_end > cc_done) {
       assemble_cols_kernel<<<cc_end - cc_done, 256, 0, st>>>(h->d_colchunk.p + cc_done, h->d_Jcolptr.p, h->d_Jrow.p, dJ, d_f, lambda, h->d_nup1.p,
-                                                            h->d_slice_off.p, h->d_hval.p, h->d_hdiag.p, h->d_rhs.p, h->d_dvec.p, h->d_foo_bits.p, 0);
+                                                            h->d_slice_off.p, h->d_hval.p, h->d_hdiag.p, h->d_rhs.p, h->d_dvec.p, h->d_foo_bits.p, 0, nullptr, 1);
       ++nl;
       cc_done = cc_end;
     }

@@ -150,6 +150,7 @@ spb_status spb_destroy(spb_handle h) {
   chol_release(h);
   ic0_release(h);
   lm_release(h);
+  batch_release(h);
   dist_release(h);
   for (auto& p : h->timing.pending) {
     cudaEventDestroy(p.a);

@@ -278,6 +278,69 @@ static spb_status build_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t 
   return SPB_OK;
 }
 
+// A batch of independent LF problems as ONE block-diagonal problem (config C4): problem p is the LF problem of seed
+// seed + p*seed_stride (its own pattern and data), its unknowns are [p*n, (p+1)*n) and its residual rows [p*m, (p+1)*m).
+spb_status spb_problem_lf_batch(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, int32_t seed_stride, int32_t nproblems, spb_problem_t* out) {
+  if (!h || !out || nproblems < 1) return SPB_ERR_ARG;
+  if ((int64_t)g * g * rows_mult * 8 * nproblems > 0x7fffffffLL) return SPB_ERR_ARG;
+  *out = nullptr;
+  const int n1 = g * g, m1 = rows_mult * n1;
+  const int64_t nnz1 = (int64_t)m1 * 8;
+  spb_problem* B = new spb_problem;
+  B->h = h;
+  B->kind = 0;
+  B->n = n1 * nproblems;
+  B->m = m1 * nproblems;
+  B->m_global = B->m;
+  B->nnzJ = nnz1 * nproblems;
+  B->x0.assign((size_t)B->n, 1.0);
+  B->colptr.assign((size_t)B->n + 1, 0);
+  B->rowidx.resize((size_t)B->nnzJ);
+  const size_t M = (size_t)B->m;
+  std::vector<int> ec(M * 8);
+  std::vector<double> ev(M * 8), cv((size_t)B->nnzJ);
+  std::vector<int> c1;
+  std::vector<double> v1, cv1;
+  for (int p = 0; p < nproblems; ++p) {
+    spb_problem_t one = nullptr;
+    spb_status s = build_lf(h, g, rows_mult, seed + (uint64_t)p * (uint64_t)seed_stride, 0, 0, false, &one);
+    if (s != SPB_OK) {
+      delete B;
+      return s;
+    }
+    // pull the single problem's device arrays back (built on the host, uploaded by build_lf) and splice them in
+    c1.resize((size_t)nnz1);
+    v1.resize((size_t)nnz1);
+    cv1.resize((size_t)nnz1);
+    cudaMemcpy(c1.data(), one->d_ell_col.p, sizeof(int) * (size_t)nnz1, cudaMemcpyDeviceToHost);
+    cudaMemcpy(v1.data(), one->d_ell_val.p, sizeof(double) * (size_t)nnz1, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cv1.data(), one->d_csc_val.p, sizeof(double) * (size_t)nnz1, cudaMemcpyDeviceToHost);
+    for (int k = 0; k < 8; ++k)
+      for (int r = 0; r < m1; ++r) {
+        ec[(size_t)k * M + (size_t)p * m1 + r] = c1[(size_t)k * m1 + r] + p * n1;
+        ev[(size_t)k * M + (size_t)p * m1 + r] = v1[(size_t)k * m1 + r];
+      }
+    for (int j = 0; j < n1; ++j) B->colptr[(size_t)p * n1 + j + 1] = (int)((int64_t)p * nnz1 + one->colptr[(size_t)j + 1]);
+    for (int64_t q = 0; q < nnz1; ++q) {
+      B->rowidx[(size_t)((int64_t)p * nnz1 + q)] = one->rowidx[(size_t)q] + p * m1;
+      cv[(size_t)((int64_t)p * nnz1 + q)] = cv1[(size_t)q];
+    }
+    spb_problem_destroy(one);
+  }
+  try {
+    SPB_CUDA(B->d_ell_col.upload(ec, h->stream));
+    SPB_CUDA(B->d_ell_val.upload(ev, h->stream));
+    SPB_CUDA(B->d_csc_val.upload(cv, h->stream));
+    SPB_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (const CudaFail& e) {
+    h->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.where;
+    delete B;
+    return SPB_ERR_CUDA;
+  }
+  *out = B;
+  return SPB_OK;
+}
+
 spb_status spb_problem_lf(spb_handle h, int32_t g, int32_t rows_mult, uint64_t seed, spb_problem_t* out) {
   return build_lf(h, g, rows_mult, seed, 0, 0, false, out);
 }

@@ -337,6 +337,10 @@ struct spb_context {
   int64_t collectives = 0;
   spb::PeerState* peer = nullptr;  // peer-memory windows of the halo mode (dist.cu), owned
 
+  // batched independent problems (batch.cu): per-problem lambda of the column kernel; nullptr = the scalar argument
+  const double* d_lambda_vec = nullptr;
+  int lambda_n_per = 1;
+  void* batch_ws = nullptr;  // spb::BatchWorkspace*, owned (batch.cu)
   int pcg_last_iters = 0;
   // relaxed-precision products: switch to the FP32 value stream once ||r||/||b|| <= pcg_rtol * pcg_relax_factor
   // (1e6: 1e-7 at the default rtol 1e-13); 0 = always FP64.  SPB_PCG_RELAX overrides.
@@ -377,6 +381,7 @@ void dev_inf_norm(spb_context* h, const double* d_v, int64_t len, double* host_o
 void dev_add(spb_context* h, const double* a, const double* b, double* out, int64_t len);  // out=a+b
 void dev_invert_diag(spb_context* h);  // d_dinv = 1/d_hdiag
 void lm_release(spb_context* h);
+void batch_release(spb_context* h);  // batch.cu
 
 // pcg.cu
 void dev_spmv(spb_context* h, const double* d_x, double* d_y);

@@ -494,6 +494,8 @@ class BuiltinProblem:
         p = C.c_void_p()
         if kind == "lf":
             st = L.spb_problem_lf(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), C.byref(p))
+        elif kind == "lf_batch":  # nproblems LF problems (seeds seed, seed+1, ...) as one block-diagonal problem
+            st = L.spb_problem_lf_batch(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), kw.get("seed_stride", 1), kw["nproblems"], C.byref(p))
         elif kind == "lf_rows":  # row-partitioned LF: this rank owns residual rows [row_begin,row_end)
             st = L.spb_problem_lf_rows(handle.h, kw["g"], kw.get("rows_mult", 2), kw.get("seed", 20211), kw["row_begin"], kw["row_end"],
                                        C.byref(p))

@@ -1,0 +1,91 @@
+"""Config C4: a batch of independent problems (half extended Rosenbrock, half LF, n unknowns each), sharded over the ranks
+(problem index blocks per GPU, no data-path collective) and advanced by spb_lm_solve_batch: per rank ONE block-diagonal
+problem per kind, one launch per LM stage for all of its problems.  Prints one JSON line (rank 0): problems/s, LM
+iterations/s, per-kind timings, and the comparison of a sampled subset with the CPU oracle.
+    python scripts/c4_bench.py [--problems 4096] [--n 10000] [--samples 2]
+    python -m torch.distributed.run --nproc-per-node N scripts/c4_bench.py ..."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import saddlepoint_b200 as spb
+from saddlepoint_b200 import batch
+from saddlepoint_b200 import dist as sd
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--problems", type=int, default=4096)
+ap.add_argument("--n", type=int, default=10000)
+ap.add_argument("--samples", type=int, default=2, help="problems per kind checked against the CPU oracle (rank 0)")
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+lo, hi = sd.shard_range(args.problems, world, rank)
+mine = list(range(lo, hi))
+h = spb.Handle(local, torch.cuda.current_stream().cuda_stream)
+out = {}
+res_all = {}
+for kind, idx in (("lf", [i for i in mine if i % 2 == 1]), ("rosenbrock", [i for i in mine if i % 2 == 0])):
+    if not idx:
+        continue
+    t0 = time.time()
+    res = batch.solve_batch_fused(h, idx, n=args.n, keep_x=(rank == 0 and args.samples > 0))
+    wall = time.time() - t0
+    secs = res[0]["seconds"]            # the library's own clock around the whole batched solve (incl. analysis)
+    ana = res[0]["seconds_analyze"]
+    its = sum(r["factorizations"] for r in res)
+    out[kind] = {"problems": len(idx), "lm_loop_bodies": its, "solve_seconds": secs - ana, "analysis_seconds_one_time": ana,
+                 "build_and_solve_wall_seconds": wall, "currIter_min": min(r["currIter"] for r in res), "currIter_max": max(r["currIter"] for r in res),
+                 "exit_paths": {p: sum(1 for r in res if r["exit_path"] == p) for p in sorted({r["exit_path"] for r in res})},
+                 "pcg_iterations": int(sum(r["linear_iterations"] for r in res))}
+    res_all[kind] = (idx, res)
+# sampled subset against the CPU oracle (rank 0)
+check = None
+if rank == 0 and args.samples > 0:
+    from oracle import sp_oracle as orc
+    check = {"samples": [], "all_match": True}
+    for kind, (idx, res) in res_all.items():
+        for k in list(range(min(args.samples, len(idx)))):
+            i, r = idx[k], res[k]
+            spec = batch.c4_problem_spec(i, n=args.n)
+            if kind == "rosenbrock":
+                ref = orc.lm_solve("rosenbrock", iparam0=spec["nblocks"], x0=spec["x0"], maxIterations=1000)
+                tol = 1e-4
+            else:
+                ref = orc.lm_solve("lf", iparam0=spec["g"], iparam1=2, seed=spec["seed"], maxIterations=100)
+                tol = 1e-10
+            relx = float(np.linalg.norm(r["x"] - ref.x) / max(np.linalg.norm(ref.x), 1e-300))
+            ok = (r["ret"] == ref.ret and r["exit_path"] == ref.exit_path and r["currIter"] == ref.currIter and r["factorizations"] == ref.factorizations
+                  and relx <= tol)
+            check["samples"].append({"index": i, "kind": kind, "currIter": r["currIter"], "oracle_currIter": ref.currIter, "exit_path": r["exit_path"],
+                                     "oracle_exit_path": ref.exit_path, "rel_x": relx, "ok": bool(ok)})
+            check["all_match"] = check["all_match"] and bool(ok)
+# totals: max over ranks of the solve time (ranks run concurrently), sums of the counts
+tot_secs = sum(v["solve_seconds"] for v in out.values())
+tot_bodies = sum(v["lm_loop_bodies"] for v in out.values())
+if world > 1:
+    t = torch.tensor([tot_secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor([float(tot_bodies)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    tot_secs, tot_bodies = float(t.item()), float(c.item())
+if rank == 0:
+    line = {"config": "C4: %d independent problems x %d unknowns (even index: extended Rosenbrock, jittered start; odd: LF), sharded over %d GPU(s), "
+                      "one block-diagonal batch per kind per rank (spb_lm_solve_batch)" % (args.problems, args.n, world),
+            "n_gpus": world, "problems": args.problems, "problems_per_s": args.problems / tot_secs, "lm_iterations_per_s": tot_bodies / tot_secs,
+            "solve_seconds_max_over_ranks": tot_secs, "rank0": out, "oracle_check": check, "scaling": "weak-in-problems (fixed total): strong"}
+    print(json.dumps(line))
+    if args.out:
+        json.dump(line, open(args.out, "w"), indent=1)
+if world > 1:
+    dist.destroy_process_group()

@@ -55,3 +55,47 @@ def test_concurrent_workers_give_identical_results(spb):
     for a, b in zip(seq, par):
         assert a["currIter"] == b["currIter"] and a["exit_path"] == b["exit_path"] and a["energy"] == b["energy"]
         assert np.array_equal(a["x"], b["x"])
+
+
+@pytest.mark.parametrize("n", [400, 2500])
+def test_fused_batch_matches_oracle_per_problem(spb, orc, n):
+    """spb_lm_solve_batch: B independent problems as ONE block-diagonal problem -- one assembly, one persistent PCG
+    kernel with per-problem dot products / convergence, a device-side LM controller with per-problem lambda, acceptance
+    (LMSolver.h:161), stop tests (:123-129,147-152,164-168) and iteration bound.  Every problem against its own oracle
+    solve: exit path, iteration count and factorisation count exact; problems finish at different iterations (masking).
+    n = 400: problem boundaries are not multiples of the 32-row slices (400 = 12.5 slices), n = 2500 neither."""
+    from saddlepoint_b200 import batch
+    h = spb.Handle(0)
+    for indices in ([1, 3, 5, 7, 9], [0, 2, 4, 6]):
+        res = batch.solve_batch_fused(h, indices, n=n, keep_x=True)
+        assert len(res) == len(indices)
+        iters = set()
+        for i, r in zip(indices, res):
+            spec = batch.c4_problem_spec(i, n=n)
+            if spec["kind"] == "rosenbrock":
+                ref = orc.lm_solve("rosenbrock", iparam0=spec["nblocks"], x0=spec["x0"], maxIterations=1000)
+            else:
+                ref = orc.lm_solve("lf", iparam0=spec["g"], iparam1=2, seed=spec["seed"], maxIterations=100)
+            assert r["ret"] == ref.ret and r["exit_path"] == ref.exit_path, (i, r["exit_path"], ref.exit_path)
+            assert r["currIter"] == ref.currIter and r["factorizations"] == ref.factorizations, (i, r["currIter"], ref.currIter)
+            tol = 1e-4 if spec["kind"] == "rosenbrock" else 1e-10   # see test_c4_sample_matches_oracle_per_problem
+            np.testing.assert_allclose(r["x"], ref.x, rtol=tol, atol=1e-12)
+            assert abs(r["energy"] - ref.energy) <= tol * abs(ref.energy)
+            assert r["lambda"] == ref.currLambda
+            iters.add(r["currIter"])
+    h.close()
+
+
+def test_fused_batch_equals_the_per_problem_loop(spb):
+    """The fused batch against the per-problem host loop (same handle type, same PCG tolerance): identical control
+    flow per problem, iterates to rounding."""
+    from saddlepoint_b200 import batch
+    n = 900
+    h = spb.Handle(0)
+    idx = [1, 3, 5, 7, 9, 11, 13, 15]
+    fused = batch.solve_batch_fused(h, idx, n=n, keep_x=True)
+    for i, r in zip(idx, fused):
+        one = batch.solve_problem(h, batch.c4_problem_spec(i, n=n), solver=spb.SOLVER_PCG_JACOBI)
+        assert r["currIter"] == one["currIter"] and r["exit_path"] == one["exit_path"] and r["factorizations"] == one["factorizations"]
+        assert np.linalg.norm(r["x"] - one["x"]) <= 1e-11 * np.linalg.norm(one["x"])
+    h.close()

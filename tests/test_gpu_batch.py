@@ -57,6 +57,13 @@ def test_concurrent_workers_give_identical_results(spb):
         assert np.array_equal(a["x"], b["x"])
 
 
+def _has_rounding_level_tie(ref):
+    """True if some loop body of the oracle's trajectory compared two energies that agree to ~1e-13 relative."""
+    p, n = ref.trace["prevEnergy2"], ref.trace["newEnergy2"]
+    with np.errstate(invalid="ignore"):
+        return bool((np.abs(p - n) <= 1e-13 * np.abs(p)).any())
+
+
 @pytest.mark.parametrize("n", [400, 2500])
 def test_fused_batch_matches_oracle_per_problem(spb, orc, n):
     """spb_lm_solve_batch: B independent problems as ONE block-diagonal problem -- one assembly, one persistent PCG
@@ -66,6 +73,7 @@ def test_fused_batch_matches_oracle_per_problem(spb, orc, n):
     n = 400: problem boundaries are not multiples of the 32-row slices (400 = 12.5 slices), n = 2500 neither."""
     from saddlepoint_b200 import batch
     h = spb.Handle(0)
+    ties = 0
     for indices in ([1, 3, 5, 7, 9], [0, 2, 4, 6]):
         res = batch.solve_batch_fused(h, indices, n=n, keep_x=True)
         assert len(res) == len(indices)
@@ -77,12 +85,22 @@ def test_fused_batch_matches_oracle_per_problem(spb, orc, n):
             else:
                 ref = orc.lm_solve("lf", iparam0=spec["g"], iparam1=2, seed=spec["seed"], maxIterations=100)
             assert r["ret"] == ref.ret and r["exit_path"] == ref.exit_path, (i, r["exit_path"], ref.exit_path)
-            assert r["currIter"] == ref.currIter and r["factorizations"] == ref.factorizations, (i, r["currIter"], ref.currIter)
             tol = 1e-4 if spec["kind"] == "rosenbrock" else 1e-10   # see test_c4_sample_matches_oracle_per_problem
+            if (r["currIter"] != ref.currIter or r["factorizations"] != ref.factorizations) and _has_rounding_level_tie(ref):
+                # The acceptance test prev > new (LMSolver.h:161) is a tie at rounding level somewhere on this trajectory
+                # (e.g. LF seed 20216, g = 50: |prev - new| = 4 ulp at the fourth body): which way it falls depends on the
+                # summation order of the two energies, so the last tiny step may or may not be taken.  Both outcomes are
+                # the reference's algorithm; the iterates agree to the size of that step.
+                assert abs(r["currIter"] - ref.currIter) <= 1 and abs(r["factorizations"] - ref.factorizations) <= 1
+                tol = max(tol, 1e-6)
+                ties += 1
+            else:
+                assert r["currIter"] == ref.currIter and r["factorizations"] == ref.factorizations, (i, r["currIter"], ref.currIter)
+                assert r["lambda"] == ref.currLambda
             np.testing.assert_allclose(r["x"], ref.x, rtol=tol, atol=1e-12)
             assert abs(r["energy"] - ref.energy) <= tol * abs(ref.energy)
-            assert r["lambda"] == ref.currLambda
             iters.add(r["currIter"])
+    assert ties <= 2   # the exception, not the rule
     h.close()
 
 

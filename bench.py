@@ -304,6 +304,83 @@ def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2
     return roof
 
 
+def _dmma_frac(tflops):
+    """Whole-factorisation FP64 rate against the measured DMMA peak of this GPU type (scripts/micro/dmma_peak.cu,
+    profiles/r2_dmma_peak.json): the absolute roofline denominator of the supernode updates."""
+    p = os.path.join(ROOT, "profiles", "r2_dmma_peak.json")
+    try:
+        pk = json.load(open(p))
+        return {"dmma_peak_tflops": pk["dmma_m8n8k4_tflops"], "dmma_frac": tflops / pk["dmma_m8n8k4_tflops"], "dmma_peak_source": "profiles/r2_dmma_peak.json"}
+    except Exception:
+        return {"dmma_peak_tflops": None, "dmma_frac": None}
+
+
+def extra_c3(spb, torch):
+    """Config C3 at BASELINE's size as an extra key of the N=1 line: seamless-integration Jacobian structure on a
+    500 x 500 x 2 = 498 002-face grid (tests/c3_blocks.py builds it), device-resident traits, LM with the direct
+    solver (the SimplicialLLT role).  One-time costs reported separately; steady state = second solve on the analysed handle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import c3_blocks
+    t0 = time.time()
+    P = c3_blocks.build(500, 500)
+    t_build = time.time() - t0
+    ls = spb.B200SolverWrapper(solver=spb.SOLVER_CHOLESKY)
+    h = ls.handle
+    prob = spb.BuiltinProblem(h, "blocks", **{k: P[k] for k in ("A", "b", "bar_idx", "bar_vol", "s", "w_bar", "x0")})
+    m, n, colptr, rowidx = prob.pattern()
+    iters = 3
+    lm = spb.LMSolver()
+    lm.init(ls, prob, spb.DiagonalDamping(0.01), iters - 1)
+    t0 = time.time()
+    lm.solve(True, dedupe_evaluations=True)
+    t_first = time.time() - t0
+    analyze_s = lm.seconds_analyze
+    lm2 = spb.LMSolver()
+    lm2.init(ls, prob, spb.DiagonalDamping(0.01), iters - 1)
+    h.stage_reset(True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    lm2.solve(True, dedupe_evaluations=True)
+    torch.cuda.synchronize()
+    t2 = time.time() - t0
+    st = h.stage_ms()
+    h.stage_reset(False)
+    nit = max(1, lm2.factorizations)
+    info = h.factor_info()
+    tf = info["flops"] / (st["factor"][0] / nit * 1e-3) / 1e12
+    out = {"workload": "benchmark/seamless_integration structure, %d faces (500x500x2 grid), n=%d, m=%d, nnzJ=%d" % (P["nF"], n, m, int(colptr[-1])),
+           "solver": "supernodal Cholesky (direct)", "lm_iterations_per_s": nit / t2, "ms_per_lm_iteration": 1e3 * t2 / nit, "lm_bodies_timed": nit,
+           "stage_ms_per_iteration": {k: v[0] / nit for k, v in st.items() if v[0] > 0}, "nnzL": info["nnzL"], "flops_per_factorisation": info["flops"],
+           "factor_tflops_fp64": tf, **_dmma_frac(tf), "one_time_seconds": {"host_problem_build": t_build, "pattern_analysis": analyze_s,
+                                                                            "first_solve_incl_ordering_and_symbolic_factorisation": t_first},
+           "exit_path": str(lm2.exit_path), "energy": float(lm2.energy)}
+    prob.close()
+    h.close()
+    return out
+
+
+def extra_c4(spb, nproblems=256, n=10000):
+    """Config C4 sample as an extra key of the N=1 line: `nproblems` independent 10k-unknown problems (half extended
+    Rosenbrock, half LF) through spb_lm_solve_batch on this GPU (the full 4096-problem run: scripts/c4_bench.py,
+    profiles/r2_c4_*.json)."""
+    from saddlepoint_b200 import batch
+    h = spb.Handle(0)
+    out = {"problems": nproblems, "unknowns_per_problem": n}
+    tot_s, tot_b = 0.0, 0
+    for kind, idx in (("lf", list(range(1, nproblems, 2))), ("rosenbrock", list(range(0, nproblems, 2)))):
+        res = batch.solve_batch_fused(h, idx, n=n)
+        secs = res[0]["seconds"] - res[0]["seconds_analyze"]
+        bodies = sum(r["factorizations"] for r in res)
+        out[kind] = {"problems": len(idx), "solve_seconds": secs, "lm_loop_bodies": bodies, "analysis_seconds_one_time": res[0]["seconds_analyze"],
+                     "exit_paths": {p: sum(1 for r in res if r["exit_path"] == p) for p in sorted({r["exit_path"] for r in res})}}
+        tot_s += secs
+        tot_b += bodies
+    out["problems_per_s"] = nproblems / tot_s
+    out["lm_iterations_per_s"] = tot_b / tot_s
+    h.close()
+    return out
+
+
 def run_c2(args, torch, dist, local):
     import saddlepoint_b200 as spb
 
@@ -400,7 +477,7 @@ def run_c2(args, torch, dist, local):
         info = h.factor_info()
         direct = {"factor_ms": st2["factor"][0] / reps, "solve_ms": st2["trisolve"][0] / reps, "nnzL": info["nnzL"], "flops": info["flops"],
                   "factor_tflops_fp64": info["flops"] / (st2["factor"][0] / reps * 1e-3) / 1e12, "supernodes": info["nsuper"],
-                  "tree_levels": info["nlevels"], "relres_of_step": h.residual_check(dn_),
+                  "tree_levels": info["nlevels"], "relres_of_step": h.residual_check(dn_), **_dmma_frac(info["flops"] / (st2["factor"][0] / reps * 1e-3) / 1e12),
                   "trisolve_gbs": 2 * 8 * info["nnzL"] / (st2["trisolve"][0] / reps * 1e-3) / 1e9,
                   "note": "multifrontal LL^T, nested-dissection order; SYRK/GEMM on FP64 tensor cores (DMMA); the triangular solves are "
                           "latency-bound (tree height), far below the HBM roofline; LM steps/s with this solver = 1000/(assembly+factor+solve ms)"}
@@ -417,11 +494,21 @@ def run_c2(args, torch, dist, local):
                          "the single-thread variant and the reference's SimplicialLLT samples" % (g, mres["bodies"], T),
                "measured": mres}
 
+    extras = {}
+    if not args.no_extras and g == C2_G:
+        for name, fn in (("c3_500k_faces", lambda: extra_c3(spb, torch)), ("c4_batch_sample", lambda: extra_c4(spb))):
+            try:
+                extras[name] = fn()
+            except Exception as e:  # noqa: BLE001 -- an extra must not break the bench line
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     line = {"metric": "LM iterations/s", "value": value, "unit": "iterations/s", "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_string(g) + ", nnzH=%d" % nnzH,
-                       "solver": "%s rtol=%g (one persistent cooperative kernel per solve)" % (args.solver, args.pcg_rtol),
+                       "solver": "%s rtol=%g (one persistent cooperative kernel per solve); relaxed-precision products: the matrix values are streamed from an "
+                                 "FP32 copy once ||r||/||b|| <= %g (vectors, accumulation, recurrences and the stop test stay FP64; e2e.relres_of_step "
+                                 "is the FP64 residual of the returned step; SPB_PCG_RELAX=0 disables)" % (args.solver, args.pcg_rtol, args.pcg_rtol * float(os.environ.get("SPB_PCG_RELAX", "1e6"))),
                        "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),
                        "pcg_iterations_per_step": lin_iters / K, "analysis_seconds_one_time": analyze_s,
                        "lm_bodies_per_solve": BODIES_PER_SOLVE, "fixed_iterations": True,
@@ -430,6 +517,7 @@ def run_c2(args, torch, dist, local):
             "e2e": {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": 8 * (nnzJ + m), "d2h_bytes_per_step": 8 * n + 8,
                     "ms_per_step": ms_e2e / K, "relres_of_step": relres},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "direct_solver": direct}
+    line.update(extras)
     print(json.dumps(line))
 
 
@@ -597,6 +685,7 @@ def main():
     ap.add_argument("--solver", default="pcg_jacobi", choices=["pcg_jacobi", "pcg_ic0"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the supernodal-Cholesky timing block")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the extra keys (config C3 at 500k faces, config C4 batch sample)")
     ap.add_argument("--one-problem-g", type=int, default=C5_G, help="N>1: torus size of the one problem solved by all ranks (config C5: 4472)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -41,8 +41,17 @@ def test_c3_lm_parity_direct_solver(spb, orc):
     assert lm.currIter == ref.currIter and lm.factorizations == ref.factorizations
     assert (lm.trace["accepted"] == ref.trace["accepted"]).all()
     np.testing.assert_allclose(lm.trace["lambda"], ref.trace["lambda"], rtol=0)
-    assert np.linalg.norm(lm.x - ref.x) <= 1e-9 * np.linalg.norm(ref.x)   # kappa ~ (1e4/1e-4)^2: tolerance scaled accordingly
-    assert abs(lm.energy - ref.energy) <= 1e-9 * max(abs(ref.energy), 1e-16 * ref.trace["prevEnergy2"][0])
+    # north_star's 1e-10, unless the oracle's own variants (the same LLT with natural instead of AMD elimination order:
+    # identical mathematics, different rounding) already disagree by more on this ill-conditioned problem (weights 1e4 vs
+    # 1e-4); measured spread here: 4.7e-12
+    st_alt = SeamlessLikeTraits(7, 6)
+    alt = orc.lm_solve("callback", x0=st_alt.initial_solution(), pattern=(st_alt.ESize, st_alt.xSize, st_alt.colptr, st_alt.rowidx),
+                       callback=lambda x, cj: st_alt.objective_jacobian(x, cj), maxIterations=30, solver_kind=2)
+    spread = np.linalg.norm(alt.x - ref.x) / np.linalg.norm(ref.x)
+    tol = max(1e-10, 10.0 * spread)
+    assert tol <= 1e-9
+    assert np.linalg.norm(lm.x - ref.x) <= tol * np.linalg.norm(ref.x)
+    assert abs(lm.energy - ref.energy) <= tol * max(abs(ref.energy), 1e-16 * ref.trace["prevEnergy2"][0])
     assert st_gpu.calls == st_ref.calls  # same objective call sequence as the reference loop
     ls.handle.close()
 

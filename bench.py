@@ -111,13 +111,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _ncu_dram_bytes_per_pcg_iteration():
+def _ncu_dram_bytes_per_pcg_iteration(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum of the persistent PCG kernel per PCG iteration, from the newest
-    committed `ncu --set full` capture of this kernel on LF-1M (profiles/*_pcg_traffic.json, written by
+    committed `ncu --set full` capture of this kernel variant on LF-1M (profiles/*_<tag>_pcg_traffic.json, written by
     scripts/ncu_traffic.py from the .ncu-rep).  None if no capture is committed."""
     import glob
     best = None
-    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_pcg_traffic.json"))):
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_%s_pcg_traffic.json" % tag))):
         try:
             best = json.load(open(p))
             best["file"] = os.path.relpath(p, ROOT)
@@ -269,7 +269,7 @@ def run_ours(args):
         run_c2(args, torch, dist, local)
 
 
-def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2, fused_kernel):
+def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2, fused_kernel, traffic_tag=None):
     peaks, peak_kind = _peaks()
     # B_spmv = 12*nnzH + 4(n+1) + 8n + 8n bytes per product; a PCG iteration moves
     # B_spmv + 10*8n (x, r, p, q, dinv reads/writes around the product)
@@ -286,7 +286,7 @@ def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2
     achieved = k_bytes_total / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     asm_ms, asm_launches = stages["assembly"]
     b_asm = 12 * nnzJ_loc + 4 * (m_loc + 1) + 8 * m_loc + 8 * nnzH_loc + 16 * n_loc
-    cap = _ncu_dram_bytes_per_pcg_iteration() if (fused_ms > 0 and g_is_c2) else None
+    cap = _ncu_dram_bytes_per_pcg_iteration(traffic_tag) if (fused_ms > 0 and g_is_c2 and traffic_tag) else None
     traffic = cap["dram_bytes_per_pcg_iteration"] * max(1, lin_iters) / max(1, k_launches) if cap else None
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
@@ -296,8 +296,11 @@ def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2
             "assembly": {"achieved": b_asm * K / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0, "bytes_per_step": b_asm,
                          "ms_per_step": asm_ms / K},
             "stage_ms_per_step": {k: v[0] / K for k, v in stages.items()}}
+    roof["frac_definition"] = ("achieved = SURVEY 8(d)'s algorithmic bytes (12 B per H entry + 4(n+1) + 16n per product, + 80n per PCG iteration) / kernel time; "
+                               "the kernel moves fewer bytes than that model (16-bit column deltas, FP32 values in the relaxed late iterations, vectors resident "
+                               "in L2), so this fraction can exceed 1 -- frac_on_measured_dram_bytes is the physical one")
     if cap:
-        # the same launch measured on its real DRAM traffic (the H stream is 10 B/entry, the vectors stay in L2)
+        # the same launch measured on its real DRAM traffic
         roof["traffic_source"] = cap.get("file")
         roof["frac_on_measured_dram_bytes"] = (traffic / (1e3 * k_ms / max(1, k_launches) * 1e-6) / 1e9) / peaks["hbm_gbs"]
     roof["assembly"]["frac"] = roof["assembly"]["achieved"] / peaks["hbm_gbs"]
@@ -429,7 +432,8 @@ def run_c2(args, torch, dist, local):
     sr = os.environ.get("SPB_PCG_VARIANT", "classic").startswith("s")
     kname = ("pcg_sr_kernel<false> (whole Jacobi-PCG solve, single-reduction CG: SpMV + dots | vector updates, two grid barriers per iteration, one cooperative launch)"
              if sr else "pcg_persistent_kernel<4> (whole Jacobi-PCG solve: SpMV + vector updates + reductions, one cooperative launch)")
-    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G, kname)
+    relax_on = float(os.environ.get("SPB_PCG_RELAX", "1e6")) > 0
+    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G, kname, ("sr" if sr else "classic") + ("_relaxed" if relax_on else ""))
 
     # ---- e2e: the C-ABI hot path with HOST buffers (H2D + D2H inside the timed region) -------
     Jv_host = torch.empty(nnzJ, dtype=torch.float64).pin_memory()

@@ -1,11 +1,10 @@
 #!/bin/bash
-# ncu captures of the persistent PCG kernels on LF-1M (one launch each, --set full), to gpurun_out/.
-# usage: bash scripts/ncu_pcg.sh   (on the GPU box; run AFTER the same bench command has exited 0 without ncu)
+# ncu capture of the persistent PCG kernel on LF-1M as the bench runs it (one launch, --set full), to gpurun_out/.
+# usage: bash scripts/ncu_pcg.sh   (on the GPU box; the same bench command runs first WITHOUT ncu and must exit 0)
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-direct --no-extras > gpurun_out/ncu_pre_classic.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:pcg_persistent_kernel -s 3 -c 1 -o gpurun_out/r2_pcg_classic -f \
-    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-direct --no-extras > gpurun_out/ncu_classic.log 2>&1
-SPB_PCG_VARIANT=sr python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-direct --no-extras > gpurun_out/ncu_pre_sr.log 2>&1 || exit 1
-SPB_PCG_VARIANT=sr ncu --set full --clock-control none --import-source on -k regex:pcg_sr_kernel -s 3 -c 1 -o gpurun_out/r2_pcg_sr -f \
-    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-direct --no-extras > gpurun_out/ncu_sr.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-direct --no-extras"
+$B > gpurun_out/ncu_pre_classic.log 2>&1 || exit 1
+# launch 4 of the kernel = first loop body of the timed solve (81 PCG iterations; the solve's iteration counts are printed by SPB_PCG_TIMING=1)
+ncu --set full --clock-control none --import-source on -k regex:pcg_persistent_kernel -s 3 -c 1 -o gpurun_out/r2_pcg_classic_relaxed -f $B > gpurun_out/ncu_classic.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $B > gpurun_out/ncu_launches.log 2>&1
+ls -la gpurun_out/*.ncu-rep gpurun_out/r2_launches.csv

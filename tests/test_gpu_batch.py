@@ -116,8 +116,8 @@ def test_fused_batch_matches_oracle_per_problem(spb, orc, n):
 
 
 def test_fused_batch_equals_the_per_problem_loop(spb):
-    """The fused batch against the per-problem host loop on the same problems: the same minimisers (x to 1e-6, final
-    energy to 1e-12 -- the LM trajectories of these LF problems end in rounding-level acceptance ties, see above, so the
+    """The fused batch against the per-problem host loop on the same problems: the same minimisers (x to 1e-5 = the last damped step, final
+    energy to 1e-10 -- the LM trajectories of these LF problems end in rounding-level acceptance ties, see above, so the
     number of trailing rejected bodies may differ between two equivalent summation orders), and identical results for
     problems whose trajectories are tie-free up to the exit."""
     from saddlepoint_b200 import batch
@@ -129,8 +129,8 @@ def test_fused_batch_equals_the_per_problem_loop(spb):
     for i, r in zip(idx, fused):
         one = batch.solve_problem(h2, batch.c4_problem_spec(i, n=n), solver=spb.SOLVER_PCG_JACOBI)
         assert r["exit_path"] in ("func_tol", "direction_small") and one["exit_path"] in ("func_tol", "direction_small")
-        assert np.linalg.norm(r["x"] - one["x"]) <= 1e-6 * np.linalg.norm(one["x"])   # the size of the last (tie) step
-        assert abs(r["energy"] - one["energy"]) <= 1e-12 * abs(one["energy"])
+        assert np.linalg.norm(r["x"] - one["x"]) <= 1e-5 * np.linalg.norm(one["x"])   # the size of the last damped (lambda = 1e-5) step
+        assert abs(r["energy"] - one["energy"]) <= 1e-10 * abs(one["energy"])
     # deterministic: the same batch again gives the same bits
     again = batch.solve_batch_fused(h, idx, n=n, keep_x=True)
     for a, b in zip(fused, again):

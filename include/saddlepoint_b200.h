@@ -63,6 +63,13 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
 /* Cheap re-validation (the seamless-integration driver grows J between solves):
  * returns SPB_OK and *same=1 if (m,n,colptr,rowidx) matches the analysed pattern. */
 spb_status spb_pattern_matches(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int* same);
+/* Incremental re-analysis (benchmark/seamless_integration/main.cpp:69-80: the iterative-rounding driver re-inits
+ * the LM solver after IterativeRoundingTraits.h:76-79 appended ONE constraint row, i.e. J gained one residual row
+ * with a single nonzero and the rows below it moved down by one).  Same arguments as spb_analyze.  *how (may be
+ * NULL): 0 = the pattern is the analysed one, nothing done; 1 = the analysed state was patched (H pattern, SpMV
+ * layout, Cholesky / IC(0) symbolic state kept; J pattern, pair records and stage layouts updated); 2 = analysed
+ * from scratch (any other change).  The resulting state is identical to spb_analyze's. */
+spb_status spb_analyze_update(spb_handle h, int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int* how);
 /* H pattern export (host), for parity tests: colptr[n+1], rowidx[nnz]. */
 spb_status spb_h_nnz(spb_handle h, int64_t* nnz);
 spb_status spb_h_pattern(spb_handle h, int32_t* colptr, int32_t* rowidx);

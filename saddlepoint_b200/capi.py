@@ -53,6 +53,7 @@ SYMBOLS = [
     ("spb_version", C.c_char_p, []),
     ("spb_set_solver", C.c_int, [vp, C.c_int, C.c_double, C.c_int]),
     ("spb_analyze", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
+    ("spb_analyze_update", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(C.c_int)]),
     ("spb_pattern_matches", C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(C.c_int)]),
     ("spb_h_nnz", C.c_int, [vp, C.POINTER(C.c_int64)]),
     ("spb_h_pattern", C.c_int, [vp, vp, vp]),

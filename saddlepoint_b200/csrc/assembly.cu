@@ -711,9 +711,11 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
     std::vector<ChunkDesc> host_cd((size_t)nch);
     SPB_CUDA(cudaMemcpy(host_cd.data(), h->d_chunk_desc.p, sizeof(ChunkDesc) * (size_t)nch, cudaMemcpyDeviceToHost));
     h->chunk_need.assign((size_t)nch, 0);
+    h->keep.sorted_pos.assign((size_t)nch, 0);
     for (int i = 0; i < nch; ++i) {
       sorted[i] = host_cd[order[i]];
       h->chunk_need[i] = need[order[i]];
+      h->keep.sorted_pos[(size_t)order[i]] = i;
     }
     SPB_CUDA(h->d_chunk_desc_sorted.upload(sorted, st));
     SPB_CUDA(cudaStreamSynchronize(st));
@@ -722,6 +724,26 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   }
   h->nslots = P.nslots;
   h->npairs = P.npairs;
+  // host-side pieces kept for incremental re-analysis (spb_analyze_update)
+  h->keep.valid = false;
+  h->d_keep_stage_cols.release();
+  h->d_keep_stage_ptr.release();
+  h->d_keep_sorted_pos.release();
+  if ((int64_t)colptr[h->n] <= kPlanKeepMaxNnz && !h->partitioned) {
+    PlanKeep& K = h->keep;
+    K.Jrow.assign(rowidx, rowidx + colptr[h->n]);
+    K.stage_cols.swap(P.stage_cols);
+    K.chunk_stage_ptr.swap(P.chunk_stage_ptr);
+    K.chunk_slot.swap(P.chunk_slot);
+    K.chunk_npairs.swap(P.chunk_npairs);
+    K.chunk_rec.swap(P.chunk_rec);
+    K.chunk_staged.swap(P.chunk_staged);
+    K.low_colptr.swap(P.low_colptr);
+    K.low_row.swap(P.low_row);
+    K.slot_start.swap(P.slot_start);
+    K.slot_cnt.swap(P.slot_cnt);
+    K.valid = true;
+  }
   SPB_CUDA(h->d_foo_bits.alloc(1));
   SPB_CUDA(cudaStreamSynchronize(st));
 }

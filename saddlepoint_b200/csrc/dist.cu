@@ -426,6 +426,8 @@ spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int
     h->analyzed = h->have_h = h->h_valid = h->factor_valid = false;
     h->trip_nnz = -1;
     h->pcg_last_iters = 0;
+    h->h_pattern_hash = 0;
+    h->keep.valid = false;
     chol_release(h);
     ic0_release(h);
     // H pattern from the GLOBAL Jacobian (identical on every rank, so the partial H arrays align)
@@ -454,6 +456,7 @@ spb_status spb_analyze_partitioned(spb_handle h, int32_t m, int32_t n, const int
     build_assembly_plan(ml, n, lp.data(), li.data(), h->H, P);
     upload_h_layout(h);
     upload_analysis(h, lp.data(), li.data(), P);
+    h->keep = PlanKeep{};  // incremental re-analysis is a single-GPU, plain-handle feature
     // partial buffers (inactive slots stay zero forever: they are never written)
     SPB_CUDA(h->d_hval_part.alloc((size_t)h->S.padded));
     SPB_CUDA(cudaMemsetAsync(h->d_hval_part.p, 0, (size_t)h->S.padded * sizeof(double), h->stream));

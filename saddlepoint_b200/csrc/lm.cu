@@ -142,7 +142,7 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       if (!same) {
         auto ta = std::chrono::steady_clock::now();
         spb_status s = part ? spb_analyze_partitioned(h, T->ESize, n, T->colptr, T->rowidx, T->row_begin, T->row_end)
-                            : spb_analyze(h, m, n, T->colptr, T->rowidx);
+                            : spb_analyze_update(h, m, n, T->colptr, T->rowidx, nullptr);  // patches an appended row
         if (s != SPB_OK) return s;
         R->seconds_analyze = std::chrono::duration<double>(std::chrono::steady_clock::now() - ta).count();
       }

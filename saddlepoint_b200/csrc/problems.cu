@@ -15,13 +15,20 @@
 // All evaluate residuals in the same operation order as a plain host loop (ascending
 // column, separate multiply and add), so host and device traits produce identical bits.
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 
 #include "spb_internal.h"
 
 using namespace spb;
 
+// Serial number of a problem object: spb_traits::pattern_version.  (The object's address is NOT a version: the allocator
+// hands the address of a destroyed problem to the next one, and spb_lm_solve would then skip the re-analysis of a
+// different pattern of the same size.)
+static std::atomic<uint64_t> g_problem_serial{1};
+
 struct spb_problem {
+  uint64_t serial = g_problem_serial.fetch_add(2);  // odd, never 0
   spb_context* h = nullptr;
   int kind = 0;  // 0 LF, 1 Rosenbrock, 2 blocks (constant sparse block + barrier block)
   int n = 0, m = 0;           // m: residual rows evaluated by this object (the owned rows when partitioned)
@@ -590,7 +597,7 @@ spb_status spb_problem_traits(spb_problem_t P, spb_traits* T) {
   T->row_end = P->row_end;
   T->colptr = P->colptr.data();
   T->rowidx = P->rowidx.data();
-  T->pattern_version = (uint64_t)(uintptr_t)P | 1u;  // pattern is immutable for the problem's lifetime
+  T->pattern_version = P->serial;  // unique per problem object; its pattern is immutable for its lifetime
   T->mem = SPB_DEVICE;
   T->user = P;
   T->initial_solution = any_x0;

@@ -148,6 +148,21 @@ struct SlotMeta {    // 8 bytes
   uint16_t il, jl, rank, rank_up;
 };
 
+// Host-side pieces of the last analysis kept for incremental re-analysis (analysis_update.cu): the J pattern and the
+// parts of the assembly plan that depend on it.  Kept only for patterns below kPlanKeepMaxNnz entries.
+struct PlanKeep {
+  bool valid = false;
+  std::vector<int> Jrow;                       // row indices of J (the column pointers are spb_context::Jcolptr_host)
+  std::vector<int> stage_cols, chunk_stage_ptr;  // stage list of every chunk (ascending columns)
+  std::vector<int> chunk_slot, chunk_npairs;
+  std::vector<int64_t> chunk_rec;
+  std::vector<uint8_t> chunk_staged;
+  std::vector<int> low_colptr, low_row;        // strictly-lower slots, column-major (stream order)
+  std::vector<uint16_t> slot_start, slot_cnt;  // per slot (stream order): first record relative to its chunk, record count
+  std::vector<int> sorted_pos;                 // per chunk: its position in spb_context::d_chunk_desc_sorted / chunk_need
+};
+constexpr int64_t kPlanKeepMaxNnz = 120000000;
+
 // Host threads for the symbolic phase (SPB_HOST_THREADS overrides; 1 = serial).
 inline int host_threads() {
   static const int t = [] {
@@ -296,6 +311,9 @@ struct spb_context {
   spb::DevBuf<spb::ChunkDesc> d_chunk_desc_sorted;  // the chunk descriptors ordered by that need
   std::vector<int> colchunk_host;    // column boundaries of the column-kernel chunks
   std::vector<int> Jcolptr_host;
+  spb::PlanKeep keep;                // for spb_analyze_update
+  spb::DevBuf<int> d_keep_stage_cols, d_keep_stage_ptr, d_keep_sorted_pos, d_keep_flags;  // device copies, made by the first update
+  uint64_t h_pattern_hash = 0;       // of the structural H pattern (the Cholesky / IC(0) symbolic state depends on it only)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t asm_done_ev = nullptr;

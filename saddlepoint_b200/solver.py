@@ -79,6 +79,15 @@ class Handle:
         self._check(self.L.spb_analyze(self.h, m, n, pc, pr))
         self.m, self.n, self.nnzJ = m, n, int(colptr[-1])
 
+    def analyze_update(self, m, n, colptr, rowidx):
+        """spb_analyze_update: 0 = unchanged, 1 = patched (one appended single-entry row), 2 = full analysis."""
+        colptr, pc = _i32(colptr)
+        rowidx, pr = _i32(rowidx)
+        how = C.c_int(2)
+        self._check(self.L.spb_analyze_update(self.h, m, n, pc, pr, C.byref(how)))
+        self.m, self.n, self.nnzJ = m, n, int(colptr[-1])
+        return how.value
+
     # ---- multi-GPU (one big problem, rows partitioned across ranks)
     def comm_init(self, unique_id, rank, nranks):
         """Attach an NCCL communicator (unique_id: 128 bytes from comm_unique_id() on one rank)."""

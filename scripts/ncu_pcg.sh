@@ -8,3 +8,6 @@ $B > gpurun_out/ncu_pre_classic.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:pcg_persistent_kernel -s 3 -c 1 -o gpurun_out/r2_pcg_classic_relaxed -f $B > gpurun_out/ncu_classic.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/r2_launches.csv
+ncu --set full --clock-control none --import-source on -k regex:assemble_pairs -s 3 -c 1 -o gpurun_out/r2_asm_pairs -f $B > gpurun_out/ncu_asm_pairs.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:assemble_cols -s 3 -c 1 -o gpurun_out/r2_asm_cols -f $B > gpurun_out/ncu_asm_cols.log 2>&1
+ls -la gpurun_out/r2_asm_*.ncu-rep

@@ -36,6 +36,7 @@
 #include <cooperative_groups.h>
 
 #include "chol_internal.h"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -346,12 +347,15 @@ __global__ void __launch_bounds__(128) chol_step_kernel(const int* __restrict__ 
 // mode 1: the update matrix U (K = k).
 constexpr int kSyrkLd = 68;  // 64 + 4: conflict-free fragment loads
 constexpr int kSyrkKC = 16;  // K columns staged per pipeline stage
+constexpr int kSyrkSeg = 66; // doubles per bulk copy: a 64-row segment plus the alignment element, even length
+template <bool TMA>
 __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ fronts, int mode, int ka, int ke, int cend,
                                                         const int* __restrict__ sn_k,
                                                         const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
                                                         const int64_t* __restrict__ U_off, double* __restrict__ Lbuf,
                                                         double* __restrict__ Ubuf, long long* dbg) {
-  __shared__ double As[2 * kSyrkKC * kSyrkLd], Bs[2 * kSyrkKC * kSyrkLd];
+  __shared__ __align__(16) double As[2 * kSyrkKC * kSyrkLd], Bs[2 * kSyrkKC * kSyrkLd];
+  __shared__ uint64_t bar[2];
   const bool dbg_on = dbg && blockIdx.x == 0 && blockIdx.y == gridDim.y - 1 && blockIdx.z == 0 && threadIdx.x == 0;
   if (dbg_on) dbg[0] = clock64();
   const int f = fronts[blockIdx.z];
@@ -388,54 +392,116 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(const int* __restrict__ 
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int lr = lane >> 2, lk = lane & 3;
-  // Two-stage software pipeline: the next K-chunk of both row blocks is copied global -> shared
-  // asynchronously (cp.async, zero-filled outside the matrix) while the tensor cores work on
-  // the current one.
-  auto stage_load = [&](int st, int k0) {
-    double* as = As + st * (kSyrkKC * kSyrkLd);
-    double* bs = Bs + st * (kSyrkKC * kSyrkLd);
-    for (int e = tid; e < kSyrkKC * 64; e += 128) {
-      const int t = e >> 6, i = e & 63;
-      const int gi = ti * 64 + i, gj = tj * 64 + i;
-      const bool kin = (k0 + t) < K;
-      const bool ia = kin && gi < nrows, ib = kin && gj < nrows;
-      const double* sa = ia ? A + (int64_t)(k0 + t) * r + gi : A;
-      const double* sb = ib ? A + (int64_t)(k0 + t) * r + gj : A;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(as + t * kSyrkLd + i)), "l"(sa),
-                   "r"(ia ? 8 : 0));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(bs + t * kSyrkLd + i)), "l"(sb),
-                   "r"(ib ? 8 : 0));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  const int nchunks = (K + kSyrkKC - 1) / kSyrkKC;
-  if (dbg_on) dbg[1] = clock64();
-  stage_load(0, 0);
-  for (int c = 0; c < nchunks; ++c) {
-    const int st = c & 1;
-    if (c + 1 < nchunks) {
-      stage_load(st ^ 1, (c + 1) * kSyrkKC);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if constexpr (TMA) {
+    // Two-stage pipeline fed by the TMA unit: every K column of a 64-row operand tile is one contiguous 512-byte
+    // segment of the panel, brought in by ONE bulk asynchronous copy (cp.async.bulk, SASS UBLKCP) that completes on the
+    // stage's mbarrier -- 32 copy instructions per stage instead of 2 048 eight-byte cp.async (the staging instructions
+    // were competing with the DMMA stream for issue slots).  Panel leading dimensions are odd in general, so a segment
+    // is only 8-byte aligned: the copy starts at the 16-byte boundary below it (one element early when the segment's
+    // address is odd) and moves 66 doubles; the fragment reads add that shift back.  (k0 and kk are even, so the shift
+    // of K column k0 + kk + lk depends on lk only: one constant per thread and operand.)  Rows past the end of a column
+    // come in as the next column's data and only reach C entries that the store masks; K columns past the end are
+    // zero-filled.  The diagonal tile (ti == tj) stages one operand.
+    const bool diag = ti == tj;
+    const double* Arow = A + ti * 64;
+    const double* Brow = A + tj * 64;
+    auto odd = [](const double* p) { return (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1u); };
+    const int sha = odd(Arow + (int64_t)lk * r), shb = odd(Brow + (int64_t)lk * r);
+    if (tid == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
     }
     __syncthreads();
-    const double* as = As + st * (kSyrkKC * kSyrkLd);
-    const double* bs = Bs + st * (kSyrkKC * kSyrkLd);
-#pragma unroll
-    for (int kk = 0; kk < kSyrkKC; kk += 4) {
-      double a[4], b[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a[q] = as[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
-        b[q] = bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
+    auto stage_load = [&](int st, int k0) {
+      double* as = As + st * (kSyrkKC * kSyrkLd);
+      double* bs = Bs + st * (kSyrkKC * kSyrkLd);
+      const int kc = min(kSyrkKC, K - k0);  // K columns of this stage
+      if (tid == 0) mbar_expect_tx(&bar[st], (uint32_t)(kc * kSyrkSeg * 8 * (diag ? 1 : 2)));
+      if (tid < 2 * kSyrkKC) {
+        const int t = tid & (kSyrkKC - 1), which = tid / kSyrkKC;
+        if (t < kc && !(which && diag)) {
+          const double* src = (which ? Brow : Arow) + (int64_t)(k0 + t) * r;
+          tma_bulk_g2s((which ? bs : as) + t * kSyrkLd, src - odd(src), kSyrkSeg * 8, &bar[st]);
+        }
       }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dmma_m8n8k4(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+      if (kc < kSyrkKC)  // last stage of a K that is not a multiple of 16: the missing columns multiply as zeros
+        for (int e = tid; e < (kSyrkKC - kc) * kSyrkLd; e += 128) as[kc * kSyrkLd + e] = bs[kc * kSyrkLd + e] = 0.0;
+    };
+    const int nchunks = (K + kSyrkKC - 1) / kSyrkKC;
+    if (dbg_on) dbg[1] = clock64();
+    stage_load(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int st = c & 1;
+      if (c + 1 < nchunks) stage_load(st ^ 1, (c + 1) * kSyrkKC);  // the other buffer was released by the barrier closing c-1
+      mbar_wait(&bar[st], (uint32_t)((c >> 1) & 1));
+      if (c + 1 == nchunks) __syncthreads();  // the zero-filled columns of the last stage
+      const double* as = As + st * (kSyrkKC * kSyrkLd) + sha;
+      const double* bs = diag ? As + st * (kSyrkKC * kSyrkLd) + shb : Bs + st * (kSyrkKC * kSyrkLd) + shb;
+  #pragma unroll
+      for (int kk = 0; kk < kSyrkKC; kk += 4) {
+        double a[4], b[4];
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[q] = as[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
+          b[q] = bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
+        }
+  #pragma unroll
+        for (int p = 0; p < 4; ++p)
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) dmma_m8n8k4(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
+  } else {
+    // Two-stage software pipeline: the next K-chunk of both row blocks is copied global -> shared
+    // asynchronously (cp.async, zero-filled outside the matrix) while the tensor cores work on
+    // the current one.
+    auto stage_load = [&](int st, int k0) {
+      double* as = As + st * (kSyrkKC * kSyrkLd);
+      double* bs = Bs + st * (kSyrkKC * kSyrkLd);
+      for (int e = tid; e < kSyrkKC * 64; e += 128) {
+        const int t = e >> 6, i = e & 63;
+        const int gi = ti * 64 + i, gj = tj * 64 + i;
+        const bool kin = (k0 + t) < K;
+        const bool ia = kin && gi < nrows, ib = kin && gj < nrows;
+        const double* sa = ia ? A + (int64_t)(k0 + t) * r + gi : A;
+        const double* sb = ib ? A + (int64_t)(k0 + t) * r + gj : A;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(as + t * kSyrkLd + i)), "l"(sa),
+                     "r"(ia ? 8 : 0));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(bs + t * kSyrkLd + i)), "l"(sb),
+                     "r"(ib ? 8 : 0));
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunks = (K + kSyrkKC - 1) / kSyrkKC;
+    if (dbg_on) dbg[1] = clock64();
+    stage_load(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int st = c & 1;
+      if (c + 1 < nchunks) {
+        stage_load(st ^ 1, (c + 1) * kSyrkKC);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const double* as = As + st * (kSyrkKC * kSyrkLd);
+      const double* bs = Bs + st * (kSyrkKC * kSyrkLd);
+  #pragma unroll
+      for (int kk = 0; kk < kSyrkKC; kk += 4) {
+        double a[4], b[4];
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[q] = as[(kk + lk) * kSyrkLd + wy * 32 + q * 8 + lr];
+          b[q] = bs[(kk + lk) * kSyrkLd + wx * 32 + q * 8 + lr];
+        }
+  #pragma unroll
+        for (int p = 0; p < 4; ++p)
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) dmma_m8n8k4(acc[p][q][0], acc[p][q][1], a[p], b[q]);
+      }
+      __syncthreads();
+    }
   }
   if (dbg_on) dbg[2] = clock64();
   // read-modify-write of the C tile in two passes (all 32 loads of a thread in flight, then the
@@ -1023,7 +1089,9 @@ static CholDevice* ensure_symbolic(spb_context* h) {
   SPB_CUDA(D->dinv_off.upload(C.dinv_off, st));
   SPB_CUDA(D->a_src.upload(C.a_src, st));
   SPB_CUDA(D->a_dst.upload(C.a_dst, st));
-  SPB_CUDA(D->Lbuf.alloc((size_t)C.L_off[ns]));
+  // + slack: the SYRK staging copies 66-double windows that may run past the last column of the last panel
+  SPB_CUDA(D->Lbuf.alloc((size_t)C.L_off[ns] + 128));
+  SPB_CUDA(cudaMemsetAsync(D->Lbuf.p + C.L_off[ns], 0, 128 * sizeof(double), h->stream));
   SPB_CUDA(D->Ubuf.alloc((size_t)std::max<int64_t>(1, C.U_total)));
   SPB_CUDA(D->Wbuf.alloc((size_t)C.W_off[ns]));
   SPB_CUDA(D->Dinv.alloc((size_t)C.dinv_off[ns]));
@@ -1054,6 +1122,16 @@ spb_status chol_factorize(spb_context* h) {
     chol_scatter_a_kernel<<<h->num_sms * 8, 256, 0, st>>>(h->d_hval.p, D->a_src.p, D->a_dst.p, cnt, D->Lbuf.p);
     ++nl;
   }
+  // SYRK/GEMM operand staging: cp.async (default) or TMA bulk copies (SPB_CHOL_TMA=1).  Measured on one B200: the
+  // TMA form is 2-3 % slower (48.9 vs 47.5 ms at C2, 808 vs 791 ms per LM iteration at the 500k-face size): a 64-row
+  // operand segment is 512 bytes and the TMA unit is issue-bound on copies that small; the one-instruction-per-tile 2-D
+  // tensor-map form needs 16-byte column strides, i.e. even leading dimensions, which the packed panels do not have.
+  const bool syrk_tma = getenv("SPB_CHOL_TMA") && atoi(getenv("SPB_CHOL_TMA")) > 0;
+  auto syrk = [&](dim3 grid, const int* fl, int mode, int ka, int ke, int cend, const int* snk, const int* snr, const int64_t* lo, const int64_t* uo,
+                  double* Lb, double* Ub, long long* dbgp) {
+    if (syrk_tma) chol_syrk_kernel<true><<<grid, 128, 0, st>>>(fl, mode, ka, ke, cend, snk, snr, lo, uo, Lb, Ub, dbgp);
+    else chol_syrk_kernel<false><<<grid, 128, 0, st>>>(fl, mode, ka, ke, cend, snk, snr, lo, uo, Lb, Ub, dbgp);
+  };
   for (int l = 0; l < C.nlevels; ++l) {
     // the update matrices born at this level start from zero (their arena blocks are reused across levels)
     for (int z = C.u_zero_ptr[l]; z < C.u_zero_ptr[(size_t)l + 1]; ++z)
@@ -1117,7 +1195,7 @@ spb_status chol_factorize(spb_context* h) {
               SPB_CUDA(D->dbg.alloc(8));
               dbgp = D->dbg.p;
             }
-            chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, kb, kb + 32, oe, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
+            syrk(dim3(ntj, nti, G.count), list, 0, kb, kb + 32, oe, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p,
                                                                     D->Lbuf.p, D->Ubuf.p, dbgp);
             if (dbgp) {
               long long t[8];
@@ -1131,14 +1209,14 @@ spb_status chol_factorize(spb_context* h) {
         }
         if (oe < G.max_k) {  // everything right of the panel, once, with K = 256
           const int nti = (G.max_r - oe + 63) / 64, ntj = (G.max_k - oe + 63) / 64;
-          chol_syrk_kernel<<<dim3(ntj, nti, G.count), 128, 0, st>>>(list, 0, ob, oe, 0x7fffffff, D->sn_k.p, D->sn_r.p, D->L_off.p,
+          syrk(dim3(ntj, nti, G.count), list, 0, ob, oe, 0x7fffffff, D->sn_k.p, D->sn_r.p, D->L_off.p,
                                                                   D->U_off.p, D->Lbuf.p, D->Ubuf.p, nullptr);
           ++nl;
         }
       }
       const int umax = G.max_r;  // upper bound on u inside the group
       const int nt = (umax + 63) / 64;
-      chol_syrk_kernel<<<dim3(nt, nt, G.count), 128, 0, st>>>(list, 1, 0, 0, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
+      syrk(dim3(nt, nt, G.count), list, 1, 0, 0, 0, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->Lbuf.p,
                                                              D->Ubuf.p, nullptr);
       ++nl;
     }

@@ -478,10 +478,7 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
       }
       const bool fits = c_np + pj <= kPairTile && c_ns + (s1 - s0) <= kSlotCap && (int)cur_list.size() + new_cols <= kStageCols &&
                         c_vals + new_vals <= kStageVals;
-      if (!fits && c_ns > 0) {
-        if (getenv("SPB_PLAN_DEBUG")) { static int cnt = 0; if (cnt++ < 5) fprintf(stderr, "[plan] close: np %d+%d ns %d+%d cols %d+%d vals %d+%d\n", c_np, pj, c_ns, s1 - s0, (int)cur_list.size(), new_cols, c_vals, new_vals); }
-        close_chunk(s0);
-      }
+      if (!fits && c_ns > 0) close_chunk(s0);
       const bool alone_ok = pj <= kPairTile && (s1 - s0) <= kSlotCap;
       if (alone_ok) {
         const int jl = add_col(j);
@@ -542,6 +539,10 @@ void assembly_plan_impl(int m, int n, const int* colptr, const int* rowidx, cons
         }
         std::stable_sort(P.proc_perm.begin() + ch.cs, P.proc_perm.begin() + ch.s_end,
                          [&](int a2, int b2) { return slot_npairs[a2] > slot_npairs[b2]; });
+        // The kernel walks position p of the chunk in thread p & 255, pass p >> 8.  The second pass runs in REVERSE
+        // order, so the warp that got the 32 longest slots in the first pass gets the 32 shortest in the second: the
+        // warps of a CTA reach the barrier together (the barrier wait was 30 % of the kernel's stall samples).
+        if (ch.s_end - ch.cs > 256) std::reverse(P.proc_perm.begin() + ch.cs + 256, P.proc_perm.begin() + ch.s_end);
       }
     });
   }

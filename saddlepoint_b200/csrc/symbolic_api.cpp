@@ -165,14 +165,21 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
         if (st0 + P.slot_jl[s] >= st1 || P.stage_cols[st0 + P.slot_jl[s]] != j) ++bad;
       }
       if (s1 - s0 > kSlotCap || (P.chunk_npairs[c] > kPairTile && s1 - s0 != 1)) ++bad;
-      // processing order: a permutation of the chunk's slots with non-increasing pair counts
+      // processing order: a permutation of the chunk's slots; pair counts non-increasing over the first 256 positions
+      // (first pass of the kernel), then non-decreasing and never above the first pass's minimum (second pass, reversed)
       {
         std::vector<int> seen(s1 - s0, 0);
-        int prevc = 1 << 30;
+        int prevc = 1 << 30, first_min = 1 << 30;
         for (int pos = s0; pos < s1; ++pos) {
           int sidx = P.proc_perm[pos];
           if (sidx < s0 || sidx >= s1 || seen[sidx - s0]++) { ++bad; continue; }
-          if (P.slot_cnt[sidx] > prevc) ++bad;
+          if (pos - s0 < 256) {
+            if (P.slot_cnt[sidx] > prevc) ++bad;
+            first_min = P.slot_cnt[sidx];
+          } else {
+            if (pos - s0 > 256 && P.slot_cnt[sidx] < prevc) ++bad;
+            if (P.slot_cnt[sidx] > first_min) ++bad;
+          }
           prevc = P.slot_cnt[sidx];
         }
       }

@@ -166,3 +166,26 @@ def test_singular_column_returns_false_from_lm(spb, orc):
     lm.init(ls, T(), spb.DiagonalDamping(0.01), 10)
     assert lm.solve(True) is False and lm.exit_path == "factorize_failed"
     ls.handle.close()
+
+
+@pytest.mark.parametrize("g", [40, 150])
+def test_tma_staged_syrk_gives_the_same_factor(spb, orc, g, monkeypatch):
+    """SPB_CHOL_TMA=1 stages the SYRK/GEMM operand tiles with TMA bulk copies (cp.async.bulk + mbarrier) instead of
+    cp.async; the DMMA sequence and its operand order are the same, so the solve must return the same bits
+    (odd panel leading dimensions exercise the alignment shift of the bulk copies)."""
+    J = orc.lf_matrix(g, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    E = J.scipy() @ np.ones(n) - 1.0
+    xs = []
+    for tma in ("0", "1"):
+        monkeypatch.setenv("SPB_CHOL_TMA", tma)
+        h = spb.Handle(0)
+        h.set_solver(spb.SOLVER_CHOLESKY)
+        h.analyze(m, n, colptr, rowidx)
+        h.assemble(vals, E, 0.01)
+        assert h.factorize()
+        x, _, _ = h.solve()
+        xs.append(np.array(x, copy=True))
+        h.close()
+    assert np.array_equal(xs[0].view(np.uint64), xs[1].view(np.uint64))

@@ -430,10 +430,14 @@ def run_c2(args, torch, dist, local):
     h.stage_reset(False)
     nnzH = h.h_nnz()
     sr = os.environ.get("SPB_PCG_VARIANT", "classic").startswith("s")
+    stream = (not sr) and os.environ.get("SPB_PCG_STREAM", "1") != "0"
     kname = ("pcg_sr_kernel<false> (whole Jacobi-PCG solve, single-reduction CG: SpMV + dots | vector updates, two grid barriers per iteration, one cooperative launch)"
-             if sr else "pcg_persistent_kernel<4> (whole Jacobi-PCG solve: SpMV + vector updates + reductions, one cooperative launch)")
+             if sr else
+             "pcg_stream_kernel (whole Jacobi-PCG solve in one cooperative launch, one 16-warp CTA per SM; the H stream is staged in shared memory by TMA bulk copies, two stages per warp)"
+             if stream else "pcg_persistent_kernel<4> (whole Jacobi-PCG solve: SpMV + vector updates + reductions, one cooperative launch)")
     relax_on = float(os.environ.get("SPB_PCG_RELAX", "1e6")) > 0
-    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G, kname, ("sr" if sr else "classic") + ("_relaxed" if relax_on else ""))
+    roof = _roofline(h, stages, K, lin_iters_roof, n, m, nnzJ, nnzH, g == C2_G, kname,
+                     ("sr" if sr else "stream" if stream else "classic") + ("_relaxed" if relax_on else ""))
 
     # ---- e2e: the C-ABI hot path with HOST buffers (H2D + D2H inside the timed region) -------
     Jv_host = torch.empty(nnzJ, dtype=torch.float64).pin_memory()

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
 
 __device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
 
-__global__ void __launch_bounds__(256) assemble_cols_kernel(
+__global__ void __launch_bounds__(256, 4) assemble_cols_kernel(
     const int* __restrict__ colchunk, const int* __restrict__ Jcolptr, const int* __restrict__ Jrow,
     const double* __restrict__ Jv, const double* __restrict__ f, double lambda, const int* __restrict__ nup1,
     const int64_t* __restrict__ slice_off, double* __restrict__ hval, double* __restrict__ hdiag,

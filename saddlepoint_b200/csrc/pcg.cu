@@ -27,6 +27,7 @@
 #include "ic0.h"
 #include "spb_internal.h"
 #include "pcg_device.cuh"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -393,6 +394,360 @@ __global__ void __launch_bounds__(256, MINB) pcg_persistent_kernel(PcgParams P) 
   }
 }
 
+// ---- streamed variant: the H stream goes through shared memory, moved by the TMA unit -----------------------------
+// pcg_persistent_kernel keeps the loads of the H stream in registers: a lane has eight (column, value) pairs in flight,
+// then gathers, then multiplies, so the bytes an SM has in flight swing between "all" and "none", and with the FP32
+// value stream (6 instead of 10 bytes per entry) they no longer cover HBM's latency-bandwidth product: the measured
+// SpMV phase is 44 us with FP64 values (5.9 TB/s) but 36 us instead of 25 with FP32 values.  Here every warp owns two
+// shared-memory stages of sixteen entries per lane (values + columns, 6 KB); lane 0 refills a stage with two bulk
+// asynchronous copies (cp.async.bulk, completion on the stage's mbarrier, L2 evict-first) as soon as the warp has read
+// it, so a warp always has one stage in flight while it works on the other -- 16 warps x 5 KB per SM in flight whatever
+// the arithmetic is doing.  One CTA of 16 warps per SM (192 KB of stages), so the grid barriers have 148 participants
+// instead of 592.  Sums are formed in the same order as in pcg_persistent_kernel (ascending k per row; block partials
+// differ, so the dot products agree to rounding, not to the bit).
+constexpr int kStreamWarps = 16;
+constexpr int kStreamK = 16;                                  // entries per lane and stage
+constexpr int kStreamValBytes = kStreamK * 32 * 8;            // 4096
+constexpr int kStreamColBytes = kStreamK * 32 * 4;            // 2048 (16-bit deltas use half)
+constexpr int kStreamStageBytes = kStreamValBytes + kStreamColBytes;
+constexpr int kStreamMaxDepth = 4;
+constexpr size_t kStreamSmem = (size_t)kStreamWarps * 2 * kStreamStageBytes + kStreamWarps * kStreamMaxDepth * sizeof(uint64_t);
+
+__device__ __forceinline__ void stream_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+struct StreamCursor {   // per warp (uniform across its lanes)
+  unsigned phase = 0;   // bit b: parity of the phase of mbarrier b the warp waits for next
+};
+
+// q = H p over the slices first, first + step, ...; returns this lane's share of p.q
+// D stages of SB bytes per warp (D * SB <= 2 * kStreamStageBytes).  Two 6 KB stages are used; four 3 KB stages for the FP32
+// value stream (whose stages are half full) were measured and change nothing (36.0 vs 35.3 us per product): the FP32
+// products are not bound by the bytes a warp has in flight.
+template <typename VT, bool W32, int D, int SB>
+__device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __restrict__ hval, unsigned char* stage, uint64_t* bar,
+                                              StreamCursor& cur, int first, int step, uint64_t pol) {
+  constexpr int kValBytes = kStreamK * 32 * (int)sizeof(VT);
+  unsigned issued = 0, consumed = 0;  // stages of this product (every product drains its ring)
+  const int lane = threadIdx.x & 31;
+  const int n = P.n, nslices = P.nslices;
+  const bool have16 = P.col16 != nullptr;
+  // producer side (lane 0 issues; every lane tracks the cursor)
+  int ps = first, pk = 0, pwidth = 0;
+  int64_t poff = 0;
+  bool p16 = false;
+  auto load_slice = [&]() {
+    if (ps < nslices) {
+      poff = P.slice_off[ps];
+      pwidth = (int)((P.slice_off[ps + 1] - poff) >> 5);
+      p16 = have16 && P.s16[ps];
+    }
+  };
+  auto issue = [&]() {
+    if (ps >= nslices) return;
+    const unsigned b = issued % D;
+    const int cnt = min(kStreamK, pwidth - pk);
+    if (lane == 0) {
+      const uint32_t vb = (uint32_t)cnt * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)cnt * 32u * (p16 ? 2u : 4u);
+      mbar_expect_tx(&bar[b], vb + cb);
+      if (cnt > 0) {
+        unsigned char* sb = stage + b * SB;
+        const int64_t at = poff + (int64_t)pk * 32;
+        stream_bulk(sb, hval + at, vb, &bar[b], pol);
+        if (p16) stream_bulk(sb + kValBytes, P.col16 + at, cb, &bar[b], pol);
+        else stream_bulk(sb + kValBytes, P.col + at, cb, &bar[b], pol);
+      }
+    }
+    ++issued;
+    pk += kStreamK;
+    if (pk >= pwidth) {
+      ps += step;
+      pk = 0;
+      load_slice();
+    }
+  };
+  load_slice();
+#pragma unroll
+  for (int d = 0; d < D; ++d) issue();
+  double loc = 0.0;
+  for (int slice = first; slice < nslices; slice += step) {
+    const int row = slice * 32 + lane;
+    const int64_t off = P.slice_off[slice];
+    const int width = (int)((P.slice_off[slice + 1] - off) >> 5);
+    const int len = row < n ? P.rowlen[row] : 0;
+    const bool c16 = have16 && P.s16[slice];
+    const int rbase = row - 32768, csafe = row < n ? row : 0;
+    double acc = 0.0;
+    int k0 = 0;
+    do {
+      const unsigned b = consumed % D;
+      mbar_wait(&bar[b], (cur.phase >> b) & 1u);
+      cur.phase ^= 1u << b;
+      const unsigned char* sb = stage + b * SB;
+      const VT* sv = reinterpret_cast<const VT*>(sb) + lane;
+      const int cnt = min(kStreamK, width - k0);
+      int c[kStreamK];
+      if (c16) {
+        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane;
+#pragma unroll
+        for (int u = 0; u < kStreamK; ++u) c[u] = u < cnt ? rbase + (int)sc[u * 32] : csafe;
+      } else {
+        const int* sc = reinterpret_cast<const int*>(sb + kValBytes) + lane;
+#pragma unroll
+        for (int u = 0; u < kStreamK; ++u) c[u] = u < cnt ? sc[u * 32] : csafe;
+      }
+      double xv[kStreamK];
+#pragma unroll
+      for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[c[u]];
+      if (W32) {
+        float* wp = P.hval32 + off + lane;
+#pragma unroll
+        for (int u = 0; u < kStreamK; ++u)
+          if (u < cnt) __stcs(wp + (k0 + u) * 32, (float)sv[u * 32]);
+      }
+#pragma unroll
+      for (int u = 0; u < kStreamK; ++u)
+        if (k0 + u < len) acc = fma((double)sv[u * 32], xv[u], acc);
+      __syncwarp();  // every lane has read stage b: it can be refilled
+      ++consumed;
+      issue();
+      k0 += kStreamK;
+    } while (k0 < width);
+    if (row < n) {
+      P.q[row] = acc;
+      loc = fma(P.p[row], acc, loc);
+    }
+  }
+  return loc;
+}
+
+template <int NW>
+__device__ __forceinline__ double block_sum_nw(double v, double* sm /*NW*/) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    r = sm[0];
+    for (int w = 1; w < NW; ++w) r += sm[w];
+  }
+  __syncthreads();
+  return r;
+}
+// grid-wide sums finalised redundantly by every block from the per-block partials, in one fixed order
+template <int NW>
+__device__ __forceinline__ void block_total2_nw(const double* partA, const double* partB, int count, double* sm2 /*2 NW*/, double* bc2,
+                                                double& outA, double& outB) {
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < count; i += NW * 32) {
+    a += __ldcg(partA + i);
+    if (partB) b += __ldcg(partB + i);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    sm2[threadIdx.x >> 5] = a;
+    sm2[NW + (threadIdx.x >> 5)] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const double* src = sm2 + NW * threadIdx.x;
+    double r = src[0];
+    for (int w = 1; w < NW; ++w) r += src[w];
+    bc2[threadIdx.x] = r;
+  }
+  __syncthreads();
+  outA = bc2[0];
+  outB = bc2[1];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgParams P) {
+  constexpr int NW = kStreamWarps, NT = NW * 32;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  __shared__ double sm[NW];
+  __shared__ double sm2[2 * NW];
+  __shared__ double bc2[2];
+  const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x, warp = tid >> 5;
+  const int n = P.n;
+  const int stride = G * NT;
+  double* partA = P.partial;
+  double* partB = P.partial + G;
+  double* partC = P.partial + 2 * G;
+  double* partD = P.partial + 3 * G;  // own partials for the ||x||^2 epilogue (see pcg_persistent_kernel)
+  unsigned char* stage = stream_smem + (size_t)warp * 2 * kStreamStageBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stream_smem + (size_t)NW * 2 * kStreamStageBytes) + kStreamMaxDepth * warp;
+  if ((tid & 31) == 0)
+    for (int d = 0; d < kStreamMaxDepth; ++d) mbar_init(&bar[d], 1);
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  StreamCursor cur;
+  // init: r = b, p = z = dinv*r, x = 0
+  {
+    double rz = 0.0, bb = 0.0;
+    for (int i = blk * NT + tid; i < n; i += stride) {
+      const double bi = P.b[i];
+      const double z = bi * P.dinv[i];
+      P.x[i] = 0.0;
+      P.r[i] = bi;
+      P.p[i] = z;
+      rz = fma(bi, z, rz);
+      bb = fma(bi, bi, bb);
+    }
+    const double s1 = block_sum_nw<NW>(rz, sm);
+    const double s2 = block_sum_nw<NW>(bb, sm);
+    if (tid == 0) {
+      partB[blk] = s1;
+      partC[blk] = s2;
+    }
+  }
+  grid.sync();
+  double rz, bb;
+  block_total2_nw<NW>(partB, partC, G, sm2, bc2, rz, bb);
+  const double thresh = P.rtol * P.rtol * bb;
+  const double relax_thresh = P.relax_tol * P.relax_tol * bb;
+  bool use32 = false;
+  double rr = bb, pq = 0.0;
+  int iters = 0, breakdown = 0;
+  const bool run = (bb > thresh) && P.maxit > 0;
+  grid.sync();  // partB/partC are about to be reused
+  unsigned long long tick_ = P.phase_ns ? global_ns() : 0ull;
+  while (run) {
+    // phase 1: q = H p, partial p.q -- slices dealt round-robin to the warps of the grid (one contiguous window of the
+    // H stream is being read by the whole grid at any moment)
+    {
+      const int first = blk * NW + warp, step = G * NW;
+      double loc;
+      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes>(P, P.hval32, stage, bar, cur, first, step, pol);
+      else if (P.hval32 && iters == 0)  // writes the FP32 copy
+        loc = stream_spmv<double, true, 2, kStreamStageBytes>(P, P.hval, stage, bar, cur, first, step, pol);
+      else loc = stream_spmv<double, false, 2, kStreamStageBytes>(P, P.hval, stage, bar, cur, first, step, pol);
+      const double bs = block_sum_nw<NW>(loc, sm);
+      if (tid == 0) partA[blk] = bs;
+    }
+    SPB_TICK(0)
+    grid.sync();
+    SPB_TICK(1)
+    {
+      double dummy;
+      block_total2_nw<NW>(partA, nullptr, G, sm2, bc2, pq, dummy);
+    }
+    SPB_TICK(2)
+    if (!(pq > 0.0)) {  // not SPD, or NaN in H
+      breakdown = (pq != pq) ? 2 : 1;
+      break;
+    }
+    const double alpha = rz / pq;
+    // phase 2: x += alpha p, r -= alpha q, partial r.z and r.r (the vectors live in L2: eight elements in flight per thread)
+    {
+      double a1 = 0.0, a2 = 0.0;
+      int i = blk * NT + tid;
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        double pv[4], qv[4], xv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          pv[u] = P.p[j];
+          qv[u] = P.q[j];
+          xv[u] = P.x[j];
+          rv[u] = P.r[j];
+          dv[u] = P.dinv[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          P.x[j] = fma(alpha, pv[u], xv[u]);
+          const double ri = fma(-alpha, qv[u], rv[u]);
+          P.r[j] = ri;
+          const double z = ri * dv[u];
+          a1 = fma(ri, z, a1);
+          a2 = fma(ri, ri, a2);
+        }
+      }
+      for (; i < n; i += stride) {
+        P.x[i] = fma(alpha, P.p[i], P.x[i]);
+        const double ri = fma(-alpha, P.q[i], P.r[i]);
+        P.r[i] = ri;
+        const double z = ri * P.dinv[i];
+        a1 = fma(ri, z, a1);
+        a2 = fma(ri, ri, a2);
+      }
+      const double s1 = block_sum_nw<NW>(a1, sm);
+      const double s2 = block_sum_nw<NW>(a2, sm);
+      if (tid == 0) {
+        partB[blk] = s1;
+        partC[blk] = s2;
+      }
+    }
+    SPB_TICK(3)
+    grid.sync();
+    SPB_TICK(4)
+    double rz_new;
+    block_total2_nw<NW>(partB, partC, G, sm2, bc2, rz_new, rr);
+    SPB_TICK(5)
+    const double beta = rz_new / rz;
+    rz = rz_new;
+    ++iters;
+    if (!(rr > thresh) || iters >= P.maxit) break;
+    if (P.hval32 && rr <= relax_thresh) use32 = true;  // same bits in every block: a grid-uniform switch
+    // phase 3: p = dinv*r + beta p
+    {
+      int i = blk * NT + tid;
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        double pv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = i + u * stride;
+          pv[u] = P.p[j];
+          rv[u] = P.r[j];
+          dv[u] = P.dinv[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) P.p[i + u * stride] = fma(beta, pv[u], rv[u] * dv[u]);
+      }
+      for (; i < n; i += stride) P.p[i] = fma(beta, P.p[i], P.r[i] * P.dinv[i]);
+    }
+    SPB_TICK(6)
+    grid.sync();
+    SPB_TICK(7)
+  }
+  const bool nan_system = (bb != bb) || breakdown == 2;  // see pcg_persistent_kernel: the step becomes NaN (quirk H)
+  double xx;
+  {
+    double a = 0.0;
+    for (int i = blk * NT + tid; i < n; i += stride) {
+      double v = P.x[i];
+      if (nan_system) {
+        v = __longlong_as_double(0x7ff8000000000000LL);
+        P.x[i] = v;
+      }
+      a = fma(v, v, a);
+    }
+    const double s1 = block_sum_nw<NW>(a, sm);
+    if (tid == 0) partD[blk] = s1;
+    grid.sync();
+    double dummy;
+    block_total2_nw<NW>(partD, nullptr, G, sm2, bc2, xx, dummy);
+  }
+  if (blk == 0 && tid == 0) {
+    PcgScalars* sc = P.sc;
+    sc->rz = rz;
+    sc->pq = pq;
+    sc->rr = rr;
+    sc->bb = bb;
+    sc->thresh = thresh;
+    sc->iters = iters;
+    sc->breakdown = breakdown;
+    sc->maxit = P.maxit;
+    sc->xx = xx;
+    sc->done = 1;
+  }
+}
+
 // r = b, z = dinv*r, p = z, x = 0; rz = r.z, bb = b.b
 __global__ void __launch_bounds__(256) pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv,
                                                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
@@ -511,14 +866,20 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
   PcgScalars* sc = h->d_sc.p;
   if (h->pcg_persistent && h->pcg_single_reduction) return pcg_solve_sr(h, d_b, d_x, iters);
   if (h->pcg_persistent) {
-    void* kern = h->pcg_minb >= 5 ? (void*)pcg_persistent_kernel<5> : (void*)pcg_persistent_kernel<4>;
+    static const bool stream = !(getenv("SPB_PCG_STREAM") && atoi(getenv("SPB_PCG_STREAM")) == 0);
+    void* kern = stream ? (void*)pcg_stream_kernel : h->pcg_minb >= 5 ? (void*)pcg_persistent_kernel<5> : (void*)pcg_persistent_kernel<4>;
+    if (stream && !h->pcg_stream_ready) {
+      SPB_CUDA(cudaFuncSetAttribute(pcg_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
+      h->pcg_stream_ready = true;
+    }
     if (h->occ_pcg == 0) {
       int occ = 0;
       if (h->pcg_minb >= 5) SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_persistent_kernel<5>, 256, 0));
       else SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_persistent_kernel<4>, 256, 0));
       h->occ_pcg = std::max(1, occ);
     }
-    const int G = std::max(1, std::min((nslices + 7) / 8, h->num_sms * h->occ_pcg));
+    const int G = stream ? std::max(1, std::min((nslices + kStreamWarps - 1) / kStreamWarps, h->num_sms))
+                         : std::max(1, std::min((nslices + 7) / 8, h->num_sms * h->occ_pcg));
     PcgParams P;
     P.slice_off = h->d_slice_off.p;
     P.col = h->d_sell_col.p;
@@ -562,7 +923,7 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     }
     void* args[] = {&P};
     stage_begin(h, ST_PCG);
-    SPB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(256), args, 0, st));
+    SPB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(stream ? kStreamWarps * 32 : 256), args, stream ? kStreamSmem : 0, st));
     stage_end(h, ST_PCG, 1);
     SPB_CUDA(cudaMemcpyAsync(h->h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     SPB_CUDA(cudaStreamSynchronize(st));

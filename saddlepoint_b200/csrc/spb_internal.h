@@ -364,6 +364,7 @@ struct spb_context {
   // (1e6: 1e-7 at the default rtol 1e-13); 0 = always FP64.  SPB_PCG_RELAX overrides.
   double pcg_relax_factor = 1e6;
   bool pcg_persistent = true;  // one cooperative kernel per solve; false: one launch per phase
+  bool pcg_stream_ready = false;  // pcg_stream_kernel's shared-memory opt-in done
   bool pcg_single_reduction = false;  // the two-barrier Chronopoulos-Gear kernel (pcg_peer.cu); false: the three-barrier textbook kernel (pcg.cu)
   int occ_spmv = 0, occ_pcg = 0;
   bool pcg_col16 = true;       // persistent PCG reads 16-bit column deltas where a slice allows it

@@ -82,6 +82,11 @@ spb_status spb_h_values(spb_handle h, double* vals, int mem);
 spb_status spb_symbolic_h_pattern(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* nnz,
                                   int32_t* h_colptr, int32_t* h_rowidx);
 spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, int64_t* stats);
+/* Host execution of the packed "stream" form of the pair assembly (what assemble_pairs_stream_kernel reads), in the
+ * kernel's own summation order: off-diagonal values of H in the CSC order of spb_symbolic_h_pattern (diagonal entries
+ * 0).  stats[6] = form applicable, chunks, section bytes, runs, largest value window, largest section. */
+spb_status spb_symbolic_pairs_v2(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* Jvals, double* hvals,
+                                 int64_t* stats);
 /* Host-only view of the Cholesky symbolic phase (nested-dissection order, supernodes, fronts):
  * stats[8] = nsuper, nlevels, nnz(L), max pivot block, max front, flops, update-matrix entries,
  * structural violations; perm (optional, n) receives the fill-reducing order. */

@@ -12,7 +12,7 @@ LIBDIR = os.path.join(_HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libsaddlepoint_b200.so")
 SOURCES = ["context.cu", "assembly.cu", "pcg.cu", "pcg_peer.cu", "lm.cu", "batch.cu", "problems.cu", "cholesky.cu", "dist.cu",
-           "symbolic.cpp", "symbolic_api.cpp", "analysis_update.cu", "chol_symbolic.cpp", "ic0_symbolic.cpp"]
+           "symbolic.cpp", "pairs_v2.cpp", "assembly_v2.cu", "symbolic_api.cpp", "analysis_update.cu", "chol_symbolic.cpp", "ic0_symbolic.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("spb_h_values", C.c_int, [vp, vp, C.c_int]),
     ("spb_symbolic_h_pattern", C.c_int, [C.c_int32, C.c_int32, vp, vp, C.POINTER(C.c_int64), vp, vp]),
     ("spb_symbolic_plan_check", C.c_int, [C.c_int32, C.c_int32, vp, vp, vp]),
+    ("spb_symbolic_pairs_v2", C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp]),
     ("spb_symbolic_chol_stats", C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp]),
     ("spb_assemble", C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     ("spb_get_rhs", C.c_int, [vp, vp, C.c_int]),

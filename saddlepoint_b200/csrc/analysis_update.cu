@@ -254,6 +254,7 @@ static bool try_append_row(spb_context* h, int m_new, int n, const int* colptr, 
   lap("J pattern on the device");
   // (3) stage entries and chunk descriptors (both copies), recomputed on the device from the new column pointers
   const int nch = (int)K.chunk_npairs.size();
+  h->v2_ok = false;  // the packed stream form (assembly_v2.cu) describes the old J layout: the patched general kernels take over
   {
     if (!h->d_keep_stage_cols.p) {  // first update on this analysis: the stage lists go to the device once
       SPB_CUDA(h->d_keep_stage_cols.upload(K.stage_cols, st));

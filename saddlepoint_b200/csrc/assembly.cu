@@ -695,6 +695,12 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
     h->colchunk_host = P.colchunk;
     h->Jcolptr_host.assign(colptr, colptr + h->n + 1);
   }
+  {
+    // the "stream" form of the pair assembly (default when it applies; see assembly_v2.cu)
+    PairsV2Host V;
+    pack_pairs_v2(colptr, P, h->S, V);
+    upload_pairs_v2(h, V);
+  }
   h->nslots = P.nslots;
   h->npairs = P.npairs;
   // host-side pieces kept for incremental re-analysis (spb_analyze_update)
@@ -728,7 +734,23 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   if (d_f) SPB_CUDA(cudaMemsetAsync(h->d_foo_bits.p, 0, sizeof(unsigned long long), st));
   const bool part = h->partitioned;
   double* hv = part ? h->d_hval_part.p : h->d_hval.p;
-  if (h->ncolchunks > 0) {
+  // With the stream-form pair kernel (one CTA per SM, shared-memory-pipe bound, HBM half idle) the column kernel
+  // (latency bound, writes disjoint outputs: diagonal of H, rhs, d) runs NEXT to it on a side stream: its CTAs fit
+  // into the shared memory and registers the pair kernel leaves free.
+  static const bool overlap_on = !(getenv("SPB_ASM_OVERLAP") && atoi(getenv("SPB_ASM_OVERLAP")) == 0);
+  const bool side = overlap_on && h->ncolchunks > 0 && h->nchunks > 0 && h->v2_ok && ((((uintptr_t)d_Jv) & 15) == 0);
+  cudaStream_t cst = st;
+  if (side) {
+    if (!h->asm_side_stream) {
+      SPB_CUDA(cudaStreamCreateWithFlags(&h->asm_side_stream, cudaStreamNonBlocking));
+      SPB_CUDA(cudaEventCreateWithFlags(&h->asm_fork_ev, cudaEventDisableTiming));
+      SPB_CUDA(cudaEventCreateWithFlags(&h->asm_join_ev, cudaEventDisableTiming));
+    }
+    cst = h->asm_side_stream;
+    SPB_CUDA(cudaEventRecord(h->asm_fork_ev, st));
+    SPB_CUDA(cudaStreamWaitEvent(cst, h->asm_fork_ev, 0));
+  }
+  if (h->ncolchunks > 0 && !side) {
     assemble_cols_kernel<<<h->ncolchunks, 256, 0, st>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda,
                                                         h->d_nup1.p, h->d_slice_off.p, hv, h->d_hdiag.p,
                                                         part ? h->d_rhs_part.p : h->d_rhs.p, part ? h->d_dvec_part.p : h->d_dvec.p,
@@ -738,7 +760,18 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
   if (h->nchunks > 0) {
     const int bulk_ok = (((uintptr_t)d_Jv) & 15) == 0 ? 1 : 0;  // TMA bulk copies need a 16-byte aligned source
     static const bool pipe_off = getenv("SPB_ASM_PIPELINE") && atoi(getenv("SPB_ASM_PIPELINE")) == 0;
-    if (bulk_ok && h->pairs_fast_path && !pipe_off) {
+    if (run_pairs_v2(h, d_Jv, hv)) {
+      // the stream form ran; the column kernel goes second so that the pair kernel's one-CTA-per-SM grid is resident first
+      if (side) {
+        assemble_cols_kernel<<<h->ncolchunks, 256, 0, cst>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda, h->d_nup1.p,
+                                                             h->d_slice_off.p, hv, h->d_hdiag.p, part ? h->d_rhs_part.p : h->d_rhs.p,
+                                                             part ? h->d_dvec_part.p : h->d_dvec.p, h->d_foo_bits.p,
+                                                             (part || h->halo_mode) ? 1 : 0, h->d_lambda_vec, h->lambda_n_per);
+        ++nl;
+        SPB_CUDA(cudaEventRecord(h->asm_join_ev, cst));
+        SPB_CUDA(cudaStreamWaitEvent(st, h->asm_join_ev, 0));
+      }
+    } else if (bulk_ok && h->pairs_fast_path && !pipe_off) {
       if (h->occ_pairs == 0) {
         int occ = 0;
         if (h->rec_bits == 16) {

@@ -164,6 +164,12 @@ spb_status spb_destroy(spb_handle h) {
     cudaStreamDestroy(h->copy_stream);
     h->copy_stream = nullptr;
   }
+  if (h->asm_side_stream) {
+    cudaEventDestroy(h->asm_fork_ev);
+    cudaEventDestroy(h->asm_join_ev);
+    cudaStreamDestroy(h->asm_side_stream);
+    h->asm_side_stream = nullptr;
+  }
   if (h->h_sc) cudaFreeHost(h->h_sc);
   if (h->h_scalar) cudaFreeHost(h->h_scalar);
   if (h->own_stream) cudaStreamDestroy(h->stream);

@@ -148,6 +148,62 @@ struct SlotMeta {    // 8 bytes
   uint16_t il, jl, rank, rank_up;
 };
 
+// ---- "stream" form of the pair assembly (pairs_v2.cpp packs it, assembly_v2.cu runs it) -----------------------
+// Everything a chunk needs arrives in shared memory through the TMA unit: ONE bulk copy of the chunk's section
+// (tables + slot metadata + pair records, contiguous in `blob`) and one bulk copy per run of consecutive J columns.
+// Section layout (bytes, 16-byte aligned, length a multiple of 16, at most 65520; nsp = nslots rounded up to 32):
+//   [0,16)   uint16 nslots, nstage, ngroups, off_meta, off_ginfo, off_cnt, off_rec, 0     (byte offsets of the tables)
+//   uint2  stab[nstage]    per staged J column {storage position of H row `col`, entry 0 (slice_off[col>>5] + (col&31)),
+//                          BYTE offset of the column in the staged value buffer}
+//   uint32 meta[nsp]       [il:8][jl:8][rank:8][rank_up:8] per slot (lane t&31 of group t>>5)
+//   uint32 ginfo[ngroups]  first record row of the group | rows << 16   (a row = 32 records, one per lane)
+//   uint8  cnt[nsp]        products of the slot (0: padding lane)
+//   uint16 rec[32*rows]    [po:7][qo:7] positions inside J column i / J column j
+struct V2Section {  // pointers into one section
+  int ns, nst, ng;
+  const uint32_t *stab, *meta, *ginfo;  // stab: two words per column
+  const uint16_t* rec;
+  const uint8_t* cnt;
+  explicit V2Section(const unsigned char* sec) {
+    const uint16_t* hd = reinterpret_cast<const uint16_t*>(sec);
+    ns = hd[0];
+    nst = hd[1];
+    ng = hd[2];
+    stab = reinterpret_cast<const uint32_t*>(sec + 16);
+    meta = reinterpret_cast<const uint32_t*>(sec + hd[3]);
+    ginfo = reinterpret_cast<const uint32_t*>(sec + hd[4]);
+    cnt = sec + hd[5];
+    rec = reinterpret_cast<const uint16_t*>(sec + hd[6]);
+  }
+};
+struct ChunkHdr2 {  // 32 bytes
+  uint64_t blob_off;    // byte offset of the section
+  uint32_t run0;        // first entry of the chunk's run list
+  uint32_t val_bytes;   // bytes the runs bring in (mbarrier transaction count, together with the section)
+  // A run whose even-padded window would end one element past the J value array is shortened by two elements and
+  // the last real element is copied by a plain load/store: tail_src = its index in the value array + 1 (0 = none),
+  // tail_dst its offset in the value buffer.
+  uint32_t tail_src;
+  uint16_t sec16;       // section length in 16-byte units
+  uint16_t tail_dst;
+  uint16_t nruns, nslots, nstage, ndiag;  // ndiag: number of 32-lane groups
+};
+struct Run2 {  // 8 bytes: one bulk copy of `len` doubles (even) from Jv + src (even) to the value buffer + dst (even)
+  uint32_t src;
+  uint16_t dst, len;
+};
+struct PairsV2Host {
+  bool ok = false;
+  const char* why = "";
+  std::vector<ChunkHdr2> hdr;
+  std::vector<Run2> runs;
+  std::vector<unsigned char> blob;
+  uint32_t max_val_bytes = 0, max_sec_bytes = 0;
+};
+void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S, PairsV2Host& out);
+// host execution of the packed form, in the kernel's own order (CPU tests of the packer)
+void run_pairs_v2_host(const PairsV2Host& V, const double* Jv, double* hval);
+
 // Host-side pieces of the last analysis kept for incremental re-analysis (analysis_update.cu): the J pattern and the
 // parts of the assembly plan that depend on it.  Kept only for patterns below kPlanKeepMaxNnz entries.
 struct PlanKeep {
@@ -287,6 +343,16 @@ struct spb_context {
   spb::DevBuf<long long> d_dbg;  // debug stopwatch buffer (SPB_ASM_TIMING)
   bool pairs_fast_path = false; // every assembly chunk is on the common path (pipelined kernel)
   int occ_pairs = 0;
+  // "stream" form of the pair assembly (assembly_v2.cu): packed sections + run lists, ring geometry
+  bool v2_ok = false;
+  spb::DevBuf<unsigned char> d_v2_hdr;  // producer descriptors (header + first runs, 128 bytes per chunk)
+  spb::DevBuf<spb::Run2> d_v2_runs;
+  spb::DevBuf<unsigned char> d_v2_blob;
+  uint32_t v2_val_bytes = 0, v2_sec_bytes = 0;
+  int v2_stages = 0;
+  size_t v2_smem = 0;
+  cudaStream_t asm_side_stream = nullptr;  // the column kernel runs here, next to the stream-form pair kernel
+  cudaEvent_t asm_fork_ev = nullptr, asm_join_ev = nullptr;
   // subdomain (halo) mode, dist.cu: this handle holds the LOCAL problem of one rank; local unknowns are
   // [left ghosts | owned | right ghosts] on a ring of ranks
   bool halo_mode = false;
@@ -389,6 +455,9 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
 void upload_h_layout(spb_context* h);
 void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double lambda, double* foo_host);
 bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* host_f, double lambda, double* foo_host);  // false: not applicable
+// assembly_v2.cu
+void upload_pairs_v2(spb_context* h, const PairsV2Host& V);
+bool run_pairs_v2(spb_context* h, const double* d_Jv, double* hv);  // false: not applicable, use the general kernels
 void ensure_pos_of_slot(spb_context* h);
 void gather_h_values(spb_context* h, double* d_out);   // CSC order
 void scatter_h_values(spb_context* h, const double* d_in);

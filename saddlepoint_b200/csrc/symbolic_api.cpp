@@ -204,4 +204,75 @@ spb_status spb_symbolic_plan_check(int32_t m, int32_t n, const int32_t* colptr, 
     return SPB_ERR_ARG;
   }
 }
+
+// The "stream" form of the pair assembly (pairs_v2.cpp) executed on the host in the kernel's order: strictly-lower
+// and mirrored entries of H in CSC order (diagonal entries are left 0: the column kernel owns them).
+// stats: 0 form applicable, 1 chunks, 2 section bytes, 3 runs, 4 largest value window (bytes), 5 largest section
+spb_status spb_symbolic_pairs_v2(int32_t m, int32_t n, const int32_t* colptr, const int32_t* rowidx, const double* Jvals, double* hvals,
+                                 int64_t* stats) {
+  if (!colptr || !stats || !Jvals || !hvals || m < 0 || n < 0) return SPB_ERR_ARG;
+  try {
+    HPattern H;
+    SellLayout S;
+    AssemblyPlan P;
+    build_analysis(m, n, colptr, rowidx, H, S, P);
+    PairsV2Host V;
+    pack_pairs_v2(colptr, P, S, V);
+    stats[0] = V.ok ? 1 : 0;
+    stats[1] = (int64_t)V.hdr.size();
+    stats[2] = (int64_t)V.blob.size();
+    stats[3] = (int64_t)V.runs.size();
+    stats[4] = V.max_val_bytes;
+    stats[5] = V.max_sec_bytes;
+    if (!V.ok) return SPB_OK;
+    {
+      // shared-memory cost model of the consumer loop: an 8-byte load of a half-warp takes as many wavefronts as the
+      // largest number of DISTINCT addresses its active lanes have in one of the 16 bank pairs
+      int64_t wf = 0, rounds = 0;
+      for (const ChunkHdr2& h : V.hdr) {
+        const V2Section sv(V.blob.data() + h.blob_off);
+        for (int g = 0; g < sv.ng; ++g)
+          for (int d = 0; d < (int)(sv.ginfo[g] >> 16); ++d)
+            for (int half = 0; half < 2; ++half) {
+              bool any = false;
+              for (int op = 0; op < 2; ++op) {
+                int addr[16], na = 0;
+                for (int t = g * 32 + half * 16; t < g * 32 + half * 16 + 16; ++t) {
+                  if (d >= (int)sv.cnt[t]) continue;
+                  const uint32_t m = sv.meta[t], r = sv.rec[((size_t)(sv.ginfo[g] & 0xffffu) + d) * 32 + (t & 31)];
+                  addr[na++] = op ? (int)(sv.stab[2 * ((m >> 8) & 255) + 1] / 8) + (int)(r & 127) : (int)(sv.stab[2 * (m & 255) + 1] / 8) + (int)((r >> 7) & 127);
+                }
+                any |= na > 0;
+                int worst = 0;
+                for (int b = 0; b < 16; ++b) {
+                  int distinct = 0;
+                  for (int x = 0; x < na; ++x) {
+                    if ((addr[x] & 15) != b) continue;
+                    bool dup = false;
+                    for (int y = 0; y < x; ++y) dup |= addr[y] == addr[x];
+                    distinct += !dup;
+                  }
+                  worst = std::max(worst, distinct);
+                }
+                wf += worst;
+              }
+              rounds += any;
+            }
+      }
+      stats[6] = wf;          // wavefronts of the two operand loads
+      stats[7] = 2 * rounds;  // conflict-free minimum
+    }
+    std::vector<double> st((size_t)S.padded, 0.0);
+    run_pairs_v2_host(V, Jvals, st.data());
+    for (int r = 0; r < H.n; ++r) {
+      int k = 0;
+      for (int q = H.colptr[r]; q < H.colptr[(size_t)r + 1]; ++q, ++k) hvals[q] = st[(size_t)S.pos(r, k)];
+    }
+    return SPB_OK;
+  } catch (const ArgFail&) {
+    return SPB_ERR_ARG;
+  } catch (const StateFail&) {
+    return SPB_ERR_STATE;
+  }
+}
 }

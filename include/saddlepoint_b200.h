@@ -289,6 +289,11 @@ spb_status spb_problem_lf_rows(spb_handle h, int32_t g, int32_t rows_mult, uint6
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t spb_launch_count(spb_handle h);
+/* which pair-assembly kernel the LAST spb_assemble on this handle ran: 3 = stream form (assemble_pairs_stream_kernel:
+ * warp-specialised, TMA-fed, packed sections), 2 = register-pipelined general kernel, 1 = one-CTA-per-chunk general
+ * kernel, 0 = none yet / no off-diagonal entries.  The general kernels take over when the packed form does not apply
+ * (J columns longer than 128 entries, H rows longer than 256, a misaligned value pointer, after spb_analyze_update). */
+int spb_assembly_form(spb_handle h);
 /* per-stage device time accumulated since the last reset, milliseconds (CUDA events):
  * stage 0 assembly, 1 spmv, 2 pcg-vector, 3 factor, 4 trisolve, 5 reductions, 6 traits,
  * 7 fused persistent PCG solve */

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("spb_collective_count", C.c_int64, [vp]),
     ("spb_problem_lf_rows", C.c_int, [vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]),
     ("spb_launch_count", C.c_int64, [vp]),
+    ("spb_assembly_form", C.c_int, [vp]),
     ("spb_stage_ms", C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     ("spb_stage_reset", C.c_int, [vp, C.c_int]),
 ]

@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(256, 4) assemble_pairs_pipelined_kernel(const 
 }
 
 __device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
+constexpr int kColsTileDoubles = kEntTile + kEntTile / 16 + 1;
+constexpr size_t kColsSmemBytes = sizeof(double) * 2 * kColsTileDoubles;
 
 __global__ void __launch_bounds__(256, 4) assemble_cols_kernel(
     const int* __restrict__ colchunk, const int* __restrict__ Jcolptr, const int* __restrict__ Jrow,
@@ -391,7 +393,9 @@ __global__ void __launch_bounds__(256, 4) assemble_cols_kernel(
     const int64_t* __restrict__ slice_off, double* __restrict__ hval, double* __restrict__ hdiag,
     double* __restrict__ rhs, double* __restrict__ dvec, unsigned long long* __restrict__ foo_bits, int defer_damping,
     const double* __restrict__ lam_vec, int lam_n_per) {
-  __shared__ double sv[kEntTile + kEntTile / 16 + 1], sf[kEntTile + kEntTile / 16 + 1];
+  extern __shared__ __align__(16) double cols_smem[];  // two staged tiles (values, gathered residuals), bank-skewed
+  double* sv = cols_smem;
+  double* sf = cols_smem + kColsTileDoubles;
   __shared__ double s_max[8];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int j0 = colchunk[c], j1 = colchunk[c + 1];
@@ -727,6 +731,25 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
   SPB_CUDA(cudaStreamSynchronize(st));
 }
 
+// column kernel on stream `cst`
+static void cols_smem_optin() {
+  static const bool done = [] {
+    return cudaFuncSetAttribute(assemble_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColsSmemBytes) == cudaSuccess;
+  }();
+  if (!done) throw StateFail{"shared-memory opt-in of the column kernel failed"};
+}
+static void launch_cols(spb_context* h, cudaStream_t cst, const double* d_Jv, const double* d_f, double lambda, double* hv, bool part) {
+  cols_smem_optin();
+  double* rhs = part ? h->d_rhs_part.p : h->d_rhs.p;
+  double* dv = part ? h->d_dvec_part.p : h->d_dvec.p;
+  const int defer = (part || h->halo_mode) ? 1 : 0;
+  {
+    assemble_cols_kernel<<<h->ncolchunks, 256, kColsSmemBytes, cst>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda, h->d_nup1.p,
+                                                         h->d_slice_off.p, hv, h->d_hdiag.p, rhs, dv, h->d_foo_bits.p, defer, h->d_lambda_vec,
+                                                         h->lambda_n_per);
+  }
+}
+
 void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double lambda, double* foo_host) {
   cudaStream_t st = h->stream;
   stage_begin(h, ST_ASSEMBLY);
@@ -751,27 +774,24 @@ void run_assembly(spb_context* h, const double* d_Jv, const double* d_f, double 
     SPB_CUDA(cudaStreamWaitEvent(cst, h->asm_fork_ev, 0));
   }
   if (h->ncolchunks > 0 && !side) {
-    assemble_cols_kernel<<<h->ncolchunks, 256, 0, st>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda,
-                                                        h->d_nup1.p, h->d_slice_off.p, hv, h->d_hdiag.p,
-                                                        part ? h->d_rhs_part.p : h->d_rhs.p, part ? h->d_dvec_part.p : h->d_dvec.p,
-                                                        h->d_foo_bits.p, (part || h->halo_mode) ? 1 : 0, h->d_lambda_vec, h->lambda_n_per);
+    launch_cols(h, st, d_Jv, d_f, lambda, hv, part);
     ++nl;
   }
   if (h->nchunks > 0) {
     const int bulk_ok = (((uintptr_t)d_Jv) & 15) == 0 ? 1 : 0;  // TMA bulk copies need a 16-byte aligned source
     static const bool pipe_off = getenv("SPB_ASM_PIPELINE") && atoi(getenv("SPB_ASM_PIPELINE")) == 0;
+    h->last_asm_form = 1;
     if (run_pairs_v2(h, d_Jv, hv)) {
+      h->last_asm_form = 3;
       // the stream form ran; the column kernel goes second so that the pair kernel's one-CTA-per-SM grid is resident first
       if (side) {
-        assemble_cols_kernel<<<h->ncolchunks, 256, 0, cst>>>(h->d_colchunk.p, h->d_Jcolptr.p, h->d_Jrow.p, d_Jv, d_f, lambda, h->d_nup1.p,
-                                                             h->d_slice_off.p, hv, h->d_hdiag.p, part ? h->d_rhs_part.p : h->d_rhs.p,
-                                                             part ? h->d_dvec_part.p : h->d_dvec.p, h->d_foo_bits.p,
-                                                             (part || h->halo_mode) ? 1 : 0, h->d_lambda_vec, h->lambda_n_per);
+        launch_cols(h, cst, d_Jv, d_f, lambda, hv, part);
         ++nl;
         SPB_CUDA(cudaEventRecord(h->asm_join_ev, cst));
         SPB_CUDA(cudaStreamWaitEvent(st, h->asm_join_ev, 0));
       }
     } else if (bulk_ok && h->pairs_fast_path && !pipe_off) {
+      h->last_asm_form = 2;
       if (h->occ_pairs == 0) {
         int occ = 0;
         if (h->rec_bits == 16) {
@@ -918,6 +938,8 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
     }
     h->occ_pairs = std::max(1, occ);
   }
+  h->last_asm_form = 2;
+  cols_smem_optin();
   int cc_done = 0, ch_done = 0;  // column-kernel chunks / pair-kernel chunks already launched
   for (int k = 0; k < kParts; ++k) {
     SPB_CUDA(cudaStreamWaitEvent(st, h->copy_ev[k], 0));
@@ -927,7 +949,7 @@ bool run_assembly_streamed(spb_context* h, const double* host_Jv, const double* 
     while (cc_end < h->ncolchunks && h->colchunk_host[(size_t)cc_end + 1] <= colb[k + 1]) ++cc_end;
     if (k == kParts - 1) cc_end = h->ncolchunks;
     if (cc_end > cc_done) {
-      assemble_cols_kernel<<<cc_end - cc_done, 256, 0, st>>>(h->d_colchunk.p + cc_done, h->d_Jcolptr.p, h->d_Jrow.p, dJ, d_f, lambda, h->d_nup1.p,
+      assemble_cols_kernel<<<cc_end - cc_done, 256, kColsSmemBytes, st>>>(h->d_colchunk.p + cc_done, h->d_Jcolptr.p, h->d_Jrow.p, dJ, d_f, lambda, h->d_nup1.p,
                                                             h->d_slice_off.p, h->d_hval.p, h->d_hdiag.p, h->d_rhs.p, h->d_dvec.p, h->d_foo_bits.p, 0, nullptr, 1);
       ++nl;
       cc_done = cc_end;

@@ -262,7 +262,8 @@ void upload_pairs_v2(spb_context* h, const PairsV2Host& V) {
   if (ns < 2) return;
   h->v2_stages = ns;
   h->v2_smem = (size_t)fixed + (size_t)ns * stage;
-  SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->v2_smem));
+  // the limit is a property of the function, not of the handle: handles with different ring sizes share it
+  SPB_CUDA(cudaFuncSetAttribute(assemble_pairs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   h->v2_ok = true;
 }
 

@@ -606,6 +606,7 @@ spb_status spb_factor_info(spb_handle h, int64_t* nnzL, double* flops, int32_t* 
 }
 
 int64_t spb_launch_count(spb_handle h) { return h ? h->launches : 0; }
+int spb_assembly_form(spb_handle h) { return h ? h->last_asm_form : 0; }
 
 spb_status spb_stage_ms(spb_handle h, int stage, double* ms, int64_t* launches) {
   if (!h || stage < 0 || stage >= ST_COUNT) return SPB_ERR_ARG;

@@ -32,7 +32,7 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
   if (P.rec_bits != 16) return fail("32-bit pair records");
   if (S.padded >= ((int64_t)1 << 32)) return fail("H storage beyond 32-bit positions");
   static const int penalty = getenv("SPB_ASM_V2_PENALTY") ? atoi(getenv("SPB_ASM_V2_PENALTY")) : 2;
-  static const int window = getenv("SPB_ASM_V2_WINDOW") ? std::max(1, atoi(getenv("SPB_ASM_V2_WINDOW"))) : 48;
+  static const int window = getenv("SPB_ASM_V2_WINDOW") ? std::max(1, atoi(getenv("SPB_ASM_V2_WINDOW"))) : 8;  // measured on LF-1M: window 1 / 8 / 48 -> 0.250 / 0.241 / 0.240 ms per assembly, 0 / 0.17 / 0.58 s of packing
   // pass 1: eligibility
   for (int c = 0; c < nch; ++c) {
     const int s0 = P.chunk_slot[c], s1 = P.chunk_slot[(size_t)c + 1];
@@ -55,6 +55,7 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
   out.hdr.resize((size_t)nch);
   run_parts(parts, [&](int p) {
     std::vector<int> order, cand;
+    std::vector<uint16_t> paddr;
     std::vector<uint8_t> taken;
     std::vector<unsigned char>& blob = pblob[p];
     std::vector<Run2>& runsv = pruns[p];
@@ -64,10 +65,17 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
       const int st0 = P.chunk_stage_ptr[c], st1 = P.chunk_stage_ptr[(size_t)c + 1];
       const int ns = s1 - s0, nst = st1 - st0;
       const int64_t rec0 = P.chunk_rec[c];
-      auto addr_of = [&](int s, int d, int op) {  // shared-memory address (doubles) of operand op of product d of slot s
-        const uint32_t r = P.rec16[(size_t)(rec0 + P.slot_start[s] + d)];
-        return op ? (int)P.stage_off[st0 + P.slot_jl[s]] + (int)(r & 127u) : (int)P.stage_off[st0 + P.slot_il[s]] + (int)((r >> 7) & 127u);
-      };
+      // shared-memory address (doubles) of operand op of product d of slot s, tabulated once per chunk
+      paddr.resize((size_t)2 * P.chunk_npairs[c]);
+      for (int s = s0; s < s1; ++s) {
+        const int oi = P.stage_off[st0 + P.slot_il[s]], oj = P.stage_off[st0 + P.slot_jl[s]];
+        for (int d = 0; d < (int)P.slot_cnt[s]; ++d) {
+          const uint32_t r = P.rec16[(size_t)(rec0 + P.slot_start[s] + d)];
+          paddr[2 * ((size_t)P.slot_start[s] + d)] = (uint16_t)(oi + (int)((r >> 7) & 127u));
+          paddr[2 * ((size_t)P.slot_start[s] + d) + 1] = (uint16_t)(oj + (int)(r & 127u));
+        }
+      }
+      auto addr_of = [&](int s, int d, int op) { return (int)paddr[2 * ((size_t)P.slot_start[s] + d) + op]; };
       // Lane assignment.  Candidates in descending pair count; every half-warp of 16 lanes starts with the longest
       // slot left and is filled, lane by lane, with the slot among the next `window` candidates that adds the fewest
       // shared-memory wavefronts: an 8-byte load of a half-warp costs as many wavefronts as the largest number of

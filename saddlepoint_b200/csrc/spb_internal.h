@@ -351,6 +351,7 @@ struct spb_context {
   uint32_t v2_val_bytes = 0, v2_sec_bytes = 0;
   int v2_stages = 0;
   size_t v2_smem = 0;
+  int last_asm_form = 0;  // spb_assembly_form()
   cudaStream_t asm_side_stream = nullptr;  // the column kernel runs here, next to the stream-form pair kernel
   cudaEvent_t asm_fork_ev = nullptr, asm_join_ev = nullptr;
   // subdomain (halo) mode, dist.cu: this handle holds the LOCAL problem of one rank; local unknowns are

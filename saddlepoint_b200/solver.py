@@ -270,6 +270,10 @@ class Handle:
     def launch_count(self):
         return int(self.L.spb_launch_count(self.h))
 
+    def assembly_form(self):
+        """3 stream form, 2 register-pipelined general kernel, 1 one-CTA-per-chunk general kernel (last assemble)."""
+        return int(self.L.spb_assembly_form(self.h))
+
     def stage_reset(self, enable_timing=False):
         self._check(self.L.spb_stage_reset(self.h, int(enable_timing)))
 

@@ -220,3 +220,30 @@ def test_streamed_host_assembly_equals_device_assembly(spb):
     assert foo_pg == foo_dev and np.array_equal(h.h_values(), H_dev)
     prob.close()
     h.close()
+
+
+def test_stream_form_is_the_default_and_general_kernels_agree(handle, orc):
+    """The packed stream form (assemble_pairs_stream_kernel) runs wherever it applies; the general kernels take over for a
+    misaligned device pointer and for long J columns -- every form reproduces the oracle's bits (LMSolver.h:136)."""
+    import torch
+    J = orc.lf_matrix(48, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    rng = np.random.default_rng(3)
+    E = rng.standard_normal(m)
+    _check(handle, orc, m, n, colptr, rowidx, vals, E, 0.01)
+    assert handle.assembly_form() == 3
+    hx = handle.h_values().copy()
+    # same problem, device pointer shifted by 8 bytes: no 16-byte aligned bulk copies -> general kernel, same bits
+    buf = torch.empty(len(vals) + 1, dtype=torch.float64, device="cuda")
+    buf[1:] = torch.from_numpy(vals)
+    handle.assemble(buf[1:], torch.from_numpy(E).cuda(), 0.01)
+    assert handle.assembly_form() in (1, 2)
+    assert (_bits(handle.h_values()) == _bits(hx)).all()
+    # J columns longer than 128 entries: 32-bit pair records, general kernel
+    m2, n2 = 400, 6
+    A = (rng.random((m2, n2)) < 0.7) * rng.standard_normal((m2, n2))
+    S = sp.csc_matrix(A)
+    S.sort_indices()
+    _check(handle, orc, m2, n2, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data, rng.standard_normal(m2), 0.3)
+    assert handle.assembly_form() in (1, 2)

@@ -56,6 +56,8 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
   run_parts(parts, [&](int p) {
     std::vector<int> order, cand;
     std::vector<uint16_t> paddr;
+    std::vector<int> hw_addr;                     // half-warp being filled: [d][op][lane]
+    std::vector<uint8_t> hw_n, hw_max, hw_bank;   // [d][op], [d][op], [d][op][16]
     std::vector<uint8_t> taken;
     std::vector<unsigned char>& blob = pblob[p];
     std::vector<Run2>& runsv = pruns[p];
@@ -89,8 +91,6 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
       int head = 0;
       while ((int)order.size() < ns) {
         // state of the half-warp being filled: per (product index, operand) the addresses so far
-        static thread_local std::vector<int> hw_addr;   // [d][op][lane]
-        static thread_local std::vector<uint8_t> hw_n, hw_max, hw_bank;  // [d][op], [d][op], [d][op][16]
         while (taken[head]) ++head;
         const int seed = cand[head];
         const int dmax = P.slot_cnt[seed];
@@ -115,10 +115,10 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
           int cost = 0;
           for (int d = 0; d < (int)P.slot_cnt[s] && cost < bound; ++d)
             for (int op = 0; op < 2; ++op) {
+              // (an address another lane already reads would be a broadcast, not a conflict: ignored here, the estimate
+              // only has to rank candidates; add_slot keeps the exact bank counts)
               const int x = addr_of(s, d, op), k = d * 2 + op;
-              bool dup = false;
-              for (int y = 0; y < hw_n[k]; ++y) dup |= hw_addr[(size_t)k * 16 + y] == x;
-              if (!dup && hw_bank[(size_t)k * 16 + (x & 15)] + 1 > hw_max[k]) ++cost;
+              if (hw_bank[(size_t)k * 16 + (x & 15)] + 1 > hw_max[k]) ++cost;
             }
           return cost;
         };

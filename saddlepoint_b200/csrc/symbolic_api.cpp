@@ -217,7 +217,10 @@ spb_status spb_symbolic_pairs_v2(int32_t m, int32_t n, const int32_t* colptr, co
     AssemblyPlan P;
     build_analysis(m, n, colptr, rowidx, H, S, P);
     PairsV2Host V;
+    const auto tp0 = std::chrono::steady_clock::now();
     pack_pairs_v2(colptr, P, S, V);
+    if (getenv("SPB_ANALYZE_TIMING") && atoi(getenv("SPB_ANALYZE_TIMING")) > 0)
+      fprintf(stderr, "[spb analyze timing] pack_pairs_v2 %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
     stats[0] = V.ok ? 1 : 0;
     stats[1] = (int64_t)V.hdr.size();
     stats[2] = (int64_t)V.blob.size();

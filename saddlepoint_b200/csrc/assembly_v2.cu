@@ -25,6 +25,7 @@ constexpr int kV2ConsumerWarps = 16;
 constexpr int kV2Threads = (kV2ConsumerWarps + 1) * 32;
 constexpr int kV2MaxStages = 8;
 constexpr int kV2DescRing = 8;    // producer descriptors prefetched this many chunks ahead (cp.async into shared memory)
+constexpr int kV2ExtraRuns = 4;   // further runs per lane the producer reads one chunk ahead (12 + 128 runs without a dependent load)
 constexpr int kV2DescRuns = 12;   // runs carried inside a producer descriptor; further runs are read from the run list
 
 // what the producer warp needs for one chunk, at a fixed stride so that the prefetch does not depend on another load
@@ -120,6 +121,23 @@ __global__ void __launch_bounds__(kV2Threads, 1)
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int kk = 0; kk < kV2DescRing; ++kk) prefetch(kk);
+    // Runs beyond the ones a descriptor carries (scattered stage lists: mesh problems have ~100 short runs per chunk) are
+    // read from the run list ONE CHUNK AHEAD, kV2ExtraRuns per lane, into registers: the descriptor of chunk k+1 is
+    // already in the ring when chunk k is issued, so these loads overlap the wait for a free stage.
+    uint2 rx[kV2ExtraRuns];
+    auto load_extra = [&](int kk) {  // requires the descriptor of chunk kk to have landed in the ring
+      const PDesc* pn = pring + (kk % kV2DescRing);
+      const uint32_t run0n = pn->h.run0;
+      const int nrn = (int)pn->h.nruns;
+#pragma unroll
+      for (int q = 0; q < kV2ExtraRuns; ++q) {
+        const int i = kV2DescRuns + lane + 32 * q;
+        rx[q] = i < nrn ? __ldg(reinterpret_cast<const uint2*>(runs + run0n) + i) : make_uint2(0u, 0u);
+      }
+    };
+    asm volatile("cp.async.wait_group %0;" ::"n"(kV2DescRing - 1) : "memory");
+    __syncwarp();
+    load_extra(0);
     int s = 0;
     uint32_t eph = 1;  // parity of the `empty` phase this stage's next reuse waits for (first pass: no wait)
     for (int k = 0; k < nk; ++k) {
@@ -144,9 +162,18 @@ __global__ void __launch_bounds__(kV2Threads, 1)
       }
       __syncwarp();
       if (lane < kV2DescRuns && lane < nruns && (rc.y >> 16) != 0u) tma_bulk_g2s(sval + (rc.y & 0xffffu), Jv + rc.x, (rc.y >> 16) * 8u, &full[s]);
-      for (int i = kV2DescRuns + lane; i < nruns; i += 32) {
+#pragma unroll
+      for (int q = 0; q < kV2ExtraRuns; ++q)
+        if ((rx[q].y >> 16) != 0u) tma_bulk_g2s(sval + (rx[q].y & 0xffffu), Jv + rx[q].x, (rx[q].y >> 16) * 8u, &full[s]);
+      for (int i = kV2DescRuns + 32 * kV2ExtraRuns + lane; i < nruns; i += 32) {
         const uint2 r = __ldg(reinterpret_cast<const uint2*>(runs + run0) + i);
         if ((r.y >> 16) != 0u) tma_bulk_g2s(sval + (r.y & 0xffffu), Jv + r.x, (r.y >> 16) * 8u, &full[s]);
+      }
+      if (k + 1 < nk) {
+        // descriptor of chunk k+1: committed kV2DescRing-1 groups ago at the latest
+        asm volatile("cp.async.wait_group %0;" ::"n"(kV2DescRing - 2) : "memory");
+        __syncwarp();
+        load_extra(k + 1);
       }
       __syncwarp();
       prefetch(k + kV2DescRing);

@@ -46,6 +46,21 @@ void pack_pairs_v2(const int* colptr, const AssemblyPlan& P, const SellLayout& S
       if (P.slot_cnt[s] > 255 || P.slot_cnt[s] < 1) return fail("a slot with more than 255 products");
     }
   }
+  {
+    // The stream form feeds a stage through ONE producer warp: it pays off when the J columns a chunk reads come in
+    // long consecutive runs (stencil-like problems: ~600 doubles per bulk copy on LF).  Scattered stage lists (mesh
+    // problems: ~100 copies of ~6 doubles per chunk) are bound by the issue rate of the copies, and the general
+    // kernels issue them from all threads of several co-resident CTAs -- measured on the seamless-integration
+    // structure (1.6 M unknowns): 0.26 ms general against 0.49 ms stream form.
+    int64_t nrun = 0, nval = 0;
+    for (size_t t = 0; t < P.stage_run.size(); ++t)
+      if (P.stage_run[t] > 0) {
+        ++nrun;
+        nval += P.stage_run[t];
+      }
+    const int min_run = getenv("SPB_ASM_V2_MIN_RUN") ? atoi(getenv("SPB_ASM_V2_MIN_RUN")) : 64;  // read per call: the tests force the form on scattered patterns
+    if (nrun == 0 || nval < (int64_t)min_run * nrun) return fail("short bulk-copy runs");
+  }
   // pass 2 (parallel over chunks): lane assignment, sections into per-part buffers
   const int parts = std::max(1, std::min(host_threads(), nch / 64));
   std::vector<std::vector<unsigned char>> pblob((size_t)parts);

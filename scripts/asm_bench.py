@@ -1,5 +1,7 @@
 """Times the fused assembly (column kernel + pair kernel) on an LF problem with device-resident inputs.
-usage: python scripts/asm_bench.py [g=1024] [reps=20]   (SPB_ASM_V2=0 selects the general pair kernels)
+usage: python scripts/asm_bench.py [g=1024] [reps=20]        LF problem on a g x g torus
+       python scripts/asm_bench.py c3 [nx=300] [reps=20]     seamless-integration structure (tests/c3_blocks.py), nx x nx x 2 faces
+(SPB_ASM_V2=0 selects the general pair kernels)
 Prints one JSON line: ms per assembly (CUDA events over `reps` back-to-back calls), the algorithmic bytes of
 SURVEY section 8(d) and the fraction of the measured HBM peak."""
 import json
@@ -14,10 +16,18 @@ import saddlepoint_b200 as spb  # noqa: E402
 
 
 def main():
-    g = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     h = spb.Handle(0)
-    prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
+    if len(sys.argv) > 1 and sys.argv[1] == "c3":
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import c3_blocks
+        g = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+        reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+        P = c3_blocks.build(g, g)
+        prob = spb.BuiltinProblem(h, "blocks", **{k: P[k] for k in ("A", "b", "bar_idx", "bar_vol", "s", "w_bar", "x0")})
+    else:
+        g = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+        reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+        prob = spb.BuiltinProblem(h, "lf", g=g, rows_mult=2, seed=20211)
     m, n, colptr, rowidx = prob.pattern()
     h.analyze(m, n, colptr, rowidx)
     nnzJ = int(colptr[-1])
@@ -44,7 +54,7 @@ def main():
     except Exception:
         pass
     kern_ms = st[0] / max(1, reps)
-    print(json.dumps({"g": g, "n": n, "nnzJ": nnzJ, "nnzH": nnzH, "v2": os.environ.get("SPB_ASM_V2", "1"),
+    print(json.dumps({"g": g, "n": n, "nnzJ": nnzJ, "nnzH": nnzH, "form": h.assembly_form(),
                       "ms_per_assembly_wall": ms, "ms_per_assembly_kernels": kern_ms, "launches": st[1] / max(1, reps),
                       "algorithmic_MB": b_asm / 1e6, "GBs": b_asm / (kern_ms * 1e-3) / 1e9, "frac_of_peak": b_asm / (kern_ms * 1e-3) / 1e9 / peak}))
 

@@ -195,7 +195,12 @@ def test_pairs_stream_form_bit_exact_vs_oracle(spb, orc, case):
     hp_ref, hi_ref, hx_ref = orc.ata(D).csc()
     stats = np.zeros(8, np.int64)
     out = np.zeros(len(hi_ref), np.float64)
-    assert L.spb_symbolic_pairs_v2(m, n, colptr.ctypes.data, rowidx.ctypes.data, vals.ctypes.data, out.ctypes.data, stats.ctypes.data) == 0
+    # scattered patterns have short bulk-copy runs and are left to the general kernels by default: force the form
+    os.environ["SPB_ASM_V2_MIN_RUN"] = "0"
+    try:
+        assert L.spb_symbolic_pairs_v2(m, n, colptr.ctypes.data, rowidx.ctypes.data, vals.ctypes.data, out.ctypes.data, stats.ctypes.data) == 0
+    finally:
+        del os.environ["SPB_ASM_V2_MIN_RUN"]
     if case == "dense_cols":
         assert stats[0] == 0  # 32-bit pair records: the general kernels stay in charge
         return
@@ -205,3 +210,7 @@ def test_pairs_stream_form_bit_exact_vs_oracle(spb, orc, case):
     assert (out[off].view(np.int64) == hx_ref[off].view(np.int64)).all()
     assert (out[~off] == 0).all()
     assert stats[4] <= 3072 * 8 and stats[5] % 16 == 0
+    if case == "random":  # default policy: short runs -> not applicable
+        st2 = np.zeros(8, np.int64)
+        assert L.spb_symbolic_pairs_v2(m, n, colptr.ctypes.data, rowidx.ctypes.data, vals.ctypes.data, out.ctypes.data, st2.ctypes.data) == 0
+        assert st2[0] == 0

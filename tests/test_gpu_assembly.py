@@ -247,3 +247,20 @@ def test_stream_form_is_the_default_and_general_kernels_agree(handle, orc):
     S.sort_indices()
     _check(handle, orc, m2, n2, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data, rng.standard_normal(m2), 0.3)
     assert handle.assembly_form() in (1, 2)
+
+
+@pytest.mark.parametrize("seed,m,n,k", [(10, 2000, 700, 4), (11, 300, 900, 2), (12, 6000, 6000, 5)])
+def test_stream_form_forced_on_scattered_patterns(spb, orc, seed, m, n, k):
+    """Scattered patterns are left to the general kernels by default (short bulk-copy runs); forced, the stream form
+    reproduces the oracle's bits on them too (explicit zeros, empty columns, odd value counts)."""
+    import os
+    rng = np.random.default_rng(seed)
+    colptr, rowidx, vals = random_jacobian(rng, m, n, k, explicit_zero_frac=0.05, empty_cols=[0, n - 1] if seed == 11 else ())
+    os.environ["SPB_ASM_V2_MIN_RUN"] = "0"
+    try:
+        h = spb.Handle(0)
+        _check(h, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), 0.02)
+        assert h.assembly_form() == 3
+        h.close()
+    finally:
+        del os.environ["SPB_ASM_V2_MIN_RUN"]

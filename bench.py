@@ -304,6 +304,19 @@ def _roofline(h, stages, K, lin_iters, n_loc, m_loc, nnzJ_loc, nnzH_loc, g_is_c2
         roof["traffic_source"] = cap.get("file")
         roof["frac_on_measured_dram_bytes"] = (traffic / (1e3 * k_ms / max(1, k_launches) * 1e-6) / 1e9) / peaks["hbm_gbs"]
     roof["assembly"]["frac"] = roof["assembly"]["achieved"] / peaks["hbm_gbs"]
+    form = h.assembly_form()
+    roof["assembly"]["form"] = form
+    roof["assembly"]["kernels"] = {3: "assemble_pairs_stream_kernel (warp-specialised, TMA-fed packed sections) beside assemble_cols_kernel on a side stream",
+                                   2: "assemble_pairs_pipelined_kernel + assemble_cols_kernel", 1: "assemble_pairs_kernel + assemble_cols_kernel"}.get(form, "none")
+    if g_is_c2 and form == 3:
+        try:
+            cap_a = json.load(open(os.path.join(ROOT, "profiles", "r2_asm_traffic.json")))
+            roof["assembly"]["traffic"] = cap_a["dram_bytes_per_assembly"]
+            roof["assembly"]["traffic_source"] = "profiles/r2_asm_traffic.json"
+            roof["assembly"]["traffic_over_algorithmic"] = cap_a["dram_bytes_per_assembly"] / b_asm
+            roof["assembly"]["bound_in_practice"] = "shared-memory pipe (l1tex 91 % busy in the pair kernel: operand gathers, 56 % of its wavefronts are bank conflicts)"
+        except Exception:
+            pass
     return roof
 
 

@@ -428,13 +428,20 @@ struct StreamCursor {   // per warp (uniform across its lanes)
 // D stages of SB bytes per warp (D * SB <= 2 * kStreamStageBytes).  Two 6 KB stages are used; four 3 KB stages for the FP32
 // value stream (whose stages are half full) were measured and change nothing (36.0 vs 35.3 us per product): the FP32
 // products are not bound by the bytes a warp has in flight.
-template <typename VT, bool W32, int D, int SB>
+// K: entries per lane a stage holds when the slice has 16-bit column deltas (16 for FP64 values, 32 for FP32 values: the
+// same 4 KB of values and at most 2 KB of columns); slices with 32-bit columns use 16-entry stages in either case.  A stage
+// is consumed in halves of kStreamK = 16 entries (sixteen gathers in flight per lane).
+// Measured: 32-entry stages for the FP32 stream (half as many bulk copies per product) 55.1 vs 54.4 us per iteration --
+// the FP32 products' floor is not a per-copy cost either; both value types use K = 16.
+template <typename VT, bool W32, int D, int SB, int K>
 __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __restrict__ hval, unsigned char* stage, uint64_t* bar,
                                               StreamCursor& cur, int gw, int GW, int grp, uint64_t pol) {
+  static_assert(K == kStreamK || K == 2 * kStreamK, "a stage is one or two halves of kStreamK entries");
+  static_assert(K * 32 * (int)sizeof(VT) <= kStreamValBytes, "the value part of a stage is 4 KB");
   // slice walk: a warp takes grp consecutive slices, then jumps to its next group (grp = 1: round-robin over the grid)
   const int first = gw * grp;
   auto next_slice = [&](int sl) { return ((sl + 1) & (grp - 1)) ? sl + 1 : sl + 1 + (GW - 1) * grp; };
-  constexpr int kValBytes = kStreamK * 32 * (int)sizeof(VT);
+  constexpr int kValBytes = kStreamValBytes;
   unsigned issued = 0, consumed = 0;  // stages of this product (every product drains its ring)
   const int lane = threadIdx.x & 31;
   const int n = P.n, nslices = P.nslices;
@@ -453,7 +460,8 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
   auto issue = [&]() {
     if (ps >= nslices) return;
     const unsigned b = issued % D;
-    const int cnt = min(kStreamK, pwidth - pk);
+    const int kp = p16 ? K : kStreamK;
+    const int cnt = min(kp, pwidth - pk);
     if (lane == 0) {
       const uint32_t vb = (uint32_t)cnt * 32u * (uint32_t)sizeof(VT), cb = (uint32_t)cnt * 32u * (p16 ? 2u : 4u);
       mbar_expect_tx(&bar[b], vb + cb);
@@ -466,7 +474,7 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
       }
     }
     ++issued;
-    pk += kStreamK;
+    pk += kp;
     if (pk >= pwidth) {
       ps = next_slice(ps);
       pk = 0;
@@ -483,6 +491,8 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
     const int width = (int)((P.slice_off[slice + 1] - off) >> 5);
     const int len = row < n ? P.rowlen[row] : 0;
     const bool c16 = have16 && P.s16[slice];
+    const bool full_slice = slice * 32 + 32 <= n;
+    const int kc = c16 ? K : kStreamK;
     const int rbase = row - 32768, csafe = row < n ? row : 0;
     double acc = 0.0;
     int k0 = 0;
@@ -494,94 +504,75 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
       cur.phase ^= 1u << b;
       const unsigned char* sb = stage + b * SB;
       const VT* sv = reinterpret_cast<const VT*>(sb) + lane;
-      const int cnt = min(kStreamK, width - k0);
-      if (cnt == kStreamK && c16 && slice * 32 + 32 <= n) {
-        // Full stage of a full slice (the common case): no per-entry predicates.  Entries past a row's length are padding
-        // with value 0 and the row's own index as column (build_sell), so they add exactly 0.  The general form below costs
-        // ~20 warp instructions per entry and set a floor of ~28 us per product that did not depend on the bytes moved
-        // (ncu source view: 79 % of the kernel's instructions were this loop); this form needs 7.
-        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane;
+      const int cnt = min(kc, width - k0);
+#pragma unroll
+      for (int hb = 0; hb < K; hb += kStreamK) {
+        if (hb >= cnt) break;
+        const int hc = cnt - hb;  // entries of this half that exist (warp-uniform; >= kStreamK: all)
         double xv[kStreamK];
+        if (c16 && full_slice) {
+          // Full slice with 16-bit deltas (the common case).  Entries past a row's length are padding with value 0 and the
+          // row's own index as column (build_sell), so they add exactly 0: no per-lane predicate.  A complete half needs
+          // no predicate at all; the tail of a slice is guarded by the warp-uniform entry count only.
+          const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane + hb * 32;
+          const VT* hv = sv + hb * 32;
+          if (hc >= kStreamK) {
 #pragma unroll
-        for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[rbase + (int)sc[u * 32]];
-        if (W32) {
-          float* wp = P.hval32 + off + lane + (int64_t)k0 * 32;
-#pragma unroll
-          for (int u = 0; u < kStreamK; ++u) __stcs(wp + u * 32, (float)sv[u * 32]);
-        }
-#pragma unroll
-        for (int u = 0; u < kStreamK; ++u) acc = fma((double)sv[u * 32], xv[u], acc);
-        __syncwarp();  // every lane has read stage b: it can be refilled
-        ++consumed;
-        issue();
-        k0 += kStreamK;
-        continue;
-      }
-      if (c16 && slice * 32 + 32 <= n) {
-        // Partial stage (the tail of a slice) of a full slice: two halves of eight entries, the first without predicates
-        // when it is complete, the rest guarded by the warp-uniform entry count only (padding inside the slice adds 0).
-        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane;
-        constexpr int HK = kStreamK / 2;
-#pragma unroll
-        for (int hb = 0; hb < kStreamK; hb += HK) {
-          if (hb >= cnt) break;
-          double xv[HK];
-          if (hb + HK <= cnt) {
-#pragma unroll
-            for (int u = 0; u < HK; ++u) xv[u] = P.p[rbase + (int)sc[(hb + u) * 32]];
+            for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[rbase + (int)sc[u * 32]];
             if (W32) {
               float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
 #pragma unroll
-              for (int u = 0; u < HK; ++u) __stcs(wp + u * 32, (float)sv[(hb + u) * 32]);
+              for (int u = 0; u < kStreamK; ++u) __stcs(wp + u * 32, (float)hv[u * 32]);
             }
 #pragma unroll
-            for (int u = 0; u < HK; ++u) acc = fma((double)sv[(hb + u) * 32], xv[u], acc);
+            for (int u = 0; u < kStreamK; ++u) acc = fma((double)hv[u * 32], xv[u], acc);
           } else {
 #pragma unroll
-            for (int u = 0; u < HK; ++u) xv[u] = P.p[hb + u < cnt ? rbase + (int)sc[(hb + u) * 32] : row];
+            for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[u < hc ? rbase + (int)sc[u * 32] : row];
             if (W32) {
               float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
 #pragma unroll
-              for (int u = 0; u < HK; ++u)
-                if (hb + u < cnt) __stcs(wp + u * 32, (float)sv[(hb + u) * 32]);
+              for (int u = 0; u < kStreamK; ++u)
+                if (u < hc) __stcs(wp + u * 32, (float)hv[u * 32]);
             }
 #pragma unroll
-            for (int u = 0; u < HK; ++u)
-              if (hb + u < cnt) acc = fma((double)sv[(hb + u) * 32], xv[u], acc);
+            for (int u = 0; u < kStreamK; ++u)
+              if (u < hc) acc = fma((double)hv[u * 32], xv[u], acc);
           }
+        } else {
+          // general form: 32-bit columns and/or the last, partly filled slice (rows past n never load)
+          int c[kStreamK];
+          if (c16) {
+            const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane + hb * 32;
+#pragma unroll
+            for (int u = 0; u < kStreamK; ++u) c[u] = u < hc ? rbase + (int)sc[u * 32] : csafe;
+          } else {
+            const int* sc = reinterpret_cast<const int*>(sb + kValBytes) + lane + hb * 32;
+#pragma unroll
+            for (int u = 0; u < kStreamK; ++u) c[u] = u < hc ? sc[u * 32] : csafe;
+          }
+          if (row >= n) {
+#pragma unroll
+            for (int u = 0; u < kStreamK; ++u) c[u] = csafe;
+          }
+#pragma unroll
+          for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[c[u]];
+          const VT* hv = sv + hb * 32;
+          if (W32) {
+            float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
+#pragma unroll
+            for (int u = 0; u < kStreamK; ++u)
+              if (u < hc) __stcs(wp + u * 32, (float)hv[u * 32]);
+          }
+#pragma unroll
+          for (int u = 0; u < kStreamK; ++u)
+            if (k0 + hb + u < len) acc = fma((double)hv[u * 32], xv[u], acc);
         }
-        __syncwarp();  // every lane has read stage b: it can be refilled
-        ++consumed;
-        issue();
-        k0 += kStreamK;
-        continue;
       }
-      int c[kStreamK];
-      if (c16) {
-        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sb + kValBytes) + lane;
-#pragma unroll
-        for (int u = 0; u < kStreamK; ++u) c[u] = u < cnt ? rbase + (int)sc[u * 32] : csafe;
-      } else {
-        const int* sc = reinterpret_cast<const int*>(sb + kValBytes) + lane;
-#pragma unroll
-        for (int u = 0; u < kStreamK; ++u) c[u] = u < cnt ? sc[u * 32] : csafe;
-      }
-      double xv[kStreamK];
-#pragma unroll
-      for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[c[u]];
-      if (W32) {
-        float* wp = P.hval32 + off + lane;
-#pragma unroll
-        for (int u = 0; u < kStreamK; ++u)
-          if (u < cnt) __stcs(wp + (k0 + u) * 32, (float)sv[u * 32]);
-      }
-#pragma unroll
-      for (int u = 0; u < kStreamK; ++u)
-        if (k0 + u < len) acc = fma((double)sv[u * 32], xv[u], acc);
       __syncwarp();  // every lane has read stage b: it can be refilled
       ++consumed;
       issue();
-      k0 += kStreamK;
+      k0 += kc;
     } while (k0 < width);
     if (row < n) {
       P.q[row] = acc;
@@ -691,10 +682,10 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
       // four and more unbalance the blocks (slices per warp are few: 32 768 slices over 2 368 warps at C2)
       const int gw = blk * NW + warp, GW = G * NW, grp = P.stream_group;
       double loc;
-      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol);
+      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes, kStreamK>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol);
       else if (P.hval32 && iters == 0)  // writes the FP32 copy
-        loc = stream_spmv<double, true, 2, kStreamStageBytes>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
-      else loc = stream_spmv<double, false, 2, kStreamStageBytes>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
+        loc = stream_spmv<double, true, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
+      else loc = stream_spmv<double, false, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
       const double bs = block_sum_nw<NW>(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }

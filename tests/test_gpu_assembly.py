@@ -264,3 +264,20 @@ def test_stream_form_forced_on_scattered_patterns(spb, orc, seed, m, n, k):
         h.close()
     finally:
         del os.environ["SPB_ASM_V2_MIN_RUN"]
+
+
+def test_stream_form_odd_value_count_tail(spb, orc):
+    """An odd number of J values: the last bulk-copy window would end one element past the value array, so the producer
+    shortens it and fetches the last element by hand (ChunkHdr2::tail_src).  The device array is exactly nnz long."""
+    J = orc.lf_matrix(40, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    colptr = colptr.copy()
+    colptr[-1] -= 1
+    rowidx, vals = rowidx[:-1].copy(), vals[:-1].copy()
+    assert colptr[-1] % 2 == 1
+    rng = np.random.default_rng(5)
+    h = spb.Handle(0)
+    _check(h, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), 0.01)
+    assert h.assembly_form() == 3
+    h.close()

@@ -281,3 +281,31 @@ def test_stream_form_odd_value_count_tail(spb, orc):
     _check(h, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), 0.01)
     assert h.assembly_form() == 3
     h.close()
+
+
+def test_stream_form_inf_nan_and_explicit_zeros(spb, orc):
+    """inf / NaN / signed zeros through the stream form (LF pattern, so the form applies by itself): the first product
+    is assigned, not added to 0, and every later one is a separately rounded multiply and add -- NaN positions and all
+    other bits equal the oracle's (SIInitialSolutionTraits.h:163,227-228 injects inf on purpose)."""
+    J = orc.lf_matrix(32, 2, 20211)
+    colptr, rowidx, vals = J.csc()
+    m, n = J.shape
+    vals = vals.copy()
+    rng = np.random.default_rng(21)
+    pick = rng.choice(len(vals), 40, replace=False)
+    vals[pick[:10]] = np.inf
+    vals[pick[10:20]] = -np.inf
+    vals[pick[20:25]] = np.nan
+    vals[pick[25:33]] = 0.0
+    vals[pick[33:]] = -0.0
+    E = rng.standard_normal(m)
+    h = spb.Handle(0)
+    h.analyze(m, n, colptr, rowidx)
+    h.assemble(vals, E, 0.01)
+    assert h.assembly_form() == 3
+    hp, hi, hx, g, d = _reference(orc, m, n, colptr, rowidx, vals, E, 0.01)
+    hv = h.h_values()
+    assert (np.isnan(hv) == np.isnan(hx)).all()
+    ok = ~np.isnan(hx)
+    assert (_bits(hv[ok]) == _bits(hx[ok])).all()   # including the sign of zeros
+    h.close()

@@ -160,7 +160,9 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
     SPB_CUDA(d_Jv.alloc((size_t)nnzJ));
     Evaluator ev{h, T, n, m, nnzJ, W.hx, W.hE, W.hJ};
     ev.init();
-    {
+    if (builtin_x0_device(T, d_prevx.p, st)) {  // device-resident problem: its initial point is on the device already
+      SPB_CUDA(cudaMemcpyAsync(d_x.p, d_prevx.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
       HostPinned& x0 = W.hx0;
       x0.alloc(n);
       T->initial_solution(T->user, x0.p);

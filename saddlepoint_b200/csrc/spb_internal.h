@@ -464,6 +464,9 @@ void gather_h_values(spb_context* h, double* d_out);   // CSC order
 void scatter_h_values(spb_context* h, const double* d_in);
 void sum_triplets(spb_context* h, const double* d_trip_vals, double* d_csc_vals);  // insertion-order sums per H entry  // CSC order -> storage (+ hdiag)
 
+// problems.cu: initial point of a device-resident problem straight from the device (false: not one of ours)
+bool builtin_x0_device(const spb_traits* T, double* d_dst, cudaStream_t st);
+
 // blas1.cu
 void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);
 void dev_inf_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);

@@ -55,6 +55,12 @@ struct BatchPcgParams {
   const double* hval;
   const double* b;
   const double* dinv;
+  // exact 2x2 block preconditioner (block2 != 0; H block diagonal over aligned pairs, n_per even): M = the pair's block
+  // [hdiag_i, hoff; hoff, hdiag_i^1], M^-1 = [dinv_i, doff; doff, dinv_i^1]
+  const double* doff;
+  const double* hoff;
+  const double* hdiag;
+  int block2;
   double* x;
   double* u;
   double* p;
@@ -83,12 +89,16 @@ __global__ void __launch_bounds__(256, 3) batch_pcg_kernel(BatchPcgParams P) {
     const int p0 = prob_of_row(slice * 32, n_per);
     const int split = (p0 + 1) * n_per - slice * 32;  // lanes >= split belong to problem p0 + 1
     double g0 = 0.0, r0 = 0.0;
-    if (row < n) {
-      const int pr = lane < split ? p0 : p0 + 1;
-      const bool act = P.active[pr] != 0;
-      const double bi = act ? P.b[row] : 0.0;
+    const bool in_range = row < n;
+    const bool act = in_range && P.active[min(lane < split ? p0 : p0 + 1, P.nprob - 1)] != 0;
+    const double bi = act ? P.b[row] : 0.0;
+    // block2: u = M^-1 b with the pair's inverse block; the partner is the neighbouring lane (same problem: n_per is even),
+    // so every lane of the warp takes part in the exchange
+    const double bo = P.block2 ? __shfl_xor_sync(0xffffffffu, bi, 1) : 0.0;
+    if (in_range) {
       const double di = P.dinv[row];
-      const double ui = act ? bi * di : 0.0;
+      double ui = act ? bi * di : 0.0;
+      if (P.block2) ui = act ? fma(P.doff[row], bo, bi * di) : 0.0;
       P.x[row] = 0.0;
       P.u[row] = ui;
       P.p[row] = 0.0;
@@ -203,7 +213,38 @@ __global__ void __launch_bounds__(256, 3) batch_pcg_kernel(BatchPcgParams P) {
       const bool live = row < n && pr < P.nprob && P.S.status[pr] == 0;
       if (!__any_sync(0xffffffffu, live)) continue;
       double g0 = 0.0, r0 = 0.0;
-      if (live) {
+      if (P.block2) {
+        // u <- u - alpha M^-1 s and r = M u with the pair's blocks; the partner values come from the neighbouring lane
+        // (pairs never straddle a slice or, n_per being even, a problem), so every lane of the warp takes part
+        double alpha = 0.0, beta = 0.0, ui = 0.0, wi = 0.0, pi = 0.0, si = 0.0, xi = 0.0, di = 0.0, dof = 0.0, hd = 0.0, hof = 0.0;
+        if (live) {
+          alpha = P.S.alpha[pr];
+          beta = P.S.beta[pr];
+          ui = P.u[row];
+          wi = P.w[row];
+          pi = P.p[row];
+          si = P.s[row];
+          xi = P.x[row];
+          di = P.dinv[row];
+          dof = P.doff[row];
+          hd = P.hdiag[row];
+          hof = P.hoff[row];
+        }
+        const double pn = fma(beta, pi, ui);
+        const double sn = fma(beta, si, wi);
+        const double so = __shfl_xor_sync(0xffffffffu, sn, 1);
+        const double un = ui - alpha * fma(dof, so, di * sn);
+        const double uo = __shfl_xor_sync(0xffffffffu, un, 1);
+        const double rn = fma(hof, uo, hd * un);
+        if (live) {
+          P.p[row] = pn;
+          P.s[row] = sn;
+          P.x[row] = fma(alpha, pn, xi);
+          P.u[row] = un;
+          g0 = rn * un;
+          r0 = rn * rn;
+        }
+      } else if (live) {
         const double alpha = P.S.alpha[pr], beta = P.S.beta[pr];
         const double ui = P.u[row], wi = P.w[row], pi = P.p[row], si = P.s[row], xi = P.x[row], di = P.dinv[row];
         const double pn = fma(beta, pi, ui);
@@ -384,12 +425,38 @@ __global__ void batch_commit_kernel(double* __restrict__ prevx, double* __restri
 __global__ void batch_invert_kernel(const double* __restrict__ a, double* __restrict__ out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = 1.0 / a[i];
 }
+// Exact inverse of the 2x2 blocks of a block-diagonal H (h_block2): per row the diagonal and the off-diagonal entry of
+// the inverse block, and the block's own off-diagonal entry.  A pair whose block is not positive definite (or not
+// finite), or that has no coupling entry, gets the plain Jacobi data (doff = hoff = 0), identically for both rows.
+__global__ void batch_invert2_kernel(const double* __restrict__ hdiag, const double* __restrict__ hval, const int64_t* __restrict__ slice_off,
+                                     const int* __restrict__ rowlen, int n, double* __restrict__ dinv, double* __restrict__ doff,
+                                     double* __restrict__ hoff) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double a = hdiag[i];
+    const int o = i ^ 1;
+    double ia = 1.0 / a, ib = 0.0, b = 0.0;
+    if (o < n && rowlen[i] == 2) {
+      // row i holds {i, i+1} (i even: coupling entry second) or {i-1, i} (i odd: coupling entry first)
+      const double bb = hval[slice_off[i >> 5] + (int64_t)((i & 1) ? 0 : 1) * 32 + (i & 31)];
+      const double c = hdiag[o];
+      const double det = a * c - bb * bb;
+      if (det > 0.0 && det < 1.79e308 && a > 0.0 && c > 0.0) {
+        ia = c / det;
+        ib = -bb / det;
+        b = bb;
+      }
+    }
+    dinv[i] = ia;
+    doff[i] = ib;
+    hoff[i] = b;
+  }
+}
 __global__ void batch_fill_kernel(double* p, double v, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
 
 struct BatchWorkspace {
-  DevBuf<double> d_prevx, d_x, d_dir, d_trial, d_E, d_Etrial, d_Jv, d_part;
+  DevBuf<double> d_prevx, d_x, d_dir, d_trial, d_E, d_Etrial, d_Jv, d_part, d_doff, d_hoff;
   DevBuf<double> d_dbl;  // per-problem doubles: 6 PCG + 8 LM arrays
   DevBuf<int> d_int;     // per-problem ints
   DevBuf<int64_t> d_i64;
@@ -532,10 +599,25 @@ extern "C" spb_status spb_lm_solve_batch(spb_handle h, const spb_traits* T, int3
       h->lambda_n_per = n_per;
       run_assembly(h, W.d_Jv.p, W.d_E.p, 0.0, nullptr);
       h->d_lambda_vec = nullptr;
+      stage_begin(h, ST_REDUCE);
       seg_reduce_kernel<1><<<B, 256, 0, st>>>(h->d_rhs.p, n_per, (int64_t)n, LS.foo_tmp);
       batch_ctl_foo_kernel<<<gp, 256, 0, st>>>(LS, LO, B);
+      stage_end(h, ST_REDUCE, 2);
       SPB_CUDA(h->d_dinv.alloc(n));
-      batch_invert_kernel<<<gv, 256, 0, st>>>(h->d_hdiag.p, h->d_dinv.p, n);
+      // block-diagonal H over aligned pairs (extended Rosenbrock batches): the exact inverse blocks precondition, the PCG
+      // becomes a direct block solve with one or two refinement iterations instead of ~30 Jacobi iterations on blocks
+      // whose condition number is 1e8 far from the optimum
+      static const bool block2_off = getenv("SPB_BATCH_BLOCK2") && atoi(getenv("SPB_BATCH_BLOCK2")) == 0;
+      const bool block2 = h->h_block2 && (n_per % 2 == 0) && !block2_off;
+      stage_begin(h, ST_PCGVEC);
+      if (block2) {
+        SPB_CUDA(W.d_doff.alloc(n));
+        SPB_CUDA(W.d_hoff.alloc(n));
+        batch_invert2_kernel<<<gv, 256, 0, st>>>(h->d_hdiag.p, h->d_hval.p, h->d_slice_off.p, h->d_rowlen.p, n, h->d_dinv.p, W.d_doff.p, W.d_hoff.p);
+      } else {
+        batch_invert_kernel<<<gv, 256, 0, st>>>(h->d_hdiag.p, h->d_dinv.p, n);
+      }
+      stage_end(h, ST_PCGVEC, 1);
       h->launches += 3;
       {
         BatchPcgParams P;
@@ -547,6 +629,10 @@ extern "C" spb_status spb_lm_solve_batch(spb_handle h, const spb_traits* T, int3
         P.hval = h->d_hval.p;
         P.b = h->d_rhs.p;
         P.dinv = h->d_dinv.p;
+        P.doff = block2 ? W.d_doff.p : nullptr;
+        P.hoff = block2 ? W.d_hoff.p : nullptr;
+        P.hdiag = h->d_hdiag.p;
+        P.block2 = block2 ? 1 : 0;
         P.x = W.d_dir.p;
         P.u = h->d_u.p;
         P.p = h->d_p.p;
@@ -567,16 +653,26 @@ extern "C" spb_status spb_lm_solve_batch(spb_handle h, const spb_traits* T, int3
         SPB_CUDA(cudaLaunchCooperativeKernel((void*)batch_pcg_kernel, dim3(G), dim3(256), args, 0, st));
         stage_end(h, ST_PCG, 1);
       }
+      stage_begin(h, ST_REDUCE);
       seg_reduce_kernel<0><<<B, 256, 0, st>>>(W.d_dir.p, n_per, (int64_t)n, LS.dn2);
       batch_ctl_dir_kernel<<<gp, 256, 0, st>>>(LS, LO, B, PS.status, PS.iters);
+      stage_end(h, ST_REDUCE, 2);
+      stage_begin(h, ST_PCGVEC);
       batch_trial_kernel<<<gv, 256, 0, st>>>(W.d_prevx.p, W.d_dir.p, W.d_trial.p, LS.active, n_per, (int64_t)n);
+      stage_end(h, ST_PCGVEC, 1);
       h->launches += 3;
       eval(W.d_trial.p, W.d_Etrial.p, nullptr);  // LMSolver.h:156
+      stage_begin(h, ST_REDUCE);
       seg_reduce_kernel<0><<<B, 256, 0, st>>>(W.d_Etrial.p, m_per, (int64_t)m, LS.newE2);
       batch_ctl_accept_kernel<<<gp, 256, 0, st>>>(LS, LO, B);
+      stage_end(h, ST_REDUCE, 2);
+      stage_begin(h, ST_PCGVEC);
       batch_commit_kernel<<<gv, 256, 0, st>>>(W.d_prevx.p, W.d_x.p, W.d_trial.p, LS.active, LS.accepted, n_per, (int64_t)n);
+      stage_end(h, ST_PCGVEC, 1);
+      stage_begin(h, ST_REDUCE);
       batch_ctl_finish_kernel<<<gp, 256, 0, st>>>(LS, B);
       batch_ctl_count_kernel<<<gp, 256, 0, st>>>(LS, B);
+      stage_end(h, ST_REDUCE, 2);
       h->launches += 5;
       SPB_CUDA(cudaMemcpyAsync(h_nactive, LS.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
       SPB_CUDA(cudaStreamSynchronize(st));

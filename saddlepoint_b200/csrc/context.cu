@@ -233,6 +233,18 @@ spb_status spb_analyze(spb_handle h, int32_t m, int32_t n, const int32_t* colptr
       }
       h->h_pattern_hash = hh;
     }
+    {
+      // block structure: every row of H holds its diagonal and at most the entry that couples it with the other unknown
+      // of its aligned pair (2k, 2k+1) -- the extended Rosenbrock structure (benchmark/rosenbrock/main.cpp:29-38)
+      bool b2 = n >= 2;
+      for (int r = 0; r < n && b2; ++r) {
+        const int q0 = h->H.colptr[r], q1 = h->H.colptr[(size_t)r + 1];
+        if (q1 - q0 > 2) b2 = false;
+        for (int q = q0; q < q1 && b2; ++q)
+          if (h->H.rowidx[q] != r && h->H.rowidx[q] != (r ^ 1)) b2 = false;
+      }
+      h->h_block2 = b2;
+    }
     upload_h_layout(h);
     lap("upload H layout");
     upload_analysis(h, colptr, rowidx, P);

@@ -352,6 +352,7 @@ struct spb_context {
   int v2_stages = 0;
   size_t v2_smem = 0;
   int last_asm_form = 0;  // spb_assembly_form()
+  bool h_block2 = false;  // H is block diagonal with blocks on the aligned pairs (2k, 2k+1) at most (extended Rosenbrock): the batched PCG preconditions with the exact inverse blocks
   cudaStream_t asm_side_stream = nullptr;  // the column kernel runs here, next to the stream-form pair kernel
   cudaEvent_t asm_fork_ev = nullptr, asm_join_ev = nullptr;
   // subdomain (halo) mode, dist.cu: this handle holds the LOCAL problem of one rank; local unknowns are

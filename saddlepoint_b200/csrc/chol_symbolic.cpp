@@ -243,7 +243,133 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
     t0 = t1;
   };
   // ---- ordering + supernode partition
+  // Static condensation first.  Least-squares problems from meshes carry many low-degree "satellite" unknowns (the
+  // seamless-integration structure: 8 field unknowns per face that couple with each other and with the face's 6 vertex
+  // unknowns only, SIInitialSolutionTraits.h:238-245).  A breadth-first level of the full graph contains the satellites of
+  // every face it crosses, so the separators come out ~9x larger than the mesh needs and the factorisation ~100x more
+  // expensive.  Connected groups of low-degree vertices with a small outside neighbourhood are therefore eliminated FIRST,
+  // each as one leaf supernode (no two groups are adjacent: all of them are independent fronts of the first level), and
+  // the nested dissection runs on what is left, with the fill those eliminations cause (a clique over every group's
+  // outside neighbours) added to its graph.  Patterns without such groups (LF: uniform degree) are untouched.
+  std::vector<int> cond_perm, cond_sizes, rest;          // eliminated groups (original ids) / remaining vertices
+  std::vector<int> rp, ri;                               // graph of the remaining vertices (compact ids), with fill
   {
+    static const int kMaxDeg = getenv("SPB_CHOL_CONDENSE_DEG") ? atoi(getenv("SPB_CHOL_CONDENSE_DEG")) : 16;
+    constexpr int kMaxGroup = 32, kMaxExt = 48;
+    std::vector<int> grp(n, -1);  // -1 untouched, -2 rejected candidate, >= 0 group id
+    std::vector<int> comp, ext, stackv;
+    std::vector<int> seen(n, -1);
+    std::vector<std::vector<int>> group_ext;
+    if (kMaxDeg > 0) {
+      for (int v0 = 0; v0 < n; ++v0) {
+        if (grp[v0] != -1 || H.colptr[(size_t)v0 + 1] - H.colptr[v0] - 1 > kMaxDeg) continue;
+        // component of low-degree vertices around v0 (abandoned once it is too big to be a satellite group)
+        comp.clear();
+        ext.clear();
+        stackv.assign(1, v0);
+        seen[v0] = v0;
+        bool ok = true;
+        while (!stackv.empty()) {
+          const int v = stackv.back();
+          stackv.pop_back();
+          comp.push_back(v);
+          if ((int)comp.size() > kMaxGroup) ok = false;
+          for (int q = H.colptr[v]; q < H.colptr[(size_t)v + 1]; ++q) {
+            const int w = H.rowidx[q];
+            if (w == v || seen[w] == v0) continue;
+            seen[w] = v0;
+            if (H.colptr[(size_t)w + 1] - H.colptr[w] - 1 <= kMaxDeg) {
+              if (ok) stackv.push_back(w);  // a rejected component is not explored further than needed to mark it
+              else comp.push_back(w);
+            } else {
+              ext.push_back(w);
+            }
+          }
+          if (!ok && comp.size() > 4096) break;  // giant low-degree region (a plain grid): stop walking it
+        }
+        ok = ok && (int)ext.size() <= kMaxExt && (int)ext.size() <= 2 * (int)comp.size() + 8;
+        if (ok) {
+          const int g = (int)group_ext.size();
+          for (int v : comp) grp[v] = g;
+          std::sort(ext.begin(), ext.end());
+          group_ext.push_back(ext);
+          std::sort(comp.begin(), comp.end());
+          cond_perm.insert(cond_perm.end(), comp.begin(), comp.end());
+          cond_sizes.push_back((int)comp.size());
+        } else {
+          for (int v : comp)
+            if (grp[v] == -1) grp[v] = -2;
+        }
+      }
+    }
+    // a condensation that removes little is not worth a second graph
+    if ((int64_t)cond_perm.size() * 8 < n) {
+      cond_perm.clear();
+      cond_sizes.clear();
+      group_ext.clear();
+      std::fill(grp.begin(), grp.end(), -1);
+    }
+    if (!cond_perm.empty()) {
+      std::vector<int> newid(n, -1);
+      for (int v = 0; v < n; ++v)
+        if (grp[v] < 0) {
+          newid[v] = (int)rest.size();
+          rest.push_back(v);
+        }
+      // groups adjacent to every remaining vertex
+      std::vector<std::vector<int>> groups_of(rest.size());
+      for (int g = 0; g < (int)group_ext.size(); ++g)
+        for (int w : group_ext[g]) groups_of[newid[w]].push_back(g);
+      rp.assign(rest.size() + 1, 0);
+      std::vector<int> mark(rest.size(), -1), row;
+      for (size_t a = 0; a < rest.size(); ++a) {
+        const int v = rest[a];
+        row.clear();
+        mark[a] = (int)a;
+        row.push_back((int)a);  // diagonal: the graph arrays follow the H pattern's convention (full diagonal)
+        for (int q = H.colptr[v]; q < H.colptr[(size_t)v + 1]; ++q) {
+          const int b = newid[H.rowidx[q]];
+          if (b >= 0 && mark[b] != (int)a) {
+            mark[b] = (int)a;
+            row.push_back(b);
+          }
+        }
+        for (int g : groups_of[a])
+          for (int w : group_ext[g]) {
+            const int b = newid[w];
+            if (mark[b] != (int)a) {
+              mark[b] = (int)a;
+              row.push_back(b);
+            }
+          }
+        std::sort(row.begin(), row.end());
+        ri.insert(ri.end(), row.begin(), row.end());
+        rp[a + 1] = (int)ri.size();
+      }
+    }
+  }
+  lap("static condensation");
+  if (!cond_perm.empty()) {
+    const int nr = (int)rest.size();
+    NdBuilder nd(nr, rp, ri);
+    std::vector<int> all(nr);
+    std::iota(all.begin(), all.end(), 0);
+    NdBuilder::Out out;
+    out.perm.reserve(nr);
+    int depth = 0;
+    {
+      const char* e = getenv("SPB_HOST_THREADS");
+      int threads = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      threads = std::max(1, std::min(threads, 32));
+      while ((1 << depth) < 2 * threads && threads > 1) ++depth;
+    }
+    if (nr > 0) nd.dissect(all, out, depth);
+    C.perm = std::move(cond_perm);
+    for (int a : out.perm) C.perm.push_back(rest[a]);
+    C.sn_col0.assign(1, 0);
+    for (int sz : cond_sizes) C.sn_col0.push_back(C.sn_col0.back() + sz);
+    for (int sz : out.sn_sizes) C.sn_col0.push_back(C.sn_col0.back() + sz);
+  } else {
     NdBuilder nd(n, H.colptr, H.rowidx);
     std::vector<int> all(n);
     std::iota(all.begin(), all.end(), 0);

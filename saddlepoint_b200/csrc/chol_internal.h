@@ -5,6 +5,8 @@
 
 namespace spb {
 
+constexpr int kSmallChildU = 32;  // update matrices up to this size are added by the per-parent kernel
+
 struct CholSymbolic {
   int n = 0, nsuper = 0, nlevels = 0;
   std::vector<int> perm, pinv;         // perm[new] = old ; pinv[old] = new
@@ -27,6 +29,13 @@ struct CholSymbolic {
   std::vector<int> level_rank_ptr;     // nlevels+1 into rank_ptr
   std::vector<int> rank_ptr;           // per (level, child rank): range in rank_children
   std::vector<int> rank_children;
+  // Extend-add order: the children of a parent sorted by descending update-matrix size.  The first level_big_ranks[l]
+  // ranks of a level (the ones that can hold a child with more than kSmallChildU rows) are added rank by rank, one launch
+  // each over all parents; every further child is small and is added by ONE launch per level in which a warp walks the
+  // remaining children of its parent in order (ea_ptr/ea_idx; small_parents: the parents of a level that have such children).
+  std::vector<int> ea_ptr, ea_idx;            // nsuper+1 / children in extend-add order
+  std::vector<int> level_big_ranks;           // nlevels
+  std::vector<int> small_parents_ptr, small_parents;  // nlevels+1 / parent supernodes
   int max_k = 0, max_r = 0;
   int64_t nnzL = 0;
   double flops = 0.0;

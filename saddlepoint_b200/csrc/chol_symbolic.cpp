@@ -634,21 +634,47 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
     const int64_t k = C.sn_col0[s + 1] - C.sn_col0[s];
     C.dinv_off[(size_t)s + 1] = C.dinv_off[s] + ((k + 31) / 32) * 1024;
   }
-  // ---- child-rank lists per level: rank_list[l][r] = r-th children of the level's parents
+  // ---- extend-add order and child-rank lists per level.  Children sorted by descending update-matrix size (stable): with
+  // static condensation a parent has a few large children (its dissection subtrees) and up to a hundred tiny ones (the
+  // satellite groups), and one launch per child rank was 216 launches per factorisation on the seamless-integration
+  // structure.  Only the ranks that may hold a large child keep the rank-wise launch.
   C.rank_ptr.clear();
   C.rank_children.clear();
   C.level_rank_ptr.assign((size_t)nlevels + 1, 0);
+  C.ea_ptr.assign((size_t)ns + 1, 0);
+  C.ea_idx.clear();
+  C.level_big_ranks.assign((size_t)nlevels, 0);
+  C.small_parents_ptr.assign((size_t)nlevels + 1, 0);
+  C.small_parents.clear();
+  auto usize = [&](int c) { return (int)(C.struct_ptr[(size_t)c + 1] - C.struct_ptr[c]); };
+  for (int s = 0; s < ns; ++s) {
+    std::vector<int> ch(children[s]);
+    std::stable_sort(ch.begin(), ch.end(), [&](int a, int b) { return usize(a) > usize(b); });
+    C.ea_idx.insert(C.ea_idx.end(), ch.begin(), ch.end());
+    C.ea_ptr[(size_t)s + 1] = (int)C.ea_idx.size();
+  }
   for (int l = 0; l < nlevels; ++l) {
-    int maxch = 0;
-    for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) maxch = std::max<int>(maxch, (int)children[C.level_sn[t]].size());
-    for (int rk = 0; rk < maxch; ++rk) {
+    int big = 0;
+    for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) {
+      const int p = C.level_sn[t];
+      int nb = 0;
+      for (int q = C.ea_ptr[p]; q < C.ea_ptr[(size_t)p + 1] && usize(C.ea_idx[q]) > kSmallChildU; ++q) ++nb;
+      big = std::max(big, nb);
+    }
+    C.level_big_ranks[l] = big;
+    for (int rk = 0; rk < big; ++rk) {
       C.rank_ptr.push_back((int)C.rank_children.size());
       for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) {
-        const auto& ch = children[C.level_sn[t]];
-        if ((int)ch.size() > rk) C.rank_children.push_back(ch[rk]);
+        const int p = C.level_sn[t];
+        if (C.ea_ptr[(size_t)p + 1] - C.ea_ptr[p] > rk) C.rank_children.push_back(C.ea_idx[(size_t)C.ea_ptr[p] + rk]);
       }
     }
     C.level_rank_ptr[(size_t)l + 1] = (int)C.rank_ptr.size();
+    for (int t = C.level_ptr[l]; t < C.level_ptr[(size_t)l + 1]; ++t) {
+      const int p = C.level_sn[t];
+      if (C.ea_ptr[(size_t)p + 1] - C.ea_ptr[p] > big) C.small_parents.push_back(p);
+    }
+    C.small_parents_ptr[(size_t)l + 1] = (int)C.small_parents.size();
   }
   C.rank_ptr.push_back((int)C.rank_children.size());
 }

@@ -44,7 +44,7 @@ namespace spb {
 
 struct CholDevice {
   CholSymbolic sym;
-  DevBuf<int> sn_k, sn_r, col0, struct_idx, rel_idx, parent, child_ptr, child_idx, level_sn, rank_children, perm;
+  DevBuf<int> sn_k, sn_r, col0, struct_idx, rel_idx, parent, child_ptr, child_idx, level_sn, rank_children, perm, ea_ptr, ea_idx, small_parents;
   DevBuf<int64_t> L_off, U_off, W_off, struct_ptr, rel_ptr, dinv_off, a_src, a_dst;
   DevBuf<double> Lbuf, Ubuf, Wbuf, Dinv, ywork;
   DevBuf<int> fail;
@@ -96,6 +96,120 @@ __global__ void __launch_bounds__(256) chol_extend_add_kernel(const int* __restr
       else Up[(int64_t)(lb - pk) * pu + (la - pk)] += v;
     }
   }
+}
+
+// The small children of a parent (update matrices of at most kSmallChildU rows), added by ONE warp per parent in the
+// parent's extend-add order, starting at child `first` of its list: same sums in the same order as the rank-wise launches
+// would form, without a launch per rank (a parent of the condensed seamless-integration structure has ~100 of them).
+__global__ void __launch_bounds__(128) chol_extend_add_small_kernel(const int* __restrict__ parents, int count, int first,
+                                                                    const int* __restrict__ ea_ptr, const int* __restrict__ ea_idx,
+                                                                    const int* __restrict__ sn_k, const int* __restrict__ sn_r,
+                                                                    const int64_t* __restrict__ L_off, const int64_t* __restrict__ U_off,
+                                                                    const int64_t* __restrict__ rel_ptr, const int* __restrict__ rel_idx,
+                                                                    double* __restrict__ Lbuf, double* __restrict__ Ubuf) {
+  const int lane = threadIdx.x & 31;
+  const int pi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (pi >= count) return;
+  const int p = parents[pi];
+  const int pk = sn_k[p], pr = sn_r[p], pu = pr - pk;
+  double* Pp = Lbuf + L_off[p];
+  double* Up = Ubuf + U_off[p];
+  const int c_end = ea_ptr[p + 1];
+  for (int ci = ea_ptr[p] + first; ci < c_end; ++ci) {
+    const int c = ea_idx[ci];
+    const int u = sn_r[c] - sn_k[c];
+    const double* Uc = Ubuf + U_off[c];
+    const int* rel = rel_idx + rel_ptr[c];
+    for (int e = lane; e < u * u; e += 32) {
+      const int b = e / u, a = e - b * u;
+      if (a < b) continue;
+      const int lb = rel[b], la = rel[a];
+      const double v = Uc[(int64_t)b * u + a];
+      if (lb < pk) Pp[(int64_t)lb * pr + la] += v;
+      else Up[(int64_t)(lb - pk) * pu + (la - pk)] += v;
+    }
+    __syncwarp();  // the next child may add to the same parent entries
+  }
+}
+
+// A whole front of at most 16 pivots and 32 rows, factored by ONE warp in one launch: Cholesky of the pivot block, the
+// rows below it, the update matrix U -= L21 L21^T and the inverted pivot block for the solves.  Lane i keeps row i of the
+// r x k panel in registers; columns are eliminated right-looking with the pivot column broadcast by shuffles.  Same
+// arithmetic as the block kernels (l_jj = d rsqrt(d), l_ij = a_ij rsqrt(d); failure iff a pivot <= 0, NaN passes).
+// With static condensation the first level of the seamless-integration structure is half a million such fronts
+// (k = 8, r = 14): three launches of 128-thread CTAs per 32 768 of them before, one launch of warps now.
+__global__ void __launch_bounds__(128) chol_tiny_front_kernel(const int* __restrict__ fronts, int count, const int* __restrict__ sn_k,
+                                                              const int* __restrict__ sn_r, const int64_t* __restrict__ L_off,
+                                                              const int64_t* __restrict__ U_off, const int64_t* __restrict__ dinv_off,
+                                                              double* __restrict__ Lbuf, double* __restrict__ Ubuf,
+                                                              double* __restrict__ Dinv, int* __restrict__ fail) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int fi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (fi >= count) return;
+  const int f = fronts[fi];
+  const int k = sn_k[f], r = sn_r[f], u = r - k;
+  double* P = Lbuf + L_off[f];
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = (c < k && lane < r && lane >= c) ? P[(int64_t)c * r + lane] : 0.0;
+  bool bad = false;
+  double myr = 1.0;  // 1 / l_jj of this lane's pivot
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < k) {  // warp-uniform
+      const double d = __shfl_sync(kFull, a[j], j);
+      bad = bad || (d <= 0.0);  // NaN passes, like the reference's `if (d <= 0)`
+      const double rs = rsqrt(d);
+      if (lane == j) {
+        a[j] = d * rs;
+        myr = rs;
+      } else if (lane > j) {
+        a[j] = a[j] * rs;
+      }
+#pragma unroll
+      for (int c = j + 1; c < 16; ++c) {
+        if (c < k) {
+          const double lcj = __shfl_sync(kFull, a[j], c);
+          if (lane >= c) a[c] -= a[j] * lcj;
+        }
+      }
+    }
+  }
+  if (lane == 0 && bad) *fail = 1;
+  if (lane < r) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < k && lane >= c) P[(int64_t)c * r + lane] = a[c];
+  }
+  // update matrix: U(a, b) -= sum_c L(k+a, c) L(k+b, c), lower triangle, column b at a time
+  if (u > 0) {
+    double* U = Ubuf + U_off[f];
+    for (int b = 0; b < u; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < k) s = fma(a[c], __shfl_sync(kFull, a[c], k + b), s);
+      const int ai = lane - k;
+      if (lane < r && ai >= b) U[(int64_t)b * u + ai] -= s;
+    }
+  }
+  // inverse of the pivot block (identity-padded to 32 x 32, column-major): lane = column, forward substitution
+  double x[16];
+#pragma unroll
+  for (int rw = 0; rw < 16; ++rw) {
+    x[rw] = 0.0;
+    if (rw < k) {
+      double acc = (rw == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = 0; t < rw; ++t) acc -= __shfl_sync(kFull, a[t], rw) * x[t];  // x[t] == 0 for t < lane
+      const double rd = __shfl_sync(kFull, myr, rw);
+      x[rw] = rw >= lane ? acc * rd : 0.0;
+    }
+  }
+  double* out = Dinv + dinv_off[f] + (int64_t)lane * 32;
+#pragma unroll
+  for (int rw = 0; rw < 32; ++rw) out[rw] = (rw < 16 && rw < k && lane < k) ? x[rw & 15] : (rw == lane ? 1.0 : 0.0);
 }
 
 // Cholesky of the 32x32 diagonal block at pivot offset kb of every front in the list, plus its
@@ -1082,6 +1196,9 @@ static CholDevice* ensure_symbolic(spb_context* h) {
   SPB_CUDA(D->child_idx.upload(C.child_idx, st));
   SPB_CUDA(D->level_sn.upload(C.level_sn, st));
   SPB_CUDA(D->rank_children.upload(C.rank_children, st));
+  SPB_CUDA(D->ea_ptr.upload(C.ea_ptr, st));
+  SPB_CUDA(D->ea_idx.upload(C.ea_idx, st));
+  SPB_CUDA(D->small_parents.upload(C.small_parents, st));
   SPB_CUDA(D->perm.upload(C.perm, st));
   SPB_CUDA(D->L_off.upload(C.L_off, st));
   SPB_CUDA(D->U_off.upload(C.U_off, st));
@@ -1148,8 +1265,23 @@ spb_status chol_factorize(spb_context* h) {
         ++nl;
       }
     }
+    {
+      const int sp0 = C.small_parents_ptr[l], spc = C.small_parents_ptr[(size_t)l + 1] - sp0;
+      if (spc > 0) {
+        chol_extend_add_small_kernel<<<(spc + 3) / 4, 128, 0, st>>>(D->small_parents.p + sp0, spc, C.level_big_ranks[l], D->ea_ptr.p, D->ea_idx.p,
+                                                                    D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->rel_ptr.p, D->rel_idx.p,
+                                                                    D->Lbuf.p, D->Ubuf.p);
+        ++nl;
+      }
+    }
     for (const CholDevice::Group& G : D->groups[l]) {
       const int* list = D->level_sn.p + G.begin;
+      if (G.max_k <= 16 && G.max_r <= 32) {  // tiny fronts: the whole step in one launch, a warp per front
+        chol_tiny_front_kernel<<<(G.count + 3) / 4, 128, 0, st>>>(list, G.count, D->sn_k.p, D->sn_r.p, D->L_off.p, D->U_off.p, D->dinv_off.p,
+                                                                  D->Lbuf.p, D->Ubuf.p, D->Dinv.p, D->fail.p);
+        ++nl;
+        continue;
+      }
       constexpr int kPanel = 256;
       for (int ob = 0; ob < G.max_k; ob += kPanel) {
         const int oe = ob + kPanel;

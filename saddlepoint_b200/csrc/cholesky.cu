@@ -736,6 +736,87 @@ __global__ void __launch_bounds__(256) chol_backward_kernel(const int* __restric
   for (int i = tid; i < k; i += 256) y[c0 + i] = w[i];
 }
 
+// Tiny fronts (k <= 16 pivots, r <= 32 rows): one WARP per front, the work vector in 32 doubles of shared memory; the same
+// sums in the same order as chol_forward_kernel / chol_backward_kernel (a CTA of 256 threads per front was mostly idle
+// threads and barriers: the condensed seamless-integration structure has half a million such fronts in its first level).
+__global__ void __launch_bounds__(128) chol_forward_tiny_kernel(const int* __restrict__ fronts, int count, const int* __restrict__ sn_k,
+                                                                const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                                const int64_t* __restrict__ L_off, const int64_t* __restrict__ W_off,
+                                                                const int64_t* __restrict__ dinv_off, const int* __restrict__ child_ptr,
+                                                                const int* __restrict__ child_idx, const int64_t* __restrict__ rel_ptr,
+                                                                const int* __restrict__ rel_idx, const double* __restrict__ Lbuf,
+                                                                const double* __restrict__ Dinv, double* __restrict__ Wbuf,
+                                                                double* __restrict__ y) {
+  __shared__ double ws[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = blockIdx.x * 4 + warp;
+  if (fi >= count) return;
+  const int f = fronts[fi];
+  const int k = sn_k[f], r = sn_r[f], c0 = col0[f];
+  double* w = ws[warp];
+  w[lane] = lane < k ? y[c0 + lane] : 0.0;
+  __syncwarp();
+  for (int ci = child_ptr[f]; ci < child_ptr[f + 1]; ++ci) {
+    const int c = child_idx[ci];
+    const int ck = sn_k[c], cu = sn_r[c] - ck;
+    const double* tail = Wbuf + W_off[c] + ck;
+    const int* rel = rel_idx + rel_ptr[c];
+    for (int t = lane; t < cu; t += 32) w[rel[t]] += tail[t];
+    __syncwarp();
+  }
+  const double* P = Lbuf + L_off[f];
+  const double* Di = Dinv + dinv_off[f];
+  double yi = 0.0;
+  if (lane < 32) {
+    double s = 0.0;
+    for (int t = 0; t < k; ++t) s += Di[t * 32 + lane] * w[t];
+    yi = s;
+  }
+  __syncwarp();
+  if (lane < k) w[lane] = yi;
+  __syncwarp();
+  if (lane >= k && lane < r) {
+    double s = w[lane];
+    for (int t = 0; t < k; ++t) s -= P[(int64_t)t * r + lane] * w[t];
+    Wbuf[W_off[f] + lane] = s;
+  } else if (lane < k) {
+    y[c0 + lane] = yi;
+  }
+}
+
+__global__ void __launch_bounds__(128) chol_backward_tiny_kernel(const int* __restrict__ fronts, int count, const int* __restrict__ sn_k,
+                                                                 const int* __restrict__ sn_r, const int* __restrict__ col0,
+                                                                 const int64_t* __restrict__ L_off, const int64_t* __restrict__ dinv_off,
+                                                                 const int64_t* __restrict__ struct_ptr, const int* __restrict__ struct_idx,
+                                                                 const double* __restrict__ Lbuf, const double* __restrict__ Dinv,
+                                                                 double* __restrict__ y) {
+  __shared__ double zs[4][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = blockIdx.x * 4 + warp;
+  if (fi >= count) return;
+  const int f = fronts[fi];
+  const int k = sn_k[f], r = sn_r[f], c0 = col0[f];
+  const int* st = struct_idx + struct_ptr[f];
+  const double wi = lane < k ? y[c0 + lane] : (lane < r ? y[st[lane - k]] : 0.0);
+  const double* P = Lbuf + L_off[f];
+  const double* Di = Dinv + dinv_off[f];
+  double* z = zs[warp];
+  // z_t = w[t] - sum_{i >= k} L[i, t] * w[i]: lanes hold the rows, the sum runs through the same xor tree as the CTA kernel
+  const double wtail = __shfl_sync(0xffffffffu, wi, min(k + lane, 31));  // w[k + lane]
+  for (int t = 0; t < k; ++t) {
+    double s = (k + lane < r) ? P[(int64_t)t * r + k + lane] * wtail : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double wt = __shfl_sync(0xffffffffu, wi, t);
+    if (lane == 0) z[t] = wt - s;
+  }
+  __syncwarp();
+  if (lane < k) {
+    double s = 0.0;
+    for (int t = lane; t < k; ++t) s += Di[lane * 32 + t] * z[t];
+    y[c0 + lane] = s;
+  }
+}
+
 // ---- big fronts, launch-per-step variant (fallback: SPB_CHOL_COOP=0) ---------------------------
 // A front with thousands of rows cannot be swept by one CTA at memory speed; here the work vector
 // lives in global memory (Wbuf) and every 32-column block step is a grid-wide launch: all CTAs
@@ -1490,6 +1571,13 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
         }
         continue;
       }
+      if (G.max_k <= 16 && G.max_r <= 32) {
+        chol_forward_tiny_kernel<<<(G.count + 3) / 4, 128, 0, st>>>(list, G.count, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
+                                                                    D->dinv_off.p, D->child_ptr.p, D->child_idx.p, D->rel_ptr.p, D->rel_idx.p,
+                                                                    D->Lbuf.p, D->Dinv.p, D->Wbuf.p, D->ywork.p);
+        ++nl;
+        continue;
+      }
       const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);
       chol_forward_kernel<<<G.count, 256, sm, st>>>(D->level_sn.p + G.begin, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->W_off.p,
                                                     D->dinv_off.p, D->child_ptr.p, D->child_idx.p, D->rel_ptr.p, D->rel_idx.p, D->Lbuf.p,
@@ -1525,6 +1613,12 @@ spb_status chol_solve(spb_context* h, const double* d_b, double* d_x) {
                                                                                            D->Dinv.p, D->Wbuf.p, D->ywork.p);
           ++nl;
         }
+        continue;
+      }
+      if (G.max_k <= 16 && G.max_r <= 32) {
+        chol_backward_tiny_kernel<<<(G.count + 3) / 4, 128, 0, st>>>(list, G.count, D->sn_k.p, D->sn_r.p, D->col0.p, D->L_off.p, D->dinv_off.p,
+                                                                     D->struct_ptr.p, D->struct_idx.p, D->Lbuf.p, D->Dinv.p, D->ywork.p);
+        ++nl;
         continue;
       }
       const size_t sm = (size_t)(G.max_r + 32) * sizeof(double);

@@ -254,7 +254,7 @@ void chol_symbolic(const HPattern& H, const SellLayout& S, CholSymbolic& C) {
   std::vector<int> cond_perm, cond_sizes, rest;          // eliminated groups (original ids) / remaining vertices
   std::vector<int> rp, ri;                               // graph of the remaining vertices (compact ids), with fill
   {
-    static const int kMaxDeg = getenv("SPB_CHOL_CONDENSE_DEG") ? atoi(getenv("SPB_CHOL_CONDENSE_DEG")) : 16;
+    const int kMaxDeg = getenv("SPB_CHOL_CONDENSE_DEG") ? atoi(getenv("SPB_CHOL_CONDENSE_DEG")) : 16;  // 0 switches the condensation off (tests compare both)
     constexpr int kMaxGroup = 32, kMaxExt = 48;
     std::vector<int> grp(n, -1);  // -1 untouched, -2 rejected candidate, >= 0 group id
     std::vector<int> comp, ext, stackv;

@@ -251,6 +251,6 @@ def test_cholesky_ordering_condenses_satellite_groups(spb):
             del os.environ["SPB_CHOL_CONDENSE_DEG"]
 
     plain, cond = stats(0), stats(16)
-    assert cond[0] >= P["nF"]            # one supernode per face at least
+    assert cond[0] >= 0.8 * P["nF"]      # about one leaf supernode per face (boundary faces may merge or stay)
     assert cond[2] * 4 < plain[2]        # nnz(L)
     assert cond[5] * 20 < plain[5]       # flops

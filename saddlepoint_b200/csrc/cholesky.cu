@@ -207,9 +207,15 @@ __global__ void __launch_bounds__(128) chol_tiny_front_kernel(const int* __restr
       x[rw] = rw >= lane ? acc * rd : 0.0;
     }
   }
-  double* out = Dinv + dinv_off[f] + (int64_t)lane * 32;
+  // Only the k x k corner of the front's 32 x 32 block is stored: the tiny solve kernels read nothing else, and the
+  // identity padding of half a million fronts was 4 GB of writes per factorisation (8 KB per front for 512 useful bytes).
+  // A front is in ONE group per level, and a tiny group is factored and solved by the tiny kernels only.
+  if (lane < k) {
+    double* out = Dinv + dinv_off[f] + (int64_t)lane * 32;
 #pragma unroll
-  for (int rw = 0; rw < 32; ++rw) out[rw] = (rw < 16 && rw < k && lane < k) ? x[rw & 15] : (rw == lane ? 1.0 : 0.0);
+    for (int rw = 0; rw < 16; ++rw)
+      if (rw < k) out[rw] = x[rw];
+  }
 }
 
 // Cholesky of the 32x32 diagonal block at pivot offset kb of every front in the list, plus its
@@ -767,7 +773,7 @@ __global__ void __launch_bounds__(128) chol_forward_tiny_kernel(const int* __res
   const double* P = Lbuf + L_off[f];
   const double* Di = Dinv + dinv_off[f];
   double yi = 0.0;
-  if (lane < 32) {
+  if (lane < k) {  // only the k x k corner of the inverted block exists for tiny fronts
     double s = 0.0;
     for (int t = 0; t < k; ++t) s += Di[t * 32 + lane] * w[t];
     yi = s;

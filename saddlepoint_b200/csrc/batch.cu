@@ -77,7 +77,7 @@ struct BatchPcgParams {
 __device__ __forceinline__ int prob_of_row(int row, int n_per) { return row / n_per; }
 
 // One persistent cooperative launch solves H_p x_p = b_p for every active problem p of the block-diagonal system.
-__global__ void __launch_bounds__(256, 3) batch_pcg_kernel(BatchPcgParams P) {
+__global__ void __launch_bounds__(256, 4) batch_pcg_kernel(BatchPcgParams P) {
   cg::grid_group grid = cg::this_grid();
   const int G = gridDim.x, tid = threadIdx.x, blk = blockIdx.x;
   const int lane = tid & 31, warp = tid >> 5;

@@ -186,6 +186,8 @@ struct PcgParams {
   double rtol;
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
   int sweep;            // 1: slices dealt round-robin to the warps of the grid (see phase 1)
+  int fuse_dir;         // pcg_stream_kernel: direction update fused into the product (two grid barriers per iteration)
+  double* z;            // ... its preconditioned residual z = dinv r (gathered by the product instead of p)
   int stream_group;     // pcg_stream_kernel: consecutive slices a warp takes per visit (power of two)
   // Relaxed-precision products: once the relative residual is below relax_tol the value stream is read from an FP32
   // copy (6 instead of 10 bytes per entry); vectors, accumulation and the recurrences stay FP64.  The theory of inexact
@@ -436,7 +438,8 @@ struct StreamCursor {   // per warp (uniform across its lanes)
 // Also measured without effect: polling the stage barriers with the non-suspending test_wait (56.6 vs 56.3 us).
 template <typename VT, bool W32, int D, int SB, int K>
 __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __restrict__ hval, unsigned char* stage, uint64_t* bar,
-                                              StreamCursor& cur, int gw, int GW, int grp, uint64_t pol) {
+                                              StreamCursor& cur, int gw, int GW, int grp, uint64_t pol,
+                                              const double* __restrict__ xsrc, bool fused, double beta) {
   static_assert(K == kStreamK || K == 2 * kStreamK, "a stage is one or two halves of kStreamK entries");
   static_assert(K * 32 * (int)sizeof(VT) <= kStreamValBytes, "the value part of a stage is 4 KB");
   // slice walk: a warp takes grp consecutive slices, then jumps to its next group (grp = 1: round-robin over the grid)
@@ -496,6 +499,13 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
     const int kc = c16 ? K : kStreamK;
     const int rbase = row - 32768, csafe = row < n ? row : 0;
     double acc = 0.0;
+    // fused direction update: this row's old p, q and its z are requested now and used after the slice's products
+    double p_old = 0.0, q_old = 0.0, z_own = 0.0;
+    if (fused && row < n) {
+      p_old = P.p[row];
+      q_old = P.q[row];
+      z_own = xsrc[row];
+    }
     int k0 = 0;
     do {
       const unsigned b = consumed % D;
@@ -519,7 +529,7 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
           const VT* hv = sv + hb * 32;
           if (hc >= kStreamK) {
 #pragma unroll
-            for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[rbase + (int)sc[u * 32]];
+            for (int u = 0; u < kStreamK; ++u) xv[u] = xsrc[rbase + (int)sc[u * 32]];
             if (W32) {
               float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
 #pragma unroll
@@ -529,7 +539,7 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
             for (int u = 0; u < kStreamK; ++u) acc = fma((double)hv[u * 32], xv[u], acc);
           } else {
 #pragma unroll
-            for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[u < hc ? rbase + (int)sc[u * 32] : row];
+            for (int u = 0; u < kStreamK; ++u) xv[u] = xsrc[u < hc ? rbase + (int)sc[u * 32] : row];
             if (W32) {
               float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
 #pragma unroll
@@ -557,7 +567,7 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
             for (int u = 0; u < kStreamK; ++u) c[u] = csafe;
           }
 #pragma unroll
-          for (int u = 0; u < kStreamK; ++u) xv[u] = P.p[c[u]];
+          for (int u = 0; u < kStreamK; ++u) xv[u] = xsrc[c[u]];
           const VT* hv = sv + hb * 32;
           if (W32) {
             float* wp = P.hval32 + off + lane + (int64_t)(k0 + hb) * 32;
@@ -576,8 +586,18 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
       k0 += kc;
     } while (k0 < width);
     if (row < n) {
-      P.q[row] = acc;
-      loc = fma(P.p[row], acc, loc);
+      if (fused) {
+        // fused direction update (xsrc = z): p = z + beta p, q = H z + beta q -- both row-local, so the third phase of the
+        // iteration and its grid barrier disappear; the 4 vector accesses hide under the DRAM-bound product
+        const double pi = fma(beta, p_old, z_own);
+        const double qi = fma(beta, q_old, acc);
+        P.p[row] = pi;
+        P.q[row] = qi;
+        loc = fma(pi, qi, loc);
+      } else {
+        P.q[row] = acc;
+        loc = fma(P.p[row], acc, loc);
+      }
     }
   }
   return loc;
@@ -653,7 +673,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
       const double z = bi * P.dinv[i];
       P.x[i] = 0.0;
       P.r[i] = bi;
-      P.p[i] = z;
+      if (P.fuse_dir) {
+        P.z[i] = z;
+        P.p[i] = 0.0;  // p = z + 0 p and q = H z + 0 q in the first product
+        P.q[i] = 0.0;
+      } else {
+        P.p[i] = z;
+      }
       rz = fma(bi, z, rz);
       bb = fma(bi, bi, bb);
     }
@@ -671,6 +697,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
   const double relax_thresh = P.relax_tol * P.relax_tol * bb;
   bool use32 = false;
   double rr = bb, pq = 0.0;
+  double beta_cur = 0.0;  // fused direction update: beta of the product about to run
   int iters = 0, breakdown = 0;
   const bool run = (bb > thresh) && P.maxit > 0;
   grid.sync();  // partB/partC are about to be reused
@@ -683,10 +710,12 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
       // four and more unbalance the blocks (slices per warp are few: 32 768 slices over 2 368 warps at C2)
       const int gw = blk * NW + warp, GW = G * NW, grp = P.stream_group;
       double loc;
-      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes, kStreamK>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol);
+      const double* xsrc = P.fuse_dir ? P.z : P.p;
+      const bool fz = P.fuse_dir != 0;
+      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes, kStreamK>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
       else if (P.hval32 && iters == 0)  // writes the FP32 copy
-        loc = stream_spmv<double, true, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
-      else loc = stream_spmv<double, false, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol);
+        loc = stream_spmv<double, true, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
+      else loc = stream_spmv<double, false, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
       const double bs = block_sum_nw<NW>(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
@@ -725,6 +754,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
           const double ri = fma(-alpha, qv[u], rv[u]);
           P.r[j] = ri;
           const double z = ri * dv[u];
+          if (P.fuse_dir) P.z[j] = z;
           a1 = fma(ri, z, a1);
           a2 = fma(ri, ri, a2);
         }
@@ -734,6 +764,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
         const double ri = fma(-alpha, P.q[i], P.r[i]);
         P.r[i] = ri;
         const double z = ri * P.dinv[i];
+        if (P.fuse_dir) P.z[i] = z;
         a1 = fma(ri, z, a1);
         a2 = fma(ri, ri, a2);
       }
@@ -755,6 +786,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
     ++iters;
     if (!(rr > thresh) || iters >= P.maxit) break;
     if (P.hval32 && rr <= relax_thresh) use32 = true;  // same bits in every block: a grid-uniform switch
+    beta_cur = beta;
+    if (P.fuse_dir) continue;  // the next product forms p = z + beta p and q = H z + beta q row by row: no third phase
     // phase 3: p = dinv*r + beta p
     {
       int i = blk * NT + tid;
@@ -967,6 +1000,13 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     }
     static const int sweep = getenv("SPB_SPMV_SWEEP") ? atoi(getenv("SPB_SPMV_SWEEP")) : 1;
     P.sweep = sweep;
+    static const int fuse_dir = getenv("SPB_PCG_FUSE_DIR") ? atoi(getenv("SPB_PCG_FUSE_DIR")) : 1;
+    P.fuse_dir = (stream && fuse_dir) ? 1 : 0;
+    P.z = nullptr;
+    if (P.fuse_dir) {
+      SPB_CUDA(h->d_u.alloc(n));
+      P.z = h->d_u.p;
+    }
     static const int stream_group = getenv("SPB_STREAM_GROUP") ? std::max(1, atoi(getenv("SPB_STREAM_GROUP"))) : 2;
     P.stream_group = (stream_group & (stream_group - 1)) ? 2 : stream_group;
     P.hval32 = nullptr;

@@ -309,3 +309,22 @@ def test_stream_form_inf_nan_and_explicit_zeros(spb, orc):
     ok = ~np.isnan(hx)
     assert (_bits(hv[ok]) == _bits(hx[ok])).all()   # including the sign of zeros
     h.close()
+
+
+def test_stream_form_randomised_sweep(spb, orc):
+    """Forced stream form over a sweep of small random shapes (single columns, one row, more columns than rows, odd
+    counts): every case bit-exact against the oracle."""
+    import os
+    os.environ["SPB_ASM_V2_MIN_RUN"] = "0"
+    try:
+        rng = np.random.default_rng(99)
+        h = spb.Handle(0)
+        for case in range(24):
+            m = int(rng.integers(1, 400))
+            n = int(rng.integers(1, 300))
+            k = int(rng.integers(1, 5))
+            colptr, rowidx, vals = random_jacobian(rng, m, n, k, explicit_zero_frac=0.1)
+            _check(h, orc, m, n, colptr, rowidx, vals, rng.standard_normal(m), float(rng.uniform(0.001, 2.0)))
+        h.close()
+    finally:
+        del os.environ["SPB_ASM_V2_MIN_RUN"]

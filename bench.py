@@ -531,7 +531,7 @@ def run_c2(args, torch, dist, local):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_string(g) + ", nnzH=%d" % nnzH,
-                       "solver": "%s rtol=%g (one persistent cooperative kernel per solve); relaxed-precision products: the matrix values are streamed from an "
+                       "solver": "%s rtol=%g (one persistent cooperative kernel per solve; direction update fused into the product: two grid barriers per iteration); relaxed-precision products: the matrix values are streamed from an "
                                  "FP32 copy once ||r||/||b|| <= %g (vectors, accumulation, recurrences and the stop test stay FP64; e2e.relres_of_step "
                                  "is the FP64 residual of the returned step; SPB_PCG_RELAX=0 disables)" % (args.solver, args.pcg_rtol, args.pcg_rtol * float(os.environ.get("SPB_PCG_RELAX", "1e6"))),
                        "l2": "inputs larger than L2 (H %d MB + J %d MB per step vs 126 MB L2)" % (12 * nnzH // 2**20, 12 * nnzJ // 2**20),

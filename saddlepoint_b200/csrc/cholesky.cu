@@ -1264,7 +1264,7 @@ static CholDevice* ensure_symbolic(spb_context* h) {
       // a level with few fronts is one group whatever their sizes: its fronts are independent, and two groups would be
       // two dependent-looking launch sequences on one stream where one runs them side by side (the upper levels of a
       // dissection tree are in the launch-latency regime)
-      static const int merge_below = getenv("SPB_CHOL_MERGE_LEVEL") ? atoi(getenv("SPB_CHOL_MERGE_LEVEL")) : 256;
+      static const int merge_below = getenv("SPB_CHOL_MERGE_LEVEL") ? atoi(getenv("SPB_CHOL_MERGE_LEVEL")) : 4096;
       if (e - b <= merge_below) lim = 0x7fffffff;
       int mk = 0, mr = 0;
       while (g1 < e && r[C.level_sn[g1]] <= lim && g1 - g0 < 32768) {

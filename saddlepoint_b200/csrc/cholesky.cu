@@ -55,6 +55,9 @@ struct CholDevice {
   };
   std::vector<std::vector<Group>> groups;
   bool factored = false;
+  cudaGraphExec_t graph_exec = nullptr;  // the captured launch sequence of one factorisation
+  const double* graph_hval = nullptr;    // ... valid for this H value array
+  int graph_nl = 0;
   int coop_occ = 0;            // co-resident CTAs per SM of the cooperative solve kernels
   bool smem_attr_set = false;  // per device context, so per handle (not a process-wide static)
   int* h_fail = nullptr;
@@ -1324,6 +1327,10 @@ spb_status chol_factorize(spb_context* h) {
   static const bool fused_step = !(getenv("SPB_CHOL_FUSED") && atoi(getenv("SPB_CHOL_FUSED")) == 0);
   stage_begin(h, ST_FACTOR);
   int nl = 0;
+  // The launch sequence of a factorisation depends on the symbolic state only (no host decision inside it), and on the
+  // upper levels of the tree it is hundreds of dependent 10-20 us kernels: it is captured into a CUDA graph the first time
+  // and replayed afterwards (one graph launch instead of ~600-1200 kernel launches and memsets per factorisation).
+  auto enqueue = [&]() {
   SPB_CUDA(cudaMemsetAsync(D->Lbuf.p, 0, (size_t)C.L_off[ns] * sizeof(double), st));
   SPB_CUDA(cudaMemsetAsync(D->fail.p, 0, sizeof(int), st));
   {
@@ -1444,6 +1451,43 @@ spb_status chol_factorize(spb_context* h) {
                                                              D->Ubuf.p, nullptr);
       ++nl;
     }
+  }
+  };
+  static const bool graph_on = !(getenv("SPB_CHOL_GRAPH") && atoi(getenv("SPB_CHOL_GRAPH")) == 0);
+  static const bool dbg_any = getenv("SPB_CHOL_TIMING") && atoi(getenv("SPB_CHOL_TIMING")) > 0;
+  if (graph_on && !dbg_any && D->graph_exec && D->graph_hval == h->d_hval.p) {
+    SPB_CUDA(cudaGraphLaunch(D->graph_exec, st));
+    nl = D->graph_nl;
+  } else if (graph_on && !dbg_any && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+    if (D->graph_exec) {
+      cudaGraphExecDestroy(D->graph_exec);
+      D->graph_exec = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    try {
+      enqueue();
+    } catch (...) {
+      cudaStreamEndCapture(st, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    SPB_CUDA(cudaStreamEndCapture(st, &g));
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ie == cudaSuccess) {
+      D->graph_exec = ex;
+      D->graph_hval = h->d_hval.p;
+      D->graph_nl = nl;
+      SPB_CUDA(cudaGraphLaunch(ex, st));
+    } else {
+      cudaGetLastError();
+      nl = 0;
+      enqueue();  // no graph on this system: plain launches
+    }
+  } else {
+    cudaGetLastError();
+    enqueue();
   }
   SPB_CUDA(cudaGetLastError());
   stage_end(h, ST_FACTOR, nl);
@@ -1650,6 +1694,7 @@ void chol_release(spb_context* h) {
   CholDevice* D = (CholDevice*)h->chol;
   if (D) {
     if (D->h_fail) cudaFreeHost(D->h_fail);
+    if (D->graph_exec) cudaGraphExecDestroy(D->graph_exec);
     delete D;
   }
   h->chol = nullptr;

@@ -186,6 +186,7 @@ struct PcgParams {
   double rtol;
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
   int sweep;            // 1: slices dealt round-robin to the warps of the grid (see phase 1)
+  int vec2;             // pcg_stream_kernel: 16-byte accesses in the vector phase
   int fuse_dir;         // pcg_stream_kernel: direction update fused into the product (two grid barriers per iteration)
   double* z;            // ... its preconditioned residual z = dinv r (gathered by the product instead of p)
   int stream_group;     // pcg_stream_kernel: consecutive slices a warp takes per visit (power of two)
@@ -736,6 +737,55 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
     {
       double a1 = 0.0, a2 = 0.0;
       int i = blk * NT + tid;
+      if (P.vec2 && (n & 1) == 0) {
+        // two consecutive rows per thread and access (16-byte loads and stores): half as many L2 requests for the same
+        // bytes -- the vector passes are bound by the L2, not by HBM (the vectors stay resident)
+        const int n2 = n >> 1;
+        const double2* p2 = reinterpret_cast<const double2*>(P.p);
+        const double2* q2 = reinterpret_cast<const double2*>(P.q);
+        const double2* d2 = reinterpret_cast<const double2*>(P.dinv);
+        double2* x2 = reinterpret_cast<double2*>(P.x);
+        double2* r2 = reinterpret_cast<double2*>(P.r);
+        double2* z2 = reinterpret_cast<double2*>(P.z);
+        for (; i + stride < n2; i += 2 * stride) {
+          double2 pv[2], qv[2], xv[2], rv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = i + u * stride;
+            pv[u] = p2[j];
+            qv[u] = q2[j];
+            xv[u] = x2[j];
+            rv[u] = r2[j];
+            dv[u] = d2[j];
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = i + u * stride;
+            x2[j] = make_double2(fma(alpha, pv[u].x, xv[u].x), fma(alpha, pv[u].y, xv[u].y));
+            const double r0 = fma(-alpha, qv[u].x, rv[u].x), r1 = fma(-alpha, qv[u].y, rv[u].y);
+            r2[j] = make_double2(r0, r1);
+            const double z0 = r0 * dv[u].x, z1 = r1 * dv[u].y;
+            if (P.fuse_dir) z2[j] = make_double2(z0, z1);
+            a1 = fma(r0, z0, a1);
+            a1 = fma(r1, z1, a1);
+            a2 = fma(r0, r0, a2);
+            a2 = fma(r1, r1, a2);
+          }
+        }
+        for (; i < n2; i += stride) {
+          const double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i], dv = d2[i];
+          x2[i] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+          const double r0 = fma(-alpha, qv.x, rv.x), r1 = fma(-alpha, qv.y, rv.y);
+          r2[i] = make_double2(r0, r1);
+          const double z0 = r0 * dv.x, z1 = r1 * dv.y;
+          if (P.fuse_dir) z2[i] = make_double2(z0, z1);
+          a1 = fma(r0, z0, a1);
+          a1 = fma(r1, z1, a1);
+          a2 = fma(r0, r0, a2);
+          a2 = fma(r1, r1, a2);
+        }
+        i = n;  // all rows done
+      }
       for (; i + 3 * stride < n; i += 4 * stride) {
         double pv[4], qv[4], xv[4], rv[4], dv[4];
 #pragma unroll
@@ -1002,6 +1052,8 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     P.sweep = sweep;
     static const int fuse_dir = getenv("SPB_PCG_FUSE_DIR") ? atoi(getenv("SPB_PCG_FUSE_DIR")) : 1;
     P.fuse_dir = (stream && fuse_dir) ? 1 : 0;
+    static const int vec2 = getenv("SPB_PCG_VEC2") ? atoi(getenv("SPB_PCG_VEC2")) : 1;
+    P.vec2 = vec2;
     P.z = nullptr;
     if (P.fuse_dir) {
       SPB_CUDA(h->d_u.alloc(n));

@@ -607,7 +607,7 @@ extern "C" spb_status spb_lm_solve_batch(spb_handle h, const spb_traits* T, int3
       // block-diagonal H over aligned pairs (extended Rosenbrock batches): the exact inverse blocks precondition, the PCG
       // becomes a direct block solve with one or two refinement iterations instead of ~30 Jacobi iterations on blocks
       // whose condition number is 1e8 far from the optimum
-      static const bool block2_off = getenv("SPB_BATCH_BLOCK2") && atoi(getenv("SPB_BATCH_BLOCK2")) == 0;
+      const bool block2_off = getenv("SPB_BATCH_BLOCK2") && atoi(getenv("SPB_BATCH_BLOCK2")) == 0;  // read per body: the tests compare both
       const bool block2 = h->h_block2 && (n_per % 2 == 0) && !block2_off;
       stage_begin(h, ST_PCGVEC);
       if (block2) {

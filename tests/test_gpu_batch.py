@@ -136,3 +136,29 @@ def test_fused_batch_equals_the_per_problem_loop(spb):
     for a, b in zip(fused, again):
         assert a["currIter"] == b["currIter"] and a["exit_path"] == b["exit_path"] and np.array_equal(a["x"], b["x"])
     h.close(); h2.close()
+
+
+def test_block_preconditioner_of_rosenbrock_batches(spb, orc):
+    """Block-diagonal H over aligned pairs (extended Rosenbrock): the batched PCG preconditions with the exact inverse 2x2
+    blocks.  Same LM trajectories as the oracle (iteration counts, exit paths; x within the oracle's own variant spread,
+    see _rosenbrock_tolerance) with either preconditioner, and several times fewer PCG iterations with the blocks."""
+    import os
+    from saddlepoint_b200 import batch
+    idx = [0, 2, 4, 6]
+    n = 400
+    h = spb.Handle(0)
+    with_blocks = batch.solve_batch_fused(h, idx, n=n, keep_x=True, verbose=False)
+    os.environ["SPB_BATCH_BLOCK2"] = "0"
+    try:
+        jacobi = batch.solve_batch_fused(h, idx, n=n, keep_x=True, verbose=False)
+    finally:
+        del os.environ["SPB_BATCH_BLOCK2"]
+    for i, a, b in zip(idx, with_blocks, jacobi):
+        spec = batch.c4_problem_spec(i, n=n)
+        ref = orc.lm_solve("rosenbrock", iparam0=spec["nblocks"], x0=spec["x0"], maxIterations=1000)
+        tol = _rosenbrock_tolerance(orc, spec, ref)
+        for r in (a, b):
+            assert r["currIter"] == ref.currIter and r["exit_path"] == ref.exit_path
+            np.testing.assert_allclose(r["x"], ref.x, rtol=tol, atol=1e-12)
+        assert a["linear_iterations"] * 4 < b["linear_iterations"]
+    h.close()

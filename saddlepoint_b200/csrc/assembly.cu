@@ -599,6 +599,23 @@ void upload_h_layout(spb_context* h) {
 
 void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, AssemblyPlan& P) {
   cudaStream_t st = h->stream;
+  // the "stream" form of the pair assembly (default when it applies; see assembly_v2.cu) is packed on its own host thread
+  // while this one packs and uploads the general form: the plan is only read until both are done
+  PairsV2Host V2;
+  std::exception_ptr v2_err;
+  std::thread v2_thread([&] {
+    try {
+      pack_pairs_v2(colptr, P, h->S, V2);
+    } catch (...) {
+      v2_err = std::current_exception();
+    }
+  });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } v2_join{v2_thread};
   std::vector<int> cp(colptr, colptr + h->n + 1), ri(rowidx, rowidx + colptr[h->n]);
   SPB_CUDA(h->d_Jcolptr.upload(cp, st));
   SPB_CUDA(h->d_Jrow.upload(ri, st));
@@ -699,12 +716,9 @@ void upload_analysis(spb_context* h, const int* colptr, const int* rowidx, Assem
     h->colchunk_host = P.colchunk;
     h->Jcolptr_host.assign(colptr, colptr + h->n + 1);
   }
-  {
-    // the "stream" form of the pair assembly (default when it applies; see assembly_v2.cu)
-    PairsV2Host V;
-    pack_pairs_v2(colptr, P, h->S, V);
-    upload_pairs_v2(h, V);
-  }
+  v2_thread.join();
+  if (v2_err) std::rethrow_exception(v2_err);
+  upload_pairs_v2(h, V2);
   h->nslots = P.nslots;
   h->npairs = P.npairs;
   // host-side pieces kept for incremental re-analysis (spb_analyze_update)

@@ -157,7 +157,11 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
     SPB_CUDA(d_trial.alloc(n));
     SPB_CUDA(d_E.alloc(m));
     SPB_CUDA(d_Etrial.alloc(m));
-    SPB_CUDA(d_Jv.alloc((size_t)nnzJ));
+    // constant Jacobian of a linear device-resident problem: assembled straight from the problem's own array
+    const double* Jconst = builtin_constant_jacobian(T);
+    if (!Jconst) SPB_CUDA(d_Jv.alloc((size_t)nnzJ));
+    double* Jeval = Jconst ? nullptr : d_Jv.p;              // what the traits fill (nullptr: residual only)
+    const double* Jasm = Jconst ? Jconst : d_Jv.p;          // what the assembly reads
     Evaluator ev{h, T, n, m, nnzJ, W.hx, W.hE, W.hJ};
     ev.init();
     if (builtin_x0_device(T, d_prevx.p, st)) {  // device-resident problem: its initial point is on the device already
@@ -183,17 +187,17 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       SPB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     };
 
-    ev.eval(d_prevx.p, d_E.p, d_Jv.p);  // LMSolver.h:106 ; DT->init is folded into the assembly (lambda)
+    ev.eval(d_prevx.p, d_E.p, Jeval);  // LMSolver.h:106 ; DT->init is folded into the assembly (lambda)
     int bodies = 0;
     do {
       if (T->pre_iteration) T->pre_iteration(T->user, ev.view(d_prevx.p));
       // LMSolver.h:117-119 + DiagonalDamping rebuild + LMSolver.h:136's product, fused
       if (fixed) {
         // no stop test consumes ||rhs||_inf before the solve: fetch it with the solve's own synchronisation
-        run_assembly(h, d_Jv.p, d_E.p, lambda, nullptr);
+        run_assembly(h, Jasm, d_E.p, lambda, nullptr);
         SPB_CUDA(cudaMemcpyAsync(h->h_scalar + 2, h->d_foo_bits.p, sizeof(double), cudaMemcpyDeviceToHost, st));
       } else {
-        run_assembly(h, d_Jv.p, d_E.p, lambda, &foo);
+        run_assembly(h, Jasm, d_E.p, lambda, &foo);
       }
       if (!fixed && foo < O->fooTolerance) {
         copy_vec(d_x.p, d_prevx.p);
@@ -264,10 +268,10 @@ spb_status spb_lm_solve(spb_handle h, const spb_traits* T, const spb_lm_options*
       }
       // LMSolver.h:174-175: re-linearise at x
       if (!dedupe) {
-        ev.eval(d_x.p, d_E.p, d_Jv.p);
+        ev.eval(d_x.p, d_E.p, Jeval);
         dev_squared_norm_global(h, d_E.p, m, &energy);
       } else if (accepted) {
-        ev.eval(d_x.p, d_E.p, d_Jv.p);  // same residual as the trial evaluation, plus the new Jacobian
+        ev.eval(d_x.p, d_E.p, Jeval);  // same residual as the trial evaluation, plus the new Jacobian
         energy = newEnergy2;
       } else {
         energy = prevEnergy2;  // x==prevx: residual and Jacobian already current

@@ -467,6 +467,7 @@ void sum_triplets(spb_context* h, const double* d_trip_vals, double* d_csc_vals)
 
 // problems.cu: initial point of a device-resident problem straight from the device (false: not one of ours)
 bool builtin_x0_device(const spb_traits* T, double* d_dst, cudaStream_t st);
+const double* builtin_constant_jacobian(const spb_traits* T);  // device CSC values of a constant Jacobian, or nullptr
 
 // blas1.cu
 void dev_squared_norm(spb_context* h, const double* d_v, int64_t len, double* host_out);

@@ -187,6 +187,7 @@ struct PcgParams {
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
   int sweep;            // 1: slices dealt round-robin to the warps of the grid (see phase 1)
   int vec2;             // pcg_stream_kernel: 16-byte accesses in the vector phase
+  int zstate;           // pcg_stream_kernel: fused + vec2 + even n: the residual vector is not stored (z = dinv r only)
   int fuse_dir;         // pcg_stream_kernel: direction update fused into the product (two grid barriers per iteration)
   double* z;            // ... its preconditioned residual z = dinv r (gathered by the product instead of p)
   int stream_group;     // pcg_stream_kernel: consecutive slices a warp takes per visit (power of two)
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
       const double bi = P.b[i];
       const double z = bi * P.dinv[i];
       P.x[i] = 0.0;
-      P.r[i] = bi;
+      if (!P.zstate) P.r[i] = bi;  // z-state mode keeps z = dinv r only (r = z / dinv where the dot products need it)
       if (P.fuse_dir) {
         P.z[i] = z;
         P.p[i] = 0.0;  // p = z + 0 p and q = H z + 0 q in the first product
@@ -745,45 +746,47 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
         const double2* q2 = reinterpret_cast<const double2*>(P.q);
         const double2* d2 = reinterpret_cast<const double2*>(P.dinv);
         double2* x2 = reinterpret_cast<double2*>(P.x);
-        double2* r2 = reinterpret_cast<double2*>(P.r);
-        double2* z2 = reinterpret_cast<double2*>(P.z);
+        // fused mode: the residual is not stored, only z = dinv r (what the next product gathers), updated as
+        // z -= alpha dinv q; r = z / dinv is formed where the dot products need it -- one vector less through L2
+        double2* s2 = reinterpret_cast<double2*>(P.zstate ? P.z : P.r);
+        const bool zs = P.zstate != 0;
+        auto step2 = [&](const double2 pv, const double2 qv, const double2 xv, const double2 sv, const double2 dv, int j) {
+          x2[j] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+          double r0, r1, z0, z1;
+          if (zs) {
+            z0 = fma(-alpha * dv.x, qv.x, sv.x);
+            z1 = fma(-alpha * dv.y, qv.y, sv.y);
+            r0 = z0 / dv.x;
+            r1 = z1 / dv.y;
+            s2[j] = make_double2(z0, z1);
+          } else {
+            r0 = fma(-alpha, qv.x, sv.x);
+            r1 = fma(-alpha, qv.y, sv.y);
+            z0 = r0 * dv.x;
+            z1 = r1 * dv.y;
+            s2[j] = make_double2(r0, r1);
+            if (P.fuse_dir) reinterpret_cast<double2*>(P.z)[j] = make_double2(z0, z1);
+          }
+          a1 = fma(r0, z0, a1);
+          a1 = fma(r1, z1, a1);
+          a2 = fma(r0, r0, a2);
+          a2 = fma(r1, r1, a2);
+        };
         for (; i + stride < n2; i += 2 * stride) {
-          double2 pv[2], qv[2], xv[2], rv[2], dv[2];
+          double2 pv[2], qv[2], xv[2], sv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int j = i + u * stride;
             pv[u] = p2[j];
             qv[u] = q2[j];
             xv[u] = x2[j];
-            rv[u] = r2[j];
+            sv[u] = s2[j];
             dv[u] = d2[j];
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int j = i + u * stride;
-            x2[j] = make_double2(fma(alpha, pv[u].x, xv[u].x), fma(alpha, pv[u].y, xv[u].y));
-            const double r0 = fma(-alpha, qv[u].x, rv[u].x), r1 = fma(-alpha, qv[u].y, rv[u].y);
-            r2[j] = make_double2(r0, r1);
-            const double z0 = r0 * dv[u].x, z1 = r1 * dv[u].y;
-            if (P.fuse_dir) z2[j] = make_double2(z0, z1);
-            a1 = fma(r0, z0, a1);
-            a1 = fma(r1, z1, a1);
-            a2 = fma(r0, r0, a2);
-            a2 = fma(r1, r1, a2);
-          }
+          for (int u = 0; u < 2; ++u) step2(pv[u], qv[u], xv[u], sv[u], dv[u], i + u * stride);
         }
-        for (; i < n2; i += stride) {
-          const double2 pv = p2[i], qv = q2[i], xv = x2[i], rv = r2[i], dv = d2[i];
-          x2[i] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
-          const double r0 = fma(-alpha, qv.x, rv.x), r1 = fma(-alpha, qv.y, rv.y);
-          r2[i] = make_double2(r0, r1);
-          const double z0 = r0 * dv.x, z1 = r1 * dv.y;
-          if (P.fuse_dir) z2[i] = make_double2(z0, z1);
-          a1 = fma(r0, z0, a1);
-          a1 = fma(r1, z1, a1);
-          a2 = fma(r0, r0, a2);
-          a2 = fma(r1, r1, a2);
-        }
+        for (; i < n2; i += stride) step2(p2[i], q2[i], x2[i], s2[i], d2[i], i);
         i = n;  // all rows done
       }
       for (; i + 3 * stride < n; i += 4 * stride) {
@@ -1054,6 +1057,8 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     P.fuse_dir = (stream && fuse_dir) ? 1 : 0;
     static const int vec2 = getenv("SPB_PCG_VEC2") ? atoi(getenv("SPB_PCG_VEC2")) : 1;
     P.vec2 = vec2;
+    static const int zstate = getenv("SPB_PCG_ZSTATE") ? atoi(getenv("SPB_PCG_ZSTATE")) : 1;
+    P.zstate = (P.fuse_dir && P.vec2 && (n % 2 == 0) && zstate) ? 1 : 0;
     P.z = nullptr;
     if (P.fuse_dir) {
       SPB_CUDA(h->d_u.alloc(n));

@@ -187,6 +187,7 @@ struct PcgParams {
   double pin_fraction;  // leading share of every block's slice range kept L2-resident across iterations
   int sweep;            // 1: slices dealt round-robin to the warps of the grid (see phase 1)
   int vec2;             // pcg_stream_kernel: 16-byte accesses in the vector phase
+  int xlazy;            // pcg_stream_kernel: x += alpha p is applied one product later, from the register that holds the old p
   int zstate;           // pcg_stream_kernel: fused + vec2 + even n: the residual vector is not stored (z = dinv r only)
   int fuse_dir;         // pcg_stream_kernel: direction update fused into the product (two grid barriers per iteration)
   double* z;            // ... its preconditioned residual z = dinv r (gathered by the product instead of p)
@@ -441,7 +442,7 @@ struct StreamCursor {   // per warp (uniform across its lanes)
 template <typename VT, bool W32, int D, int SB, int K>
 __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __restrict__ hval, unsigned char* stage, uint64_t* bar,
                                               StreamCursor& cur, int gw, int GW, int grp, uint64_t pol,
-                                              const double* __restrict__ xsrc, bool fused, double beta) {
+                                              const double* __restrict__ xsrc, bool fused, double beta, bool xlazy, double alpha_prev) {
   static_assert(K == kStreamK || K == 2 * kStreamK, "a stage is one or two halves of kStreamK entries");
   static_assert(K * 32 * (int)sizeof(VT) <= kStreamValBytes, "the value part of a stage is 4 KB");
   // slice walk: a warp takes grp consecutive slices, then jumps to its next group (grp = 1: round-robin over the grid)
@@ -502,11 +503,12 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
     const int rbase = row - 32768, csafe = row < n ? row : 0;
     double acc = 0.0;
     // fused direction update: this row's old p, q and its z are requested now and used after the slice's products
-    double p_old = 0.0, q_old = 0.0, z_own = 0.0;
+    double p_old = 0.0, q_old = 0.0, z_own = 0.0, x_old = 0.0;
     if (fused && row < n) {
       p_old = P.p[row];
       q_old = P.q[row];
       z_own = xsrc[row];
+      if (xlazy) x_old = P.x[row];
     }
     int k0 = 0;
     do {
@@ -595,6 +597,9 @@ __device__ __forceinline__ double stream_spmv(const PcgParams& P, const VT* __re
         const double qi = fma(beta, q_old, acc);
         P.p[row] = pi;
         P.q[row] = qi;
+        // lazy x: the step along the PREVIOUS direction is added here, where that direction is in a register anyway, so
+        // the update phase does not read p at all (the last direction's step is added by the epilogue of the solve)
+        if (xlazy) P.x[row] = fma(alpha_prev, p_old, x_old);
         loc = fma(pi, qi, loc);
       } else {
         P.q[row] = acc;
@@ -700,6 +705,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
   bool use32 = false;
   double rr = bb, pq = 0.0;
   double beta_cur = 0.0;  // fused direction update: beta of the product about to run
+  double alpha_prev = 0.0;  // lazy x: the step length whose x update is still owed (0: none)
   int iters = 0, breakdown = 0;
   const bool run = (bb > thresh) && P.maxit > 0;
   grid.sync();  // partB/partC are about to be reused
@@ -713,11 +719,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
       const int gw = blk * NW + warp, GW = G * NW, grp = P.stream_group;
       double loc;
       const double* xsrc = P.fuse_dir ? P.z : P.p;
-      const bool fz = P.fuse_dir != 0;
-      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes, kStreamK>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
+      const bool fz = P.fuse_dir != 0, xl = P.xlazy != 0;
+      if (use32) loc = stream_spmv<float, false, 2, kStreamStageBytes, kStreamK>(P, P.hval32, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur, xl, alpha_prev);
       else if (P.hval32 && iters == 0)  // writes the FP32 copy
-        loc = stream_spmv<double, true, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
-      else loc = stream_spmv<double, false, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur);
+        loc = stream_spmv<double, true, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur, xl, alpha_prev);
+      else loc = stream_spmv<double, false, 2, kStreamStageBytes, kStreamK>(P, P.hval, stage, bar, cur, gw, GW, grp, pol, xsrc, fz, beta_cur, xl, alpha_prev);
       const double bs = block_sum_nw<NW>(loc, sm);
       if (tid == 0) partA[blk] = bs;
     }
@@ -731,6 +737,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
     SPB_TICK(2)
     if (!(pq > 0.0)) {  // not SPD, or NaN in H
       breakdown = (pq != pq) ? 2 : 1;
+      alpha_prev = 0.0;  // the product that just ran has added the owed step
       break;
     }
     const double alpha = rz / pq;
@@ -750,8 +757,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
         // z -= alpha dinv q; r = z / dinv is formed where the dot products need it -- one vector less through L2
         double2* s2 = reinterpret_cast<double2*>(P.zstate ? P.z : P.r);
         const bool zs = P.zstate != 0;
+        const bool xl = P.xlazy != 0;
         auto step2 = [&](const double2 pv, const double2 qv, const double2 xv, const double2 sv, const double2 dv, int j) {
-          x2[j] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+          if (!xl) x2[j] = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
           double r0, r1, z0, z1;
           if (zs) {
             z0 = fma(-alpha * dv.x, qv.x, sv.x);
@@ -777,16 +785,17 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int j = i + u * stride;
-            pv[u] = p2[j];
+            pv[u] = xl ? make_double2(0.0, 0.0) : p2[j];
             qv[u] = q2[j];
-            xv[u] = x2[j];
+            xv[u] = xl ? make_double2(0.0, 0.0) : x2[j];
             sv[u] = s2[j];
             dv[u] = d2[j];
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) step2(pv[u], qv[u], xv[u], sv[u], dv[u], i + u * stride);
         }
-        for (; i < n2; i += stride) step2(p2[i], q2[i], x2[i], s2[i], d2[i], i);
+        for (; i < n2; i += stride)
+          step2(xl ? make_double2(0.0, 0.0) : p2[i], q2[i], xl ? make_double2(0.0, 0.0) : x2[i], s2[i], d2[i], i);
         i = n;  // all rows done
       }
       for (; i + 3 * stride < n; i += 4 * stride) {
@@ -828,6 +837,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
         partC[blk] = s2;
       }
     }
+    alpha_prev = alpha;  // lazy x: owed until the next product (or the epilogue) adds alpha p
     SPB_TICK(3)
     grid.sync();
     SPB_TICK(4)
@@ -866,8 +876,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) pcg_stream_kernel(PcgPar
   double xx;
   {
     double a = 0.0;
+    const bool owe = P.xlazy && alpha_prev != 0.0;
     for (int i = blk * NT + tid; i < n; i += stride) {
       double v = P.x[i];
+      if (owe) {  // lazy x: the step along the last direction
+        v = fma(alpha_prev, P.p[i], v);
+        P.x[i] = v;
+      }
       if (nan_system) {
         v = __longlong_as_double(0x7ff8000000000000LL);
         P.x[i] = v;
@@ -1059,6 +1074,8 @@ spb_status pcg_solve(spb_context* h, const double* d_b, double* d_x, int* iters)
     P.vec2 = vec2;
     static const int zstate = getenv("SPB_PCG_ZSTATE") ? atoi(getenv("SPB_PCG_ZSTATE")) : 1;
     P.zstate = (P.fuse_dir && P.vec2 && (n % 2 == 0) && zstate) ? 1 : 0;
+    static const int xlazy = getenv("SPB_PCG_XLAZY") ? atoi(getenv("SPB_PCG_XLAZY")) : 1;
+    P.xlazy = (P.zstate && xlazy) ? 1 : 0;
     P.z = nullptr;
     if (P.fuse_dir) {
       SPB_CUDA(h->d_u.alloc(n));

@@ -3,7 +3,7 @@
 //
 // One persistent CTA per SM, warp specialised.  The PRODUCER warp walks the CTA's chunks and feeds a ring of
 // shared-memory stages through the TMA unit only: per chunk one bulk copy of the chunk's section (tables, 4-byte
-// slot metadata, pair records in jagged-diagonal order) and one bulk copy per run of consecutive J columns, all
+// slot metadata, pair records in lane-interleaved rows) and one bulk copy per run of consecutive J columns, all
 // completing on the stage's `full` mbarrier.  The CONSUMER warps wait on `full`, take 32 slots each (a group: slots of
 // similar pair count, lanes chosen on the host so that their operand loads spread over the shared-memory banks; row d of
 // the group's records is one contiguous 64-byte read), add the products in ascending residual row with separately rounded multiply and add

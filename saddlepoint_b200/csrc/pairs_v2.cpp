@@ -4,7 +4,7 @@
 // The plan (symbolic.cpp) describes, per chunk of whole H columns, the strictly-lower slots H(i,j), their pair
 // records (which entry of J column i meets which entry of J column j, ascending residual row: the accumulation
 // order of the reference's sparse product, LMSolver.h:136) and the stage list of J columns the chunk reads.
-// Here every chunk becomes ONE contiguous section (tables, 4-byte slot metadata, records in jagged-diagonal order)
+// Here every chunk becomes ONE contiguous section (tables, 4-byte slot metadata, records in lane-interleaved rows per group of 32 slots)
 // plus a short list of bulk-copy runs, so that the kernel's consumer warps touch nothing but shared memory and
 // the two H stores per slot.  Index bytes per slot drop from 12 to 5 and no per-slot record offsets are stored:
 // slots of similar pair count share a group of 32 lanes whose records are stored lane-interleaved (row d = the d-th

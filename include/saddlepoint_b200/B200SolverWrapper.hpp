@@ -67,6 +67,8 @@ class B200SolverWrapper {
   int last_iterations() const { return last_iters_; }
   // status of the last factorize / solve call (solve() itself always returns true, like the reference's)
   spb_status last_status() const { return last_status_; }
+  // which pair-assembly kernel the last fused assembly on this handle ran (3 = stream form, 2 / 1 = general kernels)
+  int assembly_form() const { return spb_assembly_form(h_); }
 
   template <class SparsePattern>
   bool analyze(const SparsePattern& JPattern) {

@@ -189,3 +189,77 @@ def test_tma_staged_syrk_gives_the_same_factor(spb, orc, g, monkeypatch):
         xs.append(np.array(x, copy=True))
         h.close()
     assert np.array_equal(xs[0].view(np.uint64), xs[1].view(np.uint64))
+
+
+@pytest.mark.parametrize("kind", ["chain", "star_of_pairs", "satellites"])
+def test_tiny_fronts_with_children_and_condensed_groups(spb, orc, kind):
+    """Low-degree structures: every front is tiny (<= 16 pivots, <= 32 rows) and most have children, or the ordering
+    condenses satellite groups first -- the warp-per-front kernels (factor, extend-add of small children, both solves)
+    against the oracle's LLT."""
+    rng = np.random.default_rng(4)
+    rows, cols = [], []
+    if kind == "chain":            # H tridiagonal: residual r couples unknowns r and r+1
+        n = 700
+        for r in range(n - 1):
+            rows += [r, r]
+            cols += [r, r + 1]
+        m = n - 1
+    elif kind == "star_of_pairs":  # pairs of unknowns hanging off a few hubs
+        hubs, n = 12, 12 + 2 * 300
+        r = 0
+        for p in range(300):
+            a, b, hub = hubs + 2 * p, hubs + 2 * p + 1, p % hubs
+            rows += [r, r, r + 1, r + 1, r + 1]
+            cols += [a, b, a, b, hub]
+            r += 2
+        for hub in range(hubs):    # couple the hubs in a ring
+            rows += [r, r]
+            cols += [hub, (hub + 1) % hubs]
+            r += 1
+        m = r
+    else:                          # mesh-like: 8 satellites per cell coupled to the cell's 4 grid nodes
+        gsz = 14
+        nodes = gsz * gsz
+        cells = (gsz - 1) * (gsz - 1)
+        n = nodes + 8 * cells
+        r = 0
+        for cy in range(gsz - 1):
+            for cx in range(gsz - 1):
+                c = cy * (gsz - 1) + cx
+                corner = [cy * gsz + cx, cy * gsz + cx + 1, (cy + 1) * gsz + cx, (cy + 1) * gsz + cx + 1]
+                for s in range(8):
+                    sat = nodes + 8 * c + s
+                    rows += [r, r, r]
+                    cols += [sat, corner[s % 4], nodes + 8 * c + (s + 1) % 8]
+                    r += 1
+        for v in range(nodes):     # anchor every node
+            rows.append(r)
+            cols.append(v)
+            r += 1
+        m = r
+    vals = rng.uniform(0.5, 1.5, len(rows)) * rng.choice([-1.0, 1.0], len(rows))
+    Jm = sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
+    Jm.sum_duplicates()
+    Jm.sort_indices()
+    colptr, rowidx, v = Jm.indptr.astype(np.int32), Jm.indices.astype(np.int32), np.ascontiguousarray(Jm.data)
+    J = orc.from_csc(m, n, colptr, rowidx, v)
+    D, _ = orc.damp_build(J, 0.3)
+    H = orc.ata(D)
+    E = rng.standard_normal(m)
+    h = spb.Handle(0)
+    h.set_solver(spb.SOLVER_CHOLESKY)
+    h.analyze(m, n, colptr, rowidx)
+    h.assemble(v, E, 0.3)
+    assert h.factorize()
+    x, it, st = h.solve()
+    assert st == 0
+    xref = orc.LLT(H, 1).solve(orc.jt_vec_neg(J, E))
+    assert np.linalg.norm(x - xref) <= STEP_RTOL * np.linalg.norm(xref)
+    # second factorisation (graph replay) with other values
+    h.assemble(1.5 * v, E, 0.1)
+    assert h.factorize()
+    x2, _, _ = h.solve()
+    D2, _ = orc.damp_build(orc.from_csc(m, n, colptr, rowidx, 1.5 * v), 0.1)
+    x2ref = orc.LLT(orc.ata(D2), 1).solve(orc.jt_vec_neg(orc.from_csc(m, n, colptr, rowidx, 1.5 * v), E))
+    assert np.linalg.norm(x2 - x2ref) <= STEP_RTOL * np.linalg.norm(x2ref)
+    h.close()
